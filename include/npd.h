@@ -1,0 +1,159 @@
+/*
+ * npd.h -- C ABI of libnpd.so, the B200 (sm_100a) Monte-Carlo polar/PAC decode path.
+ *
+ * The reference (hebbarashwin/neural_polar_decoder) has no FFI layer: its boundary is the Python
+ * method surface of PolarCode / PAC / RNN_decoder / convNet.  The Python drop-in in
+ * neural_polar_decoder_b200/ keeps those signatures and forwards every hot-path call to the entry
+ * points below through ctypes (INTEGRATION.md shows the binding).  Each entry point cites the
+ * reference interface it replaces.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes only.  Every tensor argument is a caller-owned DEVICE
+ *    pointer to a contiguous row-major float32 array unless its name starts with `h_` (host).
+ *  - BPSK convention of the reference: bit 0 <-> +1.0f, bit 1 <-> -1.0f (polar.py:130-132).
+ *  - Kernels are enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream)
+ *    on the CURRENT device; the call returns without synchronising.  No per-call allocation: scratch
+ *    is passed in by the caller.  Handles own small device-side tables / repacked weights.
+ *  - Return value: 0 on success, a negative NPD_E* code otherwise; npd_last_error() gives a
+ *    thread-local message.  There is no CPU fallback anywhere: without a CUDA device every compute
+ *    entry point returns NPD_ECUDA.
+ */
+#ifndef NPD_H_
+#define NPD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NPD_VERSION 100 /* 0.1.0 */
+
+#define NPD_OK 0
+#define NPD_EINVAL (-1)       /* bad argument */
+#define NPD_ECUDA (-2)        /* CUDA runtime error / no device */
+#define NPD_EUNSUPPORTED (-3) /* valid request outside the implemented envelope */
+#define NPD_ENOMEM (-4)
+
+typedef struct npd_code npd_code_t; /* code object: (N, K, info set, frozen mask, PAC taps) */
+typedef struct npd_gru npd_gru_t;   /* CRISP GRU decoder weights, repacked for the kernel */
+typedef struct npd_conv npd_conv_t; /* convNet weights, repacked for the kernel */
+
+int npd_version(void);
+const char *npd_last_error(void);
+
+/* Number of SMs / name of the current device (diagnostics; NPD_ECUDA if none). */
+int npd_device_info(int *sm_count, int *cc_major, int *cc_minor, char *name, int name_len);
+
+/* ---- code objects ------------------------------------------------------------------------------
+ * Replaces PolarCode.__init__ (polar.py:66-117: info/frozen sets, infty) and PAC.__init__
+ * (pac_code.py:97-119: g -> tap array, RM info set).  `h_info` = sorted info positions (host int32),
+ * n = log2 N (1..12).  `pac_g` = 0 for a plain polar code, else the generator polynomial as the
+ * reference passes it (e.g. 53 -> taps 1,1,0,1,0,1, MSB first).  `infty` = frozen prior
+ * (polar.py:81, 471-472); ignored by the PAC decoder, which has no priors (pac_code.py:265-345). */
+int npd_code_create(int n, int K, const int32_t *h_info, float infty, uint32_t pac_g,
+                    npd_code_t **out);
+int npd_code_destroy(npd_code_t *code);
+
+/* ---- encoder + channel -------------------------------------------------------------------------
+ * npd_polar_encode: PolarCode.encode_plotkin(message) (polar.py:128-148, scaling=None) and, for a
+ * PAC code object, PAC.pac_encode(msg) (pac_code.py:220-224: rate profile -> rate-1 convolutional
+ * pre-coder -> Plotkin transform).  msg[B,K] in {+1,-1} -> x[B,N] in {+1,-1}. */
+int npd_polar_encode(const npd_code_t *code, const float *msg, float *x, int64_t B, void *stream);
+
+/* npd_awgn: PolarCode.channel / PAC.channel (polar.py:201-207, pac_code.py:226-231):
+ * y = x + sigma * z, z ~ N(0,1).  The reference draws z with torch.randn on the CPU generator; here
+ * z is Philox4x32-10 + Box-Muller keyed by (seed, point) and counted by the GLOBAL codeword index
+ * cw_offset + row, so a sweep gives identical noise for any GPU count / batch split. */
+int npd_awgn(const float *x, float *y, int64_t B, int N, float sigma, uint64_t seed,
+             uint32_t point, uint64_t cw_offset, void *stream);
+
+/* npd_gen_encode_awgn: fused message generation (rnn_all.py:1771 / polar.py:1259: iid +-1) +
+ * encode + channel for one SNR point.  Writes y[B,N]; msg[B,K] and x[B,N] are optional outputs
+ * (NULL to skip).  Messages depend only on (seed, global codeword index), noise also on `point`. */
+int npd_gen_encode_awgn(const npd_code_t *code, float *msg, float *x, float *y, int64_t B,
+                        float sigma, uint64_t seed, uint32_t point, uint64_t cw_offset,
+                        void *stream);
+
+/* ---- successive-cancellation decoders ----------------------------------------------------------
+ * npd_sc_decode: PolarCode.sc_decode_new(y, snr, use_gt) (polar.py:465-484 with 361-463 and
+ * utils.py:272-275).  llr_scale = fp32(2/sigma^2) (torch rounds the Python scalar to fp32 before
+ * the multiply).  Bit-exact fp32 min-sum SC: f = min(|a|,|b|)*sign(a)*sign(b), g = u*a + b with
+ * u in {-1,0,+1}, leaf = L + infty*frozen, u = sign(leaf) (sign(0) = 0 and propagates).
+ *   use_gt   [B,N] or NULL : genie decisions in {-1,0,+1} used for ALL positions (polar.py:480-481)
+ *   leaf_llr [B,N] or NULL : llr_array[:,0,:] (includes the frozen prior)
+ *   decoded  [B,K]         : u_hat[:, info_positions] in {-1,0,+1}
+ * For a PAC code object use npd_pac_sc_decode. */
+int npd_sc_decode(const npd_code_t *code, const float *y, float llr_scale, const float *use_gt,
+                  float *leaf_llr, float *decoded, int64_t B, void *stream);
+
+/* npd_pac_sc_decode: PAC.pac_sc_decode(y, snr, use_gt_codeword) (pac_code.py:534-573): min-sum SC
+ * without priors + convolutional-state tracking.  Outputs leaf_llr[B,N] (optional), v_hat[B,K]
+ * (= v_hat[:, B-set], 0 where a tie left v undecided), u_hat[B,N] (optional). */
+int npd_pac_sc_decode(const npd_code_t *code, const float *y, float llr_scale,
+                      const float *use_gt_codeword, float *leaf_llr, float *v_hat, float *u_hat,
+                      int64_t B, void *stream);
+
+/* ---- error counting ----------------------------------------------------------------------------
+ * npd_count_errors: numerators of errors_ber (utils.py:17-25) and errors_bler (utils.py:37-51):
+ * counts[0] += #{round(a) != round(b)}, counts[1] += #rows with any mismatch, over a[B,K], b[B,K].
+ * counts is a device uint64[2] that the call ACCUMULATES into (zero it first). */
+int npd_count_errors(const float *a, const float *b, int64_t B, int K, uint64_t *counts,
+                     void *stream);
+
+/* ---- fused Monte-Carlo SC sweep ----------------------------------------------------------------
+ * The inner loop of polar.py:1258-1291 / rnn_all.py:843-856 for one SNR point without any host
+ * round trip: generate B messages (global indices cw_offset..cw_offset+B), encode, add noise,
+ * SC-decode, count.  counts (device uint64[3]) accumulates bit errors, block errors, frames.
+ * `workspace` is caller-owned device scratch of at least npd_mc_sc_workspace_bytes(code, chunk)
+ * bytes; the batch is processed in chunks of `chunk` codewords. */
+size_t npd_mc_sc_workspace_bytes(const npd_code_t *code, int64_t chunk);
+int npd_mc_sc_sweep(const npd_code_t *code, int64_t B, int64_t chunk, float sigma, float llr_scale,
+                    uint64_t seed, uint32_t point, uint64_t cw_offset, void *workspace,
+                    size_t workspace_bytes, uint64_t *counts, void *stream);
+
+/* ---- CRISP GRU sequential decoder --------------------------------------------------------------
+ * npd_gru_create: repack the parameters of RNN_Model('GRU', N+2, H, 1, L=2, ...) (rnn_all.py:294-343;
+ * state_dict keys rnn.weight_ih_l{0,1}, rnn.weight_hh_l{0,1}, rnn.bias_*, linear.weight/bias) from
+ * host fp32 into the kernel's bf16 layouts.  h_* are host pointers, PyTorch layouts:
+ *   w_ih0[3H, N+2], w_hh0[3H,H], b_ih0[3H], b_hh0[3H], w_ih1[3H,H], w_hh1[3H,H], b_ih1[3H],
+ *   b_hh1[3H], w_out[H], b_out[1].  Gate order r,z,n. */
+int npd_gru_create(int N, int H, const float *h_w_ih0, const float *h_w_hh0, const float *h_b_ih0,
+                   const float *h_b_hh0, const float *h_w_ih1, const float *h_w_hh1,
+                   const float *h_b_ih1, const float *h_b_hh1, const float *h_w_out,
+                   const float *h_b_out, npd_gru_t **out);
+int npd_gru_destroy(npd_gru_t *gru);
+
+/* npd_gru_decode: RNN_decoder.decode(net, False, y) test branch, decoding_type 'y_input', onehot
+ * (rnn_all.py:514-521, 532-547) with RNN_Model.forward (387-398): N autoregressive steps, hidden
+ * state zero-initialised, input [y | onehot(prev decision)], decision = sign(logit) on info
+ * positions, +1 elsewhere.
+ *   y       [B,N]          raw channel output (not LLR; rnn_all.py:533-534)
+ *   forced  [B,N] or NULL  when given, step i feeds back forced[:, i-1] instead of the decoder's own
+ *                          decision (logit parity under identical feedback; also the genie mode)
+ *   logits  [B,N] or NULL  head output of every step
+ *   decoded [B,N]          +-1/0 decisions on `loss positions` (the code's info set), +1 elsewhere
+ * workspace: device scratch of npd_gru_workspace_bytes(gru, B) bytes. */
+size_t npd_gru_workspace_bytes(const npd_gru_t *gru, int64_t B);
+int npd_gru_decode(const npd_gru_t *gru, const npd_code_t *code, const float *y,
+                   const float *forced, float *logits, float *decoded, int64_t B, void *workspace,
+                   size_t workspace_bytes, void *stream);
+
+/* ---- convNet one-shot decoder ------------------------------------------------------------------
+ * npd_conv_create / npd_conv_forward: convNet.forward (models.py:742-767; layers 701-740) with
+ * embed_dim = 2*C (C = 64), max_len = N: ten dilated k=7 Conv1d + GELU with three residual adds,
+ * flatten, Linear(2C*N,4N) GELU Linear(4N,N) GELU Linear(N,N), LayerNorm(N, eps=1e-6).
+ * h_params: host fp32 blob in state_dict order (see neural_polar_decoder_b200/models.py).
+ * logits[B,N] out; bits = sign(logits) is left to the caller. */
+int npd_conv_create(int N, int embed_dim, const float *h_params, size_t n_params,
+                    npd_conv_t **out);
+int npd_conv_destroy(npd_conv_t *conv);
+size_t npd_conv_workspace_bytes(const npd_conv_t *conv, int64_t B);
+int npd_conv_forward(const npd_conv_t *conv, const float *y, float *logits, int64_t B,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NPD_H_ */

@@ -1,0 +1,95 @@
+// count_sweep.cu -- BER/BLER numerators and the fused Monte-Carlo SC sweep.
+//
+// Replaces errors_ber / errors_bler (reference utils.py:17-25, 37-51: round() both tensors, count
+// mismatching elements and rows with any mismatch; the reference goes through CPU numpy for BLER) and
+// the per-SNR inner loop of polar.py:1258-1291 / rnn_all.py:843-856.
+#include "npd_common.cuh"
+
+namespace {
+
+// one warp per row chunk: lanes stride over K (coalesced), ballot for the row flag
+__global__ void __launch_bounds__(256) count_kernel(const float *__restrict__ a, const float *__restrict__ b,
+                                                    int64_t B, int K, unsigned long long *counts,
+                                                    unsigned long long add_frames)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    unsigned long long bits = 0, blocks = 0;
+    for (int64_t r = warp; r < B; r += nwarps) {
+        uint32_t mism = 0;
+        for (int k = lane; k < K; k += 32)
+            mism += rintf(a[r * K + k]) != rintf(b[r * K + k]);  // torch.round = half-to-even
+        const uint32_t any = __ballot_sync(NPD_FULL, mism != 0);
+        bits += mism;
+        if (lane == 0 && any) blocks += 1;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) bits += __shfl_xor_sync(NPD_FULL, bits, s);
+    if (lane == 0) {
+        if (bits) atomicAdd(counts + 0, bits);
+        if (blocks) atomicAdd(counts + 1, blocks);
+        if (warp == 0 && add_frames) atomicAdd(counts + 2, add_frames);
+    }
+}
+
+int launch_count(const float *a, const float *b, int64_t B, int K, uint64_t *counts,
+                 uint64_t add_frames, cudaStream_t st)
+{
+    DeviceProps dp;
+    if (npd_get_device_props(&dp)) return NPD_ECUDA;
+    int64_t grid = (B + 7) / 8;
+    const int64_t cap = (int64_t)dp.sm_count * 8;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    count_kernel<<<(unsigned)grid, 256, 0, st>>>(a, b, B, K, (unsigned long long *)counts,
+                                                 (unsigned long long)add_frames);
+    NPD_CHECK_CUDA(cudaGetLastError());
+    return NPD_OK;
+}
+
+}  // namespace
+
+NPD_API int npd_count_errors(const float *a, const float *b, int64_t B, int K, uint64_t *counts,
+                             void *stream)
+{
+    NPD_REQUIRE(a && b && counts, "npd_count_errors: null argument");
+    NPD_REQUIRE(B >= 0 && K >= 1, "npd_count_errors: bad shape");
+    if (B == 0) return NPD_OK;
+    return launch_count(a, b, B, K, counts, 0, (cudaStream_t)stream);
+}
+
+NPD_API size_t npd_mc_sc_workspace_bytes(const npd_code_t *code, int64_t chunk)
+{
+    if (!code || chunk <= 0) return 0;
+    // msg[chunk,K] + y[chunk,N] + decoded[chunk,K], each region 256-byte aligned
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    return al((size_t)chunk * code->K * 4) * 2 + al((size_t)chunk * code->N * 4);
+}
+
+NPD_API int npd_mc_sc_sweep(const npd_code_t *code, int64_t B, int64_t chunk, float sigma,
+                            float llr_scale, uint64_t seed, uint32_t point, uint64_t cw_offset,
+                            void *workspace, size_t workspace_bytes, uint64_t *counts, void *stream)
+{
+    NPD_REQUIRE(code && workspace && counts, "npd_mc_sc_sweep: null argument");
+    NPD_REQUIRE(B >= 0 && chunk > 0, "npd_mc_sc_sweep: bad sizes");
+    NPD_REQUIRE(code->pac_g == 0, "npd_mc_sc_sweep: polar code objects only");
+    NPD_REQUIRE(workspace_bytes >= npd_mc_sc_workspace_bytes(code, chunk),
+                "npd_mc_sc_sweep: workspace too small (%zu < %zu)", workspace_bytes,
+                npd_mc_sc_workspace_bytes(code, chunk));
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    char *ws = (char *)workspace;
+    float *msg = (float *)ws;
+    float *dec = (float *)(ws + al((size_t)chunk * code->K * 4));
+    float *y = (float *)(ws + 2 * al((size_t)chunk * code->K * 4));
+    for (int64_t done = 0; done < B; done += chunk) {
+        const int64_t b = (B - done < chunk) ? (B - done) : chunk;
+        int rc = npd_gen_encode_awgn(code, msg, nullptr, y, b, sigma, seed, point, cw_offset + done, stream);
+        if (rc) return rc;
+        rc = npd_sc_decode(code, y, llr_scale, nullptr, nullptr, dec, b, stream);
+        if (rc) return rc;
+        rc = launch_count(msg, dec, b, code->K, counts, (uint64_t)b, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return NPD_OK;
+}

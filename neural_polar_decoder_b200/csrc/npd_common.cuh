@@ -1,0 +1,108 @@
+// npd_common.cuh -- shared declarations for libnpd.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "npd.h"
+
+#define NPD_API extern "C" __attribute__((visibility("default")))
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void npd_set_error(const char *fmt, ...);
+
+#define NPD_CHECK_CUDA(expr)                                                                  \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            npd_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+            return NPD_ECUDA;                                                                 \
+        }                                                                                     \
+    } while (0)
+
+#define NPD_REQUIRE(cond, ...)                                                                \
+    do {                                                                                      \
+        if (!(cond)) {                                                                        \
+            npd_set_error(__VA_ARGS__);                                                       \
+            return NPD_EINVAL;                                                                \
+        }                                                                                     \
+    } while (0)
+
+// ---- code object ------------------------------------------------------------------------------
+struct npd_code {
+    int n, N, K;
+    float infty;
+    uint32_t pac_g;     // 0 = plain polar
+    int pac_M;          // number of taps incl. the leading one (pac_code.py:101)
+    uint32_t pac_taps;  // bit (j-1) set <=> g[j] == -1, j = 1..M-1 (state[j-1] multiplies u)
+    int device;
+    int sm_count;
+    int32_t *d_info;          // [K] sorted info positions
+    uint32_t *d_frozen_words; // [max(N/32,1)] bit i = position i frozen
+    uint32_t *d_info_words;   // complement of frozen within N
+    int32_t *h_info;          // host copy
+};
+
+struct DeviceProps {
+    int device;
+    int sm_count;
+    int smem_optin;
+    int cc_major, cc_minor;
+};
+int npd_get_device_props(DeviceProps *p);
+
+// ---- device helpers ---------------------------------------------------------------------------
+#define NPD_FULL 0xffffffffu
+
+// utils.py:272-275: min(|a|,|b|) * sign(a) * sign(b).  Multiplying by +-1 is exact and a zero operand
+// makes the min zero, so the product equals min(|a|,|b|) carrying sign(a) xor sign(b) (a signed zero
+// where the reference yields one) -- bit-identical for all finite inputs.
+__device__ __forceinline__ float npd_f_minsum(float a, float b)
+{
+    float m = fminf(fabsf(a), fabsf(b));
+    uint32_t sg = (__float_as_uint(a) ^ __float_as_uint(b)) & 0x80000000u;
+    return __uint_as_float(__float_as_uint(m) | sg);
+}
+
+// polar.py:414/445: u*a + b with u in {-1,0,+1} carried as (s = "u is -1", z = "u is 0").
+// u*a is exact, so (s ? -a : a) + b rounds identically; u = 0 gives (+-0) + b == b.
+__device__ __forceinline__ float npd_g_trit(uint32_t s, uint32_t z, float a, float b)
+{
+    float t = __uint_as_float(__float_as_uint(a) ^ (s << 31));
+    float r = t + b;
+    return z ? b : r;
+}
+
+// ---- Philox4x32-10 (counter-based RNG; restated in oracle/npd_oracle.c) ------------------------
+#define NPD_STREAM_MSG 0u
+#define NPD_STREAM_NOISE 1u  // + SNR point index
+
+__device__ __forceinline__ uint4 npd_philox4x32_10(uint4 c, uint2 k)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        uint4 nxt;
+        nxt.x = hi1 ^ c.y ^ k.x;
+        nxt.y = lo1;
+        nxt.z = hi0 ^ c.w ^ k.y;
+        nxt.w = lo0;
+        c = nxt;
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// Box-Muller on two 32-bit words -> two N(0,1) samples.  u = (float(r) + 0.5) * 2^-32 in (0,1].
+__device__ __forceinline__ float2 npd_box_muller(uint32_t r0, uint32_t r1)
+{
+    float u0 = ((float)r0 + 0.5f) * 2.3283064365386963e-10f;
+    float u1 = ((float)r1 + 0.5f) * 2.3283064365386963e-10f;
+    float rad = sqrtf(-2.0f * __logf(u0));
+    float sn, cs;
+    __sincosf(6.283185307179586f * u1, &sn, &cs);
+    return make_float2(rad * cs, rad * sn);
+}

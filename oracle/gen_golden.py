@@ -1,0 +1,266 @@
+"""Mint tests/golden/*.npz from the LIVE reference (/root/reference through oracle/ref_shim.py).
+
+Run in the build container only:  python oracle/gen_golden.py [--big]
+The fixtures pin the oracle (tests/test_oracle_golden.py, CPU) and are the committed parity targets
+of the GPU tests (tests/test_gpu_parity.py).  Inputs are generated with numpy RandomState so that the
+script is reproducible; outputs are whatever the reference returns on this torch build.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+import ref_shim  # noqa: E402
+from neural_polar_decoder_b200 import construct, synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def bpsk_msgs(rs, B, K):
+    return (1.0 - 2.0 * rs.randint(0, 2, size=(B, K))).astype(np.float32)
+
+
+def noisy(rs, x, snr, ties=False):
+    sigma = 10 ** (-snr / 20)
+    y = (x + sigma * rs.randn(*x.shape)).astype(np.float32)
+    if ties:
+        y = (np.round(y * 2) / 2).astype(np.float32)  # half-integers: exact cancellations -> sign(0)
+    return y
+
+
+def polar_cases(big):
+    polar = ref_shim.load("polar")
+    rs = np.random.RandomState(1234)
+    out = {}
+    meta = []
+
+    def add(name, code, y, snr, use_gt=None, msg=None, x=None):
+        llr, dec = code.sc_decode_new(torch.from_numpy(y), snr,
+                                      use_gt=None if use_gt is None else torch.from_numpy(use_gt))
+        out[name + "_y"] = y
+        out[name + "_snr"] = np.float64(snr)
+        out[name + "_info"] = np.asarray(code.info_positions, dtype=np.int32)
+        out[name + "_llr"] = llr.numpy()
+        out[name + "_dec"] = dec.numpy()
+        if use_gt is not None:
+            out[name + "_gt"] = use_gt
+        if msg is not None:
+            out[name + "_msg"] = msg
+            out[name + "_x"] = x
+        meta.append(name)
+
+    # SURVEY.md App. B KAT1-4 (inputs written out; outputs recomputed from the live reference)
+    c84 = polar.PolarCode(3, 4, ref_shim.make_args(8, 4), use_cuda=False)
+    msg = np.array([[-1, 1, 1, -1], [1, -1, -1, -1]], dtype=np.float32)
+    x = c84.encode_plotkin(torch.from_numpy(msg)).numpy()
+    y = np.array([[0.9, -1.2, 0.3, -0.4, -1.1, 0.8, -0.2, 1.5],
+                  [-0.5, 0.5, 1, -1, 0.25, -0.25, 2, -2]], dtype=np.float32)
+    add("kat1", c84, y, 1.0, msg=msg, x=x)
+    add("kat2", c84, np.array([[1, -1, 1, 1, 1, 1, 1, 1]], dtype=np.float32), 0.0)
+    c22 = polar.PolarCode(1, 2, ref_shim.make_args(2, 2), use_cuda=False)
+    add("kat3", c22, np.array([[1, -1]], dtype=np.float32), 0.0)
+    add("kat4", c22, np.array([[0, -1]], dtype=np.float32), 0.0)
+
+    configs = [(2, 1, None), (4, 2, None), (8, 4, None), (16, 8, None), (16, 16, None), (16, 1, None),
+               (32, 16, "polar"), (64, 22, "polar"), (64, 22, "rev_polar"), (128, 64, "polar"),
+               (256, 128, "polar"), (512, 256, "pw"), (1024, 512, "pw"), (1024, 512, None)]
+    if big:
+        configs.append((2048, 1024, "pw"))
+    for N, K, prof in configs:
+        n = int(np.log2(N))
+        if prof in ("polar", "rev_polar"):
+            code = ref_shim.get_code("Polar", prof, N, K)
+        elif prof == "pw":
+            code = polar.PolarCode(n, K, ref_shim.make_args(N, K), F=construct.pw_frozen_set(N, K),
+                                   use_cuda=False)
+        else:
+            code = polar.PolarCode(n, K, ref_shim.make_args(N, K), use_cuda=False)
+        B = 37 if N <= 64 else (9 if N <= 256 else (3 if N <= 1024 else 2))
+        msg = bpsk_msgs(rs, B, K)
+        x = code.encode_plotkin(torch.from_numpy(msg)).numpy()
+        tag = "p%d_%d_%s" % (N, K, prof or "last")
+        snrs = (0.0, 2.0) if N <= 256 else (2.0,)
+        for si, snr in enumerate(snrs):
+            add("%s_s%d" % (tag, si), code, noisy(rs, x, snr), snr, msg=msg, x=x)
+        add(tag + "_ties", code, noisy(rs, x, 0.0, ties=True), 0.0)
+        if N <= 256:
+            u = np.ones((B, N), dtype=np.float32)
+            u[:, code.info_positions] = msg
+            add(tag + "_gt", code, noisy(rs, x, 1.0), 1.0, use_gt=u)
+        print("polar", tag, "done", flush=True)
+    out["names"] = np.array(meta)
+    np.savez_compressed(os.path.join(OUT, "polar_sc.npz"), **out)
+
+
+def pac_cases():
+    rs = np.random.RandomState(4321)
+    out = {}
+    meta = []
+    for N, K, g in [(32, 16, 53), (16, 8, 13), (64, 32, 53), (8, 4, 7), (128, 64, 133), (32, 16, 3)]:
+        pac = ref_shim.get_code("PAC", "RM", N, K, g=g)
+        B = 33 if N <= 64 else 7
+        msg = bpsk_msgs(rs, B, K)
+        x = pac.pac_encode(torch.from_numpy(msg)).numpy()
+        for tag, snr, ties, gt in [("a", 0.0, False, False), ("b", 2.0, False, False),
+                                   ("t", 0.0, True, False), ("g", 1.0, False, True)]:
+            y = noisy(rs, x, snr, ties)
+            name = "pac%d_%d_%d_%s" % (N, K, g, tag)
+            gtc = None
+            if gt:
+                # genie mode wants the true u (pre-transform) sequence: conv-encoded rate-profiled msg
+                v = pac.rate_profiler(torch.from_numpy(msg), scheme="RM")
+                gtc = pac.convolutional_encode(v).numpy()
+            llr, vh, uh = pac.pac_sc_decode(torch.from_numpy(y), snr,
+                                            use_gt_codeword=None if gtc is None else torch.from_numpy(gtc))
+            out[name + "_y"] = y
+            out[name + "_snr"] = np.float64(snr)
+            out[name + "_g"] = np.int64(g)
+            out[name + "_info"] = np.asarray(pac.B, dtype=np.int32)
+            out[name + "_msg"] = msg
+            out[name + "_x"] = x
+            out[name + "_llr"] = llr.numpy()
+            out[name + "_v"] = vh.numpy()
+            out[name + "_u"] = uh.numpy()
+            if gtc is not None:
+                out[name + "_gt"] = gtc
+            meta.append(name)
+        print("pac", N, K, g, "done", flush=True)
+    out["names"] = np.array(meta)
+    np.savez_compressed(os.path.join(OUT, "pac_sc.npz"), **out)
+
+
+def _ref_gru_logits(ra, net, dec, y, N, info, forced=None):
+    """Step the reference RNN_Model exactly as RNN_decoder.decode's test branch does
+    (rnn_all.py:532-547), also collecting the head output of every step."""
+    net.eval()
+    B = y.shape[0]
+    decoded = torch.ones(B, N)
+    logits = torch.zeros(B, N)
+    hidden = torch.zeros(net.num_rnn_layers, B, net.feature_size)
+    info = set(int(i) for i in info)
+    with torch.no_grad():
+        for ii in range(N):
+            if ii == 0:
+                prev = torch.ones(B)
+            elif forced is not None:
+                prev = forced[:, ii - 1]
+            else:
+                prev = decoded[:, ii - 1].sign()
+            inp = torch.cat([y.unsqueeze(1), ra.get_onehot(prev).view(-1, 1, net.input_size - N)], 2)
+            out, hidden = net(inp, hidden)
+            logits[:, ii] = out.squeeze()
+            if ii in info:
+                decoded[:, ii] = out.squeeze().sign()
+    return decoded, logits
+
+
+def gru_cases():
+    ra = ref_shim.load("rnn_all")
+    rs = np.random.RandomState(99)
+    out = {}
+    meta = []
+    for name, N, K, H, seed, gain, B in [("gru64", 64, 22, 512, 11, 8.0, 160), ("gru32", 32, 16, 512, 12, 8.0, 70),
+                                         ("gru16_h64", 16, 8, 64, 13, 4.0, 21)]:
+        code = ref_shim.get_code("Polar", "polar", N, K)
+        sd = synth.gru_state_dict(seed, N, H, 2, head_gain=gain)
+        net = ra.RNN_Model("GRU", N + 2, H, 1, 2, N, 0, 0, out_linear_depth=1)
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        dec = ra.RNN_decoder("y_input", N, code.info_positions, onehot=True)
+        msg = bpsk_msgs(rs, B, K)
+        x = code.encode_plotkin(torch.from_numpy(msg)).numpy()
+        y = noisy(rs, x, 1.0)
+        d_ref = dec.decode(net, False, torch.from_numpy(y))
+        d2, lg = _ref_gru_logits(ra, net, dec, torch.from_numpy(y), N, code.info_positions)
+        assert torch.equal(d_ref, d2)
+        out[name + "_y"] = y
+        out[name + "_info"] = np.asarray(code.info_positions, dtype=np.int32)
+        out[name + "_cfg"] = np.array([N, K, H, seed], dtype=np.int64)
+        out[name + "_gain"] = np.float64(gain)
+        out[name + "_decoded"] = d_ref.numpy()
+        out[name + "_logits"] = lg.numpy()
+        if H <= 64:  # small net: store the weights themselves too (pins synth.gru_state_dict)
+            for k, v in sd.items():
+                out[name + "_w_" + k] = v
+        meta.append(name)
+        print("gru", name, "|logit| mean", float(lg.abs().mean()), flush=True)
+    out["names"] = np.array(meta)
+    np.savez_compressed(os.path.join(OUT, "gru.npz"), **out)
+
+
+def conv_cases():
+    import argparse as ap
+    md = ref_shim.load("models")
+    rs = np.random.RandomState(7)
+    out = {}
+    for name, N, K, E, seed, B in [("conv64", 64, 22, 128, 21, 72)]:
+        code = ref_shim.get_code("Polar", "polar", N, K)
+        sd = synth.conv_state_dict(seed, N, E)
+        net = md.convNet(ap.Namespace(embed_dim=E, max_len=N, N=N, dont_use_bias=False, dropout=0.1))
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        net.eval()
+        msg = bpsk_msgs(rs, B, K)
+        x = code.encode_plotkin(torch.from_numpy(msg)).numpy()
+        y = noisy(rs, x, 1.0)
+        with torch.no_grad():
+            probs, bits, _, logits, in4 = net(torch.from_numpy(y), None, None, "cpu")
+        out[name + "_y"] = y
+        out[name + "_cfg"] = np.array([N, K, E, seed], dtype=np.int64)
+        out[name + "_logits"] = logits.squeeze(-1).numpy()
+        out[name + "_bits"] = bits.squeeze(-1).numpy()
+        print("conv", name, "|logit| mean", float(logits.abs().mean()), flush=True)
+    out["names"] = np.array(["conv64"])
+    np.savez_compressed(os.path.join(OUT, "conv.npz"), **out)
+
+
+def misc_cases():
+    """Info sets and the reference's error counters on small hand-made inputs."""
+    ra = ref_shim.load("rnn_all")
+    out = {}
+    for N, K, prof in [(64, 22, "polar"), (64, 22, "rev_polar"), (32, 16, "polar"), (16, 8, "polar"),
+                       (128, 64, "polar"), (256, 128, "polar"), (64, 22, "RM")]:
+        code = ref_shim.get_code("Polar", prof, N, K)
+        out["info_%s_%d_%d" % (prof, N, K)] = np.asarray(code.info_positions, dtype=np.int32)
+    for N, K, g in [(32, 16, 53), (64, 32, 53), (128, 64, 133)]:
+        pac = ref_shim.get_code("PAC", "RM", N, K, g=g)
+        out["pacinfo_%d_%d" % (N, K)] = np.asarray(pac.B, dtype=np.int32)
+        out["pacg_%d" % g] = np.asarray(pac.g_array, dtype=np.int32)
+    rs = np.random.RandomState(5)
+    a = (1.0 - 2.0 * rs.randint(0, 2, size=(50, 22))).astype(np.float32)
+    b = a.copy()
+    flip = rs.rand(50, 22) < 0.07
+    b[flip] *= -1
+    b[3, 4] = 0.0   # a tie counts as an error (round(0) != +-1)
+    b[9, :] = a[9, :]
+    out["err_a"] = a
+    out["err_b"] = b
+    out["err_ber"] = np.float64(ra.errors_ber(torch.from_numpy(a), torch.from_numpy(b)).item())
+    out["err_bler"] = np.float64(ra.errors_bler(torch.from_numpy(a), torch.from_numpy(b)))
+    np.savez_compressed(os.path.join(OUT, "misc.npz"), **out)
+
+
+if __name__ == "__main__":
+    p = argparse.ArgumentParser()
+    p.add_argument("--big", action="store_true", help="also run the reference at N=2048 (minutes)")
+    p.add_argument("--only", default="")
+    a = p.parse_args()
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    todo = a.only.split(",") if a.only else ["misc", "pac", "gru", "conv", "polar"]
+    if "misc" in todo:
+        misc_cases()
+    if "pac" in todo:
+        pac_cases()
+    if "gru" in todo:
+        gru_cases()
+    if "conv" in todo:
+        conv_cases()
+    if "polar" in todo:
+        polar_cases(a.big)
+    print("golden fixtures written to", OUT)

@@ -1,0 +1,283 @@
+"""ctypes front-end of the CPU oracle (oracle/npd_oracle.c) plus the fp32 torch oracles for the two
+floating-point decoders (GRU, CNN).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package never imports this module.
+
+Parity status: pinned against the live reference through tests/golden/ (oracle/gen_golden.py) and,
+where /root/reference is present, tests/test_oracle_vs_reference.py.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+_f32p = ctypes.POINTER(ctypes.c_float)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+_u32p = ctypes.POINTER(ctypes.c_uint32)
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "libnpd_oracle.so")
+    src = os.path.join(_HERE, "npd_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libnpd_oracle.so"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(build())
+        _LIB.npdo_sc_decode.restype = ctypes.c_int
+        _LIB.npdo_pac_sc_decode.restype = ctypes.c_int
+    return _LIB
+
+
+def _f32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+def _ptr(a, t=_f32p):
+    return None if a is None else a.ctypes.data_as(t)
+
+
+def frozen_mask(N, info):
+    m = np.ones(N, dtype=np.uint8)
+    m[np.asarray(info, dtype=np.int64)] = 0
+    return m
+
+
+def llr_scale(snr_db: float) -> np.float32:
+    """fp32(2/sigma^2) exactly as torch computes `(2/sigma**2) * tensor` (polar.py:467-469,
+    utils.py:5-6): double arithmetic, then the Python scalar is rounded to fp32."""
+    sigma = 10 ** (-snr_db * 1.0 / 20)
+    return np.float32(2 / sigma ** 2)
+
+
+def polar_encode(msg, n, info):
+    msg = _f32(msg)
+    B, K = msg.shape
+    info = np.ascontiguousarray(info, dtype=np.int32)
+    x = np.empty((B, 1 << n), dtype=np.float32)
+    lib().npdo_polar_encode(_ptr(msg), ctypes.c_int64(B), n, K, _ptr(info, _i32p), _ptr(x))
+    return x
+
+
+def sc_decode(y, snr_db, n, info, infty=1000.0, use_gt=None, scale=None):
+    """-> (leaf_llr[B,N], u_hat[B,N], decoded[B,K]) following polar.py:465-484."""
+    y = _f32(y)
+    B, N = y.shape
+    assert N == 1 << n
+    info = np.ascontiguousarray(info, dtype=np.int32)
+    K = info.shape[0]
+    fr = frozen_mask(N, info)
+    gt = None if use_gt is None else _f32(use_gt)
+    leaf = np.empty((B, N), dtype=np.float32)
+    uh = np.empty((B, N), dtype=np.float32)
+    dec = np.empty((B, K), dtype=np.float32)
+    s = llr_scale(snr_db) if scale is None else np.float32(scale)
+    rc = lib().npdo_sc_decode(_ptr(y), ctypes.c_int64(B), n, K, _ptr(info, _i32p), _ptr(fr, _u8p),
+                              ctypes.c_float(s), ctypes.c_float(infty), _ptr(gt), _ptr(leaf),
+                              _ptr(uh), _ptr(dec))
+    assert rc == 0
+    return leaf, uh, dec
+
+
+def pac_g_array(g: int):
+    """pac_code.py:101-103: M = floor(log2 g)+1 bits, MSB first, mapped to 1-2*bit."""
+    M = int(np.floor(np.log2(g))) + 1
+    bits = np.array([(g >> (M - 1 - i)) & 1 for i in range(M)], dtype=np.float32)
+    return (1.0 - 2.0 * bits).astype(np.float32)
+
+
+def pac_encode(msg, n, info, g):
+    msg = _f32(msg)
+    B, K = msg.shape
+    info = np.ascontiguousarray(info, dtype=np.int32)
+    ga = pac_g_array(g)
+    x = np.empty((B, 1 << n), dtype=np.float32)
+    lib().npdo_pac_encode(_ptr(msg), ctypes.c_int64(B), n, K, _ptr(info, _i32p), _ptr(ga),
+                          len(ga), _ptr(x))
+    return x
+
+
+def pac_sc_decode(y, snr_db, n, info, g, use_gt_codeword=None, scale=None):
+    """-> (leaf_llr[B,N], v_hat[B,K], u_hat[B,N]) following pac_code.py:534-573."""
+    y = _f32(y)
+    B, N = y.shape
+    info = np.ascontiguousarray(info, dtype=np.int32)
+    K = info.shape[0]
+    fr = frozen_mask(N, info)
+    ga = pac_g_array(g)
+    gt = None if use_gt_codeword is None else _f32(use_gt_codeword)
+    leaf = np.empty((B, N), dtype=np.float32)
+    vh = np.empty((B, K), dtype=np.float32)
+    uh = np.empty((B, N), dtype=np.float32)
+    s = llr_scale(snr_db) if scale is None else np.float32(scale)
+    rc = lib().npdo_pac_sc_decode(_ptr(y), ctypes.c_int64(B), n, K, _ptr(info, _i32p),
+                                  _ptr(fr, _u8p), _ptr(ga), len(ga), ctypes.c_float(s), _ptr(gt),
+                                  _ptr(leaf), _ptr(vh), _ptr(uh))
+    assert rc == 0
+    return leaf, vh, uh
+
+
+def count_errors(a, b):
+    """-> (bit_errors, block_errors) = numerators of utils.py:17-25 / 37-51."""
+    a = _f32(a)
+    b = _f32(b)
+    a = a.reshape(a.shape[0], -1)
+    b = b.reshape(b.shape[0], -1)
+    out = np.zeros(2, dtype=np.uint64)
+    lib().npdo_count_errors(_ptr(a), _ptr(b), ctypes.c_int64(a.shape[0]), a.shape[1],
+                            _ptr(out, _u64p))
+    return int(out[0]), int(out[1])
+
+
+def philox4x32_10(ctr, key):
+    c = np.ascontiguousarray(ctr, dtype=np.uint32)
+    k = np.ascontiguousarray(key, dtype=np.uint32)
+    o = np.zeros(4, dtype=np.uint32)
+    lib().npdo_philox4x32_10(_ptr(c, _u32p), _ptr(k, _u32p), _ptr(o, _u32p))
+    return o
+
+
+def gen_msg(seed, cw0, B, K):
+    m = np.empty((B, K), dtype=np.float32)
+    lib().npdo_gen_msg(ctypes.c_uint64(seed), ctypes.c_uint64(cw0), ctypes.c_int64(B), K, _ptr(m))
+    return m
+
+
+def gen_noise(seed, cw0, pt, B, N):
+    z = np.empty((B, N), dtype=np.float32)
+    lib().npdo_gen_noise(ctypes.c_uint64(seed), ctypes.c_uint64(cw0), ctypes.c_uint32(pt),
+                         ctypes.c_int64(B), N, _ptr(z))
+    return z
+
+
+# --------------------------------------------------------------------------------------------------
+# fp32 torch oracles for the floating-point decoders.
+# --------------------------------------------------------------------------------------------------
+
+def gru_decode(sd, y, N, info, forced=None, H=None, round_bf16=False):
+    """fp32 restatement of RNN_decoder.decode(net, False, y) for decoding_type 'y_input', onehot,
+    GRU (rnn_all.py:514-521, 532-547) with RNN_Model.forward (387-398) written out gate by gate
+    (PyTorch nn.GRU gate order r,z,n).  The y-part of the layer-0 input projection is
+    hoisted out of the step loop -- bit-for-bit equal to the literal form was
+    checked against the live reference in tests/test_oracle_vs_reference.py within fp32 round-off.
+
+    sd: state_dict-like mapping with the a7 key names (torch tensors or numpy arrays).
+    forced: optional [B,N] of +-1: when given, step ii feeds back forced[:, ii-1] instead of the
+            decoder's own decision (used for logit parity under identical feedback).
+    round_bf16: emulate the kernel's operand rounding (weights, h and y operands to bf16, fp32
+            accumulate) to size tolerances; not a parity target.
+    -> (decoded[B,N] in {-1,0,+1} with +1 on non-info positions, logits[B,N])
+    """
+    import torch
+
+    def T(v):
+        return torch.as_tensor(np.asarray(v) if not torch.is_tensor(v) else v).float().cpu()
+
+    def rb(t):
+        return t.to(torch.bfloat16).float() if round_bf16 else t
+
+    y = T(y)
+    B = y.shape[0]
+    L = 0
+    while ("rnn.weight_ih_l%d" % L) in sd:
+        L += 1
+    Wih = [T(sd["rnn.weight_ih_l%d" % l]) for l in range(L)]
+    Whh = [T(sd["rnn.weight_hh_l%d" % l]) for l in range(L)]
+    bih = [T(sd["rnn.bias_ih_l%d" % l]) for l in range(L)]
+    bhh = [T(sd["rnn.bias_hh_l%d" % l]) for l in range(L)]
+    Wo = T(sd["linear.weight"])
+    bo = T(sd["linear.bias"])
+    Hs = Whh[0].shape[1]
+    info_set = set(int(i) for i in info)
+    h = [torch.zeros(B, Hs) for _ in range(L)]
+    decoded = torch.ones(B, N)
+    logits = torch.zeros(B, N)
+    Gy = rb(y) @ rb(Wih[0][:, :N]).t()  # hoisted y projection
+    col_m1 = Wih[0][:, N]      # onehot(-1) = [1,0]  (rnn_all.py:258-260)
+    col_p1 = Wih[0][:, N + 1]  # onehot(+1) = [0,1]
+    for ii in range(N):
+        if ii == 0:
+            prev = torch.ones(B)
+        elif forced is not None:
+            prev = T(forced)[:, ii - 1]
+        else:
+            prev = decoded[:, ii - 1].sign()
+        sel = (0.5 + 0.5 * prev).long()  # 0 -> column N, 1 -> column N+1 (sign 0 maps to 0)
+        gi = Gy + torch.where(sel[:, None] == 1, col_p1[None, :], col_m1[None, :]) + bih[0]
+        x = None
+        for l in range(L):
+            if l > 0:
+                gi = rb(x) @ rb(Wih[l]).t() + bih[l]
+            gh = rb(h[l]) @ rb(Whh[l]).t() + bhh[l]
+            r = torch.sigmoid(gi[:, :Hs] + gh[:, :Hs])
+            z = torch.sigmoid(gi[:, Hs:2 * Hs] + gh[:, Hs:2 * Hs])
+            n = torch.tanh(gi[:, 2 * Hs:] + r * gh[:, 2 * Hs:])
+            h[l] = (1 - z) * n + z * h[l]
+            x = h[l]
+        out = (rb(x) @ rb(Wo).t() + bo).view(-1) if round_bf16 else (x @ Wo.t() + bo).view(-1)
+        logits[:, ii] = out
+        if ii in info_set:
+            decoded[:, ii] = out.sign()
+    return decoded.numpy(), logits.numpy()
+
+
+_CONV_SPEC = [  # (sequential name, index, dilation)   models.py:701-730, padding = 3*dilation
+    ("layers1", 0, 1), ("layers1", 2, 2),
+    ("layers2", 0, 4), ("layers2", 2, 1),
+    ("layers3", 0, 2), ("layers3", 2, 4),
+    ("layers4", 0, 1), ("layers4", 2, 2),
+    ("layers5", 0, 4), ("layers5", 2, 1),
+]
+
+
+def conv_forward(sd, y, round_bf16=False):
+    """fp32 restatement of convNet.forward (models.py:742-767): 10 dilated k=7 Conv1d + exact GELU with
+    three residual adds, flatten, 3-layer MLP, LayerNorm(N, eps=1e-6).  -> logits[B,N]."""
+    import torch
+    import torch.nn.functional as F
+
+    def T(v):
+        return torch.as_tensor(np.asarray(v) if not torch.is_tensor(v) else v).float().cpu()
+
+    def rb(t):
+        return t.to(torch.bfloat16).float() if round_bf16 else t
+
+    def conv(x, name, idx, dil):
+        w = T(sd["%s.%d.weight" % (name, idx)])
+        b = sd.get("%s.%d.bias" % (name, idx))
+        b = None if b is None else T(b)
+        return F.gelu(F.conv1d(rb(x), rb(w), b, padding=3 * dil, dilation=dil))
+
+    x = T(y).unsqueeze(1)
+    acts = []
+    cur = x
+    for gi in range(5):
+        a = conv(cur, *_CONV_SPEC[2 * gi])
+        a = conv(a, *_CONV_SPEC[2 * gi + 1])
+        if gi in (1, 2, 3):
+            a = a + cur
+        cur = a
+        acts.append(cur)
+    v = torch.flatten(cur, start_dim=1)
+    for li, idx in enumerate((0, 2, 4)):
+        w = T(sd["layersFin.%d.weight" % idx])
+        b = sd.get("layersFin.%d.bias" % idx)
+        v = rb(v) @ rb(w).t()
+        if b is not None:
+            v = v + T(b)
+        if li < 2:
+            v = F.gelu(v)
+    Nn = v.shape[1]
+    v = F.layer_norm(v, (Nn,), T(sd["layer_norm.weight"]), T(sd["layer_norm.bias"]), 1e-6)
+    return v.numpy()

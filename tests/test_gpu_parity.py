@@ -1,0 +1,186 @@
+"""GPU: the CUDA path (through the drop-in -> C ABI) against the committed reference fixtures and
+against the oracle on seeded inputs.  Bit-exact for encoder / SC / PAC / counters."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _n(N):
+    return int(np.log2(N))
+
+
+def _frozen(N, info):
+    return np.array(sorted(set(range(N)) - set(int(i) for i in info)), dtype=np.int64)
+
+
+def _code(N, info, **kw):
+    from neural_polar_decoder_b200 import PolarCode
+    return PolarCode(_n(N), len(info), None, F=_frozen(N, info), **kw)
+
+
+def test_library_loaded_and_device():
+    from neural_polar_decoder_b200 import _lib
+    lib = _lib.load()
+    assert lib.npd_version() == 100
+    import ctypes
+    sm, maj, mi = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    name = ctypes.create_string_buffer(128)
+    _lib.check(lib.npd_device_info(ctypes.byref(sm), ctypes.byref(maj), ctypes.byref(mi), name, 128))
+    assert maj.value == 10, "built for sm_100a (B200); found %s cc %d.%d" % (name.value, maj.value, mi.value)
+
+
+def test_polar_fixtures_bit_exact(golden):
+    g = golden("polar_sc")
+    for nm in [str(s) for s in g["names"]]:
+        y, info, snr = g[nm + "_y"], g[nm + "_info"], float(g[nm + "_snr"])
+        code = _code(y.shape[1], info)
+        gt = torch.from_numpy(g[nm + "_gt"]).cuda() if nm + "_gt" in g.files else None
+        llr, dec = code.sc_decode_new(torch.from_numpy(y).cuda(), snr, use_gt=gt)
+        assert np.array_equal(llr.cpu().numpy(), g[nm + "_llr"]), nm
+        assert np.array_equal(dec.cpu().numpy(), g[nm + "_dec"]), nm
+        if nm + "_msg" in g.files:
+            x = code.encode_plotkin(torch.from_numpy(g[nm + "_msg"]).cuda())
+            assert np.array_equal(x.cpu().numpy(), g[nm + "_x"]), nm
+
+
+def test_pac_fixtures_bit_exact(golden):
+    from neural_polar_decoder_b200 import PAC
+    g = golden("pac_sc")
+    for nm in [str(s) for s in g["names"]]:
+        y, info, snr, gp = g[nm + "_y"], g[nm + "_info"], float(g[nm + "_snr"]), int(g[nm + "_g"])
+        N, K = y.shape[1], len(info)
+        pac = PAC(None, N, K, gp)
+        assert np.array_equal(pac.B, info)
+        x = pac.pac_encode(torch.from_numpy(g[nm + "_msg"]).cuda())
+        assert np.array_equal(x.cpu().numpy(), g[nm + "_x"]), nm
+        gt = torch.from_numpy(g[nm + "_gt"]).cuda() if nm + "_gt" in g.files else None
+        llr, v, u = pac.pac_sc_decode(torch.from_numpy(y).cuda(), snr, use_gt_codeword=gt)
+        assert np.array_equal(llr.cpu().numpy(), g[nm + "_llr"]), nm
+        assert np.array_equal(v.cpu().numpy(), g[nm + "_v"]), nm
+        assert np.array_equal(u.cpu().numpy(), g[nm + "_u"]), nm
+
+
+@pytest.mark.parametrize("N,K,B", [(2, 1, 5), (4, 3, 33), (32, 16, 1000), (64, 22, 2049), (128, 64, 300),
+                                    (256, 128, 257), (512, 256, 65), (1024, 512, 41), (2048, 1024, 9),
+                                    (4096, 2048, 5)])
+def test_sc_vs_oracle_seeded(N, K, B):
+    from neural_polar_decoder_b200 import construct
+    rs = np.random.RandomState(N + K)
+    info = np.sort(construct.polarization_weight_order(N)[:K])
+    code = _code(N, info)
+    msg = (1.0 - 2.0 * rs.randint(0, 2, size=(B, K))).astype(np.float32)
+    x = code.encode_plotkin(torch.from_numpy(msg).cuda()).cpu().numpy()
+    assert np.array_equal(x, oracle.polar_encode(msg, _n(N), info))
+    for snr, ties in [(1.0, False), (0.0, True)]:
+        y = (x + 10 ** (-snr / 20) * rs.randn(B, N)).astype(np.float32)
+        if ties:
+            y = (np.round(2 * y) / 2).astype(np.float32)
+        llr, dec = code.sc_decode_new(torch.from_numpy(y).cuda(), snr)
+        lo, _, do = oracle.sc_decode(y, snr, _n(N), info)
+        assert np.array_equal(llr.cpu().numpy(), lo)
+        assert np.array_equal(dec.cpu().numpy(), do)
+        _, dec2 = code.sc_decode_new(torch.from_numpy(y).cuda(), snr, return_llr=False)
+        assert torch.equal(dec2, dec)
+
+
+def test_sc_frozen_prior_not_forced():
+    """|L| > infty on a frozen leaf must flip the decision: use a tiny infty."""
+    from neural_polar_decoder_b200 import construct
+    N, K, B = 64, 22, 500
+    rs = np.random.RandomState(3)
+    info = np.sort(construct.reference_rs256()[construct.reference_rs256() < N][:K])
+    code = _code(N, info, infty=2.0)
+    y = rs.randn(B, N).astype(np.float32) * 2
+    llr, dec = code.sc_decode_new(torch.from_numpy(y).cuda(), 1.0)
+    lo, uo, do = oracle.sc_decode(y, 1.0, 6, info, infty=2.0)
+    fr = _frozen(N, info)
+    assert (uo[:, fr] == -1).any(), "test must exercise a flipped frozen bit"
+    assert np.array_equal(llr.cpu().numpy(), lo) and np.array_equal(dec.cpu().numpy(), do)
+
+
+def test_empty_and_host_inputs():
+    from neural_polar_decoder_b200 import construct
+    info = np.sort(construct.polarization_weight_order(16)[:8])
+    code = _code(16, info)
+    llr, dec = code.sc_decode_new(torch.zeros(0, 16).cuda(), 1.0)
+    assert llr.shape == (0, 16) and dec.shape == (0, 8)
+    # host tensors in -> host tensors out (H2D / D2H inside the call)
+    y = torch.randn(7, 16)
+    llr, dec = code.sc_decode_new(y, 1.0)
+    assert llr.device.type == "cpu" and dec.device.type == "cpu"
+    lo, _, do = oracle.sc_decode(y.numpy(), 1.0, 4, info)
+    assert np.array_equal(llr.numpy(), lo) and np.array_equal(dec.numpy(), do)
+
+
+def test_count_errors_matches_reference_fixture(golden):
+    from neural_polar_decoder_b200 import errors_ber, errors_bler
+    g = golden("misc")
+    a, b = torch.from_numpy(g["err_a"]).cuda(), torch.from_numpy(g["err_b"]).cuda()
+    assert errors_ber(a, b).item() == pytest.approx(float(g["err_ber"]), abs=1e-7)
+    assert errors_bler(a, b) == pytest.approx(float(g["err_bler"]), abs=1e-12)
+    rs = np.random.RandomState(0)
+    a = rs.randint(-1, 2, size=(5000, 22)).astype(np.float32)
+    b = rs.randint(-1, 2, size=(5000, 22)).astype(np.float32)
+    bit, blk = oracle.count_errors(a, b)
+    assert errors_ber(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()).item() == pytest.approx(bit / a.size)
+    assert errors_bler(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()) == pytest.approx(blk / 5000)
+
+
+def test_gen_encode_awgn_vs_oracle():
+    """Messages are bit-exact Philox; noise matches the host Box-Muller restatement to 2e-5 (device
+    __logf/__sincosf are not bit-reproducible on the host) and is independent of the batch split."""
+    import ctypes
+    from neural_polar_decoder_b200 import _lib, construct
+    N, K, B, seed, pt = 64, 22, 777, 12345, 3
+    info = np.sort(construct.polarization_weight_order(N)[:K])
+    code = _code(N, info)
+    h = code._handle()
+    lib = _lib.load()
+    msg = torch.empty(B, K, device="cuda")
+    x = torch.empty(B, N, device="cuda")
+    y = torch.empty(B, N, device="cuda")
+    sigma = float(np.float32(10 ** (-1.0 / 20)))
+    _lib.check(lib.npd_gen_encode_awgn(h.h, _lib.ptr(msg), _lib.ptr(x), _lib.ptr(y), B, sigma, seed, pt, 1000,
+                                       _lib.stream_ptr()))
+    mo = oracle.gen_msg(seed, 1000, B, K)
+    assert np.array_equal(msg.cpu().numpy(), mo)
+    assert np.array_equal(x.cpu().numpy(), oracle.polar_encode(mo, 6, info))
+    z = oracle.gen_noise(seed, 1000, pt, B, N)
+    np.testing.assert_allclose(y.cpu().numpy(), x.cpu().numpy() + np.float32(sigma) * z, rtol=0, atol=2e-5)
+    # split invariance: second half generated separately is identical
+    y2 = torch.empty(B - 300, N, device="cuda")
+    _lib.check(lib.npd_gen_encode_awgn(h.h, None, None, _lib.ptr(y2), B - 300, sigma, seed, pt, 1300,
+                                       _lib.stream_ptr()))
+    assert torch.equal(y2, y[300:])
+    # statistics of the noise
+    zz = ((y - x) / sigma).cpu().numpy().ravel()
+    assert abs(zz.mean()) < 0.02 and abs(zz.std() - 1) < 0.02
+
+
+def test_mc_sweep_matches_stepwise():
+    import ctypes
+    from neural_polar_decoder_b200 import _lib, construct, utils
+    N, K, B, seed = 128, 64, 5000, 7
+    info = np.sort(construct.polarization_weight_order(N)[:K])
+    code = _code(N, info)
+    h = code._handle()
+    lib = _lib.load()
+    snr = 2.0
+    sigma = float(np.float32(utils.snr_db2sigma(snr)))
+    chunk = 2048
+    ws_bytes = lib.npd_mc_sc_workspace_bytes(h.h, chunk)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    counts = torch.zeros(3, dtype=torch.int64, device="cuda")
+    _lib.check(lib.npd_mc_sc_sweep(h.h, B, chunk, sigma, utils.llr_scale(snr), seed, 0, 0, _lib._vp(ws.data_ptr()),
+                                   ws_bytes, _lib._vp(counts.data_ptr()), _lib.stream_ptr()))
+    msg = torch.empty(B, K, device="cuda")
+    y = torch.empty(B, N, device="cuda")
+    _lib.check(lib.npd_gen_encode_awgn(h.h, _lib.ptr(msg), None, _lib.ptr(y), B, sigma, seed, 0, 0, _lib.stream_ptr()))
+    _, _, do = oracle.sc_decode(y.cpu().numpy(), snr, 7, info)
+    bit, blk = oracle.count_errors(msg.cpu().numpy(), do)
+    assert counts.tolist() == [bit, blk, B]
+    assert 0 < blk < B

@@ -1,0 +1,102 @@
+"""CPU: the oracle (oracle/npd_oracle.c + oracle/oracle.py) against the fixtures minted from the live
+reference (oracle/gen_golden.py).  This is what pins the oracle; bit-exact for SC / encoder / counters,
+fp32 round-off for the GRU / CNN restatements."""
+import numpy as np
+import pytest
+
+import oracle
+
+
+def _n(N):
+    return int(np.log2(N))
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors: philox4x32_10
+    assert [hex(v) for v in oracle.philox4x32_10([0, 0, 0, 0], [0, 0])] == \
+        ['0x6627e8d5', '0xe169c58d', '0xbc57ac4c', '0x9b00dbd8']
+    assert [hex(v) for v in oracle.philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2)] == \
+        ['0x408f276d', '0x41c83b0e', '0xa20bc7c6', '0x6d5451fd']
+    assert [hex(v) for v in oracle.philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344],
+                                                 [0xa4093822, 0x299f31d0])] == \
+        ['0xd16cfe09', '0x94fdcceb', '0x5001e420', '0x24126ea1']
+
+
+def test_survey_kat_values(golden):
+    """SURVEY.md App. B KAT1-4 as literal numbers (independent of the fixture file)."""
+    info = np.array([4, 5, 6, 7], dtype=np.int32)
+    x = oracle.polar_encode(np.array([[-1, 1, 1, -1], [1, -1, -1, -1]], np.float32), 3, info)
+    assert x.tolist() == [[1, -1, -1, -1, 1, -1, -1, -1], [-1, 1, 1, -1, -1, 1, 1, -1]]
+    llr, _, dec = oracle.sc_decode(np.array([[1, -1, 1, 1, 1, 1, 1, 1]], np.float32), 0.0, 3, info)
+    assert llr.tolist() == [[998, 1000, 1000, 1004, 0, 0, 4, 8]]
+    assert dec.tolist() == [[0, 0, 1, 1]]
+    llr, _, dec = oracle.sc_decode(np.array([[0, -1]], np.float32), 0.0, 1, np.array([0, 1], np.int32))
+    assert llr.tolist() == [[0, -2]] and dec.tolist() == [[0, -1]]
+    y0 = np.array([[0.9, -1.2, 0.3, -0.4, -1.1, 0.8, -0.2, 1.5]], np.float32)
+    llr, _, dec = oracle.sc_decode(y0, 1.0, 3, info)
+    np.testing.assert_allclose(llr[0], [1000.50354, 1001.51068, 1002.76965, 994.20892, 0.25178510,
+                                        -1.25892544, 0.75535518, 4.53213167], rtol=1e-7)
+    assert dec.tolist() == [[1, -1, 1, 1]]
+
+
+def test_polar_sc_against_reference_fixtures(golden):
+    g = golden("polar_sc")
+    names = [str(s) for s in g["names"]]
+    assert len(names) > 30
+    ties = 0
+    for nm in names:
+        y, info, snr = g[nm + "_y"], g[nm + "_info"], float(g[nm + "_snr"])
+        n = _n(y.shape[1])
+        gt = g[nm + "_gt"] if nm + "_gt" in g.files else None
+        llr, _, dec = oracle.sc_decode(y, snr, n, info, use_gt=gt)
+        assert np.array_equal(llr, g[nm + "_llr"]), nm
+        assert np.array_equal(dec, g[nm + "_dec"]), nm
+        ties += int((g[nm + "_dec"] == 0).sum())
+        if nm + "_msg" in g.files:
+            assert np.array_equal(oracle.polar_encode(g[nm + "_msg"], n, info), g[nm + "_x"]), nm
+    assert ties > 0, "fixtures must exercise sign(0) = 0"
+
+
+def test_pac_against_reference_fixtures(golden):
+    g = golden("pac_sc")
+    for nm in [str(s) for s in g["names"]]:
+        y, info, snr, gp = g[nm + "_y"], g[nm + "_info"], float(g[nm + "_snr"]), int(g[nm + "_g"])
+        n = _n(y.shape[1])
+        assert np.array_equal(oracle.pac_encode(g[nm + "_msg"], n, info, gp), g[nm + "_x"]), nm
+        gt = g[nm + "_gt"] if nm + "_gt" in g.files else None
+        llr, v, u = oracle.pac_sc_decode(y, snr, n, info, gp, use_gt_codeword=gt)
+        assert np.array_equal(llr, g[nm + "_llr"]), nm
+        assert np.array_equal(v, g[nm + "_v"]), nm
+        assert np.array_equal(u, g[nm + "_u"]), nm
+
+
+def test_error_counters(golden):
+    g = golden("misc")
+    a, b = g["err_a"], g["err_b"]
+    bit, blk = oracle.count_errors(a, b)
+    assert bit / a.size == pytest.approx(float(g["err_ber"]), abs=1e-7)
+    assert blk / a.shape[0] == pytest.approx(float(g["err_bler"]), abs=1e-12)
+
+
+def test_gru_oracle_against_reference_fixtures(golden):
+    from neural_polar_decoder_b200 import synth
+    g = golden("gru")
+    for nm in [str(s) for s in g["names"]]:
+        N, K, H, seed = [int(v) for v in g[nm + "_cfg"]]
+        sd = synth.gru_state_dict(seed, N, H, 2, head_gain=float(g[nm + "_gain"]))
+        if H <= 64:  # weights stored in the fixture: pins synth's determinism
+            for k, v in sd.items():
+                assert np.array_equal(v, g[nm + "_w_" + k]), k
+        dec, lg = oracle.gru_decode(sd, g[nm + "_y"], N, g[nm + "_info"], forced=g[nm + "_decoded"])
+        np.testing.assert_allclose(lg, g[nm + "_logits"], rtol=0, atol=2e-5)
+        # decisions identical wherever the reference logit is not within round-off of zero
+        safe = np.abs(g[nm + "_logits"]) > 1e-4
+        assert np.array_equal(dec[safe], g[nm + "_decoded"][safe])
+
+
+def test_conv_oracle_against_reference_fixtures(golden):
+    from neural_polar_decoder_b200 import synth
+    g = golden("conv")
+    N, K, E, seed = [int(v) for v in g["conv64_cfg"]]
+    lg = oracle.conv_forward(synth.conv_state_dict(seed, N, E), g["conv64_y"])
+    np.testing.assert_allclose(lg, g["conv64_logits"], rtol=0, atol=2e-5)
