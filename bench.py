@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- decoded codewords/sec of the Monte-Carlo decode hot path on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sc1024|gru64|...] [--impl reference]
+
+One "step" = one pass of the hot path over one batch of synthetic AWGN frames that is already
+resident in HBM (value), or starts in pinned host memory and ends in host memory (e2e).
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition of every field.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "decoded codewords/sec"
+UNIT = "codewords/s"
+
+WORKLOADS = {
+    # name: N, K, snr_db, per-GPU batch (y = B*N*4 bytes must exceed the 126 MB L2)
+    "sc1024": dict(kind="sc", N=1024, K=512, snr=2.0, batch=131072,
+                   desc="SC Polar(1024,512), polarization-weight frozen set, AWGN 2 dB"),
+    "sc256": dict(kind="sc", N=256, K=128, snr=2.0, batch=524288,
+                  desc="SC Polar(256,128), reference reliability table, AWGN 2 dB"),
+    "sc4096": dict(kind="sc", N=4096, K=2048, snr=2.0, batch=32768,
+                   desc="SC Polar(4096,2048), polarization-weight frozen set, AWGN 2 dB"),
+    "sc64": dict(kind="sc", N=64, K=22, snr=0.0, batch=2097152,
+                 desc="SC Polar(64,22), reference 'polar' profile, AWGN 0 dB"),
+    "gru64": dict(kind="gru", N=64, K=22, snr=0.0, batch=37888,
+                  desc="CRISP GRU(2x512, y_input, onehot) Polar(64,22), AWGN 0 dB, synthetic weights"),
+}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=float(d["hbm_gbs"]), bf16=float(d["bf16_tflops"]),
+                    bf16_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")  # B200_PROFILING.md
+
+
+def make_code(w):
+    from neural_polar_decoder_b200 import PolarCode, construct
+    N, K = w["N"], w["K"]
+    n = int(np.log2(N))
+    if N <= 256:
+        rs = construct.reference_rs256()
+        return PolarCode(n, K, None, rs=rs[rs < N])
+    return PolarCode(n, K, None, F=construct.pw_frozen_set(N, K))
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=1.0)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm: the CPU restatement of the reference (oracle/) on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_rate_sc(w, seconds, threads, rng_seed=0):
+    """Time oracle.sc_decode (the C restatement of polar.py:465-484) on a bounded sample.
+    -> (codewords/s, sample description)"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    N, K = w["N"], w["K"]
+    n = int(np.log2(N))
+    from neural_polar_decoder_b200 import construct
+    if N <= 256:
+        rs = construct.reference_rs256()
+        info = np.sort(rs[rs < N][:K])
+    else:
+        info = np.sort(construct.polarization_weight_order(N)[:K])
+    r = np.random.RandomState(rng_seed)
+
+    def frames(B):
+        msg = (1.0 - 2.0 * r.randint(0, 2, size=(B, K))).astype(np.float32)
+        x = oracle.polar_encode(msg, n, info)
+        return (x + 10 ** (-w["snr"] / 20) * r.randn(B, N)).astype(np.float32)
+
+    def run(y):
+        t0 = time.perf_counter()
+        oracle.run_threaded(lambda lo, hi: oracle.sc_decode(y[lo:hi], w["snr"], n, info), y.shape[0], threads)
+        return time.perf_counter() - t0
+
+    probe = max(threads, 8)
+    dt = run(frames(probe))
+    B = int(max(threads, min(1 << 20, probe / dt * seconds)))
+    dt = run(frames(B))
+    return B / dt, B, dt
+
+
+def reference_arm(args, w):
+    threads = os.cpu_count() or 1
+    total_budget = 150.0
+    per_step = min(3.0, total_budget / max(1, args.steps + args.warmup))
+    rates, B = [], 0
+    if w["kind"] == "sc":
+        for i in range(args.warmup + args.steps):
+            rate, B, dt = cpu_rate_sc(w, per_step, threads, rng_seed=i)
+            if i >= args.warmup:
+                rates.append((B, dt))
+    else:
+        from neural_polar_decoder_b200 import bench_neural
+        for i in range(args.warmup + args.steps):
+            rate, B, dt = bench_neural.cpu_rate(w, per_step, threads, seed=i)
+            if i >= args.warmup:
+                rates.append((B, dt))
+    tot_cw = sum(b for b, _ in rates)
+    tot_t = sum(t for _, t in rates)
+    value = tot_cw / tot_t
+    sample = "%d steps x ~%d codewords (%.1f s of CPU work)" % (len(rates), B, tot_t)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, len(rates)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": w["desc"], "N": w["N"], "K": w["K"], "snr_db": w["snr"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# product arm
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=os.environ.get("NPD_BENCH_WORKLOAD", "default"))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU codewords per step (0 = workload default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.workload == "default":
+        args.workload = default_workload()
+    w = dict(WORKLOADS[args.workload])
+    if args.batch:
+        w["batch"] = args.batch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            reference_arm(args, w)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device; the B200 path has no CPU fallback"}))
+        return 1
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    if w["kind"] == "sc":
+        res = bench_sc(args, w, rank, world, local_rank)
+    else:
+        from neural_polar_decoder_b200 import bench_neural
+        res = bench_neural.bench(args, w, rank, world, local_rank, ClockSampler, measured_peaks)
+
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            if w["kind"] == "sc":
+                threads = os.cpu_count() or 1
+                rate, B, dt = cpu_rate_sc(w, 12.0, threads)
+                res["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                       "sample": "%d codewords of the same workload, %.1f s" % (B, dt)}
+            else:
+                from neural_polar_decoder_b200 import bench_neural
+                res["cpu_baseline"] = bench_neural.cpu_baseline(w)
+        print(json.dumps(res))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def default_workload():
+    """The headline metric names CRISP-GRU Polar(64,22) and SC Polar(1024,512); the GRU line becomes
+    the default once its kernel is built into libnpd.so."""
+    try:
+        from neural_polar_decoder_b200 import bench_neural
+        if bench_neural.available():
+            return "gru64"
+    except Exception:
+        pass
+    return "sc1024"
+
+
+def bench_sc(args, w, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from neural_polar_decoder_b200 import _lib, utils
+    lib = _lib.load()
+    N, K, B, snr = w["N"], w["K"], w["batch"], w["snr"]
+    code = make_code(w)
+    h = code._handle()
+    dev = torch.device("cuda", local_rank)
+    sigma = float(np.float32(utils.snr_db2sigma(snr)))
+    scale = utils.llr_scale(snr)
+    seed = 2026
+
+    # synthetic frames, generated on the device by the fused generator (global codeword index =
+    # rank*B + row, so the union over ranks is one reproducible stream), resident in HBM
+    msg = torch.empty(B, K, device=dev)
+    y = torch.empty(B, N, device=dev)
+    dec = torch.empty(B, K, device=dev)
+    counts = torch.zeros(3, dtype=torch.int64, device=dev)
+    _lib.check(lib.npd_gen_encode_awgn(h.h, _lib.ptr(msg), None, _lib.ptr(y), B, sigma, seed, 0, rank * B,
+                                       _lib.stream_ptr()))
+    st = _lib.stream_ptr()
+
+    def step():
+        _lib.check(lib.npd_sc_decode(h.h, _lib.ptr(y), scale, None, None, _lib.ptr(dec), B, st))
+        _lib.check(lib.npd_count_errors(_lib.ptr(msg), _lib.ptr(dec), B, K, _lib._vp(counts.data_ptr()), st))
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync()
+    counts.zero_()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    sync()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(args.steps):
+        ev[i][0].record()
+        _lib.check(lib.npd_sc_decode(h.h, _lib.ptr(y), scale, None, None, _lib.ptr(dec), B, st))
+        ev[i][1].record()
+        _lib.check(lib.npd_count_errors(_lib.ptr(msg), _lib.ptr(dec), B, K, _lib._vp(counts.data_ptr()), st))
+        ev[i][2].record()
+    if world > 1:
+        dist.all_reduce(counts)  # the path's only collective: [bit errors, block errors, frames]
+    t_end.record()
+    sync()
+    clocks = sampler.stop()
+    elapsed_ms = t_start.elapsed_time(t_end)
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in ev]))
+    count_ms = float(np.mean([b.elapsed_time(c) for _, b, c in ev]))
+    value = world * B * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the drop-in with HOST buffers (H2D + kernel + D2H every step) ----
+    e2e_B = min(B, 32768)
+    y_host = y[:e2e_B].cpu().pin_memory()
+    msg_host = msg[:e2e_B].cpu().pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        code.sc_decode_new(y_host, snr, return_llr=False)
+    sync()
+    t0 = time.perf_counter()
+    errs = 0
+    for _ in range(e2e_steps):
+        _, d_host = code.sc_decode_new(y_host, snr, return_llr=False)  # returns host tensors
+        errs += int((d_host != msg_host).sum())                        # the step's result is read on the host
+    torch.cuda.synchronize()
+    e2e_dt = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_B * e2e_steps / float(e2e_t.item())
+
+    peaks = measured_peaks()
+    alg_bytes = (4 * N + 4 * K) * B  # fp32 y in + fp32 decisions out, per launch
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    cnt = counts.tolist()
+    res = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": w["desc"], "N": N, "K": K, "snr_db": snr,
+                   "batch_per_gpu": B, "l2_policy": "inputs larger than L2 (y = %d MB per GPU)" % (B * N * 4 >> 20),
+                   "step": "npd_sc_decode (y in HBM -> decisions in HBM) + npd_count_errors; one NCCL all-reduce "
+                           "of the 3 counters at the end of the timed region when n_gpus > 1"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_B * N * 4,
+                "d2h_bytes_per_step": e2e_B * K * 4, "batch_per_gpu": e2e_B, "steps": e2e_steps,
+                "api": "PolarCode.sc_decode_new(host y, snr) -> host decisions"},
+        "gpu_launches": 2 * args.steps,
+        "roofline": {"kernel": "sc_group_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm"],
+                     "unit": "GB/s", "frac": achieved / peaks["hbm"], "traffic": None,
+                     "peak_source": peaks["src"], "kernel_ms": kern_ms, "count_kernel_ms": count_ms,
+                     "alg_bytes_per_launch": alg_bytes,
+                     "llr_updates_per_s": N * int(np.log2(N)) * B / (kern_ms * 1e-3)},
+        "ber": cnt[0] / float(world * B * args.steps * K), "bler": cnt[1] / float(world * B * args.steps),
+        "frames": world * B * args.steps,
+    }
+    return res
+
+
+if __name__ == "__main__":
+    sys.exit(main())

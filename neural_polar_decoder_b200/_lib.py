@@ -103,6 +103,19 @@ def to_device_f32(t, device=None):
     return t.contiguous()
 
 
+def to_host(t, like):
+    """Device tensor -> host tensor shaped like the caller's input: pinned in, pinned out (async copy +
+    one stream sync), pageable otherwise."""
+    if t is None:
+        return None
+    if like.is_pinned():
+        out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        out.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(t.device).synchronize()
+        return out
+    return t.to(like.device)
+
+
 class CodeHandle:
     """Owns an npd_code_t (device-side info / frozen tables)."""
 

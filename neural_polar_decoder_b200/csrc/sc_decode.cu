@@ -2,15 +2,25 @@
 //
 // Replaces PolarCode.sc_decode_new (reference polar.py:465-484 with 361-463, utils.py:272-275) and
 // PAC.pac_sc_decode (pac_code.py:534-573).  The reference re-encodes the partial sums from scratch
-// after every bit (O(N^2) torch.cat calls); here they are kept as two bit planes (sign, is-zero) that
-// are Plotkin-transformed in place, which is exact because products of {-1,0,+1} floats are exact.
+// after every bit (O(N^2) torch.cat calls); here they are bit planes that are Plotkin-transformed in
+// place, which is exact because products of {-1,0,+1} floats are exact.
 //
-// Mapping ("group" kernel): one warp decodes G codewords in lockstep (the SC schedule is data
-// independent).  Every LLR array of the tree lives in shared memory interleaved as [element][G], so
-// a min-sum update over a child array of h elements is G*h independent lane-items with conflict-free
-// consecutive addresses -- lanes stay busy down to h = 32/G.  The root LLRs are never staged: the two
-// top-level updates read y straight from global memory (coalesced for N >= 64).  G is chosen per N so
-// that 4*G*(N-1) bytes of tree per warp leave >= 6 warps resident per SM ("SC decoder").
+// Two kernels (DESIGN.md "SC decoder"):
+//
+//  * sc_lane_kernel -- the fast path.  One warp decodes 32 codewords, lane = codeword (the SC schedule
+//    is data independent, so the warp never diverges).  The bottom 32-leaf subtree of the LLR tree is
+//    fully unrolled and lives in registers (63 floats); the levels above it live in shared memory as
+//    [element][33] (conflict-free for lane = codeword AND for the lane = element transposed stores);
+//    the topmost levels are never stored: they are recomputed from y in global memory (coalesced,
+//    lane = element) whenever the first stored level is refreshed.  Partial sums and decisions are one
+//    sign bit per leaf.  A leaf LLR that is exactly 0 (sign(0) = 0, which the reference propagates as a
+//    zero partial sum) cannot be represented in one bit: the codeword is flagged by a NaN sentinel in
+//    decoded[cw][0] and re-decoded by
+//
+//  * sc_group_kernel -- the exact tie path (also the general path for K = 0).  One warp decodes G
+//    codewords with the whole tree in shared memory as [element][G] and two bit planes per quantity
+//    (sign, is-zero), so û in {-1,0,+1} is carried exactly.  In scan mode it visits only the flagged
+//    codewords.  Ties need an exact fp32 cancellation; they do not occur on real-valued noise.
 #include "npd_common.cuh"
 
 namespace {
@@ -27,6 +37,8 @@ struct ScParams {
     int n, K;
     float scale, infty;
     uint32_t pac_taps, pac_state_mask;
+    int scan_flagged;      // group kernel: 1 = only codewords whose decoded[cw][0] is the NaN sentinel
+    int slog;              // lane kernel: highest stored level
 };
 
 template <int G>
@@ -40,6 +52,14 @@ template <> struct Log2<32> { static constexpr int v = 5; };
 
 __host__ __device__ inline int plane_stride(int N) { return ((N + 31) >> 5) | 1; }  // odd: no bank clash
 
+__device__ __forceinline__ float trit_value(uint32_t s, uint32_t z)
+{
+    return z ? 0.0f : (s ? -1.0f : 1.0f);
+}
+
+// =================================================================================================
+// exact tie path: G codewords per warp, whole tree in shared memory, (sign, zero) planes
+// =================================================================================================
 template <int G, bool PAC>
 __host__ __device__ inline size_t sc_warp_smem_bytes(int N)
 {
@@ -48,20 +68,14 @@ __host__ __device__ inline size_t sc_warp_smem_bytes(int N)
 }
 
 template <int G, bool PAC>
-__global__ void __launch_bounds__(64) sc_group_kernel(const ScParams p)
+__device__ void sc_group_decode(const ScParams &p, unsigned char *base, const int64_t my_cw, const int lane)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // my_cw: lanes c < G hold the codeword index of slot c (-1 = empty slot)
     constexpr int LG = Log2<G>::v;
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int wpb = blockDim.x >> 5;
     const int n = p.n;
     const int N = 1 << n;
-    const int NW = (N + 31) >> 5;
     const int NWP = plane_stride(N);
-
-    unsigned char *base = smem_raw + (size_t)warp * sc_warp_smem_bytes<G, PAC>(N);
-    float *buf = reinterpret_cast<float *>(base);              // level lv at G*(2^lv - 1)
+    float *buf = reinterpret_cast<float *>(base);                            // level lv at G*(2^lv - 1)
     uint32_t *PS = reinterpret_cast<uint32_t *>(buf + (size_t)G * (N - 1));  // transformed sums: sign
     uint32_t *PZ = PS + G * NWP;                                             // transformed sums: zero
     uint32_t *US = PZ + G * NWP;                                             // raw decisions: sign
@@ -69,51 +83,49 @@ __global__ void __launch_bounds__(64) sc_group_kernel(const ScParams p)
     uint32_t *VS = UZ + G * NWP;                                             // PAC: v_hat sign
     uint32_t *VZ = VS + G * NWP;                                             // PAC: v_hat undecided
 
-    const int64_t ngroups = (p.B + G - 1) / G;
-    for (int64_t grp = (int64_t)blockIdx.x * wpb + warp; grp < ngroups;
-         grp += (int64_t)gridDim.x * wpb) {
-        const int64_t cw0 = grp * G;
-        const int nvalid = (int)min((int64_t)G, p.B - cw0);
+    for (int i = lane; i < (PAC ? 6 : 4) * G * NWP; i += 32) PS[i] = 0u;
+    __syncwarp();
 
-        for (int i = lane; i < (PAC ? 6 : 4) * G * NWP; i += 32) PS[i] = 0u;
-        __syncwarp();
+    uint32_t pac_state = 0u;  // lane c < G: shift register of codeword c, bit j = state[j] is -1
+    uint32_t frozen_word = 0u;
 
-        uint32_t pac_state = 0u;  // lane c < G: shift register of codeword c, bit j = state[j] is -1
-        uint32_t frozen_word = 0u;
-
-        for (int o = 0; o < N; ++o) {
-            const int top = (o == 0) ? n - 1 : (__ffs(o) - 1);
-            for (int lv = top; lv >= 0; --lv) {
-                const int h = 1 << lv;
-                const bool is_g = (o != 0) && (lv == top);
-                const int psbit0 = o - h;  // first partial-sum bit used by g
-                float *ch = buf + (size_t)G * (h - 1);
-                if (lv == n - 1) {
-                    // parent = root = scale * y, read from global (polar.py:468-469)
-                    if (h >= 32) {
-                        for (int c = 0; c < G; ++c) {
-                            const bool ok = c < nvalid;
-                            const float *row = p.y + (cw0 + (ok ? c : 0)) * N;
-                            for (int e = lane; e < h; e += 32) {
-                                float a = ok ? p.scale * __ldg(row + e) : 0.f;
-                                float b = ok ? p.scale * __ldg(row + e + h) : 0.f;
-                                float r;
-                                if (is_g) {
-                                    const int bit = psbit0 + e;
-                                    uint32_t s = (PS[c * NWP + (bit >> 5)] >> (bit & 31)) & 1u;
-                                    uint32_t z = (PZ[c * NWP + (bit >> 5)] >> (bit & 31)) & 1u;
-                                    r = npd_g_trit(s, z, a, b);
-                                } else {
-                                    r = npd_f_minsum(a, b);
-                                }
-                                ch[e * G + c] = r;
+    for (int o = 0; o < N; ++o) {
+        const int top = (o == 0) ? n - 1 : (__ffs(o) - 1);
+        for (int lv = top; lv >= 0; --lv) {
+            const int h = 1 << lv;
+            const bool is_g = (o != 0) && (lv == top);
+            const int psbit0 = o - h;  // first partial-sum bit used by g
+            float *ch = buf + (size_t)G * (h - 1);
+            if (lv == n - 1) {
+                // parent = root = scale * y, read from global (polar.py:468-469)
+                if (h >= 32) {
+                    for (int c = 0; c < G; ++c) {
+                        const int64_t cw = __shfl_sync(NPD_FULL, my_cw, c);
+                        const bool ok = cw >= 0;
+                        const float *row = p.y + (ok ? cw : 0) * N;
+                        for (int e = lane; e < h; e += 32) {
+                            float a = ok ? p.scale * __ldg(row + e) : 0.f;
+                            float b = ok ? p.scale * __ldg(row + e + h) : 0.f;
+                            float r;
+                            if (is_g) {
+                                const int bit = psbit0 + e;
+                                uint32_t s = (PS[c * NWP + (bit >> 5)] >> (bit & 31)) & 1u;
+                                uint32_t z = (PZ[c * NWP + (bit >> 5)] >> (bit & 31)) & 1u;
+                                r = npd_g_trit(s, z, a, b);
+                            } else {
+                                r = npd_f_minsum(a, b);
                             }
+                            ch[e * G + c] = r;
                         }
-                    } else {
-                        for (int idx = lane; idx < G * h; idx += 32) {
-                            const int c = idx & (G - 1), e = idx >> LG;
-                            const bool ok = c < nvalid;
-                            const float *row = p.y + (cw0 + (ok ? c : 0)) * N;
+                    }
+                } else {
+                    for (int idx0 = 0; idx0 < G * h; idx0 += 32) {
+                        const int idx = idx0 + lane;
+                        const int c = idx & (G - 1), e = idx >> LG;
+                        const int64_t cw = __shfl_sync(NPD_FULL, my_cw, c);
+                        if (idx < G * h) {
+                            const bool ok = cw >= 0;
+                            const float *row = p.y + (ok ? cw : 0) * N;
                             float a = ok ? p.scale * __ldg(row + e) : 0.f;
                             float b = ok ? p.scale * __ldg(row + e + h) : 0.f;
                             float r;
@@ -128,119 +140,452 @@ __global__ void __launch_bounds__(64) sc_group_kernel(const ScParams p)
                             ch[idx] = r;
                         }
                     }
-                } else {
-                    const float *par = buf + (size_t)G * (2 * h - 1);
-                    if (is_g) {
-                        for (int idx = lane; idx < G * h; idx += 32) {
-                            const int c = idx & (G - 1), e = idx >> LG;
-                            const int bit = psbit0 + e;
-                            uint32_t s = (PS[c * NWP + (bit >> 5)] >> (bit & 31)) & 1u;
-                            uint32_t z = (PZ[c * NWP + (bit >> 5)] >> (bit & 31)) & 1u;
-                            ch[idx] = npd_g_trit(s, z, par[idx], par[idx + G * h]);
-                        }
-                    } else {
-                        for (int idx = lane; idx < G * h; idx += 32)
-                            ch[idx] = npd_f_minsum(par[idx], par[idx + G * h]);
+                }
+            } else {
+                const float *par = buf + (size_t)G * (2 * h - 1);
+                if (is_g) {
+                    for (int idx = lane; idx < G * h; idx += 32) {
+                        const int c = idx & (G - 1), e = idx >> LG;
+                        const int bit = psbit0 + e;
+                        uint32_t s = (PS[c * NWP + (bit >> 5)] >> (bit & 31)) & 1u;
+                        uint32_t z = (PZ[c * NWP + (bit >> 5)] >> (bit & 31)) & 1u;
+                        ch[idx] = npd_g_trit(s, z, par[idx], par[idx + G * h]);
                     }
+                } else {
+                    for (int idx = lane; idx < G * h; idx += 32)
+                        ch[idx] = npd_f_minsum(par[idx], par[idx + G * h]);
+                }
+            }
+            __syncwarp();
+        }
+
+        // ---- leaf o: decision (polar.py:471-481 / pac_code.py:543-568) ----
+        if ((o & 31) == 0) frozen_word = __ldg(p.frozen_words + (o >> 5));
+        const bool frozen = (frozen_word >> (o & 31)) & 1u;
+        const int w = o >> 5, bpos = o & 31;
+        if (lane < G) {
+            const int c = lane;
+            const bool ok = my_cw >= 0;
+            float L = buf[c];
+            if (!PAC) L = L + (frozen ? p.infty : 0.0f);
+            if (p.leaf_llr && ok) p.leaf_llr[my_cw * N + o] = L;
+            uint32_t s = L < 0.0f, z = (L == 0.0f);
+            bool have_gt = false;
+            if (p.use_gt && ok) {
+                float t = p.use_gt[my_cw * N + o];
+                s = t < 0.0f;
+                z = (t == 0.0f);
+                have_gt = true;
+            }
+            if (PAC) {
+                const uint32_t par_bit = __popc(pac_state & p.pac_taps) & 1u;
+                uint32_t vs = 0u, vz = 0u;
+                if (frozen) {
+                    if (!have_gt) {  // u = conv(+1, state), state <- shift in +1
+                        s = par_bit;
+                        z = 0u;
+                        pac_state = (pac_state << 1) & p.pac_state_mask;
+                    }
+                } else {
+                    if (z) {
+                        vz = 1u;  // neither branch matches a 0: v stays 0, state unchanged
+                    } else {
+                        vs = s ^ par_bit;
+                        pac_state = ((pac_state << 1) | vs) & p.pac_state_mask;
+                    }
+                }
+                VS[c * NWP + w] |= vs << bpos;
+                VZ[c * NWP + w] |= vz << bpos;
+            }
+            US[c * NWP + w] |= s << bpos;
+            UZ[c * NWP + w] |= z << bpos;
+            // in-word merges of the transformed partial sums (blocks < 32 bits)
+            uint32_t ps = PS[c * NWP + w] | (s << bpos);
+            uint32_t pz = PZ[c * NWP + w] | (z << bpos);
+            const int m = __ffs(~o) - 1;  // trailing ones of o = number of completed merges
+            const int mi = min(m, min(n, 5));
+#pragma unroll 1
+            for (int j = 0; j < mi; ++j) {
+                const int hb = 1 << j;
+                const uint32_t mask = ((1u << hb) - 1u) << ((o + 1 - 2 * hb) & 31);
+                ps ^= (ps >> hb) & mask;
+                pz |= (pz >> hb) & mask;
+            }
+            PS[c * NWP + w] = ps;
+            PZ[c * NWP + w] = pz;
+        }
+        __syncwarp();
+        // word-level merges (blocks >= 32 bits)
+        {
+            const int m = min(__ffs(~o) - 1, n);
+            for (int j = 5; j < m; ++j) {
+                const int nw = 1 << (j - 5);
+                const int wl = (o + 1 - 2 * (1 << j)) >> 5;
+                for (int idx = lane; idx < G * nw; idx += 32) {
+                    const int c = idx >> (j - 5), i = idx & (nw - 1);
+                    PS[c * NWP + wl + i] ^= PS[c * NWP + wl + nw + i];
+                    PZ[c * NWP + wl + i] |= PZ[c * NWP + wl + nw + i];
                 }
                 __syncwarp();
             }
+        }
+    }
 
-            // ---- leaf o: decision (polar.py:471-481 / pac_code.py:543-568) ----
-            if ((o & 31) == 0) frozen_word = __ldg(p.frozen_words + (o >> 5));
-            const bool frozen = (frozen_word >> (o & 31)) & 1u;
-            const int w = o >> 5, bpos = o & 31;
-            if (lane < G) {
-                const int c = lane;
-                const bool ok = c < nvalid;
-                float L = buf[c];
-                if (!PAC) L = L + (frozen ? p.infty : 0.0f);
-                if (p.leaf_llr && ok) p.leaf_llr[(cw0 + c) * N + o] = L;
-                uint32_t s = L < 0.0f, z = (L == 0.0f);
-                bool have_gt = false;
-                if (p.use_gt && ok) {
-                    float t = p.use_gt[(cw0 + c) * N + o];
-                    s = t < 0.0f;
-                    z = (t == 0.0f);
-                    have_gt = true;
+    // ---- outputs ----
+    const uint32_t *OS = PAC ? VS : US;
+    const uint32_t *OZ = PAC ? VZ : UZ;
+    for (int c = 0; c < G; ++c) {
+        const int64_t cw = __shfl_sync(NPD_FULL, my_cw, c);
+        if (cw < 0) continue;
+        float *dst = p.decoded + cw * p.K;
+        for (int k = lane; k < p.K; k += 32) {
+            const int pos = __ldg(p.info + k);
+            uint32_t s = (OS[c * NWP + (pos >> 5)] >> (pos & 31)) & 1u;
+            uint32_t z = (OZ[c * NWP + (pos >> 5)] >> (pos & 31)) & 1u;
+            dst[k] = trit_value(s, z);
+        }
+        if (PAC && p.u_hat) {
+            float *du = p.u_hat + cw * N;
+            for (int e = lane; e < N; e += 32) {
+                uint32_t s = (US[c * NWP + (e >> 5)] >> (e & 31)) & 1u;
+                uint32_t z = (UZ[c * NWP + (e >> 5)] >> (e & 31)) & 1u;
+                du[e] = trit_value(s, z);
+            }
+        }
+    }
+    __syncwarp();
+}
+
+template <int G, bool PAC>
+__global__ void __launch_bounds__(64) sc_group_kernel(const ScParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int wpb = blockDim.x >> 5;
+    const int N = 1 << p.n;
+    unsigned char *base = smem_raw + (size_t)warp * sc_warp_smem_bytes<G, PAC>(N);
+
+    if (!p.scan_flagged) {
+        const int64_t ngroups = (p.B + G - 1) / G;
+        for (int64_t grp = (int64_t)blockIdx.x * wpb + warp; grp < ngroups; grp += (int64_t)gridDim.x * wpb) {
+            const int64_t cw = grp * G + lane;
+            sc_group_decode<G, PAC>(p, base, (lane < G && cw < p.B) ? cw : -1, lane);
+        }
+    } else {
+        // visit chunks of 32 codewords; re-decode those flagged by the lane kernel's NaN sentinel
+        const int64_t nchunks = (p.B + 31) / 32;
+        for (int64_t ch = (int64_t)blockIdx.x * wpb + warp; ch < nchunks; ch += (int64_t)gridDim.x * wpb) {
+            const int64_t cw = ch * 32 + lane;
+            bool flag = false;
+            if (cw < p.B) {
+                const float v = p.decoded[cw * p.K];
+                flag = (v != v);
+            }
+            uint32_t mask = __ballot_sync(NPD_FULL, flag);
+            while (mask) {
+                // slot c <- c-th flagged lane
+                int64_t mine = -1;
+                if (lane < G) {
+                    const uint32_t src = __fns(mask, 0, lane + 1);
+                    if (src < 32u) mine = ch * 32 + src;
                 }
-                if (PAC) {
-                    const uint32_t par_bit = __popc(pac_state & p.pac_taps) & 1u;
-                    uint32_t vs = 0u, vz = 0u;
-                    if (frozen) {
-                        if (!have_gt) {  // u = conv(+1, state), state <- shift in +1
-                            s = par_bit;
-                            z = 0u;
-                            pac_state = (pac_state << 1) & p.pac_state_mask;
-                        }
-                    } else {
-                        if (z) {
-                            vz = 1u;  // neither branch matches a 0: v stays 0, state unchanged
-                        } else {
-                            vs = s ^ par_bit;
-                            pac_state = ((pac_state << 1) | vs) & p.pac_state_mask;
+                sc_group_decode<G, PAC>(p, base, mine, lane);
+                for (int i = 0; i < G && mask; ++i) mask &= mask - 1;  // drop the G lowest set bits
+            }
+        }
+    }
+}
+
+// =================================================================================================
+// fast path: lane = codeword
+// =================================================================================================
+template <int BLOG, bool PAC, bool EXTRAS>
+struct LaneCtx {
+    uint32_t ps;      // transformed partial sums of the current block (bit i = leaf i of the block)
+    uint32_t us;      // raw decisions of the block
+    uint32_t vs;      // PAC: v_hat sign bits of the block
+    uint32_t frozen;  // frozen mask of the block
+    uint32_t gt_s;    // EXTRAS: genie bits of the block
+    uint32_t tie;     // a leaf LLR (or genie value) was exactly zero somewhere in this codeword
+    uint32_t pac_state;
+    uint32_t pac_taps, pac_state_mask;
+    float infty;
+    float *llr_out;   // EXTRAS: leaf_llr + cw*N + block offset, or null
+    bool have_gt;
+};
+
+template <int O, int BLOG, bool PAC, bool EXTRAS>
+__device__ __forceinline__ void lane_leaf(float L, LaneCtx<BLOG, PAC, EXTRAS> &c)
+{
+    const bool frozen = (c.frozen >> O) & 1u;
+    if (!PAC) L = L + (frozen ? c.infty : 0.0f);  // polar.py:399,415,471-472
+    if (EXTRAS) {
+        if (c.llr_out) c.llr_out[O] = L;
+    }
+    uint32_t s = L < 0.0f;
+    c.tie |= (L == 0.0f);
+    if (EXTRAS) {
+        if (c.have_gt) s = (c.gt_s >> O) & 1u;
+    }
+    if (PAC) {
+        const uint32_t par_bit = __popc(c.pac_state & c.pac_taps) & 1u;
+        if (frozen) {
+            if (!(EXTRAS && c.have_gt)) {
+                s = par_bit;
+                c.pac_state = (c.pac_state << 1) & c.pac_state_mask;
+            }
+        } else {
+            const uint32_t v = s ^ par_bit;
+            c.vs |= v << O;
+            c.pac_state = ((c.pac_state << 1) | v) & c.pac_state_mask;
+        }
+    }
+    c.us |= s << O;
+    c.ps |= s << O;
+}
+
+// node covering leaves [O, O+S) of the current block; L = its S LLRs in registers
+template <int S, int O, int BLOG, bool PAC, bool EXTRAS>
+__device__ __forceinline__ void lane_node(const float (&L)[S], LaneCtx<BLOG, PAC, EXTRAS> &c)
+{
+    if constexpr (S == 1) {
+        lane_leaf<O>(L[0], c);
+    } else {
+        constexpr int H = S / 2;
+        float C[H];
+#pragma unroll
+        for (int j = 0; j < H; ++j) C[j] = npd_f_minsum(L[j], L[j + H]);
+        lane_node<H, O>(C, c);
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            const uint32_t sg = (c.ps << (31 - (O + j))) & 0x80000000u;
+            C[j] = __uint_as_float(__float_as_uint(L[j]) ^ sg) + L[j + H];
+        }
+        lane_node<H, O + H>(C, c);
+        constexpr uint32_t lowmask = (H >= 32) ? 0xffffffffu : ((1u << H) - 1u);
+        c.ps ^= (c.ps >> H) & (lowmask << O);
+    }
+}
+
+// First stored level (level slog, hS = 2^slog elements) of every codeword of the group, recomputed from
+// y for the path to leaf block o.  lane = element (coalesced global loads), transposed store into
+// dst[element][33].  DEPTH = n-1-slog unstored levels sit between level slog and the root, so one output
+// element j folds the T = 2^(DEPTH+1) root values y[j + t*hS]; level L combines the values t and
+// t + half (element j + t*hS of that level's node) with g when the node on the path is a right child
+// (bit L of o set; partial sums of its left sibling = bits [s-h, s), s = node start) and f otherwise.
+// U work items are loaded before any is reduced so that U*T global loads are in flight per lane.
+template <int DEPTH, int U>
+__device__ __forceinline__ void lane_top_phase(const ScParams &p, float *dst, const uint32_t *PS,
+                                               int64_t cw0, int nvalid, int o, int lane)
+{
+    constexpr int T = 2 << DEPTH;
+    const int N = 1 << p.n;
+    const int slog = p.slog;
+    const int hS = 1 << slog;
+    const int ilog = slog - 5;          // log2(iterations per codeword)
+    const int total = nvalid << ilog;   // work items: (codeword, 32-element slice)
+    for (int it0 = 0; it0 < total; it0 += U) {
+        float v[U][T];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int it = min(it0 + u, total - 1);
+            const int cc = it >> ilog;
+            const int j = ((it & ((1 << ilog) - 1)) << 5) + lane;
+            const float *yrow = p.y + (cw0 + cc) * N + j;
+#pragma unroll
+            for (int t = 0; t < T; ++t) v[u][t] = __ldg(yrow + t * hS);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int it = it0 + u;
+            const int cc = min(it, total - 1) >> ilog;
+            const int j = ((it & ((1 << ilog) - 1)) << 5) + lane;
+#pragma unroll
+            for (int t = 0; t < T; ++t) v[u][t] = p.scale * v[u][t];  // polar.py:468-469
+#pragma unroll
+            for (int d = 0; d <= DEPTH; ++d) {
+                const int lv = p.n - 1 - d;        // level being produced
+                const int h = 1 << lv;
+                constexpr int dummy = 0; (void)dummy;
+                const int half = T >> (d + 1);
+                if (o & h) {
+                    const int bit0 = (o & ~(h - 1)) - h + j;
+#pragma unroll
+                    for (int t = 0; t < T / 2; ++t) {
+                        if (t < half) {
+                            const int bit = bit0 + t * hS;
+                            const uint32_t sg = ((PS[(bit >> 5) * 32 + cc] >> (bit & 31)) & 1u) << 31;
+                            v[u][t] = __uint_as_float(__float_as_uint(v[u][t]) ^ sg) + v[u][t + half];
                         }
                     }
-                    VS[c * NWP + w] |= vs << bpos;
-                    VZ[c * NWP + w] |= vz << bpos;
+                } else {
+#pragma unroll
+                    for (int t = 0; t < T / 2; ++t)
+                        if (t < half) v[u][t] = npd_f_minsum(v[u][t], v[u][t + half]);
                 }
-                US[c * NWP + w] |= s << bpos;
-                UZ[c * NWP + w] |= z << bpos;
-                // in-word merges of the transformed partial sums (blocks < 32 bits)
-                uint32_t ps = PS[c * NWP + w] | (s << bpos);
-                uint32_t pz = PZ[c * NWP + w] | (z << bpos);
-                const int m = __ffs(~o) - 1;  // trailing ones of o = number of completed merges
-                const int mi = min(m, min(n, 5));
-#pragma unroll 1
-                for (int j = 0; j < mi; ++j) {
-                    const int hb = 1 << j;
-                    const uint32_t mask = ((1u << hb) - 1u) << ((o + 1 - 2 * hb) & 31);
-                    ps ^= (ps >> hb) & mask;
-                    pz |= (pz >> hb) & mask;
-                }
-                PS[c * NWP + w] = ps;
-                PZ[c * NWP + w] = pz;
             }
-            __syncwarp();
-            // word-level merges (blocks >= 32 bits)
-            {
-                const int m = min(__ffs(~o) - 1, n);
-                for (int j = 5; j < m; ++j) {
-                    const int nw = 1 << (j - 5);
-                    const int wl = (o + 1 - 2 * (1 << j)) >> 5;
-                    for (int idx = lane; idx < G * nw; idx += 32) {
-                        const int c = idx / nw, i = idx - c * nw;
-                        PS[c * NWP + wl + i] ^= PS[c * NWP + wl + nw + i];
-                        PZ[c * NWP + wl + i] |= PZ[c * NWP + wl + nw + i];
+            if (it < total) dst[j * 33 + cc] = v[u][0];
+        }
+    }
+}
+
+__host__ __device__ inline size_t lane_warp_smem_bytes(int n, int slog, bool pac)
+{
+    if (n <= 5) return 16;
+    const int NW = (1 << n) >> 5;
+    const size_t tree = (size_t)4 * 33 * ((2u << slog) - 32u);
+    return tree + (size_t)4 * (pac ? 3 : 2) * NW * 32;
+}
+
+template <int BLOG, bool PAC, bool EXTRAS>
+__global__ void __launch_bounds__(128) sc_lane_kernel(const ScParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int BS = 1 << BLOG;  // leaves per bottom block
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int wpb = blockDim.x >> 5;
+    const int n = p.n;
+    const int N = 1 << n;
+    const int NW = N >> 5;  // words per plane (only used when n > 5)
+    const int slog = p.slog;
+
+    unsigned char *base = smem_raw + (size_t)warp * lane_warp_smem_bytes(n, slog, PAC);
+    float *tree = reinterpret_cast<float *>(base);  // level lv (5 <= lv <= slog) at 33*(2^lv - 32)
+    uint32_t *PS = reinterpret_cast<uint32_t *>(tree + (size_t)33 * ((2u << slog) - 32u));
+    uint32_t *US = PS + NW * 32;
+    uint32_t *VS = US + NW * 32;
+
+    const int64_t ngroups = (p.B + 31) / 32;
+    for (int64_t grp = (int64_t)blockIdx.x * wpb + warp; grp < ngroups; grp += (int64_t)gridDim.x * wpb) {
+        const int64_t cw0 = grp * 32;
+        const int64_t cw = cw0 + lane;
+        const bool ok = cw < p.B;
+        const int nvalid = (int)min((int64_t)32, p.B - cw0);
+
+        LaneCtx<BLOG, PAC, EXTRAS> c;
+        c.tie = 0u;
+        c.pac_state = 0u;
+        c.pac_taps = p.pac_taps;
+        c.pac_state_mask = p.pac_state_mask;
+        c.infty = p.infty;
+        c.have_gt = EXTRAS && (p.use_gt != nullptr);
+        c.llr_out = nullptr;
+        c.gt_s = 0u;
+
+        const int nblocks = N >> BLOG;
+        for (int q = 0; q < nblocks; ++q) {
+            const int o = q << BLOG;
+            float L[BS];
+            if (n > BLOG) {
+                // ---- refresh the stored levels on the path to block q (only possible when BLOG == 5) ----
+                const int top = (q == 0) ? n - 1 : (BLOG + __ffs(q) - 1);
+                if (top >= slog) {
+                    // first stored level, from y (coalesced, lane = element), transposed store
+                    float *dst = tree + (size_t)33 * ((1u << slog) - 32u);
+                    __syncwarp();
+                    switch (n - 1 - slog) {
+                    case 0: lane_top_phase<0, 8>(p, dst, PS, cw0, nvalid, o, lane); break;
+                    case 1: lane_top_phase<1, 8>(p, dst, PS, cw0, nvalid, o, lane); break;
+                    case 2: lane_top_phase<2, 4>(p, dst, PS, cw0, nvalid, o, lane); break;
+                    case 3: lane_top_phase<3, 2>(p, dst, PS, cw0, nvalid, o, lane); break;
+                    default: lane_top_phase<4, 1>(p, dst, PS, cw0, nvalid, o, lane); break;
                     }
                     __syncwarp();
                 }
+                // stored level -> stored level, lane = codeword
+                for (int lv = min(top, slog - 1); lv >= BLOG; --lv) {
+                    const int h = 1 << lv;
+                    const float *par = tree + (size_t)33 * ((2u << lv) - 32u) + lane;
+                    float *ch = tree + (size_t)33 * ((1u << lv) - 32u) + lane;
+                    if (lv == top) {  // right child (q > 0): g with bits [o-h, o)
+                        const int wbase = (o - h) >> 5;
+                        for (int e0 = 0; e0 < h; e0 += 32) {
+                            const uint32_t w = PS[(wbase + (e0 >> 5)) * 32 + lane];
+#pragma unroll 8
+                            for (int e = 0; e < 32; ++e) {
+                                const float a = par[(e0 + e) * 33], b = par[(e0 + e + h) * 33];
+                                const uint32_t sg = ((w >> e) & 1u) << 31;
+                                ch[(e0 + e) * 33] = __uint_as_float(__float_as_uint(a) ^ sg) + b;
+                            }
+                        }
+                    } else {
+#pragma unroll 8
+                        for (int e = 0; e < h; ++e) ch[e * 33] = npd_f_minsum(par[e * 33], par[(e + h) * 33]);
+                    }
+                }
+                const float *src = tree + lane;  // level BLOG (= 5) sits at offset 0
+#pragma unroll
+                for (int e = 0; e < BS; ++e) L[e] = src[e * 33];
+            } else {
+                // the whole code is one block: root straight from global (N <= 32)
+#pragma unroll
+                for (int e = 0; e < BS; ++e) L[e] = ok ? p.scale * __ldg(p.y + cw * N + e) : 0.0f;
             }
-        }
 
-        // ---- outputs ----
-        const uint32_t *OS = PAC ? VS : US;
-        const uint32_t *OZ = PAC ? VZ : UZ;
-        for (int c = 0; c < nvalid; ++c) {
-            float *dst = p.decoded + (cw0 + c) * p.K;
-            for (int k = lane; k < p.K; k += 32) {
-                const int pos = __ldg(p.info + k);
-                uint32_t s = (OS[c * NWP + (pos >> 5)] >> (pos & 31)) & 1u;
-                uint32_t z = (OZ[c * NWP + (pos >> 5)] >> (pos & 31)) & 1u;
-                dst[k] = z ? 0.0f : (s ? -1.0f : 1.0f);
+            c.ps = 0u;
+            c.us = 0u;
+            c.vs = 0u;
+            c.frozen = __ldg(p.frozen_words + (o >> 5));
+            if (EXTRAS) {
+                c.llr_out = (p.leaf_llr && ok) ? p.leaf_llr + cw * N + o : nullptr;
+                if (c.have_gt) {
+                    uint32_t gs = 0u;
+                    if (ok)
+                        for (int e = 0; e < BS; ++e) {
+                            const float t = p.use_gt[cw * N + o + e];
+                            gs |= (uint32_t)(t < 0.0f) << e;
+                            c.tie |= (t == 0.0f);
+                        }
+                    c.gt_s = gs;
+                }
             }
-            if (PAC && p.u_hat) {
-                float *du = p.u_hat + (cw0 + c) * N;
-                for (int e = lane; e < N; e += 32) {
-                    uint32_t s = (US[c * NWP + (e >> 5)] >> (e & 31)) & 1u;
-                    uint32_t z = (UZ[c * NWP + (e >> 5)] >> (e & 31)) & 1u;
-                    du[e] = z ? 0.0f : (s ? -1.0f : 1.0f);
+            lane_node<BS, 0>(L, c);
+
+            if (n > BLOG) {
+                PS[q * 32 + lane] = c.ps;
+                US[q * 32 + lane] = c.us;
+                if (PAC) VS[q * 32 + lane] = c.vs;
+                // word-level merges: every trailing one of q completes a block of 2^(5+j+1) leaves
+                const int m = __ffs(~q) - 1;
+                for (int j = 0; j < m; ++j) {
+                    const int nw = 1 << j;
+                    const int wl = q + 1 - 2 * nw;
+                    for (int i = 0; i < nw; ++i) PS[(wl + i) * 32 + lane] ^= PS[(wl + nw + i) * 32 + lane];
                 }
             }
         }
+
+        // ---- outputs (coalesced: lane = k), then the tie sentinel ----
+        if (n > BLOG) {
+            __syncwarp();
+            const uint32_t *OS = PAC ? VS : US;
+            for (int cc = 0; cc < nvalid; ++cc) {
+                float *dst = p.decoded + (cw0 + cc) * p.K;
+                for (int k = lane; k < p.K; k += 32) {
+                    const int pos = __ldg(p.info + k);
+                    dst[k] = ((OS[(pos >> 5) * 32 + cc] >> (pos & 31)) & 1u) ? -1.0f : 1.0f;
+                }
+                if (PAC && p.u_hat) {
+                    float *du = p.u_hat + (cw0 + cc) * N;
+                    for (int e = lane; e < N; e += 32)
+                        du[e] = ((US[(e >> 5) * 32 + cc] >> (e & 31)) & 1u) ? -1.0f : 1.0f;
+                }
+            }
+            __syncwarp();
+        } else if (ok) {
+            const uint32_t os = PAC ? c.vs : c.us;
+            for (int k = 0; k < p.K; ++k) {
+                const int pos = __ldg(p.info + k);
+                p.decoded[cw * p.K + k] = ((os >> pos) & 1u) ? -1.0f : 1.0f;
+            }
+            if (PAC && p.u_hat)
+                for (int e = 0; e < N; ++e) p.u_hat[cw * N + e] = ((c.us >> e) & 1u) ? -1.0f : 1.0f;
+        }
+        if (ok && c.tie) p.decoded[cw * p.K] = __int_as_float(0x7fc00000);  // re-decode in the exact path
         __syncwarp();
     }
-    (void)NW;
 }
 
 int env_int(const char *name, int dflt)
@@ -249,6 +594,7 @@ int env_int(const char *name, int dflt)
     return v ? atoi(v) : dflt;
 }
 
+// ---- launchers ----------------------------------------------------------------------------------
 template <int G, bool PAC>
 int launch_group(const npd_code *code, const ScParams &p, cudaStream_t st)
 {
@@ -267,14 +613,12 @@ int launch_group(const npd_code *code, const ScParams &p, cudaStream_t st)
     if (warps_per_sm < 1) warps_per_sm = 1;
     int wpb = 1;
     if (warps_per_sm >= 16 && per_warp * 2 + 1024 <= budget) wpb = 2;
-    const int forced_wpb = env_int("NPD_SC_WPB", 0);
-    if (forced_wpb == 1 || forced_wpb == 2) wpb = forced_wpb;
     int blocks_per_sm = (int)((size_t)(228 * 1024) / (per_warp * wpb + 1024));
     if (blocks_per_sm > 32) blocks_per_sm = 32;
     if (blocks_per_sm < 1) blocks_per_sm = 1;
-    const int64_t ngroups = (p.B + G - 1) / G;
+    const int64_t units = p.scan_flagged ? (p.B + 31) / 32 : (p.B + G - 1) / G;
     int64_t grid = (int64_t)dp.sm_count * blocks_per_sm;
-    const int64_t need = (ngroups + wpb - 1) / wpb;
+    const int64_t need = (units + wpb - 1) / wpb;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     auto kern = sc_group_kernel<G, PAC>;
@@ -296,7 +640,7 @@ int default_group(int n)
 }
 
 template <bool PAC>
-int dispatch(const npd_code *code, const ScParams &p, cudaStream_t st)
+int dispatch_group(const npd_code *code, const ScParams &p, cudaStream_t st)
 {
     int G = env_int("NPD_SC_G", 0);
     if (G != 1 && G != 2 && G != 4 && G != 8 && G != 16 && G != 32) G = default_group(code->n);
@@ -308,6 +652,78 @@ int dispatch(const npd_code *code, const ScParams &p, cudaStream_t st)
     case 16: return launch_group<16, PAC>(code, p, st);
     default: return launch_group<32, PAC>(code, p, st);
     }
+}
+
+int default_slog(int n, bool pac)
+{
+    if (n <= 5) return 5;
+    // highest stored level: as many levels as fit in ~56 KB per warp (>= 4 warps per SM), at most four
+    // unstored levels above it
+    int slog = n - 1;
+    while (slog > 5 && lane_warp_smem_bytes(n, slog, pac) > 56 * 1024 && (n - 1 - (slog - 1)) <= 4) --slog;
+    return slog;
+}
+
+template <int BLOG, bool PAC, bool EXTRAS>
+int launch_lane(const npd_code *code, ScParams p, cudaStream_t st)
+{
+    DeviceProps dp;
+    if (npd_get_device_props(&dp)) return NPD_ECUDA;
+    const int n = code->n;
+    int slog = env_int("NPD_SC_SLOG", 0);
+    if (slog < 5 || slog > n - 1 || n - 1 - slog > 4) slog = default_slog(n, PAC);
+    p.slog = slog;
+    const size_t per_warp = lane_warp_smem_bytes(n, slog, PAC);
+    const size_t budget = (size_t)dp.smem_optin;
+    if (per_warp + 1024 > budget) {
+        npd_set_error("SC lane kernel: N=%d needs %zu B of shared memory per warp", code->N, per_warp);
+        return NPD_EUNSUPPORTED;
+    }
+    int warps_per_sm = (int)((size_t)(228 * 1024) / (per_warp + 1024));
+    const int max_warps = env_int("NPD_SC_WARPS", 20);  // register file: 96 regs/thread -> <= 20 warps
+    if (warps_per_sm > max_warps) warps_per_sm = max_warps;
+    if (warps_per_sm < 1) warps_per_sm = 1;
+    int wpb = 1;
+    while (wpb < 4 && warps_per_sm % (wpb * 2) == 0 && per_warp * wpb * 2 + 1024 <= budget) wpb *= 2;
+    const int blocks_per_sm = warps_per_sm / wpb;
+    const int64_t ngroups = (p.B + 31) / 32;
+    int64_t grid = (int64_t)dp.sm_count * blocks_per_sm;
+    const int64_t need = (ngroups + wpb - 1) / wpb;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    auto kern = sc_lane_kernel<BLOG, PAC, EXTRAS>;
+    NPD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(per_warp * wpb)));
+    kern<<<(unsigned)grid, 32 * wpb, per_warp * wpb, st>>>(p);
+    NPD_CHECK_CUDA(cudaGetLastError());
+    return NPD_OK;
+}
+
+template <bool PAC, bool EXTRAS>
+int dispatch_lane_blog(const npd_code *code, const ScParams &p, cudaStream_t st)
+{
+    switch (code->n) {
+    case 1: return launch_lane<1, PAC, EXTRAS>(code, p, st);
+    case 2: return launch_lane<2, PAC, EXTRAS>(code, p, st);
+    case 3: return launch_lane<3, PAC, EXTRAS>(code, p, st);
+    case 4: return launch_lane<4, PAC, EXTRAS>(code, p, st);
+    default: return launch_lane<5, PAC, EXTRAS>(code, p, st);
+    }
+}
+
+template <bool PAC>
+int dispatch(const npd_code *code, ScParams p, cudaStream_t st)
+{
+    const bool use_lane = code->K >= 1 && env_int("NPD_SC_IMPL_GROUP", 0) == 0;
+    if (!use_lane) {
+        p.scan_flagged = 0;
+        return dispatch_group<PAC>(code, p, st);
+    }
+    const bool extras = p.use_gt != nullptr || p.leaf_llr != nullptr;
+    int rc = extras ? dispatch_lane_blog<PAC, true>(code, p, st) : dispatch_lane_blog<PAC, false>(code, p, st);
+    if (rc) return rc;
+    p.scan_flagged = 1;  // exact re-decode of codewords that hit sign(0) = 0
+    return dispatch_group<PAC>(code, p, st);
 }
 
 }  // namespace

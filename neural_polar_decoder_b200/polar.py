@@ -105,7 +105,8 @@ class PolarCode:
         """reference polar.py:465-484: min-sum SC, bit-exact in fp32.
         -> (leaf LLRs [B,N] incl. the +infty frozen prior, u_hat[:, info_positions] [B,K] in {-1,0,+1}).
         return_llr=False skips the LLR output (first element is None)."""
-        src_dev = corrupted_codewords.device
+        src = corrupted_codewords
+        src_dev = src.device
         y = _lib.to_device_f32(corrupted_codewords)
         assert y.dim() == 2 and y.shape[1] == self.N, tuple(y.shape)
         B = y.shape[0]
@@ -118,6 +119,5 @@ class PolarCode:
                 _lib.check(_lib.load().npd_sc_decode(h.h, _lib.ptr(y), llr_scale(snr), _lib.ptr(gt),
                                                      _lib.ptr(llr), _lib.ptr(dec), B, _lib.stream_ptr()))
         if src_dev.type != "cuda":
-            llr = None if llr is None else llr.to(src_dev)
-            dec = dec.to(src_dev)
+            llr, dec = _lib.to_host(llr, src), _lib.to_host(dec, src)
         return llr, dec

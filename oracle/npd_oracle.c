@@ -17,6 +17,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define NPDO_API __attribute__((visibility("default")))
 
@@ -64,6 +67,7 @@ typedef struct {
 
 static int work_alloc(sc_work_t *w, int n)
 {
+    memset(w, 0, sizeof(*w));
     w->n = n;
     w->N = 1 << n;
     w->llr = (float *)calloc((size_t)(n + 1) * w->N, sizeof(float));
@@ -137,31 +141,42 @@ NPDO_API int npdo_sc_decode(const float *y, int64_t B, int n, int K, const int32
                             const uint8_t *frozen, float scale, float infty, const float *use_gt,
                             float *leaf_llr, float *u_hat_out, float *decoded)
 {
-    sc_work_t w;
-    if (work_alloc(&w, n)) return -1;
-    const int N = w.N;
-    float *prior = (float *)calloc(N, sizeof(float));
-    float *u_hat = (float *)calloc(N, sizeof(float));
-    for (int i = 0; i < N; ++i) prior[i] = frozen[i] ? infty : 0.0f;
-    for (int64_t b = 0; b < B; ++b) {
-        memset(w.llr, 0, sizeof(float) * (size_t)(n + 1) * N);
-        memset(w.ps, 0, sizeof(float) * (size_t)(n + 1) * N);
-        memset(u_hat, 0, sizeof(float) * N);
-        for (int i = 0; i < N; ++i) w.llr[(size_t)n * N + i] = scale * y[b * N + i];
-        for (int ii = 0; ii < N; ++ii) {
-            update_llr(&w, ii, prior);
-            u_hat[ii] = use_gt ? use_gt[b * N + ii] : sgnf(w.llr[ii]);
-            update_partial_sums(&w, ii, u_hat);
+    const int N = 1 << n;
+    int fail = 0;
+    /* codewords are independent: one work set per thread (bench.py's CPU baseline uses all cores) */
+#pragma omp parallel
+    {
+        sc_work_t w;
+        float *prior = (float *)calloc(N, sizeof(float));
+        float *u_hat = (float *)calloc(N, sizeof(float));
+        int bad = work_alloc(&w, n) || !prior || !u_hat;
+        if (bad) {
+#pragma omp atomic write
+            fail = 1;
+        } else {
+            for (int i = 0; i < N; ++i) prior[i] = frozen[i] ? infty : 0.0f;
+#pragma omp for schedule(dynamic, 1)
+            for (int64_t b = 0; b < B; ++b) {
+                memset(w.llr, 0, sizeof(float) * (size_t)(n + 1) * N);
+                memset(w.ps, 0, sizeof(float) * (size_t)(n + 1) * N);
+                memset(u_hat, 0, sizeof(float) * N);
+                for (int i = 0; i < N; ++i) w.llr[(size_t)n * N + i] = scale * y[b * N + i];
+                for (int ii = 0; ii < N; ++ii) {
+                    update_llr(&w, ii, prior);
+                    u_hat[ii] = use_gt ? use_gt[b * N + ii] : sgnf(w.llr[ii]);
+                    update_partial_sums(&w, ii, u_hat);
+                }
+                if (leaf_llr) memcpy(leaf_llr + b * N, w.llr, sizeof(float) * N);
+                if (u_hat_out) memcpy(u_hat_out + b * N, u_hat, sizeof(float) * N);
+                if (decoded)
+                    for (int k = 0; k < K; ++k) decoded[b * K + k] = u_hat[info[k]];
+            }
         }
-        if (leaf_llr) memcpy(leaf_llr + b * N, w.llr, sizeof(float) * N);
-        if (u_hat_out) memcpy(u_hat_out + b * N, u_hat, sizeof(float) * N);
-        if (decoded)
-            for (int k = 0; k < K; ++k) decoded[b * K + k] = u_hat[info[k]];
+        free(prior);
+        free(u_hat);
+        if (!bad) work_free(&w);
     }
-    free(prior);
-    free(u_hat);
-    work_free(&w);
-    return 0;
+    return fail ? -1 : 0;
 }
 
 /* pac_code.py:193-200 conv1bTrans_batch for one row.  g[M] holds +-1 (1 - 2*bit, MSB first,
@@ -346,4 +361,14 @@ NPDO_API void npdo_gen_noise(uint64_t seed, uint64_t cw0, uint32_t pt, int64_t B
             }
         }
     }
+}
+
+/* Number of threads the OpenMP loops above will use (1 without OpenMP). */
+NPDO_API int npdo_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
 }

@@ -281,3 +281,13 @@ def conv_forward(sd, y, round_bf16=False):
     Nn = v.shape[1]
     v = F.layer_norm(v, (Nn,), T(sd["layer_norm.weight"]), T(sd["layer_norm.bias"]), 1e-6)
     return v.numpy()
+
+
+def run_threaded(fn, B, threads):
+    """Split rows [0,B) over `threads` Python threads (ctypes releases the GIL inside the C oracle).
+    fn(lo, hi) is called once per slice; returns the list of results in slice order."""
+    from concurrent.futures import ThreadPoolExecutor
+    threads = max(1, min(int(threads), B))
+    bounds = [(B * t) // threads for t in range(threads + 1)]
+    with ThreadPoolExecutor(threads) as ex:
+        return list(ex.map(lambda t: fn(bounds[t], bounds[t + 1]), range(threads)))
