@@ -1,0 +1,184 @@
+"""bench.py legs for the neural decoders (CRISP GRU): device-resident throughput, end-to-end through the
+drop-in API, tensor-pipe roofline, and the CPU baseline (torch eager nn.GRU stepping = what the reference's
+RNN_decoder.decode does, rnn_all.py:532-547)."""
+import json
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import _lib, construct, synth, utils
+from .rnn_all import RNN_Model, RNN_decoder, gru_decode
+
+METRIC = "decoded codewords/sec"
+UNIT = "codewords/s"
+
+
+def available():
+    try:
+        lib = _lib.load()
+    except Exception:
+        return False
+    # the stub returns NPD_EUNSUPPORTED without touching CUDA; a real build validates its arguments first
+    import ctypes
+    h = ctypes.c_void_p()
+    rc = lib.npd_gru_create(0, 0, None, None, None, None, None, None, None, None, None, None, ctypes.byref(h))
+    return rc == _lib.NPD_EINVAL
+
+
+def flops_per_codeword(N, H=512):
+    """SURVEY.md App. D (hoisted form): N steps x (3 GEMV-equivalents H->3H + head) + the y projection."""
+    return N * (2 * 3 * H * 3 * H + 2 * H) + 2 * N * 3 * H
+
+
+def _setup(w, seed=11):
+    N, K = w["N"], w["K"]
+    rs = construct.reference_rs256()
+    info = np.sort(rs[rs < N][:K])
+    sd = synth.gru_state_dict(seed, N, 512, 2, head_gain=8.0)
+    net = RNN_Model('GRU', N + 2, 512, 1, 2, N, 0, 0)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    return net, info
+
+
+def bench(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
+    import torch.distributed as dist
+    from .polar import PolarCode
+    N, K, B, snr = w["N"], w["K"], w["batch"], w["snr"]
+    dev = torch.device("cuda", local_rank)
+    net, info = _setup(w)
+    rs = construct.reference_rs256()
+    code = PolarCode(int(np.log2(N)), K, None, rs=rs[rs < N])
+    dec = RNN_decoder('y_input', N, info, onehot=True)
+    lib = _lib.load()
+    h = code._handle()
+    sigma = float(np.float32(utils.snr_db2sigma(snr)))
+    msg = torch.empty(B, K, device=dev)
+    y = torch.empty(B, N, device=dev)
+    _lib.check(lib.npd_gen_encode_awgn(h.h, _lib.ptr(msg), None, _lib.ptr(y), B, sigma, 2026, 0, rank * B,
+                                       _lib.stream_ptr()))
+    gh = net.npd_handle(N)
+    loss_code = dec._loss_code(info)
+    decoded = torch.empty(B, N, device=dev)
+    info_t = torch.as_tensor(info, device=dev)
+    counts = torch.zeros(3, dtype=torch.int64, device=dev)
+    st = _lib.stream_ptr()
+    dec_info = torch.empty(B, K, device=dev)
+
+    def step():
+        _lib.check(lib.npd_gru_decode(gh.h, loss_code.h, _lib.ptr(y), None, None, _lib.ptr(decoded), B, None, 0, st))
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sync()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(args.steps):
+        ev[i][0].record()
+        step()
+        ev[i][1].record()
+        torch.index_select(decoded, 1, info_t, out=dec_info)
+        _lib.check(lib.npd_count_errors(_lib.ptr(msg), _lib.ptr(dec_info), B, K, _lib._vp(counts.data_ptr()), st))
+    if world > 1:
+        dist.all_reduce(counts)
+    t_end.record()
+    sync()
+    clocks = sampler.stop()
+    t = torch.tensor([t_start.elapsed_time(t_end)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    value = world * B * args.steps / (elapsed_ms * 1e-3)
+
+    # end to end through the drop-in (pinned host y -> H2D -> fused decode -> D2H decisions)
+    e2e_B = min(B, 18944)
+    y_host = y[:e2e_B].cpu().pin_memory()
+    e2e_steps = max(3, min(args.steps, 5))
+    for _ in range(2):
+        dec.decode(net, False, y_host)
+    sync()
+    t0 = time.perf_counter()
+    acc = 0.0
+    for _ in range(e2e_steps):
+        d_host = dec.decode(net, False, y_host)
+        acc += float(d_host[:, int(info[0])].sum())
+    torch.cuda.synchronize()
+    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_B * e2e_steps / float(e2e_t.item())
+
+    peaks = measured_peaks()
+    fl = flops_per_codeword(N) * B
+    achieved = fl / (kern_ms * 1e-3) / 1e12
+    cnt = counts.tolist()
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": w["desc"], "N": N, "K": K, "snr_db": snr, "batch_per_gpu": B,
+                   "l2_policy": "weights (4.8 MB bf16) are L2-resident by design; y = %.1f MB per GPU is read once per "
+                                "launch" % (B * N * 4 / 2 ** 20),
+                   "step": "npd_gru_decode (all N autoregressive steps, one launch) + info-bit gather + "
+                           "npd_count_errors; one NCCL all-reduce of the counters when n_gpus > 1",
+                   "weights": "synthetic U(-1/sqrt(H), 1/sqrt(H)) (neural_polar_decoder_b200.synth, seed 11)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_B * N * 4,
+                "d2h_bytes_per_step": e2e_B * N * 4, "batch_per_gpu": e2e_B, "steps": e2e_steps,
+                "api": "RNN_decoder.decode(net, False, host y) -> host decisions"},
+        "gpu_launches": 3 * args.steps,
+        "roofline": {"kernel": "gru_decode_kernel", "bound": "tensor", "achieved": achieved,
+                     "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
+                     "traffic": None, "peak_source": peaks["src"] + " (sustained bf16 GEMM)", "kernel_ms": kern_ms,
+                     "alg_flops_per_launch": fl, "flops_per_codeword": flops_per_codeword(N)},
+        "ber": cnt[0] / float(world * B * args.steps * K), "bler": cnt[1] / float(world * B * args.steps),
+        "frames": world * B * args.steps,
+    }
+
+
+def cpu_rate(w, seconds, threads, seed=0):
+    """CPU leg: the reference's own per-step structure -- torch eager nn.GRU(seq_len 1) + nn.Linear + sign
+    feedback for N steps (rnn_all.py:532-547), fp32, all host threads."""
+    torch.set_num_threads(threads)
+    N, K = w["N"], w["K"]
+    net, info = _setup(w)
+    net = net.cpu().eval()
+    info_set = set(int(i) for i in info)
+    rng = np.random.RandomState(seed)
+
+    def run(B):
+        y = torch.from_numpy((rng.choice([-1.0, 1.0], size=(B, N)) + 0.9 * rng.randn(B, N)).astype(np.float32))
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            decoded = torch.ones(B, N)
+            hidden = torch.zeros(2, B, net.feature_size)
+            for ii in range(N):
+                prev = torch.ones(B) if ii == 0 else decoded[:, ii - 1].sign()
+                onehot = torch.eye(2)[(0.5 + 0.5 * prev).long()]
+                out, hidden = net(torch.cat([y.unsqueeze(1), onehot.view(B, 1, 2)], 2), hidden)
+                if ii in info_set:
+                    decoded[:, ii] = out.squeeze().sign()
+        return time.perf_counter() - t0
+
+    dt = run(256)
+    B = int(max(256, min(65536, 256 / dt * seconds)))
+    dt = run(B)
+    return B / dt, B, dt
+
+
+def cpu_baseline(w):
+    threads = os.cpu_count() or 1
+    rate, B, dt = cpu_rate(w, 12.0, threads)
+    return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d codewords, torch eager nn.GRU stepping as in rnn_all.py:532-547, %.1f s" % (B, dt)}

@@ -1,0 +1,587 @@
+// gru_decode.cu -- CRISP GRU sequential decoder as one persistent tcgen05 kernel per codeword tile.
+//
+// Replaces RNN_decoder.decode(net, False, y) (reference rnn_all.py:514-521, 532-547; decoding_type
+// 'y_input', onehot) with RNN_Model.forward (387-398) = 2-layer nn.GRU + Linear(H,1) head, for all N
+// autoregressive steps in ONE launch.  PyTorch GRU cell, gate order r,z,n:
+//     r = s(W_ir x + b_ir + W_hr h + b_hr)       z = s(W_iz x + b_iz + W_hz h + b_hz)
+//     n = tanh(W_in x + b_in + r * (W_hn h + b_hn))       h' = (1 - z) * n + z * h
+// Layer-0 input x = [y (N) | onehot(prev decision) (2)]: the y part is an MMA over K = N (padded to
+// 64), the one-hot part selects one of two weight columns and is added in the epilogue.
+//
+// Mapping (DESIGN.md "GRU decoder"): a CTA owns TILE_B = 64 codewords for the whole decode.  GEMMs
+// are computed transposed, D[gate unit, codeword] = W[gate unit, k] * h[codeword, k]^T, so that
+//   * the weights are the A operand: 128-row x 64-k bf16 tiles (16 KB, pre-swizzled on the host into
+//     the canonical K-major SWIZZLE_128B layout) streamed from L2 by cp.async.bulk through an mbarrier
+//     ring, in exactly the order the MMA warp consumes them (a 4.8 MB "program" per step),
+//   * the hidden states are the B operand: h0, h1 and y live in shared memory as bf16
+//     [64 codewords x K] K-major swizzled tiles for the whole kernel and are rewritten in place by the
+//     epilogue warps (generic stores + fence.proxy.async),
+//   * accumulators live in TMEM: one "job" = 128 hidden units x 4 accumulators (r, z, n_i, n_h) x 64
+//     codewords = 256 columns; two jobs are in flight (512 columns) so the MMAs of job k+1 overlap the
+//     gate math of job k,
+//   * every epilogue thread owns one hidden unit (TMEM lane) and 32 codewords (columns): biases and
+//     the one-hot columns are per-thread constants, the GRU cell is thread-local, the new state of a
+//     layer is staged in registers until the layer's last MMA has read the old state, and the head
+//     dot product is a butterfly reduction across lanes.
+// Warp roles: warps 0-7 epilogue (TMEM lane quarter = warp % 4, column half = warp / 4), warp 8 = bulk
+// copy producer, warp 9 = MMA issuer + TMEM allocator.
+#include <cuda_bf16.h>
+
+#include <vector>
+
+#include "npd_common.cuh"
+
+namespace {
+
+constexpr int TILE_B = 64;         // codewords per CTA
+constexpr int JOB_UNITS = 128;     // hidden units per job (UMMA M)
+constexpr int A_TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
+constexpr int B_CHUNK_BYTES = TILE_B * 128;  // 64 rows x 64 bf16
+constexpr int NUM_STAGES = 5;
+constexpr int EPI_THREADS = 256;
+constexpr int NUM_THREADS = 320;
+
+// program entry (one per weight tile, in consumption order)
+//  bits 0-1 acc (0 R, 1 Z, 2 NI, 3 NH) | 2-3 bsrc (0 y, 1 h0, 2 h1) | 4-7 k chunk | 8 first (overwrite)
+//  9 job_begin (wait tmem_empty) | 10 job_end (commit tmem_full) | 11 wait_h0 | 12 wait_h1
+constexpr uint32_t P_FIRST = 1u << 8, P_JOB_BEGIN = 1u << 9, P_JOB_END = 1u << 10, P_WAIT_H0 = 1u << 11,
+                   P_WAIT_H1 = 1u << 12;
+
+struct GruParams {
+    const unsigned char *wpack;  // tiles_per_step * 16 KB
+    const uint32_t *program;     // tiles_per_step entries
+    const float *consts0;        // [H][12]: b_r b_z b_in b_hn cr0 cr1 cz0 cz1 cn0 cn1 - -
+    const float *consts1;        // [H][4] : b_r b_z b_in b_hn
+    const float *w_out;          // [H]
+    float b_out;
+    const float *y;              // [B,N]
+    const float *forced;         // [B,N] or null
+    const uint32_t *info_words;  // bit i = position i is an info (loss) position
+    float *logits;               // [B,N] or null
+    float *decoded;              // [B,N]
+    int64_t B;
+    int N, H, KY, tiles_per_step;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor: 8-row groups 1024 B apart, version 1
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr)
+{
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
+{
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8])
+{
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ float sigmoid_f(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_f(float x)
+{
+    // 1 - 2/(e^{2x}+1): exact limits at +-inf, abs error ~1e-7 with the fast exp / rcp pair
+    return 1.0f - 2.0f * __frcp_rn(1.0f + __expf(2.0f * x));
+}
+
+// byte offset of element (row c, k) inside a K-major SWIZZLE_128B operand buffer of 64-row chunks
+__device__ __forceinline__ uint32_t b_off(int c, int k)
+{
+    return (uint32_t)((k >> 6) * B_CHUNK_BYTES + c * 128 + ((((k & 63) >> 3) ^ (c & 7)) << 4) + (k & 7) * 2);
+}
+
+struct Smem {
+    // dynamic shared memory carve-up (all operand regions 1024-byte aligned)
+    static __host__ __device__ size_t ring() { return 0; }
+    static __host__ __device__ size_t h0(int) { return (size_t)NUM_STAGES * A_TILE_BYTES; }
+    static __host__ __device__ size_t h1(int H) { return h0(H) + (size_t)(H / 64) * B_CHUNK_BYTES; }
+    static __host__ __device__ size_t yb(int H) { return h1(H) + (size_t)(H / 64) * B_CHUNK_BYTES; }
+    static __host__ __device__ size_t red(int H, int KY) { return yb(H) + (size_t)KY * B_CHUNK_BYTES; }   // [4][64] floats
+    static __host__ __device__ size_t prog(int H, int KY) { return red(H, KY) + 4 * TILE_B * 4; }
+    static __host__ __device__ size_t bars(int H, int KY, int tiles) { return (prog(H, KY) + (size_t)tiles * 4 + 15) & ~(size_t)15; }
+    static __host__ __device__ size_t total(int H, int KY, int tiles) { return bars(H, KY, tiles) + 256; }
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruParams p)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int H = p.H, N = p.N, KY = p.KY, KH = H >> 6;
+    const int jobs_per_layer = H / JOB_UNITS;
+    const int64_t cw0 = (int64_t)blockIdx.x * TILE_B;
+
+    unsigned char *s_ring = smem + Smem::ring();
+    unsigned char *s_h0 = smem + Smem::h0(H);
+    unsigned char *s_h1 = smem + Smem::h1(H);
+    unsigned char *s_y = smem + Smem::yb(H);
+    float *s_red = reinterpret_cast<float *>(smem + Smem::red(H, KY));
+    uint32_t *s_prog = reinterpret_cast<uint32_t *>(smem + Smem::prog(H, KY));
+    uint64_t *s_bars = reinterpret_cast<uint64_t *>(smem + Smem::bars(H, KY, p.tiles_per_step));
+    // barriers: full[5], empty[5], tmem_full[2], tmem_empty[2], h_ready[2]
+    const uint32_t bar_full = smem_u32(s_bars), bar_empty = bar_full + 8 * NUM_STAGES,
+                   bar_tfull = bar_empty + 8 * NUM_STAGES, bar_tempty = bar_tfull + 16, bar_hready = bar_tempty + 16;
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bars + 2 * NUM_STAGES + 6);
+    uint32_t *s_bits = s_tmem + 1;  // [2]: feedback bits of the 64 codewords (1 = previous decision was +1)
+
+    // ---- one-time setup ----
+    if (tid == 0) {
+        for (int i = 0; i < NUM_STAGES; ++i) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_tempty + 8 * i, EPI_THREADS);
+            mbar_init(bar_hready + 8 * i, EPI_THREADS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_bits[0] = 0xffffffffu;  // step 0 feeds back +1 (rnn_all.py:542-543)
+        s_bits[1] = 0xffffffffu;
+    }
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    for (int i = tid; i < p.tiles_per_step; i += NUM_THREADS) s_prog[i] = p.program[i];
+    // h0 = h1 = 0 (rnn_all.py:538); y tile: fp32 -> bf16, K padded to KY*64 with zeros
+    for (int i = tid; i < (2 * KH * B_CHUNK_BYTES) / 16; i += NUM_THREADS)
+        reinterpret_cast<uint4 *>(s_h0)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < TILE_B * KY * 64; i += NUM_THREADS) {
+        const int c = i / (KY * 64), k = i % (KY * 64);
+        float v = 0.0f;
+        if (k < N && cw0 + c < p.B) v = p.y[(cw0 + c) * N + k];
+        *reinterpret_cast<__nv_bfloat16 *>(s_y + b_off(c, k)) = __float2bfloat16(v);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 8) {
+        // ================= producer: stream the weight program, once per step =================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int step = 0; step < N; ++step) {
+                const unsigned char *src = p.wpack;
+                for (int t = 0; t < p.tiles_per_step; ++t, src += A_TILE_BYTES) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    mbar_expect_tx(bar_full + 8 * stage, A_TILE_BYTES);
+                    bulk_g2s(smem_u32(s_ring + stage * A_TILE_BYTES), src, A_TILE_BYTES, bar_full + 8 * stage);
+                    if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            // M = 128, N = 64, bf16 x bf16 -> fp32, both operands K-major
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE_B >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t b_y = smem_u32(s_y), b_h0 = smem_u32(s_h0), b_h1 = smem_u32(s_h1);
+            uint32_t stage = 0, phase = 0;
+            uint32_t job = 0;       // global job counter -> TMEM slot job & 1
+            uint32_t hphase0 = 0, hphase1 = 0;
+            for (int step = 0; step < N; ++step) {
+                for (int t = 0; t < p.tiles_per_step; ++t) {
+                    const uint32_t e = s_prog[t];
+                    const uint32_t slot = job & 1;
+                    if (e & P_JOB_BEGIN) {
+                        mbar_wait(bar_tempty + 8 * slot, ((job >> 1) & 1) ^ 1);
+                        tc_fence_after();
+                    }
+                    if (e & P_WAIT_H0) {  // needs this step's h0 (layer-1 input stream)
+                        mbar_wait(bar_hready + 0, hphase0);
+                        hphase0 ^= 1;
+                        tc_fence_after();
+                    }
+                    if ((e & P_WAIT_H1) && step > 0) {  // needs the previous step's h1
+                        mbar_wait(bar_hready + 8, hphase1);
+                        hphase1 ^= 1;
+                        tc_fence_after();
+                    }
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t acc = e & 3u, bsrc = (e >> 2) & 3u, kc = (e >> 4) & 15u;
+                    const uint32_t d_tmem = tmem_base + slot * 256 + acc * TILE_B;
+                    const uint32_t a_addr = smem_u32(s_ring + stage * A_TILE_BYTES);
+                    const uint32_t b_addr = (bsrc == 0 ? b_y : (bsrc == 1 ? b_h0 : b_h1)) + kc * B_CHUNK_BYTES;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), idesc,
+                                  ((e & P_FIRST) && k == 0) ? 0u : 1u);
+                    umma_commit(bar_empty + 8 * stage);  // frees the ring slot when these MMAs retire
+                    if (e & P_JOB_END) {
+                        umma_commit(bar_tfull + 8 * slot);
+                        ++job;
+                    }
+                    if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ================= epilogue warps: gate math, state update, head, feedback =================
+        const int q = warp & 3, half = warp >> 2;
+        const int col0 = half * 32;                       // this thread's 32 codewords
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        uint32_t job = 0;
+        uint32_t staged[2 * 32];  // up to 4 jobs x 32 codewords, bf16 pairs (codeword 2i, 2i+1)
+        // fp32 master copy of this thread's slice of both hidden states (2 layers x 4 jobs x 32 codewords):
+        // thread-private, indexed at run time -> local memory (L2-resident, coalesced across lanes).  Only
+        // the MMA operand copy in shared memory is rounded to bf16.
+        float hstate[2 * 4 * 32];
+#pragma unroll 1
+        for (int i = 0; i < 2 * 4 * 32; ++i) hstate[i] = 0.0f;
+        float head[32];
+        const uint32_t info0 = p.info_words[0], info1 = N > 32 ? p.info_words[1] : 0u,
+                       info2 = N > 64 ? p.info_words[2] : 0u, info3 = N > 96 ? p.info_words[3] : 0u;
+
+        for (int step = 0; step < N; ++step) {
+            const uint32_t bits = s_bits[half];
+            for (int layer = 0; layer < 2; ++layer) {
+                unsigned char *s_h = layer ? s_h1 : s_h0;
+                if (layer == 1) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) head[i] = 0.0f;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (j >= jobs_per_layer) break;
+                    const int u = j * JOB_UNITS + q * 32 + lane;  // hidden unit of this thread
+                    float b_r, b_z, b_in, b_hn, cr0 = 0.f, cr1 = 0.f, cz0 = 0.f, cz1 = 0.f, cn0 = 0.f, cn1 = 0.f, wo = 0.f;
+                    if (layer == 0) {
+                        const float4 c0 = __ldg(reinterpret_cast<const float4 *>(p.consts0 + (size_t)u * 12));
+                        const float4 c1 = __ldg(reinterpret_cast<const float4 *>(p.consts0 + (size_t)u * 12 + 4));
+                        const float2 c2 = __ldg(reinterpret_cast<const float2 *>(p.consts0 + (size_t)u * 12 + 8));
+                        b_r = c0.x; b_z = c0.y; b_in = c0.z; b_hn = c0.w;
+                        cr0 = c1.x; cr1 = c1.y; cz0 = c1.z; cz1 = c1.w; cn0 = c2.x; cn1 = c2.y;
+                    } else {
+                        const float4 c0 = __ldg(reinterpret_cast<const float4 *>(p.consts1 + (size_t)u * 4));
+                        b_r = c0.x; b_z = c0.y; b_in = c0.z; b_hn = c0.w;
+                        wo = __ldg(p.w_out + u);
+                    }
+                    float *hst = hstate + (layer * 4 + j) * 32;
+                    const uint32_t slot = job & 1;
+                    mbar_wait(bar_tfull + 8 * slot, (job >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t t0 = tmem_base + lane_addr + slot * 256 + col0;
+#pragma unroll
+                    for (int cc = 0; cc < 32; cc += 8) {
+                        float aR[8], aZ[8], aNI[8], aNH[8];
+                        tmem_ld8(t0 + 0 * TILE_B + cc, aR);
+                        tmem_ld8(t0 + 1 * TILE_B + cc, aZ);
+                        tmem_ld8(t0 + 2 * TILE_B + cc, aNI);
+                        tmem_ld8(t0 + 3 * TILE_B + cc, aNH);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float gr = aR[i] + b_r, gz = aZ[i] + b_z, gn = aNI[i] + b_in;
+                            if (layer == 0) {
+                                const bool plus = (bits >> (cc + i)) & 1u;
+                                gr += plus ? cr1 : cr0;
+                                gz += plus ? cz1 : cz0;
+                                gn += plus ? cn1 : cn0;
+                            }
+                            const float r = sigmoid_f(gr), z = sigmoid_f(gz);
+                            const float nn = tanh_f(gn + r * (aNH[i] + b_hn));
+                            const float hold = hst[cc + i];
+                            const float hnew = (1.0f - z) * nn + z * hold;
+                            hst[cc + i] = hnew;
+                            if (layer == 1) head[cc + i] += wo * hnew;
+                            const uint32_t hb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(hnew));
+                            const int si = j * 16 + ((cc + i) >> 1);
+                            if ((i & 1) == 0) staged[si] = hb; else staged[si] |= hb << 16;
+                        }
+                    }
+                    tc_fence_before();
+                    mbar_arrive(bar_tempty + 8 * slot);
+                    ++job;
+                }
+                // every MMA that reads the old state of this layer has retired (tmem_full of the last
+                // job): write the new state in place
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (j >= jobs_per_layer) break;
+                    const int u = j * JOB_UNITS + q * 32 + lane;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const uint32_t pr = staged[j * 16 + i];
+                        *reinterpret_cast<unsigned short *>(s_h + b_off(col0 + 2 * i, u)) = (unsigned short)(pr & 0xffffu);
+                        *reinterpret_cast<unsigned short *>(s_h + b_off(col0 + 2 * i + 1, u)) = (unsigned short)(pr >> 16);
+                    }
+                }
+                fence_async_smem();
+                mbar_arrive(bar_hready + 8 * layer);
+            }
+
+            // ---- head: logit[c] = w_out . h1[c] + b_out ; butterfly over the 32 lanes (units) ----
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) {
+#pragma unroll
+                for (int i = 0; i < s; ++i) {
+                    const bool up = (lane & s) != 0;
+                    const float send = up ? head[i] : head[i + s];
+                    const float keep = up ? head[i + s] : head[i];
+                    head[i] = keep + __shfl_xor_sync(NPD_FULL, send, s);
+                }
+            }
+            s_red[q * TILE_B + col0 + lane] = head[0];  // lane l holds column col0 + l of this lane quarter
+            epi_bar_sync();
+            if (warp < 2) {
+                const int c = warp * 32 + lane;
+                const float logit = ((s_red[c] + s_red[TILE_B + c]) + (s_red[2 * TILE_B + c] + s_red[3 * TILE_B + c])) + p.b_out;
+                const uint32_t iw = step < 32 ? info0 : step < 64 ? info1 : step < 96 ? info2 : info3;
+                const bool is_info = (iw >> (step & 31)) & 1u;
+                float dec = 1.0f;  // decoded = ones; only loss positions are overwritten (rnn_all.py:520, 546-547)
+                if (is_info) dec = (logit > 0.0f) ? 1.0f : ((logit < 0.0f) ? -1.0f : 0.0f);
+                const bool valid = cw0 + c < p.B;
+                if (valid) {
+                    if (p.logits) p.logits[(cw0 + c) * N + step] = logit;
+                    p.decoded[(cw0 + c) * N + step] = dec;
+                }
+                float prev = dec;  // next step feeds back sign(decoded[:, step]) ...
+                if (p.forced && valid) prev = p.forced[(cw0 + c) * N + step];  // ... or the forced sequence
+                // get_onehot (rnn_all.py:258-260): index = (0.5 + 0.5*prev).long() -> 1 only for prev = +1
+                const uint32_t m = __ballot_sync(NPD_FULL, prev >= 1.0f);
+                if (lane == 0) s_bits[warp] = m;
+            }
+            epi_bar_sync();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+
+}  // namespace
+
+// ---- host side ----------------------------------------------------------------------------------
+struct npd_gru {
+    int N, H, KY, tiles_per_step;
+    float b_out;
+    unsigned char *d_wpack;
+    uint32_t *d_program;
+    float *d_consts0, *d_consts1, *d_w_out;
+    size_t smem_bytes;
+};
+
+namespace {
+
+// write one 128 x 64 bf16 tile in K-major SWIZZLE_128B order; src(r, k) gives the fp32 weight
+template <class F>
+void pack_tile(std::vector<unsigned short> &out, F src)
+{
+    const size_t base = out.size();
+    out.resize(base + 128 * 64);
+    for (int r = 0; r < 128; ++r)
+        for (int kk = 0; kk < 64; ++kk) {
+            const size_t off = (size_t)r * 128 + ((((kk >> 3) ^ (r & 7)) << 4)) + (kk & 7) * 2;
+            __nv_bfloat16 b = __float2bfloat16(src(r, kk));
+            out[base + off / 2] = *reinterpret_cast<unsigned short *>(&b);
+        }
+}
+
+}  // namespace
+
+NPD_API int npd_gru_create(int N, int H, const float *w_ih0, const float *w_hh0, const float *b_ih0,
+                           const float *b_hh0, const float *w_ih1, const float *w_hh1, const float *b_ih1,
+                           const float *b_hh1, const float *w_out, const float *b_out, npd_gru_t **out)
+{
+    NPD_REQUIRE(out, "npd_gru_create: null out");
+    *out = nullptr;
+    NPD_REQUIRE(w_ih0 && w_hh0 && b_ih0 && b_hh0 && w_ih1 && w_hh1 && b_ih1 && b_hh1 && w_out && b_out,
+                "npd_gru_create: null weight pointer");
+    if (N < 1 || N > 128 || H < 128 || H > 512 || (H % 128) != 0) {
+        npd_set_error("npd_gru_create: supported envelope is 1 <= N <= 128, H in {128,256,384,512} (got N=%d H=%d)", N, H);
+        return NPD_EUNSUPPORTED;
+    }
+    DeviceProps dp;
+    if (npd_get_device_props(&dp)) return NPD_ECUDA;
+    const int KY = (N + 63) / 64, KH = H / 64, JOBS = H / 128, IN0 = N + 2;
+    std::vector<unsigned short> pack;
+    std::vector<uint32_t> prog;
+    auto emit = [&](uint32_t acc, uint32_t bsrc, uint32_t kc, uint32_t flags) { prog.push_back(acc | (bsrc << 2) | (kc << 4) | flags); };
+    // layer 0: per job R (h0 chunks, y chunks), Z (same), NI (y chunks), NH (h0 chunks)
+    for (int j = 0; j < JOBS; ++j) {
+        for (int g = 0; g < 2; ++g) {  // R, Z
+            for (int kc = 0; kc < KH; ++kc) {
+                pack_tile(pack, [&](int r, int kk) { return w_hh0[(size_t)(g * H + j * 128 + r) * H + kc * 64 + kk]; });
+                emit(g, 1, kc, (kc == 0 ? P_FIRST : 0) | ((g == 0 && kc == 0) ? P_JOB_BEGIN : 0));
+            }
+            for (int kc = 0; kc < KY; ++kc) {
+                pack_tile(pack, [&](int r, int kk) {
+                    const int k = kc * 64 + kk;
+                    return k < N ? w_ih0[(size_t)(g * H + j * 128 + r) * IN0 + k] : 0.0f;
+                });
+                emit(g, 0, kc, 0);
+            }
+        }
+        for (int kc = 0; kc < KY; ++kc) {  // NI
+            pack_tile(pack, [&](int r, int kk) {
+                const int k = kc * 64 + kk;
+                return k < N ? w_ih0[(size_t)(2 * H + j * 128 + r) * IN0 + k] : 0.0f;
+            });
+            emit(2, 0, kc, kc == 0 ? P_FIRST : 0);
+        }
+        for (int kc = 0; kc < KH; ++kc) {  // NH
+            pack_tile(pack, [&](int r, int kk) { return w_hh0[(size_t)(2 * H + j * 128 + r) * H + kc * 64 + kk]; });
+            emit(3, 1, kc, (kc == 0 ? P_FIRST : 0) | (kc == KH - 1 ? P_JOB_END : 0));
+        }
+    }
+    // layer 1: per job the hidden-state stream first (needs only the previous step's h1), then the input
+    // stream (needs this step's h0): NH, R_h, Z_h, R_x, Z_x, NI
+    for (int j = 0; j < JOBS; ++j) {
+        for (int kc = 0; kc < KH; ++kc) {
+            pack_tile(pack, [&](int r, int kk) { return w_hh1[(size_t)(2 * H + j * 128 + r) * H + kc * 64 + kk]; });
+            emit(3, 2, kc, (kc == 0 ? (P_FIRST | P_JOB_BEGIN) : 0) | ((j == 0 && kc == 0) ? P_WAIT_H1 : 0));
+        }
+        for (int g = 0; g < 2; ++g)
+            for (int kc = 0; kc < KH; ++kc) {
+                pack_tile(pack, [&](int r, int kk) { return w_hh1[(size_t)(g * H + j * 128 + r) * H + kc * 64 + kk]; });
+                emit(g, 2, kc, kc == 0 ? P_FIRST : 0);
+            }
+        for (int g = 0; g < 2; ++g)
+            for (int kc = 0; kc < KH; ++kc) {
+                pack_tile(pack, [&](int r, int kk) { return w_ih1[(size_t)(g * H + j * 128 + r) * H + kc * 64 + kk]; });
+                emit(g, 1, kc, (j == 0 && g == 0 && kc == 0) ? P_WAIT_H0 : 0);
+            }
+        for (int kc = 0; kc < KH; ++kc) {
+            pack_tile(pack, [&](int r, int kk) { return w_ih1[(size_t)(2 * H + j * 128 + r) * H + kc * 64 + kk]; });
+            emit(2, 1, kc, (kc == 0 ? P_FIRST : 0) | (kc == KH - 1 ? P_JOB_END : 0));
+        }
+    }
+    std::vector<float> c0((size_t)H * 12, 0.0f), c1((size_t)H * 4, 0.0f);
+    for (int u = 0; u < H; ++u) {
+        float *a = &c0[(size_t)u * 12];
+        a[0] = b_ih0[u] + b_hh0[u];
+        a[1] = b_ih0[H + u] + b_hh0[H + u];
+        a[2] = b_ih0[2 * H + u];
+        a[3] = b_hh0[2 * H + u];
+        // onehot(-1) = [1,0] -> column N ; onehot(+1) = [0,1] -> column N+1 (rnn_all.py:258-260)
+        a[4] = w_ih0[(size_t)u * IN0 + N];            a[5] = w_ih0[(size_t)u * IN0 + N + 1];
+        a[6] = w_ih0[(size_t)(H + u) * IN0 + N];      a[7] = w_ih0[(size_t)(H + u) * IN0 + N + 1];
+        a[8] = w_ih0[(size_t)(2 * H + u) * IN0 + N];  a[9] = w_ih0[(size_t)(2 * H + u) * IN0 + N + 1];
+        float *b = &c1[(size_t)u * 4];
+        b[0] = b_ih1[u] + b_hh1[u];
+        b[1] = b_ih1[H + u] + b_hh1[H + u];
+        b[2] = b_ih1[2 * H + u];
+        b[3] = b_hh1[2 * H + u];
+    }
+    npd_gru *g = (npd_gru *)calloc(1, sizeof(npd_gru));
+    if (!g) return NPD_ENOMEM;
+    g->N = N; g->H = H; g->KY = KY; g->tiles_per_step = (int)prog.size(); g->b_out = b_out[0];
+    g->smem_bytes = Smem::total(H, KY, g->tiles_per_step);
+    if (g->smem_bytes > (size_t)dp.smem_optin) {
+        npd_set_error("npd_gru_create: needs %zu B of shared memory (limit %d)", g->smem_bytes, dp.smem_optin);
+        free(g);
+        return NPD_EUNSUPPORTED;
+    }
+    cudaError_t e = cudaMalloc(&g->d_wpack, pack.size() * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_program, prog.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_consts0, c0.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_consts1, c1.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_w_out, (size_t)H * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(g->d_wpack, pack.data(), pack.size() * 2, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(g->d_program, prog.data(), prog.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(g->d_consts0, c0.data(), c0.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(g->d_consts1, c1.data(), c1.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(g->d_w_out, w_out, (size_t)H * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gru_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bytes);
+    if (e != cudaSuccess) {
+        npd_set_error("npd_gru_create: %s", cudaGetErrorString(e));
+        npd_gru_destroy(g);
+        return NPD_ECUDA;
+    }
+    *out = g;
+    return NPD_OK;
+}
+
+NPD_API int npd_gru_destroy(npd_gru_t *g)
+{
+    if (!g) return NPD_OK;
+    cudaFree(g->d_wpack);
+    cudaFree(g->d_program);
+    cudaFree(g->d_consts0);
+    cudaFree(g->d_consts1);
+    cudaFree(g->d_w_out);
+    free(g);
+    return NPD_OK;
+}
+
+NPD_API size_t npd_gru_workspace_bytes(const npd_gru_t *, int64_t) { return 0; }
+
+NPD_API int npd_gru_decode(const npd_gru_t *g, const npd_code_t *code, const float *y, const float *forced,
+                           float *logits, float *decoded, int64_t B, void *, size_t, void *stream)
+{
+    NPD_REQUIRE(g && code && y && decoded, "npd_gru_decode: null argument");
+    NPD_REQUIRE(B >= 0, "npd_gru_decode: negative batch");
+    NPD_REQUIRE(code->N == g->N, "npd_gru_decode: code length %d != decoder input length %d", code->N, g->N);
+    if (B == 0) return NPD_OK;
+    GruParams p{};
+    p.wpack = g->d_wpack; p.program = g->d_program; p.consts0 = g->d_consts0; p.consts1 = g->d_consts1;
+    p.w_out = g->d_w_out; p.b_out = g->b_out; p.y = y; p.forced = forced; p.info_words = code->d_info_words;
+    p.logits = logits; p.decoded = decoded; p.B = B; p.N = g->N; p.H = g->H; p.KY = g->KY;
+    p.tiles_per_step = g->tiles_per_step;
+    const int64_t grid = (B + TILE_B - 1) / TILE_B;
+    gru_decode_kernel<<<(unsigned)grid, NUM_THREADS, g->smem_bytes, (cudaStream_t)stream>>>(p);
+    NPD_CHECK_CUDA(cudaGetLastError());
+    return NPD_OK;
+}
