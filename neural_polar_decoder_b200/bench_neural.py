@@ -126,9 +126,9 @@ def bench(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
     return {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "config": {"workload": args.workload, "desc": w["desc"], "N": N, "K": K, "snr_db": snr, "batch_per_gpu": B,
-                   "l2_policy": "weights (4.8 MB bf16) are L2-resident by design; y = %.1f MB per GPU is read once per "
+                   "l2_policy": "weights (4.8 MB fp16) are L2-resident by design; y = %.1f MB per GPU is read once per "
                                 "launch" % (B * N * 4 / 2 ** 20),
                    "step": "npd_gru_decode (all N autoregressive steps, one launch) + info-bit gather + "
                            "npd_count_errors; one NCCL all-reduce of the counters when n_gpus > 1",
@@ -140,7 +140,7 @@ def bench(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
         "gpu_launches": 3 * args.steps,
         "roofline": {"kernel": "gru_decode_kernel", "bound": "tensor", "achieved": achieved,
                      "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
-                     "traffic": None, "peak_source": peaks["src"] + " (sustained bf16 GEMM)", "kernel_ms": kern_ms,
+                     "traffic": None, "peak_source": peaks["src"] + " (sustained 16-bit dense GEMM, cuBLAS bf16)", "kernel_ms": kern_ms,
                      "alg_flops_per_launch": fl, "flops_per_codeword": flops_per_codeword(N)},
         "ber": cnt[0] / float(world * B * args.steps * K), "bler": cnt[1] / float(world * B * args.steps),
         "frames": world * B * args.steps,

@@ -10,10 +10,10 @@
 //
 // Mapping (DESIGN.md "GRU decoder"): a CTA owns TILE_B = 64 codewords for the whole decode.  GEMMs
 // are computed transposed, D[gate unit, codeword] = W[gate unit, k] * h[codeword, k]^T, so that
-//   * the weights are the A operand: 128-row x 64-k bf16 tiles (16 KB, pre-swizzled on the host into
+//   * the weights are the A operand: 128-row x 64-k fp16 tiles (16 KB, pre-swizzled on the host into
 //     the canonical K-major SWIZZLE_128B layout) streamed from L2 by cp.async.bulk through an mbarrier
 //     ring, in exactly the order the MMA warp consumes them (a 4.8 MB "program" per step),
-//   * the hidden states are the B operand: h0, h1 and y live in shared memory as bf16
+//   * the hidden states are the B operand: h0, h1 and y live in shared memory as fp16
 //     [64 codewords x K] K-major swizzled tiles for the whole kernel and are rewritten in place by the
 //     epilogue warps (generic stores + fence.proxy.async),
 //   * accumulators live in TMEM: one "job" = 128 hidden units x 4 accumulators (r, z, n_i, n_h) x 64
@@ -25,7 +25,7 @@
 //     dot product is a butterfly reduction across lanes.
 // Warp roles: warps 0-7 epilogue (TMEM lane quarter = warp % 4, column half = warp / 4), warp 8 = bulk
 // copy producer, warp 9 = MMA issuer + TMEM allocator.
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <vector>
 
@@ -35,8 +35,8 @@ namespace {
 
 constexpr int TILE_B = 64;         // codewords per CTA
 constexpr int JOB_UNITS = 128;     // hidden units per job (UMMA M)
-constexpr int A_TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
-constexpr int B_CHUNK_BYTES = TILE_B * 128;  // 64 rows x 64 bf16
+constexpr int A_TILE_BYTES = 128 * 128;  // 128 rows x 64 fp16
+constexpr int B_CHUNK_BYTES = TILE_B * 128;  // 64 rows x 64 fp16
 constexpr int NUM_STAGES = 5;
 constexpr int EPI_THREADS = 256;
 constexpr int NUM_THREADS = 320;
@@ -100,7 +100,7 @@ __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
+__device__ __forceinline__ void umma_fp16(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -134,12 +134,21 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8])
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-__device__ __forceinline__ float sigmoid_f(float x) { return __frcp_rn(1.0f + __expf(-x)); }
-__device__ __forceinline__ float tanh_f(float x)
+__device__ __forceinline__ float ex2_approx(float x)
 {
-    // 1 - 2/(e^{2x}+1): exact limits at +-inf, abs error ~1e-7 with the fast exp / rcp pair
-    return 1.0f - 2.0f * __frcp_rn(1.0f + __expf(2.0f * x));
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// 2 MUFU + 2 FP32 ops each; relative error ~2^-22, exact limits at +-inf
+__device__ __forceinline__ float sigmoid_f(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh_f(float x) { return 1.0f - 2.0f * rcp_approx(1.0f + ex2_approx(2.8853900817779268f * x)); }
 
 // byte offset of element (row c, k) inside a K-major SWIZZLE_128B operand buffer of 64-row chunks
 __device__ __forceinline__ uint32_t b_off(int c, int k)
@@ -200,14 +209,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     for (int i = tid; i < p.tiles_per_step; i += NUM_THREADS) s_prog[i] = p.program[i];
-    // h0 = h1 = 0 (rnn_all.py:538); y tile: fp32 -> bf16, K padded to KY*64 with zeros
+    // h0 = h1 = 0 (rnn_all.py:538); y tile: fp32 -> fp16, K padded to KY*64 with zeros
     for (int i = tid; i < (2 * KH * B_CHUNK_BYTES) / 16; i += NUM_THREADS)
         reinterpret_cast<uint4 *>(s_h0)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < TILE_B * KY * 64; i += NUM_THREADS) {
         const int c = i / (KY * 64), k = i % (KY * 64);
         float v = 0.0f;
         if (k < N && cw0 + c < p.B) v = p.y[(cw0 + c) * N + k];
-        *reinterpret_cast<__nv_bfloat16 *>(s_y + b_off(c, k)) = __float2bfloat16(v);
+        *reinterpret_cast<__half *>(s_y + b_off(c, k)) = __float2half_rn(v);
     }
     fence_async_smem();
     tc_fence_before();
@@ -232,8 +241,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
     } else if (warp == 9) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            // M = 128, N = 64, bf16 x bf16 -> fp32, both operands K-major
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE_B >> 3) << 17) | ((128u >> 4) << 24);
+            // M = 128, N = 64, fp16 x fp16 -> fp32 (a_format = b_format = 0), both operands K-major
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(TILE_B >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t b_y = smem_u32(s_y), b_h0 = smem_u32(s_h0), b_h1 = smem_u32(s_h1);
             uint32_t stage = 0, phase = 0;
             uint32_t job = 0;       // global job counter -> TMEM slot job & 1
@@ -264,7 +273,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
                     const uint32_t b_addr = (bsrc == 0 ? b_y : (bsrc == 1 ? b_h0 : b_h1)) + kc * B_CHUNK_BYTES;
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma_bf16(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), idesc,
+                        umma_fp16(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), idesc,
                                   ((e & P_FIRST) && k == 0) ? 0u : 1u);
                     umma_commit(bar_empty + 8 * stage);  // frees the ring slot when these MMAs retire
                     if (e & P_JOB_END) {
@@ -281,13 +290,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
         const int col0 = half * 32;                       // this thread's 32 codewords
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         uint32_t job = 0;
-        uint32_t staged[2 * 32];  // up to 4 jobs x 32 codewords, bf16 pairs (codeword 2i, 2i+1)
-        // fp32 master copy of this thread's slice of both hidden states (2 layers x 4 jobs x 32 codewords):
-        // thread-private, indexed at run time -> local memory (L2-resident, coalesced across lanes).  Only
-        // the MMA operand copy in shared memory is rounded to bf16.
-        float hstate[2 * 4 * 32];
-#pragma unroll 1
-        for (int i = 0; i < 2 * 4 * 32; ++i) hstate[i] = 0.0f;
+        uint32_t staged[2 * 32];  // up to 4 jobs x 32 codewords, fp16 pairs (codeword 2i, 2i+1)
         float head[32];
         const uint32_t info0 = p.info_words[0], info1 = N > 32 ? p.info_words[1] : 0u,
                        info2 = N > 64 ? p.info_words[2] : 0u, info3 = N > 96 ? p.info_words[3] : 0u;
@@ -316,7 +319,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
                         b_r = c0.x; b_z = c0.y; b_in = c0.z; b_hn = c0.w;
                         wo = __ldg(p.w_out + u);
                     }
-                    float *hst = hstate + (layer * 4 + j) * 32;
                     const uint32_t slot = job & 1;
                     mbar_wait(bar_tfull + 8 * slot, (job >> 1) & 1);
                     tc_fence_after();
@@ -340,11 +342,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
                             }
                             const float r = sigmoid_f(gr), z = sigmoid_f(gz);
                             const float nn = tanh_f(gn + r * (aNH[i] + b_hn));
-                            const float hold = hst[cc + i];
+                            const float hold = __half2float(*reinterpret_cast<const __half *>(s_h + b_off(col0 + cc + i, u)));
                             const float hnew = (1.0f - z) * nn + z * hold;
-                            hst[cc + i] = hnew;
                             if (layer == 1) head[cc + i] += wo * hnew;
-                            const uint32_t hb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(hnew));
+                            const uint32_t hb = (uint32_t)__half_as_ushort(__float2half_rn(hnew));
                             const int si = j * 16 + ((cc + i) >> 1);
                             if ((i & 1) == 0) staged[si] = hb; else staged[si] |= hb << 16;
                         }
@@ -424,7 +425,7 @@ struct npd_gru {
 
 namespace {
 
-// write one 128 x 64 bf16 tile in K-major SWIZZLE_128B order; src(r, k) gives the fp32 weight
+// write one 128 x 64 fp16 tile in K-major SWIZZLE_128B order; src(r, k) gives the fp32 weight
 template <class F>
 void pack_tile(std::vector<unsigned short> &out, F src)
 {
@@ -433,7 +434,7 @@ void pack_tile(std::vector<unsigned short> &out, F src)
     for (int r = 0; r < 128; ++r)
         for (int kk = 0; kk < 64; ++kk) {
             const size_t off = (size_t)r * 128 + ((((kk >> 3) ^ (r & 7)) << 4)) + (kk & 7) * 2;
-            __nv_bfloat16 b = __float2bfloat16(src(r, kk));
+            __half b = __float2half_rn(src(r, kk));
             out[base + off / 2] = *reinterpret_cast<unsigned short *>(&b);
         }
 }
@@ -454,6 +455,17 @@ NPD_API int npd_gru_create(int N, int H, const float *w_ih0, const float *w_hh0,
     }
     DeviceProps dp;
     if (npd_get_device_props(&dp)) return NPD_ECUDA;
+    {
+        // operands are rounded to fp16 (fp32 accumulate): refuse weights outside its finite range
+        const struct { const float *p; size_t n; } arrs[] = {
+            {w_ih0, (size_t)3 * H * (N + 2)}, {w_hh0, (size_t)3 * H * H}, {w_ih1, (size_t)3 * H * H}, {w_hh1, (size_t)3 * H * H}};
+        for (const auto &a : arrs)
+            for (size_t i = 0; i < a.n; ++i)
+                if (!(fabsf(a.p[i]) <= 65504.0f)) {
+                    npd_set_error("npd_gru_create: weight magnitude %g is outside the fp16 range", (double)a.p[i]);
+                    return NPD_EUNSUPPORTED;
+                }
+    }
     const int KY = (N + 63) / 64, KH = H / 64, JOBS = H / 128, IN0 = N + 2;
     std::vector<unsigned short> pack;
     std::vector<uint32_t> prog;
