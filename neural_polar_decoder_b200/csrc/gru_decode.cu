@@ -61,6 +61,7 @@ struct GruParams {
     float *decoded;              // [B,N]
     int64_t B;
     int N, H, KY, tiles_per_step;
+    int dbg;  // bench-only experiments: 1 = skip bulk copies, 2 = skip MMAs (results are garbage)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -92,6 +93,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -181,7 +188,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
     unsigned char *s_h1 = smem + Smem::h1(H);
     unsigned char *s_y = smem + Smem::yb(H);
     float *s_red = reinterpret_cast<float *>(smem + Smem::red(H, KY));
-    uint32_t *s_prog = reinterpret_cast<uint32_t *>(smem + Smem::prog(H, KY));
     uint64_t *s_bars = reinterpret_cast<uint64_t *>(smem + Smem::bars(H, KY, p.tiles_per_step));
     // barriers: full[5], empty[5], tmem_full[2], tmem_empty[2], h_ready[2]
     const uint32_t bar_full = smem_u32(s_bars), bar_empty = bar_full + 8 * NUM_STAGES,
@@ -208,7 +214,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    for (int i = tid; i < p.tiles_per_step; i += NUM_THREADS) s_prog[i] = p.program[i];
     // h0 = h1 = 0 (rnn_all.py:538); y tile: fp32 -> fp16, K padded to KY*64 with zeros
     for (int i = tid; i < (2 * KH * B_CHUNK_BYTES) / 16; i += NUM_THREADS)
         reinterpret_cast<uint4 *>(s_h0)[i] = make_uint4(0, 0, 0, 0);
@@ -232,56 +237,89 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
                 const unsigned char *src = p.wpack;
                 for (int t = 0; t < p.tiles_per_step; ++t, src += A_TILE_BYTES) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    mbar_expect_tx(bar_full + 8 * stage, A_TILE_BYTES);
-                    bulk_g2s(smem_u32(s_ring + stage * A_TILE_BYTES), src, A_TILE_BYTES, bar_full + 8 * stage);
+                    if (p.dbg & 1) {
+                        mbar_arrive(bar_full + 8 * stage);
+                    } else {
+                        mbar_expect_tx(bar_full + 8 * stage, A_TILE_BYTES);
+                        bulk_g2s(smem_u32(s_ring + stage * A_TILE_BYTES), src, A_TILE_BYTES, bar_full + 8 * stage);
+                    }
                     if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 9) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            // M = 128, N = 64, fp16 x fp16 -> fp32 (a_format = b_format = 0), both operands K-major
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(TILE_B >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t b_y = smem_u32(s_y), b_h0 = smem_u32(s_h0), b_h1 = smem_u32(s_h1);
-            uint32_t stage = 0, phase = 0;
-            uint32_t job = 0;       // global job counter -> TMEM slot job & 1
-            uint32_t hphase0 = 0, hphase1 = 0;
-            for (int step = 0; step < N; ++step) {
-                for (int t = 0; t < p.tiles_per_step; ++t) {
-                    const uint32_t e = s_prog[t];
-                    const uint32_t slot = job & 1;
-                    if (e & P_JOB_BEGIN) {
-                        mbar_wait(bar_tempty + 8 * slot, ((job >> 1) & 1) ^ 1);
-                        tc_fence_after();
-                    }
-                    if (e & P_WAIT_H0) {  // needs this step's h0 (layer-1 input stream)
-                        mbar_wait(bar_hready + 0, hphase0);
-                        hphase0 ^= 1;
-                        tc_fence_after();
-                    }
-                    if ((e & P_WAIT_H1) && step > 0) {  // needs the previous step's h1
-                        mbar_wait(bar_hready + 8, hphase1);
-                        hphase1 ^= 1;
-                        tc_fence_after();
-                    }
-                    mbar_wait(bar_full + 8 * stage, phase);
-                    tc_fence_after();
-                    const uint32_t acc = e & 3u, bsrc = (e >> 2) & 3u, kc = (e >> 4) & 15u;
-                    const uint32_t d_tmem = tmem_base + slot * 256 + acc * TILE_B;
-                    const uint32_t a_addr = smem_u32(s_ring + stage * A_TILE_BYTES);
-                    const uint32_t b_addr = (bsrc == 0 ? b_y : (bsrc == 1 ? b_h0 : b_h1)) + kc * B_CHUNK_BYTES;
+        // The whole warp runs the (warp-uniform) schedule so that every address and flag lives in uniform
+        // registers; one elected lane issues the tcgen05 instructions.  The tile order is the order in which
+        // npd_gru_create packed the weight program.
+        // M = 128, N = 64, fp16 x fp16 -> fp32 (a_format = b_format = 0), both operands K-major
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(TILE_B >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t b_y = smem_u32(s_y), b_h0 = smem_u32(s_h0), b_h1 = smem_u32(s_h1);
+        const uint32_t ring0 = smem_u32(s_ring);
+        const bool no_mma = (p.dbg & 2) != 0;
+        uint32_t stage = 0, phase = 0;
+        uint32_t job = 0;  // global job counter -> TMEM slot job & 1
+        uint32_t hphase0 = 0, hphase1 = 0;
+
+        // consume one weight tile: D[slot, acc] (+)= A(ring stage) * B(b_addr)^T over K = 64
+        auto tile = [&](uint32_t d_tmem, uint32_t b_addr, bool first) {
+            mbar_wait(bar_full + 8 * stage, phase);
+            tc_fence_after();
+            const uint32_t a_addr = ring0 + stage * A_TILE_BYTES;
+            if (elect_one()) {
+                if (!no_mma) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         umma_fp16(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), idesc,
-                                  ((e & P_FIRST) && k == 0) ? 0u : 1u);
-                    umma_commit(bar_empty + 8 * stage);  // frees the ring slot when these MMAs retire
-                    if (e & P_JOB_END) {
-                        umma_commit(bar_tfull + 8 * slot);
-                        ++job;
-                    }
-                    if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+                                  (first && k == 0) ? 0u : 1u);
                 }
+                umma_commit(bar_empty + 8 * stage);  // frees the ring slot when these MMAs retire
+            }
+            __syncwarp();
+            if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+        };
+        auto run = [&](uint32_t d_tmem, uint32_t b_base, int nchunks, bool first) {
+            for (int kc = 0; kc < nchunks; ++kc) tile(d_tmem, b_base + kc * B_CHUNK_BYTES, first && kc == 0);
+        };
+
+        for (int step = 0; step < N; ++step) {
+            // ---- layer 0: R (h0, y), Z (h0, y), NI (y), NH (h0) ----
+            for (int j = 0; j < jobs_per_layer; ++j, ++job) {
+                const uint32_t slot = job & 1, d0 = tmem_base + slot * 256;
+                mbar_wait(bar_tempty + 8 * slot, ((job >> 1) & 1) ^ 1);
+                tc_fence_after();
+                run(d0 + 0 * TILE_B, b_h0, KH, true);
+                run(d0 + 0 * TILE_B, b_y, KY, false);
+                run(d0 + 1 * TILE_B, b_h0, KH, true);
+                run(d0 + 1 * TILE_B, b_y, KY, false);
+                run(d0 + 2 * TILE_B, b_y, KY, true);
+                run(d0 + 3 * TILE_B, b_h0, KH, true);
+                if (elect_one()) umma_commit(bar_tfull + 8 * slot);
+                __syncwarp();
+            }
+            // ---- layer 1: hidden-state stream first (previous step's h1), then this step's h0 ----
+            for (int j = 0; j < jobs_per_layer; ++j, ++job) {
+                const uint32_t slot = job & 1, d0 = tmem_base + slot * 256;
+                mbar_wait(bar_tempty + 8 * slot, ((job >> 1) & 1) ^ 1);
+                tc_fence_after();
+                if (j == 0 && step > 0) {
+                    mbar_wait(bar_hready + 8, hphase1);
+                    hphase1 ^= 1;
+                    tc_fence_after();
+                }
+                run(d0 + 3 * TILE_B, b_h1, KH, true);
+                run(d0 + 0 * TILE_B, b_h1, KH, true);
+                run(d0 + 1 * TILE_B, b_h1, KH, true);
+                if (j == 0) {
+                    mbar_wait(bar_hready + 0, hphase0);
+                    hphase0 ^= 1;
+                    tc_fence_after();
+                }
+                run(d0 + 0 * TILE_B, b_h0, KH, false);
+                run(d0 + 1 * TILE_B, b_h0, KH, false);
+                run(d0 + 2 * TILE_B, b_h0, KH, true);
+                if (elect_one()) umma_commit(bar_tfull + 8 * slot);
+                __syncwarp();
             }
         }
     } else {
@@ -592,6 +630,7 @@ NPD_API int npd_gru_decode(const npd_gru_t *g, const npd_code_t *code, const flo
     p.w_out = g->d_w_out; p.b_out = g->b_out; p.y = y; p.forced = forced; p.info_words = code->d_info_words;
     p.logits = logits; p.decoded = decoded; p.B = B; p.N = g->N; p.H = g->H; p.KY = g->KY;
     p.tiles_per_step = g->tiles_per_step;
+    { const char *d = getenv("NPD_GRU_DBG"); p.dbg = d ? atoi(d) : 0; }
     const int64_t grid = (B + TILE_B - 1) / TILE_B;
     gru_decode_kernel<<<(unsigned)grid, NUM_THREADS, g->smem_bytes, (cudaStream_t)stream>>>(p);
     NPD_CHECK_CUDA(cudaGetLastError());
