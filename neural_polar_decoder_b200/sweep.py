@@ -1,0 +1,216 @@
+"""BER/BLER sweep loops of the reference on the B200 path, plus the multi-GPU Monte-Carlo
+driver.
+
+  polar_RNN_full_test  reference rnn_all.py:821-966   (GRU vs SC on a polar code)
+  test_full_data       reference rnn_all.py:730-776   (GRU vs SC ("Dumer") on a PAC code)
+  testXformer          reference run_models.py:297-371 (one-shot model, e.g. convNet, vs SC)
+  mc_sc_sweep / mc_decoder_sweep  -- generate -> encode -> channel -> decode -> count entirely on the device,
+                       sharded over torch.distributed ranks with ONE all-reduce of the counters at the end.
+
+The reference loops read module globals (`args`, `code`, `decoder`, `device`); here they are keyword
+arguments.  Semantics kept: the same codewords are re-noised for every SNR point, per-batch error RATES are
+averaged (`+= ber / num_test_batches`), results are Python lists indexed by SNR point.  Counters stay on the
+device and are read back once per call (the reference syncs with .item() after every decoder call).
+Decoders the hot path does not cover (SC-list, ML/MAP, RNN list, Fano) are skipped: their lists stay 0."""
+import numpy as np
+import torch
+
+from . import _lib, rng, utils
+
+
+def _counts_buf(n_rows, device):
+    return torch.zeros(n_rows, 2, dtype=torch.int64, device=device)
+
+
+def _count_into(buf_row, a, b):
+    a = a.contiguous()
+    b = b.contiguous()
+    _lib.check(_lib.load().npd_count_errors(_lib.ptr(a), _lib.ptr(b), a.shape[0], a.shape[1],
+                                            _lib._vp(buf_row.data_ptr()), _lib.stream_ptr()))
+
+
+def _rates(counts, sizes, K, n_snr, n_dec):
+    """counts [batches, n_snr, n_dec, 2] -> per decoder (ber list, bler list) as averages of per-batch rates."""
+    c = counts.cpu().numpy().astype(np.float64)
+    nb = len(sizes)
+    out = []
+    for d in range(n_dec):
+        ber = [float(sum(c[k, s, d, 0] / (sizes[k] * K) for k in range(nb)) / nb) for s in range(n_snr)]
+        bler = [float(sum(c[k, s, d, 1] / sizes[k] for k in range(nb)) / nb) for s in range(n_snr)]
+        out.append((ber, bler))
+    return out
+
+
+def polar_RNN_full_test(net, polar, snr_range, Test_Data_Generator, run_ML=False, run_SCL=False, run_RNNL=False,
+                        decoder=None, device=None, seed=None):
+    """-> (bers_RNN, blers_RNN, bers_SC, blers_SC, bers_SCL, blers_SCL, bers_RNNL, blers_RNNL, bers_ML, blers_ML)."""
+    assert decoder is not None, "pass the RNN_decoder (a module global in the reference)"
+    _lib.require_cuda()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    snr_range = list(snr_range)
+    nb, ns = len(Test_Data_Generator), len(snr_range)
+    info = torch.as_tensor(np.asarray(polar.info_positions), device=device)
+    counts = torch.zeros(nb, ns, 2, 2, dtype=torch.int64, device=device)
+    sizes, frame0 = [], 0
+    seed = rng.get_seed() if seed is None else seed
+    with torch.cuda.device(device):
+        for k, msg_bits in enumerate(Test_Data_Generator):
+            msg = _lib.to_device_f32(msg_bits, device)
+            sizes.append(msg.shape[0])
+            x = polar.encode_plotkin(msg)
+            for si, snr in enumerate(snr_range):
+                y = polar.channel(x, snr, point=(1 << 31) | si, cw_offset=frame0, seed=seed)
+                _, dec_sc = polar.sc_decode_new(y, snr, return_llr=False)
+                _count_into(counts[k, si, 1], msg, dec_sc)  # .sign() is the identity on {-1,0,+1}
+                dec = decoder.decode(net, False, y)
+                _count_into(counts[k, si, 0], msg, dec.index_select(1, info))
+            frame0 += msg.shape[0]
+    (ber_r, bler_r), (ber_s, bler_s) = _rates(counts, sizes, polar.K, ns, 2)
+    zeros = [0. for _ in snr_range]
+    return (ber_r, bler_r, ber_s, bler_s, list(zeros), list(zeros), list(zeros), list(zeros), list(zeros),
+            list(zeros))
+
+
+def test_full_data(net, code, snr_range, Test_Data_Generator, run_fano=False, run_dumer=True, decoder=None,
+                   device=None, seed=None):
+    """PAC sweep -> (bers_RNN, blers_RNN, bers_Dumer, blers_Dumer, bers_ML, blers_ML, bers_fano, blers_fano)."""
+    assert decoder is not None
+    _lib.require_cuda()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    snr_range = list(snr_range)
+    nb, ns = len(Test_Data_Generator), len(snr_range)
+    info = torch.as_tensor(np.asarray(code.B), device=device)
+    counts = torch.zeros(nb, ns, 2, 2, dtype=torch.int64, device=device)
+    sizes, frame0 = [], 0
+    seed = rng.get_seed() if seed is None else seed
+    with torch.cuda.device(device):
+        for k, msg_bits in enumerate(Test_Data_Generator):
+            msg = _lib.to_device_f32(msg_bits, device)
+            sizes.append(msg.shape[0])
+            x = code.pac_encode(msg)
+            for si, snr in enumerate(snr_range):
+                y = code.channel(x, snr, point=(1 << 31) | si, cw_offset=frame0, seed=seed)
+                dec = decoder.decode(net, False, y)
+                _count_into(counts[k, si, 0], msg, dec.index_select(1, info))
+                if run_dumer:
+                    _, v_hat, _ = code.pac_sc_decode(y, snr)
+                    _count_into(counts[k, si, 1], msg, v_hat)
+            frame0 += msg.shape[0]
+    (ber_r, bler_r), (ber_d, bler_d) = _rates(counts, sizes, code.K, ns, 2)
+    zeros = [0. for _ in snr_range]
+    return ber_r, bler_r, ber_d, bler_d, list(zeros), list(zeros), list(zeros), list(zeros)
+
+
+def testXformer(net, polar, snr_range, Test_Data_Generator, device, Test_Data_Mask=None, run_ML=False,
+                bitwise_snr_idx=-1, seed=None):
+    """One-shot decoders (net.decode(y, info_positions, mask, device) -> (bits[B,N,1], mask)).
+    -> the reference's 11 values; SCL / ML / bitwise-MAP entries stay 0 (out of the hot path)."""
+    _lib.require_cuda()
+    device = torch.device(device)
+    snr_range = list(snr_range)
+    nb, ns = len(Test_Data_Generator), len(snr_range)
+    info = torch.as_tensor(np.asarray(polar.info_positions), device=device)
+    counts = torch.zeros(nb, ns, 2, 2, dtype=torch.int64, device=device)
+    bitwise = torch.zeros((1, polar.K), device=device)
+    sizes, frame0 = [], 0
+    seed = rng.get_seed() if seed is None else seed
+    with torch.cuda.device(device):
+        for k, msg_bits in enumerate(Test_Data_Generator):
+            msg = _lib.to_device_f32(msg_bits, device)
+            sizes.append(msg.shape[0])
+            x = polar.encode_plotkin(msg)
+            for si, snr in enumerate(snr_range):
+                y = polar.channel(x, snr, point=(1 << 31) | si, cw_offset=frame0, seed=seed)
+                _, dec_sc = polar.sc_decode_new(y, snr, return_llr=False)
+                _count_into(counts[k, si, 1], msg, dec_sc)
+                bits, _ = net.decode(y, polar.info_positions, None, device)
+                dec = bits.reshape(bits.shape[0], -1).index_select(1, info)
+                _count_into(counts[k, si, 0], msg, dec)
+                if si == bitwise_snr_idx % ns and bitwise_snr_idx != -1:
+                    bitwise += utils.errors_bitwise_ber(msg, dec.sign()).reshape(1, -1) / nb
+            frame0 += msg.shape[0]
+    (ber_x, bler_x), (ber_s, bler_s) = _rates(counts, sizes, polar.K, ns, 2)
+    zeros = [0. for _ in snr_range]
+    return (ber_x, bler_x, ber_s, bler_s, list(zeros), list(zeros), list(zeros), list(zeros), bitwise, list(zeros),
+            list(zeros))
+
+
+# ---------------------------------------------------------------------------------------------------
+# multi-GPU Monte-Carlo drivers: contiguous global frame ranges per rank, Philox counters =
+# global frame index, one all-reduce(sum) of an int64 [n_snr, 3] tensor at the end.
+# ---------------------------------------------------------------------------------------------------
+def shard_range(total, rank, world):
+    """Contiguous slice [lo, hi) of `total` frames owned by `rank` (sizes differ by at most one)."""
+    base, rem = divmod(int(total), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def reduce_counts(counts, group=None):
+    """Sum the [n_snr, 3] counter tensor over all ranks (no-op without an initialised process group)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    return counts
+
+
+def finalize(counts, K):
+    """[n_snr, 3] (bit errors, block errors, frames) -> (ber list, bler list, frames list)."""
+    c = counts.cpu().numpy().astype(np.float64)
+    frames = np.maximum(c[:, 2], 1)
+    return (c[:, 0] / (frames * K)).tolist(), (c[:, 1] / frames).tolist(), c[:, 2].astype(np.int64).tolist()
+
+
+def mc_sc_sweep(polar, snr_range, total_frames, chunk=1 << 17, seed=0, rank=None, world=None, group=None):
+    """SC BER/BLER of `total_frames` frames per SNR point, fused on the device (npd_mc_sc_sweep)."""
+    import torch.distributed as dist
+    _lib.require_cuda()
+    if rank is None:
+        rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    lo, hi = shard_range(total_frames, rank, world)
+    lib = _lib.load()
+    h = polar._handle()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    snr_range = list(snr_range)
+    counts = torch.zeros(len(snr_range), 3, dtype=torch.int64, device=dev)
+    chunk = int(max(1, min(chunk, max(hi - lo, 1))))
+    ws_bytes = lib.npd_mc_sc_workspace_bytes(h.h, chunk)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    for si, snr in enumerate(snr_range):
+        if hi > lo:
+            _lib.check(lib.npd_mc_sc_sweep(h.h, hi - lo, chunk, float(np.float32(utils.snr_db2sigma(snr))),
+                                           utils.llr_scale(snr), int(seed), si, lo, _lib._vp(ws.data_ptr()), ws_bytes,
+                                           _lib._vp(counts[si].data_ptr()), _lib.stream_ptr()))
+    reduce_counts(counts, group)
+    return finalize(counts, polar.K) + (counts,)
+
+
+def mc_decoder_sweep(polar, decode_fn, snr_range, total_frames, chunk=1 << 15, seed=0, rank=None, world=None,
+                     group=None):
+    """Same for any decoder: decode_fn(y[B,N]) -> decisions [B,N] (e.g. lambda y: decoder.decode(net, False, y))."""
+    import torch.distributed as dist
+    _lib.require_cuda()
+    if rank is None:
+        rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    lo, hi = shard_range(total_frames, rank, world)
+    lib = _lib.load()
+    h = polar._handle()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    snr_range = list(snr_range)
+    info = torch.as_tensor(np.asarray(polar.info_positions), device=dev)
+    counts = torch.zeros(len(snr_range), 3, dtype=torch.int64, device=dev)
+    for si, snr in enumerate(snr_range):
+        for f0 in range(lo, hi, chunk):
+            b = min(chunk, hi - f0)
+            msg = torch.empty(b, polar.K, device=dev)
+            y = torch.empty(b, polar.N, device=dev)
+            _lib.check(lib.npd_gen_encode_awgn(h.h, _lib.ptr(msg), None, _lib.ptr(y), b,
+                                               float(np.float32(utils.snr_db2sigma(snr))), int(seed), si, f0,
+                                               _lib.stream_ptr()))
+            dec = decode_fn(y).index_select(1, info)
+            _count_into(counts[si], msg, dec)
+            counts[si, 2] += b
+    reduce_counts(counts, group)
+    return finalize(counts, polar.K) + (counts,)
