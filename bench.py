@@ -347,7 +347,7 @@ def bench_sc(args, w, rank, world, local_rank):
                 "d2h_bytes_per_step": e2e_B * K * 4, "batch_per_gpu": e2e_B, "steps": e2e_steps,
                 "api": "PolarCode.sc_decode_new(host y, snr) -> host decisions"},
         "gpu_launches": 2 * args.steps,
-        "roofline": {"kernel": "sc_group_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm"],
+        "roofline": {"kernel": "sc_lane_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm"],
                      "unit": "GB/s", "frac": achieved / peaks["hbm"], "traffic": None,
                      "peak_source": peaks["src"], "kernel_ms": kern_ms, "count_kernel_ms": count_ms,
                      "alg_bytes_per_launch": alg_bytes,
