@@ -144,13 +144,18 @@ int npd_gru_decode(const npd_gru_t *gru, const npd_code_t *code, const float *y,
  * npd_conv_create / npd_conv_forward: convNet.forward (models.py:742-767; layers 701-740) with
  * embed_dim = 2*C (C = 64), max_len = N: ten dilated k=7 Conv1d + GELU with three residual adds,
  * flatten, Linear(2C*N,4N) GELU Linear(4N,N) GELU Linear(N,N), LayerNorm(N, eps=1e-6).
- * h_params: host fp32 blob in state_dict order (see neural_polar_decoder_b200/models.py).
- * logits[B,N] out; bits = sign(logits) is left to the caller. */
+ * h_params: host fp32 blob in state_dict order with every bias present (zeros under dont_use_bias):
+ * layers1.0.weight, layers1.0.bias, layers1.2.*, layers2.0.*, ..., layers5.2.*, layersFin.0.*, layersFin.2.*,
+ * layersFin.4.*, layer_norm.weight, layer_norm.bias (neural_polar_decoder_b200/models.py packs it).
+ * logits[B,N] out (the LayerNorm output; bits = sign(logits) and probs = sigmoid(logits) are left to the
+ * caller); in4[B,C,N] or NULL = forward()'s 5th return value (input4, models.py:752, 765).
+ * workspace: device scratch of npd_conv_workspace_bytes(conv, B) bytes (fp16 rows of the flattened last
+ * conv activation, at most 1 GiB; larger batches are processed in chunks). */
 int npd_conv_create(int N, int embed_dim, const float *h_params, size_t n_params,
                     npd_conv_t **out);
 int npd_conv_destroy(npd_conv_t *conv);
 size_t npd_conv_workspace_bytes(const npd_conv_t *conv, int64_t B);
-int npd_conv_forward(const npd_conv_t *conv, const float *y, float *logits, int64_t B,
+int npd_conv_forward(const npd_conv_t *conv, const float *y, float *logits, float *in4, int64_t B,
                      void *workspace, size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus

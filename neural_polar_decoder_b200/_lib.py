@@ -36,7 +36,7 @@ SIGNATURES = {
     "npd_conv_create": (_int, [_int, _int, _vp, _sz, _c.POINTER(_vp)]),
     "npd_conv_destroy": (_int, [_vp]),
     "npd_conv_workspace_bytes": (_sz, [_vp, _i64]),
-    "npd_conv_forward": (_int, [_vp, _vp, _vp, _i64, _vp, _sz, _vp]),
+    "npd_conv_forward": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
 }
 
 _lib = None

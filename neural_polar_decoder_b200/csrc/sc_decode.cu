@@ -654,14 +654,14 @@ int dispatch_group(const npd_code *code, const ScParams &p, cudaStream_t st)
     }
 }
 
-int default_slog(int n, bool pac)
+int default_slog(int n, bool)
 {
-    if (n <= 5) return 5;
-    // highest stored level: as many levels as fit in ~56 KB per warp (>= 4 warps per SM), at most four
-    // unstored levels above it
-    int slog = n - 1;
-    while (slog > 5 && lane_warp_smem_bytes(n, slog, pac) > 56 * 1024 && (n - 1 - (slog - 1)) <= 4) --slog;
-    return slog;
+    // highest stored level (tuned on B200, tools/tune_sc.sh): all levels for N <= 128; above that, trade
+    // recomputation of the top levels from y against resident warps per SM (4*33*(2^(slog+1)-32) B each)
+    if (n <= 7) return n <= 5 ? 5 : n - 1;
+    if (n == 8) return 6;
+    if (n <= 10) return 7;
+    return 8;
 }
 
 template <int BLOG, bool PAC, bool EXTRAS>
@@ -680,7 +680,16 @@ int launch_lane(const npd_code *code, ScParams p, cudaStream_t st)
         return NPD_EUNSUPPORTED;
     }
     int warps_per_sm = (int)((size_t)(228 * 1024) / (per_warp + 1024));
-    const int max_warps = env_int("NPD_SC_WARPS", 20);  // register file: 96 regs/thread -> <= 20 warps
+    int max_warps = 20;  // register file: 96 regs/thread -> <= 20 warps
+    if (n - 1 - slog > 0) {
+        // the unstored top levels re-read y (2^(n-1-slog+1) times per codeword): keep the y rows of all
+        // resident codewords (warps * 32 * 4N bytes per SM) inside ~80 MB of the 126 MB L2 so that only the
+        // first read comes from HBM (ncu: 7x DRAM read traffic at 6 warps/SM for N = 1024, 1.0x at <= 4)
+        const size_t per_warp_y = (size_t)32 * 4 * code->N * dp.sm_count;
+        const int l2_warps = (int)((size_t)80 * 1024 * 1024 / per_warp_y);
+        if (l2_warps < max_warps) max_warps = l2_warps < 2 ? 2 : l2_warps;
+    }
+    max_warps = env_int("NPD_SC_WARPS", max_warps);
     if (warps_per_sm > max_warps) warps_per_sm = max_warps;
     if (warps_per_sm < 1) warps_per_sm = 1;
     int wpb = 1;

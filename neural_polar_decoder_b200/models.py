@@ -1,0 +1,153 @@
+"""Drop-in for the hot-path half of the reference's models.py: convNet (models.py:691-772), the one-shot CNN
+decoder of run_alt.sh / run_conv_c2n.sh.  The module keeps the reference's layer structure so that reference
+checkpoints (`checkpoint['xformer']`, run_models.py:980-983) load with load_state_dict; forward() and decode()
+run the two fused libnpd.so kernels (csrc/conv_net.cu) instead of ten cuDNN convolutions.
+
+Out of scope: the transformer / rnnAttn research models, training (dropout is the identity in
+eval mode, which is the only mode the accelerated path implements)."""
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+def _blob(sd, N, embed_dim):
+    """fp32 parameter blob in the order include/npd.h documents; missing biases (dont_use_bias) become zeros."""
+    C = embed_dim // 2
+    parts = []
+
+    def take(name, shape, optional=False):
+        if name not in sd:
+            assert optional, "missing parameter %s" % name
+            parts.append(np.zeros(shape, dtype=np.float32).ravel())
+            return
+        t = sd[name]
+        a = t.detach().float().cpu().numpy() if torch.is_tensor(t) else np.asarray(t, dtype=np.float32)
+        assert tuple(a.shape) == tuple(shape), (name, tuple(a.shape), tuple(shape))
+        parts.append(np.ascontiguousarray(a, dtype=np.float32).ravel())
+
+    convs = [("layers1.0", C, 1), ("layers1.2", C, C), ("layers2.0", C, C), ("layers2.2", C, C),
+             ("layers3.0", C, C), ("layers3.2", C, C), ("layers4.0", C, C), ("layers4.2", C, C),
+             ("layers5.0", 2 * C, C), ("layers5.2", 2 * C, 2 * C)]
+    for name, co, ci in convs:
+        take(name + ".weight", (co, ci, 7))
+        take(name + ".bias", (co,), optional=True)
+    for idx, (o, i) in zip((0, 2, 4), [(4 * N, embed_dim * N), (N, 4 * N), (N, N)]):
+        take("layersFin.%d.weight" % idx, (o, i))
+        take("layersFin.%d.bias" % idx, (o,), optional=True)
+    take("layer_norm.weight", (N,))
+    take("layer_norm.bias", (N,))
+    return np.concatenate(parts)
+
+
+class ConvHandle:
+    """Owns an npd_conv_t (fp16 weight slots / tiles in HBM) and the activation workspace."""
+
+    def __init__(self, N, embed_dim, sd):
+        _lib.require_cuda()
+        lib = _lib.load()
+        blob = _blob(sd, N, embed_dim)
+        h = ctypes.c_void_p()
+        _lib.check(lib.npd_conv_create(int(N), int(embed_dim), ctypes.c_void_p(blob.ctypes.data), blob.size,
+                                       ctypes.byref(h)))
+        self.h, self.N, self.embed_dim = h, N, embed_dim
+        self._ws = None
+
+    def workspace(self, B, device):
+        need = _lib.load().npd_conv_workspace_bytes(self.h, B)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
+        return self._ws
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) and _lib._lib is not None:
+                _lib._lib.npd_conv_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def conv_forward(handle, y, want_in4=False):
+    """Two fused launches per chunk: y [B,N] (device fp32) -> (logits [B,N], in4 [B,C,N] or None)."""
+    B, N = y.shape
+    logits = torch.empty(B, N, dtype=torch.float32, device=y.device)
+    in4 = torch.empty(B, handle.embed_dim // 2, N, dtype=torch.float32, device=y.device) if want_in4 else None
+    if B > 0:
+        ws = handle.workspace(B, y.device)
+        _lib.check(_lib.load().npd_conv_forward(handle.h, _lib.ptr(y), _lib.ptr(logits), _lib.ptr(in4), B,
+                                                ctypes.c_void_p(ws.data_ptr()), ws.numel(), _lib.stream_ptr()))
+    return logits, in4
+
+
+class convNet(nn.Module):
+    """reference models.py:691-772; config needs .embed_dim .max_len .N .dont_use_bias .dropout."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.hidden_dim = config.embed_dim
+        self.input_len = config.max_len
+        self.output_len = config.N
+        bias = not config.dont_use_bias
+        self.kernel = 7
+        self.padding = int((self.kernel - 1) / 2)
+        h2, h, k, p = int(self.hidden_dim / 2), self.hidden_dim, self.kernel, self.padding
+
+        def pair(ci, co_a, co_b, d_a, d_b):
+            return nn.Sequential(nn.Conv1d(ci, co_a, k, padding=d_a * p, dilation=d_a, bias=bias), nn.GELU(),
+                                 nn.Conv1d(co_a, co_b, k, padding=d_b * p, dilation=d_b, bias=bias), nn.GELU())
+
+        self.layers1 = pair(1, h2, h2, 1, 2)
+        self.layers2 = pair(h2, h2, h2, 4, 1)
+        self.layers3 = pair(h2, h2, h2, 2, 4)
+        self.layers4 = pair(h2, h2, h2, 1, 2)
+        self.layers5 = pair(h2, h, h, 4, 1)
+        self.layersFin = nn.Sequential(nn.Linear(h * self.output_len, 4 * self.output_len), nn.GELU(),
+                                       nn.Linear(4 * self.output_len, self.output_len), nn.GELU(),
+                                       nn.Linear(self.output_len, self.output_len))
+        self.layer_norm = nn.LayerNorm(self.output_len, eps=1e-6)
+        self.dropout = nn.Dropout(config.dropout)
+        self._npd = None
+
+    def npd_handle(self):
+        sd = self.state_dict()
+        key = (torch.cuda.current_device(),) + tuple((k, v._version, v.data_ptr()) for k, v in sd.items())
+        if self._npd is not None and self._npd[0] == key:
+            return self._npd[1]
+        handle = ConvHandle(self.output_len, self.hidden_dim, sd)
+        self._npd = (key, handle)
+        return handle
+
+    def forward(self, noisy_enc, mask, trg_seq, device):
+        """-> (probs [B,N,2], bits [B,N,1], mask, logits [B,N,1], input4 [B,C,N])  (models.py:742-767)."""
+        if self.training and self.dropout.p > 0:
+            raise NotImplementedError("the accelerated path is inference-only (call net.eval()); training is out of scope")
+        logits, in4, src = self._run(noisy_enc, want_in4=True)
+        logits = logits.squeeze().unsqueeze(-1)  # the reference's squeeze(): B = 1 collapses the batch axis too
+        decoded_msg_bits = logits.sign()
+        output = torch.sigmoid(logits)
+        output = torch.cat((1 - output, output), -1)
+        return output, decoded_msg_bits, mask, logits, in4
+
+    def decode(self, noisy_enc, info_positions, mask, device, trg_seq=None):
+        """-> (bits [B,N,1], mask); info_positions is ignored as in the reference (models.py:769-772)."""
+        logits, _, _ = self._run(noisy_enc, want_in4=False)
+        return logits.squeeze().unsqueeze(-1).sign(), mask
+
+    def logits(self, noisy_enc):
+        """LayerNorm output [B,N] (what parity is judged on)."""
+        return self._run(noisy_enc, want_in4=False)[0]
+
+    def _run(self, noisy_enc, want_in4):
+        src = noisy_enc
+        yd = _lib.to_device_f32(noisy_enc)
+        assert yd.dim() == 2 and yd.shape[1] == self.input_len
+        with torch.cuda.device(yd.device):
+            logits, in4 = conv_forward(self.npd_handle(), yd, want_in4)
+        if src.device.type != "cuda":
+            logits = _lib.to_host(logits, src)
+            in4 = _lib.to_host(in4, src)
+        return logits, in4, src

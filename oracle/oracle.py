@@ -241,9 +241,10 @@ _CONV_SPEC = [  # (sequential name, index, dilation)   models.py:701-730, paddin
 ]
 
 
-def conv_forward(sd, y, round_bf16=False):
+def conv_forward(sd, y, round_bf16=False, return_in4=False):
     """fp32 restatement of convNet.forward (models.py:742-767): 10 dilated k=7 Conv1d + exact GELU with
-    three residual adds, flatten, 3-layer MLP, LayerNorm(N, eps=1e-6).  -> logits[B,N]."""
+    three residual adds, flatten, 3-layer MLP, LayerNorm(N, eps=1e-6).  -> logits[B,N]
+    (+ input4 [B,C,N], forward()'s 5th return value, when return_in4)."""
     import torch
     import torch.nn.functional as F
 
@@ -280,6 +281,8 @@ def conv_forward(sd, y, round_bf16=False):
             v = F.gelu(v)
     Nn = v.shape[1]
     v = F.layer_norm(v, (Nn,), T(sd["layer_norm.weight"]), T(sd["layer_norm.bias"]), 1e-6)
+    if return_in4:
+        return v.numpy(), acts[2].numpy()
     return v.numpy()
 
 

@@ -254,3 +254,92 @@ def test_gru_vs_oracle_ragged_batch():
     err = np.abs(lg.cpu().numpy() - lo)
     assert (err <= _gru_tol(lo)).all(), err.max()
     assert (d.cpu().numpy()[:, [i for i in range(N) if i not in set(info.tolist())]] == 1).all()
+
+
+# ---------------------------------------------------------------------------------------------------
+# convNet one-shot decoder (fp16 tensor-core operands, fp32 accumulate, tanh-form GELU).  Parity is judged on
+# the LayerNorm output (the reference's `logits`): |d| <= 1e-2 * |ref| + 2e-3 (the absolute floor
+# covers logits near zero); decisions identical wherever |ref logit| exceeds that tolerance.
+# ---------------------------------------------------------------------------------------------------
+def _conv_tol(ref):
+    return 1e-2 * np.abs(ref) + 2e-3
+
+
+def _conv_net(N, E, seed):
+    import argparse
+    from neural_polar_decoder_b200 import synth
+    from neural_polar_decoder_b200.models import convNet
+    sd = synth.conv_state_dict(seed, N, E)
+    net = convNet(argparse.Namespace(embed_dim=E, max_len=N, N=N, dont_use_bias=False, dropout=0.1))
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    net.eval()
+    return net, sd
+
+
+def test_conv_logits_vs_reference_fixture(golden):
+    g = golden("conv")
+    N, K, E, seed = [int(v) for v in g["conv64_cfg"]]
+    net, _ = _conv_net(N, E, seed)
+    y = torch.from_numpy(g["conv64_y"]).cuda()
+    ref = g["conv64_logits"]
+    probs, bits, mask, logits, in4 = net(y, None, None, "cuda")
+    assert probs.shape == (y.shape[0], N, 2) and bits.shape == (y.shape[0], N, 1) and logits.shape == (y.shape[0], N, 1)
+    assert in4.shape == (y.shape[0], E // 2, N) and mask is None
+    lg = logits.squeeze(-1).cpu().numpy()
+    err, tol = np.abs(lg - ref), _conv_tol(ref)
+    print("conv64: logit err max %.3e mean %.3e, worst err/tol %.3f" % (err.max(), err.mean(), (err / tol).max()))
+    assert (err <= tol).all(), "max err %.3e at %s" % (err.max(), np.unravel_index(err.argmax(), err.shape))
+    safe = np.abs(ref) > tol
+    assert np.array_equal(bits.squeeze(-1).cpu().numpy()[safe], g["conv64_bits"][safe])
+    assert torch.allclose(probs[..., 1], torch.sigmoid(logits.squeeze(-1))) and torch.allclose(probs.sum(-1), torch.ones_like(probs[..., 0]))
+    bits2, _ = net.decode(y, None, None, "cuda")
+    assert torch.equal(bits2, bits)
+
+
+@pytest.mark.parametrize("B", [1, 5, 6, 7, 127, 129, 1000])
+def test_conv_vs_oracle_ragged_batches(B):
+    """Batch sizes around the 6-codeword CTA pass and the 128-codeword GEMM tile; oracle = fp32 torch
+    restatement of models.py:742-767 (pinned to the live reference by tests/test_oracle_golden.py)."""
+    N, E = 64, 128
+    net, sd = _conv_net(N, E, 5)
+    rng = np.random.RandomState(B)
+    y = (rng.choice([-1.0, 1.0], size=(B, N)) + 0.9 * rng.randn(B, N)).astype(np.float32)
+    ref, ref_in4 = oracle.conv_forward(sd, y, return_in4=True)
+    from neural_polar_decoder_b200.models import conv_forward
+    lg, in4 = conv_forward(net.npd_handle(), torch.from_numpy(y).cuda(), want_in4=True)
+    err = np.abs(lg.cpu().numpy() - ref)
+    assert (err <= _conv_tol(ref)).all(), "B=%d max err %.3e" % (B, err.max())
+    e4 = np.abs(in4.cpu().numpy() - ref_in4)
+    assert (e4 <= 1e-2 * np.abs(ref_in4) + 2e-3).all(), "input4 max err %.3e" % e4.max()
+    # host tensors in -> host tensors out
+    if B == 7:
+        bits, _ = net.decode(torch.from_numpy(y), None, None, "cpu")
+        assert bits.device.type == "cpu" and bits.shape == (B, N, 1)
+        safe = np.abs(ref) > _conv_tol(ref)
+        assert np.array_equal(bits.squeeze(-1).numpy()[safe], np.sign(ref)[safe])
+
+
+def test_conv_chunked_workspace_and_envelope():
+    """A workspace of one tile forces the chunk loop; unsupported shapes fail loudly (no fallback)."""
+    import ctypes
+    from neural_polar_decoder_b200 import _lib
+    N, E, B = 64, 128, 300
+    net, sd = _conv_net(N, E, 9)
+    h = net.npd_handle()
+    rng = np.random.RandomState(1)
+    y = torch.from_numpy(rng.randn(B, N).astype(np.float32)).cuda()
+    from neural_polar_decoder_b200.models import conv_forward
+    full, _ = conv_forward(h, y)
+    lib = _lib.load()
+    one_tile = lib.npd_conv_workspace_bytes(h.h, 1)
+    assert one_tile == 128 * 8192 * 2
+    ws = torch.empty(one_tile, dtype=torch.uint8, device="cuda")
+    out = torch.empty(B, N, device="cuda")
+    _lib.check(lib.npd_conv_forward(h.h, _lib.ptr(y), _lib.ptr(out), None, B, ctypes.c_void_p(ws.data_ptr()), one_tile,
+                                    _lib.stream_ptr()))
+    assert torch.equal(out, full)
+    rc = lib.npd_conv_forward(h.h, _lib.ptr(y), _lib.ptr(out), None, B, ctypes.c_void_p(ws.data_ptr()), 1024, _lib.stream_ptr())
+    assert rc == _lib.NPD_EINVAL
+    hh = ctypes.c_void_p()
+    blob = np.zeros(16, dtype=np.float32)
+    assert lib.npd_conv_create(32, 128, ctypes.c_void_p(blob.ctypes.data), 16, ctypes.byref(hh)) == _lib.NPD_EUNSUPPORTED
