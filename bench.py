@@ -34,6 +34,10 @@ WORKLOADS = {
                  desc="SC Polar(64,22), reference 'polar' profile, AWGN 0 dB"),
     "gru64": dict(kind="gru", N=64, K=22, snr=0.0, batch=37888,
                   desc="CRISP GRU(2x512, y_input, onehot) Polar(64,22), AWGN 0 dB, synthetic weights"),
+    "gru32": dict(kind="gru", N=32, K=16, snr=0.0, batch=37888,
+                  desc="CRISP GRU(2x512, y_input, onehot) Polar(32,16), AWGN 0 dB, synthetic weights"),
+    "conv64": dict(kind="conv", N=64, K=22, snr=0.0, batch=131072,
+                   desc="convNet(embed_dim 128) one-shot decoder Polar(64,22), AWGN 0 dB, synthetic weights"),
 }
 
 

@@ -43,6 +43,12 @@ def _setup(w, seed=11):
 
 
 def bench(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
+    if w["kind"] == "conv":
+        return bench_conv(args, w, rank, world, local_rank, ClockSampler, measured_peaks)
+    return bench_gru(args, w, rank, world, local_rank, ClockSampler, measured_peaks)
+
+
+def bench_gru(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
     import torch.distributed as dist
     from .polar import PolarCode
     N, K, B, snr = w["N"], w["K"], w["batch"], w["snr"]
@@ -148,6 +154,12 @@ def bench(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
 
 
 def cpu_rate(w, seconds, threads, seed=0):
+    if w["kind"] == "conv":
+        return cpu_rate_conv(w, seconds, threads, seed)
+    return cpu_rate_gru(w, seconds, threads, seed)
+
+
+def cpu_rate_gru(w, seconds, threads, seed=0):
     """CPU leg: the reference's own per-step structure -- torch eager nn.GRU(seq_len 1) + nn.Linear + sign
     feedback for N steps (rnn_all.py:532-547), fp32, all host threads."""
     torch.set_num_threads(threads)
@@ -180,5 +192,161 @@ def cpu_rate(w, seconds, threads, seed=0):
 def cpu_baseline(w):
     threads = os.cpu_count() or 1
     rate, B, dt = cpu_rate(w, 12.0, threads)
+    how = ("torch eager Conv1d/GELU/Linear/LayerNorm stack as in models.py:742-767" if w["kind"] == "conv" else
+           "torch eager nn.GRU stepping as in rnn_all.py:532-547")
     return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "%d codewords, torch eager nn.GRU stepping as in rnn_all.py:532-547, %.1f s" % (B, dt)}
+            "sample": "%d codewords, %s, %.1f s" % (B, how, dt)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# convNet (reference models.py:691-772)
+# ---------------------------------------------------------------------------------------------------
+CONV_FLOPS_PER_CODEWORD = 2 * 26001408  # 26.0 M MAC (zero padding not discounted)
+
+
+def _setup_conv(w, seed=21):
+    import argparse
+    from .models import convNet
+    N = w["N"]
+    sd = synth.conv_state_dict(seed, N, 128)
+    net = convNet(argparse.Namespace(embed_dim=128, max_len=N, N=N, dont_use_bias=False, dropout=0.1))
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    net.eval()
+    return net
+
+
+def bench_conv(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
+    import ctypes
+    import torch.distributed as dist
+    from .polar import PolarCode
+    N, K, B, snr = w["N"], w["K"], w["batch"], w["snr"]
+    dev = torch.device("cuda", local_rank)
+    net = _setup_conv(w)
+    rs = construct.reference_rs256()
+    code = PolarCode(int(np.log2(N)), K, None, rs=rs[rs < N])
+    info = code.info_positions
+    lib = _lib.load()
+    h = code._handle()
+    sigma = float(np.float32(utils.snr_db2sigma(snr)))
+    msg = torch.empty(B, K, device=dev)
+    y = torch.empty(B, N, device=dev)
+    _lib.check(lib.npd_gen_encode_awgn(h.h, _lib.ptr(msg), None, _lib.ptr(y), B, sigma, 2026, 0, rank * B,
+                                       _lib.stream_ptr()))
+    ch = net.npd_handle()
+    ws = ch.workspace(B, dev)
+    wsp, wsn = ctypes.c_void_p(ws.data_ptr()), ws.numel()
+    logits = torch.empty(B, N, device=dev)
+    info_t = torch.as_tensor(info, device=dev)
+    dec_info = torch.empty(B, K, device=dev)
+    counts = torch.zeros(3, dtype=torch.int64, device=dev)
+    st = _lib.stream_ptr()
+    chunks = -(-B // (wsn // (128 * 8192 * 2) * 128))
+
+    def step():
+        _lib.check(lib.npd_conv_forward(ch.h, _lib.ptr(y), _lib.ptr(logits), None, B, wsp, wsn, st))
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sync()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(args.steps):
+        ev[i][0].record()
+        step()
+        ev[i][1].record()
+        # decisions on the info positions = sign(logits) (run_models.py:338-339), then the error counters
+        torch.sign(torch.index_select(logits, 1, info_t), out=dec_info)
+        _lib.check(lib.npd_count_errors(_lib.ptr(msg), _lib.ptr(dec_info), B, K, _lib._vp(counts.data_ptr()), st))
+    if world > 1:
+        dist.all_reduce(counts)
+    t_end.record()
+    sync()
+    clocks = sampler.stop()
+    t = torch.tensor([t_start.elapsed_time(t_end)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    value = world * B * args.steps / (elapsed_ms * 1e-3)
+
+    e2e_B = min(B, 65536)
+    y_host = y[:e2e_B].cpu().pin_memory()
+    e2e_steps = max(3, min(args.steps, 5))
+    for _ in range(2):
+        net.decode(y_host, info, None, dev)
+    sync()
+    t0 = time.perf_counter()
+    acc = 0.0
+    for _ in range(e2e_steps):
+        bits, _ = net.decode(y_host, info, None, dev)  # host bits [B,N,1]
+        acc += float(bits[:, int(info[0]), 0].sum())
+    torch.cuda.synchronize()
+    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_B * e2e_steps / float(e2e_t.item())
+
+    peaks = measured_peaks()
+    fl = CONV_FLOPS_PER_CODEWORD * B
+    achieved = fl / (kern_ms * 1e-3) / 1e12
+    cnt = counts.tolist()
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": w["desc"], "N": N, "K": K, "snr_db": snr, "batch_per_gpu": B,
+                   "l2_policy": "every step streams %.1f GB of fp16 activations through HBM between the two kernels "
+                                "(workspace %.2f GB > L2), which evicts y and the weights' L2 lines each step"
+                                % (2 * B * 16384 / 1e9, wsn / 1e9),
+                   "step": "npd_conv_forward (conv_stack_kernel + conv_fc_kernel per %d-codeword chunk) + sign/gather of "
+                           "the info positions + npd_count_errors; one NCCL all-reduce of the counters when n_gpus > 1"
+                           % (wsn // (128 * 8192 * 2) * 128),
+                   "weights": "synthetic PyTorch-default-init (neural_polar_decoder_b200.synth, seed 21)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_B * N * 4,
+                "d2h_bytes_per_step": e2e_B * N * 4, "batch_per_gpu": e2e_B, "steps": e2e_steps,
+                "api": "convNet.decode(host y, info_positions, None, device) -> host bits"},
+        "gpu_launches": (2 * chunks + 4) * args.steps,
+        "roofline": {"kernel": "conv_stack_kernel + conv_fc_kernel (one npd_conv_forward call)", "bound": "tensor",
+                     "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["bf16_sustained"], "traffic": None,
+                     "peak_source": peaks["src"] + " (sustained 16-bit dense GEMM, cuBLAS bf16)", "kernel_ms": kern_ms,
+                     "alg_flops_per_launch": fl, "flops_per_codeword": CONV_FLOPS_PER_CODEWORD},
+        "ber": cnt[0] / float(world * B * args.steps * K), "bler": cnt[1] / float(world * B * args.steps),
+        "frames": world * B * args.steps,
+    }
+
+
+def cpu_rate_conv(w, seconds, threads, seed=0):
+    """CPU leg: the reference's forward (models.py:742-767) with torch eager modules, fp32, all host threads."""
+    torch.set_num_threads(threads)
+    N = w["N"]
+    net = _setup_conv(w).cpu()
+    rng = np.random.RandomState(seed)
+
+    def run(B):
+        y = torch.from_numpy((rng.choice([-1.0, 1.0], size=(B, N)) + 0.9 * rng.randn(B, N)).astype(np.float32))
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            x2 = net.layers1(y.unsqueeze(1))
+            x3 = net.layers2(x2) + x2
+            x4 = net.layers3(x3) + x3
+            x5 = net.layers4(x4) + x4
+            x6 = net.layers5(x5)
+            out = net.layer_norm(net.dropout(net.layersFin(torch.flatten(x6, start_dim=1))))
+            out.sign()
+        return time.perf_counter() - t0
+
+    dt = run(256)
+    B = int(max(256, min(1 << 17, 256 / dt * seconds)))
+    dt = run(B)
+    return B / dt, B, dt

@@ -11,7 +11,7 @@
 // A = the same buffer addressed (t-3)d rows further on (the swizzle depends only on the absolute address, so
 // a row-shifted descriptor start is legal) and W_t = a pre-swizzled fp16 tile streamed from L2 by
 // cp.async.bulk through an mbarrier ring.  Accumulators (2 tiles x <=128 channels per group) sit in TMEM.
-// While the 8 epilogue warps turn group A's accumulators into the next layer's operand rows (bias, GELU,
+// While the 16 epilogue warps turn group A's accumulators into the next layer's operand rows (bias, GELU,
 // residual, fp16, swizzled store), the MMA warp runs the same layer for group B, reusing the weight slots
 // still resident in the ring (64-channel layers are loaded once per pair of groups).  The last layer's
 // epilogue writes the 128-channel rows straight into the A-operand tiles of kernel 2.
@@ -20,8 +20,9 @@
 // 3-stage bulk-copy pipeline), then GELU -> fp16 operand in shared memory -> W2 (N = 64) -> GELU -> W3
 // (N = 64) as two more MMA passes, and LayerNorm(64, eps 1e-6) in registers (one thread = one codeword).
 //
-// Precision: fp16 operands (weights, activations), fp32 accumulation / bias / GELU / LayerNorm.  GELU is the
-// tanh form (tc_common.cuh); parity target is the reference's logits within 1e-2 relative + 2e-3 absolute.
+// Precision: fp16 operands (weights, activations), fp32 accumulation and bias; the conv-stack GELU runs on fp16
+// pairs (its result is the next fp16 operand), the Linear-head GELUs and LayerNorm in fp32.  GELU is the tanh
+// form (tc_common.cuh); parity target is the reference's logits within 1e-2 relative + 2e-3 absolute.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -45,7 +46,8 @@ constexpr int CV_BUF = CV_ROWS * 128;      // one 64-channel activation buffer
 constexpr int CV_SLOT = 16384;             // weight ring slot: 128 rows x 64 k fp16
 constexpr int CV_STAGES = 5;
 constexpr int CV_CW = 2 * CV_G;            // codewords per CTA pass
-constexpr int CV_THREADS = 320;
+constexpr int CV_EPI_WARPS = 16;
+constexpr int CV_THREADS = (CV_EPI_WARPS + 2) * 32;
 constexpr int CV_LAYERS = 10;
 static_assert(CV_G * CV_PITCH <= 128 * CV_TILES, "group does not fit its tiles");
 static_assert(CV_BUF % 1024 == 0, "activation buffers must keep the 1024 B swizzle phase");
@@ -86,8 +88,47 @@ struct ConvParams {
     unsigned char *act;          // kernel-2 A operand tiles: [ceil(B/128)][FC_KC][128 rows][128 B]
     float *in4;                  // optional [B,64,64]
     int64_t B, n_pass;
+    int dbg;  // bench-only experiments (NPD_CONV_DBG): 1 = no MMAs, 2 = no epilogue math, 4 = no weight copies
     LayerDesc layers[CV_LAYERS];
 };
+
+// One epilogue block: 32 accumulator columns [c, c+32) of the thread's TMEM lane -> + bias (fp32) -> GELU on fp16
+// pairs (-> + residual row, in place) -> four 16-byte chunks of the K-major SWIZZLE_128B operand row `orow`
+// (swizzle phase `sw`).  IN4 also stores the fp32 copy that forward() returns as input4.
+template <bool RES, bool IN4, bool GLOBAL_OUT>
+__device__ __forceinline__ void epi_block(uint32_t taddr, int c, const float *bias, unsigned char *orow, uint32_t sw,
+                                          bool store, float *in4)
+{
+    float v[32];
+    tmem_ld32(taddr + c, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int cc = c + 8 * j;
+        const float4 b0 = *reinterpret_cast<const float4 *>(bias + cc);
+        const float4 b1 = *reinterpret_cast<const float4 *>(bias + cc + 4);
+        uint4 pk;
+        pk.x = gelu_h2(pack_half2(v[8 * j + 0] + b0.x, v[8 * j + 1] + b0.y));
+        pk.y = gelu_h2(pack_half2(v[8 * j + 2] + b0.z, v[8 * j + 3] + b0.w));
+        pk.z = gelu_h2(pack_half2(v[8 * j + 4] + b1.x, v[8 * j + 5] + b1.y));
+        pk.w = gelu_h2(pack_half2(v[8 * j + 6] + b1.z, v[8 * j + 7] + b1.w));
+        uint4 *dst = reinterpret_cast<uint4 *>(orow + ((((cc & 63) >> 3) ^ sw) << 4));
+        if (RES) {  // input_{k+1} = layers_k(input_k) + input_k (models.py:748-755)
+            const uint4 xr = *dst;
+            pk.x = hadd2_u32(pk.x, xr.x); pk.y = hadd2_u32(pk.y, xr.y);
+            pk.z = hadd2_u32(pk.z, xr.z); pk.w = hadd2_u32(pk.w, xr.w);
+        }
+        if (IN4) {
+            if (in4 != nullptr) {
+                const float2 f0 = unpack_half2(pk.x), f1 = unpack_half2(pk.y), f2 = unpack_half2(pk.z), f3 = unpack_half2(pk.w);
+                float *d4 = in4 + (size_t)(8 * j) * CN;
+                d4[0] = f0.x; d4[CN] = f0.y; d4[2 * CN] = f1.x; d4[3 * CN] = f1.y;
+                d4[4 * CN] = f2.x; d4[5 * CN] = f2.y; d4[6 * CN] = f3.x; d4[7 * CN] = f3.y;
+            }
+        }
+        if (store) *dst = pk;
+    }
+}
 
 __global__ void __launch_bounds__(CV_THREADS, 1) conv_stack_kernel(const ConvParams p)
 {
@@ -107,11 +148,11 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_stack_kernel(const ConvPar
         }
         for (int g = 0; g < 2; ++g) {
             mbar_init(bar_acc + 8 * g, 1);
-            mbar_init(bar_act + 8 * g, 256);
+            mbar_init(bar_act + 8 * g, CV_EPI_WARPS * 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 9) tmem_alloc(smem_u32(s_tmem), 512);
+    if (warp == CV_EPI_WARPS + 1) tmem_alloc(smem_u32(s_tmem), 512);
     for (int i = tid; i < 4 * CV_BUF / 16; i += CV_THREADS) reinterpret_cast<uint4 *>(s_bufs)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < CV_LAYERS * 128; i += CV_THREADS) s_bias[i] = p.bias[i];
     fence_async_smem();
@@ -120,7 +161,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_stack_kernel(const ConvPar
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
-    if (warp == 8) {
+    if (warp == CV_EPI_WARPS) {
         // ================= producer: weight slots in consumption order =================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
@@ -133,14 +174,18 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_stack_kernel(const ConvPar
                         const unsigned char *src = p.wpack + (size_t)ld.slot0 * CV_SLOT;
                         for (int j = 0; j < ld.nslots; ++j, src += CV_SLOT) {
                             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                            mbar_expect_tx(bar_full + 8 * stage, CV_SLOT);
-                            bulk_g2s(smem_u32(smem + CV_OFF_RING + stage * CV_SLOT), src, CV_SLOT, bar_full + 8 * stage);
+                            if (p.dbg & 4) {
+                                mbar_arrive(bar_full + 8 * stage);
+                            } else {
+                                mbar_expect_tx(bar_full + 8 * stage, CV_SLOT);
+                                bulk_g2s(smem_u32(smem + CV_OFF_RING + stage * CV_SLOT), src, CV_SLOT, bar_full + 8 * stage);
+                            }
                             if (++stage == CV_STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
                 }
         }
-    } else if (warp == 9) {
+    } else if (warp == CV_EPI_WARPS + 1) {
         // ================= MMA issuer (warp-uniform schedule, one elected lane issues) =================
         const uint32_t ring0 = smem_u32(smem + CV_OFF_RING), bufs0 = smem_u32(s_bufs);
         uint32_t stage = 0, phase = 0, nact0 = 0, nact1 = 0;
@@ -164,18 +209,27 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_stack_kernel(const ConvPar
                         const uint32_t slot = ring0 + st * CV_SLOT;
                         if (elect_one()) {
                             const int nent = ld.cout == 64 ? 2 : 1;
-                            for (int e = 0; e < nent; ++e) {
+                            for (int e = 0; e < nent && !(p.dbg & 1); ++e) {
                                 int tap, chunk = 0;
                                 if (ld.cout == 64) tap = 2 * j + e;
                                 else if (ld.chunks == 1) tap = j;
                                 else { tap = j >> 1; chunk = j & 1; }
                                 if (tap >= 7) break;
-                                const uint32_t b_addr = slot + e * 8192;
-                                const uint32_t a_base = (chunk ? in1 : in0) + (uint32_t)((CV_HALO + (tap - 3) * ld.dil) * 128);
-                                for (int m = 0; m < CV_TILES; ++m)
-                                    for (int k = 0; k < ld.ksteps; ++k)
-                                        umma_f16(d0 + m * 128, umma_desc(a_base + m * 128 * 128 + k * 32),
-                                                 umma_desc(b_addr + k * 32), idesc, (j | e | k) ? 1u : 0u);
+                                const uint32_t b_lo = umma_desc_lo(slot + e * 8192);
+                                const uint32_t a_lo = umma_desc_lo((chunk ? in1 : in0) + (uint32_t)((CV_HALO + (tap - 3) * ld.dil) * 128));
+                                if (ld.ksteps == 4) {
+#pragma unroll
+                                    for (int m = 0; m < CV_TILES; ++m)
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k)
+                                            umma_f16(d0 + m * 128, umma_desc_from_lo(a_lo + m * 1024 + k * 2),
+                                                     umma_desc_from_lo(b_lo + k * 2), idesc, (j | e | k) ? 1u : 0u);
+                                } else {
+#pragma unroll
+                                    for (int m = 0; m < CV_TILES; ++m)
+                                        umma_f16(d0 + m * 128, umma_desc_from_lo(a_lo + m * 1024), umma_desc_from_lo(b_lo), idesc,
+                                                 (j | e) ? 1u : 0u);
+                                }
                             }
                             if (!hold) umma_commit(bar_empty + 8 * st);
                         }
@@ -188,8 +242,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_stack_kernel(const ConvPar
                 }
             }
     } else {
-        // ================= epilogue warps: one thread = one row (position) of one tile =================
-        const int q = warp & 3, m = warp >> 2;
+        // ================= epilogue warps: one thread = one row (position) of one tile, half its channels ===========
+        const int q = warp & 3, m = (warp >> 2) & 1, hc = warp >> 3;
         const int o = m * 128 + q * 32 + lane;
         const int gi = o / CV_PITCH, l = o - gi * CV_PITCH;
         const bool in_cw = gi < CV_G && l < CN;
@@ -200,7 +254,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_stack_kernel(const ConvPar
             // ---- layer-1 input: y as channel 0 of the row (k-step 0 = chunks 0 and 1) ----
             for (int g = 0; g < 2; ++g) {
                 const int64_t cw = ps * CV_CW + g * CV_G + gi;
-                if (in_cw) {
+                if (in_cw && hc == 0) {
                     const float yv = cw < p.B ? p.y[cw * CN + l] : 0.0f;
                     unsigned char *xr = s_bufs + (g * 2) * CV_BUF + row * 128;
                     *reinterpret_cast<uint4 *>(xr + ((0 ^ sw) << 4)) = make_uint4(pack_half2(yv, 0.0f), 0, 0, 0);
@@ -211,8 +265,6 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_stack_kernel(const ConvPar
                 mbar_arrive(bar_act + 8 * g);
             }
             for (int L = 0; L < CV_LAYERS; ++L) {
-                const int cout = p.layers[L].cout;
-                const bool res = L == 3 || L == 5 || L == 7;
                 const float *bias = s_bias + L * 128;
                 for (int g = 0; g < 2; ++g) {
                     uint32_t &nacc = g ? nacc1 : nacc0;
@@ -222,45 +274,28 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_stack_kernel(const ConvPar
                     const int64_t cw = ps * CV_CW + g * CV_G + gi;
                     const bool valid = in_cw && cw < p.B;
                     unsigned char *bx = s_bufs + (g * 2) * CV_BUF, *bt = bx + CV_BUF;
-                    unsigned char *out0 = (L & 1) ? bx : bt;
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 2 + m) * 128;
-                    for (int c0 = 0; c0 < cout; c0 += 32) {
-                        float v[32];
-                        tmem_ld32(taddr + c0, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int c = c0 + 8 * j;
-                            const float4 b0 = *reinterpret_cast<const float4 *>(bias + c);
-                            const float4 b1 = *reinterpret_cast<const float4 *>(bias + c + 4);
-                            float r[8];
-                            r[0] = gelu_f(v[8 * j + 0] + b0.x); r[1] = gelu_f(v[8 * j + 1] + b0.y);
-                            r[2] = gelu_f(v[8 * j + 2] + b0.z); r[3] = gelu_f(v[8 * j + 3] + b0.w);
-                            r[4] = gelu_f(v[8 * j + 4] + b1.x); r[5] = gelu_f(v[8 * j + 5] + b1.y);
-                            r[6] = gelu_f(v[8 * j + 6] + b1.z); r[7] = gelu_f(v[8 * j + 7] + b1.w);
-                            const uint32_t coff = (uint32_t)((((c & 63) >> 3) ^ sw) << 4);
-                            if (res) {  // input_{k+1} = layers_k(input_k) + input_k (models.py:748-755), in place
-                                const uint4 xr = *reinterpret_cast<const uint4 *>(bx + row * 128 + coff);
-                                const float2 x0 = unpack_half2(xr.x), x1 = unpack_half2(xr.y), x2 = unpack_half2(xr.z),
-                                             x3 = unpack_half2(xr.w);
-                                r[0] += x0.x; r[1] += x0.y; r[2] += x1.x; r[3] += x1.y;
-                                r[4] += x2.x; r[5] += x2.y; r[6] += x3.x; r[7] += x3.y;
-                            }
-                            if (L == 5 && p.in4 != nullptr && valid) {  // 5th return value of forward(): input4
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) p.in4[(cw * CC + c + i) * CN + l] = r[i];
-                            }
-                            const uint4 pk = make_uint4(pack_half2(r[0], r[1]), pack_half2(r[2], r[3]),
-                                                        pack_half2(r[4], r[5]), pack_half2(r[6], r[7]));
-                            if (L < CV_LAYERS - 1) {
-                                if (in_cw) *reinterpret_cast<uint4 *>(((c >> 6) ? bx : out0) + row * 128 + coff) = pk;
-                            } else if (valid) {
-                                // flatten + Linear operand: tile (cw / 128, k chunk 2 l + c / 64), row cw % 128
-                                unsigned char *dst = p.act + ((size_t)(cw >> 7) * FC_KC + (size_t)(2 * l + (c >> 6))) * FC_A_BYTES +
-                                                     (size_t)(cw & 127) * 128 + ((((c & 63) >> 3) ^ (uint32_t)(cw & 7)) << 4);
-                                *reinterpret_cast<uint4 *>(dst) = pk;
-                            }
-                        }
+                    if (p.dbg & 2) {
+                    } else if (L < 8) {
+                        // 64 channels -> the other buffer (odd layers) or, with the residual, in place (even layers)
+                        unsigned char *orow = ((L & 1) ? bx : bt) + row * 128;
+                        const int c = hc * 32;
+                        if (L == 3 || L == 7 || (L == 5 && p.in4 == nullptr))
+                            epi_block<true, false, false>(taddr, c, bias, orow, sw, in_cw, nullptr);
+                        else if (L == 5)
+                            epi_block<true, true, false>(taddr, c, bias, orow, sw, in_cw, valid ? p.in4 + (cw * CC + c) * CN + l : nullptr);
+                        else
+                            epi_block<false, false, false>(taddr, c, bias, orow, sw, in_cw, nullptr);
+                    } else if (L == 8) {
+                        // 128 channels: 0-63 -> T, 64-127 -> X (free once this layer's MMAs have read it)
+                        unsigned char *orow = (hc ? bx : bt) + row * 128;
+                        epi_block<false, false, false>(taddr, hc * 64, bias, orow, sw, in_cw, nullptr);
+                        epi_block<false, false, false>(taddr, hc * 64 + 32, bias, orow, sw, in_cw, nullptr);
+                    } else {
+                        // flatten + Linear operand: tile (cw / 128, k chunk 2 l + c / 64), row cw % 128
+                        unsigned char *orow = p.act + ((size_t)(cw >> 7) * FC_KC + (size_t)(2 * l + hc)) * FC_A_BYTES + (size_t)(cw & 127) * 128;
+                        epi_block<false, false, true>(taddr, hc * 64, bias, orow, (uint32_t)(cw & 7), valid, nullptr);
+                        epi_block<false, false, true>(taddr, hc * 64 + 32, bias, orow, (uint32_t)(cw & 7), valid, nullptr);
                     }
                     tc_fence_before();
                     if (L < CV_LAYERS - 1) {
@@ -274,7 +309,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_stack_kernel(const ConvPar
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) tmem_dealloc(tmem_base, 512);
+    if (warp == CV_EPI_WARPS + 1) tmem_dealloc(tmem_base, 512);
 }
 
 struct FcParams {
@@ -647,6 +682,7 @@ NPD_API int npd_conv_forward(const npd_conv_t *cv, const float *y, float *logits
         cp.in4 = in4 ? in4 + b0 * CC * CN : nullptr;
         cp.B = nb; cp.n_pass = (nb + CV_CW - 1) / CV_CW;
         memcpy(cp.layers, cv->layers, sizeof(cp.layers));
+        { const char *d = getenv("NPD_CONV_DBG"); cp.dbg = d ? atoi(d) : 0; }
         const unsigned g1 = (unsigned)(cp.n_pass < cv->sm_count ? cp.n_pass : cv->sm_count);
         conv_stack_kernel<<<g1, CV_THREADS, CV_SMEM, st>>>(cp);
         NPD_CHECK_CUDA(cudaGetLastError());

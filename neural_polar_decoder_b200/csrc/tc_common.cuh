@@ -66,6 +66,13 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr)
 {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// the same descriptor from its low word ((address & 0x3FFFF) >> 4): consecutive K steps / row shifts are plain
+// adds on that word, which keeps the single issuing thread ahead of the tensor pipe
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return (saddr & 0x3FFFF) >> 4; }
+__device__ __forceinline__ uint64_t umma_desc_from_lo(uint32_t lo)
+{
+    return (uint64_t)lo | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
 // instruction descriptor: fp16 A/B (format 0), fp32 accumulate, both operands K-major, M x N tile
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N)
 {
@@ -118,6 +125,29 @@ __device__ __forceinline__ float gelu_f(float x)
     const float k1 = -0.1029432396f;   // k0 * 0.044715
     const float w = x * fmaf(x * x, k1, k0);
     return x * rcp_approx(1.0f + ex2_approx(w));
+}
+// Same GELU on two fp16 lanes: 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))) with one MUFU.TANH for the pair
+// (6 half2 instructions per two elements).  Inputs are the fp32 accumulator + bias rounded to fp16; the result
+// is the fp16 operand of the next layer, so every intermediate carries the precision of its consumer.
+__device__ __forceinline__ uint32_t gelu_h2(uint32_t xb)
+{
+    const __half2 x = *reinterpret_cast<const __half2 *>(&xb);
+    const __half2 k0 = __floats2half2_rn(0.7978845608f, 0.7978845608f);
+    const __half2 k1 = __floats2half2_rn(0.0356774081f, 0.0356774081f);
+    const __half2 hf = __floats2half2_rn(0.5f, 0.5f);
+    const __half2 u = __hmul2(__hfma2(__hmul2(x, x), k1, k0), x);
+    uint32_t tb;
+    const uint32_t ub = *reinterpret_cast<const uint32_t *>(&u);
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(tb) : "r"(ub));
+    const __half2 t = *reinterpret_cast<const __half2 *>(&tb);
+    const __half2 h = __hmul2(x, hf);
+    const __half2 g = __hfma2(h, t, h);
+    return *reinterpret_cast<const uint32_t *>(&g);
+}
+__device__ __forceinline__ uint32_t hadd2_u32(uint32_t a, uint32_t b)
+{
+    const __half2 r = __hadd2(*reinterpret_cast<const __half2 *>(&a), *reinterpret_cast<const __half2 *>(&b));
+    return *reinterpret_cast<const uint32_t *>(&r);
 }
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi)
 {

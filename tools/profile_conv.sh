@@ -1,0 +1,7 @@
+set -e
+CMD="python bench.py --workload conv64 --steps 1 --warmup 3 --batch 65536 --no-cpu-baseline"
+$CMD > gpurun_out/plain_conv.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches_conv.csv $CMD > gpurun_out/ncu_launches_conv.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:conv_stack_kernel -s 3 -c 1 -f -o gpurun_out/prof_conv $CMD > gpurun_out/ncu_full_conv.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:conv_fc_kernel -s 3 -c 1 -f -o gpurun_out/prof_convfc $CMD > gpurun_out/ncu_full_convfc.log 2>&1
+tail -2 gpurun_out/ncu_full_conv.log
