@@ -588,6 +588,299 @@ __global__ void __launch_bounds__(128) sc_lane_kernel(const ScParams p)
     }
 }
 
+// =================================================================================================
+// quad path: 4 lanes per codeword, 8 codewords per warp, simplified SC (rate-0 / rate-1 nodes pruned)
+// =================================================================================================
+// The lane kernel above keeps 32 codewords per warp, so at N >= 256 shared-memory capacity leaves only a few
+// warps per SM and the unstored top levels are recomputed from y again and again.  Here a codeword is spread
+// over 4 lanes (element e of every level lives on lane quarter e mod 4), a warp holds 8 codewords, every level
+// from 6 to n-2 is stored ([element][8 codewords], XOR-swizzled so that both the lane = element writes of the
+// top phase and the lane = (quarter, codeword) accesses are conflict-free) and only level n-1 is folded into
+// the computation of level n-2 from y.  The bottom 32-leaf block is unrolled in registers (8+4+2+1 values per
+// lane, the last two levels replicated through shuffles).  Inside it, subtrees of >= 4 leaves that are
+// entirely frozen or entirely information are not traversed (simplified SC, Alamdar-Yazdi & Kschischang):
+//   * rate-1: the node's partial sums are the hard decisions of its LLRs and u = x F^(x)s; with min-sum f / g
+//     this is what the reference's leaf-by-leaf walk produces whenever no LLR of the node is exactly 0
+//     (sign(f) = sign(a) sign(b), g = sign(b) (|a| + |b|));
+//   * rate-0: every leaf satisfies |L| <= sum |alpha_i|, so if that sum is below the frozen prior all decisions
+//     are +1 exactly as sign(L + infty) gives (polar.py:399, 471-472).
+// A codeword that violates either condition (or hits a zero leaf LLR) is flagged with the NaN sentinel and
+// re-decoded by the exact path, so the results stay bit-identical to the reference.
+struct QuadCtx {
+    uint32_t ps, us, frozen, flag;
+    float thr0, infty;
+    int sub;
+};
+
+template <int O>
+__device__ __forceinline__ void quad_leaf(float L, QuadCtx &c)
+{
+    L = L + (((c.frozen >> O) & 1u) ? c.infty : 0.0f);  // polar.py:399,415,471-472
+    const uint32_t s = L < 0.0f;
+    c.flag |= (L == 0.0f);
+    c.us |= s << O;
+    c.ps |= s << O;
+}
+
+// node of 2 leaves; v = element (sub & 1), replicated on the lane quarters sub and sub ^ 2
+template <int O>
+__device__ __forceinline__ void quad_pair(float v, QuadCtx &c)
+{
+    const float w = __shfl_xor_sync(NPD_FULL, v, 8);
+    const float a = (c.sub & 1) ? w : v, b = (c.sub & 1) ? v : w;
+    quad_leaf<O>(npd_f_minsum(a, b), c);
+    const uint32_t sg = (c.ps << (31 - O)) & 0x80000000u;
+    quad_leaf<O + 1>(__uint_as_float(__float_as_uint(a) ^ sg) + b, c);
+    c.ps ^= (c.ps >> 1) & (1u << O);
+}
+
+// node covering leaves [O, O+S) of the block, S >= 4; L[i] = element 4 i + sub
+template <int S, int O>
+__device__ __forceinline__ void quad_node(const float (&L)[S / 4], QuadCtx &c)
+{
+    constexpr uint32_t M = (S >= 32) ? 0xffffffffu : ((1u << S) - 1u);
+    const uint32_t fm = (c.frozen >> O) & M;  // warp-uniform
+    if (fm == M) {
+        // rate-0: all decisions +1 provided sum |alpha| < infty (checked; else exact re-decode)
+        float sm = fabsf(L[0]);
+#pragma unroll
+        for (int i = 1; i < S / 4; ++i) sm += fabsf(L[i]);
+        sm += __shfl_xor_sync(NPD_FULL, sm, 8);
+        sm += __shfl_xor_sync(NPD_FULL, sm, 16);
+        c.flag |= !(sm < c.thr0);
+        return;
+    }
+    if (fm == 0u) {
+        // rate-1: partial sums = hard decisions, u = x F^(x)s
+        uint32_t x = 0u;
+#pragma unroll
+        for (int i = 0; i < S / 4; ++i) {
+            x |= (__float_as_uint(L[i]) >> 31) << (4 * i);
+            c.flag |= (L[i] == 0.0f);
+        }
+        x <<= c.sub;
+        x |= __shfl_xor_sync(NPD_FULL, x, 8);
+        x |= __shfl_xor_sync(NPD_FULL, x, 16);
+        uint32_t u = x;
+#pragma unroll
+        for (int h = 1; h < S; h <<= 1) {
+            // positions of the node whose index bit h is 0
+            uint32_t mk = 0u;
+#pragma unroll
+            for (int b = 0; b < S; ++b)
+                if (!(b & h)) mk |= 1u << b;
+            u ^= (u >> h) & mk;
+        }
+        c.ps |= x << O;
+        c.us |= u << O;
+        return;
+    }
+    if constexpr (S == 4) {
+        const float w = __shfl_xor_sync(NPD_FULL, L[0], 16);
+        const float a = (c.sub & 2) ? w : L[0], b = (c.sub & 2) ? L[0] : w;
+        quad_pair<O>(npd_f_minsum(a, b), c);
+        const uint32_t sg = (c.ps << (31 - O - (c.sub & 1))) & 0x80000000u;
+        quad_pair<O + 2>(__uint_as_float(__float_as_uint(a) ^ sg) + b, c);
+        c.ps ^= (c.ps >> 2) & (3u << O);
+    } else {
+        constexpr int H = S / 2, HQ = H / 4;
+        float C[HQ];
+#pragma unroll
+        for (int i = 0; i < HQ; ++i) C[i] = npd_f_minsum(L[i], L[i + HQ]);
+        quad_node<H, O>(C, c);
+#pragma unroll
+        for (int i = 0; i < HQ; ++i) {
+            const uint32_t sg = ((c.ps >> (O + 4 * i)) >> c.sub) << 31;
+            C[i] = __uint_as_float(__float_as_uint(L[i]) ^ sg) + L[i + HQ];
+        }
+        quad_node<H, O + H>(C, c);
+        constexpr uint32_t lowmask = (H >= 32) ? 0xffffffffu : ((1u << H) - 1u);
+        c.ps ^= (c.ps >> H) & (lowmask << O);
+    }
+}
+
+// word index of element e of codeword c inside a stored level: [element][8], codeword XOR-swizzled
+__device__ __forceinline__ int quad_idx(int e, int c) { return e * 8 + (c ^ ((e >> 2) & 7)); }
+
+__host__ __device__ inline size_t quad_warp_smem_bytes(int n)
+{
+    const int slog = n - 2;
+    return (size_t)4 * 8 * ((2u << slog) - 64u) + (size_t)4 * 2 * ((1u << n) >> 5) * 8;
+}
+
+// Level slog = n-2 of the 8 codewords of the group for the quarter r of the code, from y: lane = element
+// (coalesced loads of y[j], y[j+h], y[j+2h], y[j+3h], h = N/4), level n-1 is folded in.
+template <int U>
+__device__ __forceinline__ void quad_top_phase(const ScParams &p, float *dst, const uint32_t *PS, int64_t cw0,
+                                               int nvalid, int r, int lane)
+{
+    const int n = p.n, N = 1 << n, hS = N >> 2;
+    const int ilog = n - 2 - 5;        // log2(32-element slices per codeword)
+    const int total = 8 << ilog;       // work items: (codeword, slice); codewords >= nvalid read row 0 of the group
+    const bool g1 = (r & 2) != 0, g0 = (r & 1) != 0;
+    const int b0base = (r - 1) * hS;   // level n-2 g: partial sums of the left sibling quarter
+    for (int it0 = 0; it0 < total; it0 += U) {
+        float v[U][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int it = it0 + u;
+            const int cc = it >> ilog;
+            const int j = ((it & ((1 << ilog) - 1)) << 5) + lane;
+            const float *yrow = p.y + (cw0 + (cc < nvalid ? cc : 0)) * N + j;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) v[u][t] = __ldg(yrow + t * hS);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int it = it0 + u;
+            const int cc = it >> ilog;
+            const int j = ((it & ((1 << ilog) - 1)) << 5) + lane;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) v[u][t] = p.scale * v[u][t];  // polar.py:468-469
+            float a0, a1;  // level n-1 elements j and j + hS
+            if (g1) {
+                const uint32_t w0 = PS[(j >> 5) * 8 + cc], w1 = PS[((j + hS) >> 5) * 8 + cc];
+                const uint32_t s0 = ((w0 >> (j & 31)) & 1u) << 31, s1 = ((w1 >> (j & 31)) & 1u) << 31;
+                a0 = __uint_as_float(__float_as_uint(v[u][0]) ^ s0) + v[u][2];
+                a1 = __uint_as_float(__float_as_uint(v[u][1]) ^ s1) + v[u][3];
+            } else {
+                a0 = npd_f_minsum(v[u][0], v[u][2]);
+                a1 = npd_f_minsum(v[u][1], v[u][3]);
+            }
+            float o;
+            if (g0) {
+                const int bit = b0base + j;
+                const uint32_t sg = ((PS[(bit >> 5) * 8 + cc] >> (bit & 31)) & 1u) << 31;
+                o = __uint_as_float(__float_as_uint(a0) ^ sg) + a1;
+            } else {
+                o = npd_f_minsum(a0, a1);
+            }
+            dst[quad_idx(j, cc)] = o;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) sc_quad_kernel(const ScParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int wpb = blockDim.x >> 5;
+    const int n = p.n, N = 1 << n, NW = N >> 5, slog = n - 2;
+    const int sub = lane >> 3, cl = lane & 7;
+
+    unsigned char *base = smem_raw + (size_t)warp * quad_warp_smem_bytes(n);
+    float *tree = reinterpret_cast<float *>(base);  // level lv (6 <= lv <= slog) at 8 * (2^lv - 64)
+    uint32_t *PS = reinterpret_cast<uint32_t *>(tree + (size_t)8 * ((2u << slog) - 64u));
+    uint32_t *US = PS + NW * 8;
+
+    QuadCtx c;
+    c.sub = sub;
+    c.infty = p.infty;
+    c.thr0 = 0.99f * p.infty;
+
+    const int64_t ngroups = (p.B + 7) / 8;
+    for (int64_t grp = (int64_t)blockIdx.x * wpb + warp; grp < ngroups; grp += (int64_t)gridDim.x * wpb) {
+        const int64_t cw0 = grp * 8;
+        const int64_t cw = cw0 + cl;
+        const bool ok = cw < p.B;
+        const int nvalid = (int)min((int64_t)8, p.B - cw0);
+        c.flag = 0u;
+
+        const int nblocks = N >> 5;
+        for (int q = 0; q < nblocks; ++q) {
+            const int o = q << 5;
+            const int top = (q == 0) ? n - 1 : (5 + __ffs(q) - 1);
+            if (top >= slog) {
+                __syncwarp();
+                quad_top_phase<4>(p, tree + (size_t)8 * ((1u << slog) - 64u), PS, cw0, nvalid, q >> (slog - 5), lane);
+                __syncwarp();
+            }
+            // stored level -> stored level: lane quarter `sub` owns elements 4 i + sub
+            for (int lv = min(top, slog - 1); lv >= 6; --lv) {
+                const int h = 1 << lv;
+                const float *par = tree + (size_t)8 * ((2u << lv) - 64u);
+                float *ch = tree + (size_t)8 * ((1u << lv) - 64u);
+                if (lv == top) {  // right child: g with the partial sums of leaves [o-h, o)
+                    const int wbase = (o - h) >> 5;
+                    for (int i0 = 0; i0 < h / 4; i0 += 8) {
+                        const uint32_t w = PS[(wbase + (i0 >> 3)) * 8 + cl] >> sub;
+#pragma unroll
+                        for (int ii = 0; ii < 8; ++ii) {
+                            const int idx = 32 * (i0 + ii) + 8 * sub + (cl ^ ii);
+                            const float a = par[idx], b = par[idx + 8 * h];
+                            const uint32_t sg = ((w >> (4 * ii)) & 1u) << 31;
+                            ch[idx] = __uint_as_float(__float_as_uint(a) ^ sg) + b;
+                        }
+                    }
+                } else {
+                    for (int i0 = 0; i0 < h / 4; i0 += 8) {
+#pragma unroll
+                        for (int ii = 0; ii < 8; ++ii) {
+                            const int idx = 32 * (i0 + ii) + 8 * sub + (cl ^ ii);
+                            ch[idx] = npd_f_minsum(par[idx], par[idx + 8 * h]);
+                        }
+                    }
+                }
+            }
+            // level 5 straight into registers: L[i] = element 4 i + sub
+            float L[8];
+            {
+                const float *par = tree;  // level 6 sits at offset 0
+                if (top == 5) {
+                    const uint32_t w = PS[(q - 1) * 8 + cl] >> sub;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int idx = 32 * i + 8 * sub + (cl ^ i);
+                        const uint32_t sg = ((w >> (4 * i)) & 1u) << 31;
+                        L[i] = __uint_as_float(__float_as_uint(par[idx]) ^ sg) + par[idx + 256];
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int idx = 32 * i + 8 * sub + (cl ^ i);
+                        L[i] = npd_f_minsum(par[idx], par[idx + 256]);
+                    }
+                }
+            }
+            c.ps = 0u;
+            c.us = 0u;
+            c.frozen = __ldg(p.frozen_words + q);
+            quad_node<32, 0>(L, c);
+
+            if (sub == 0) {
+                PS[q * 8 + cl] = c.ps;
+                US[q * 8 + cl] = c.us;
+            }
+            __syncwarp();
+            // word-level merges: every trailing one of q completes a block of 2^(5+j+1) leaves
+            const int m = __ffs(~q) - 1;
+            for (int j = 0; j < m; ++j) {
+                const int nw = 1 << j;
+                const int wl = q + 1 - 2 * nw;
+                for (int i = sub; i < nw; i += 4) PS[(wl + i) * 8 + cl] ^= PS[(wl + nw + i) * 8 + cl];
+                __syncwarp();
+            }
+        }
+
+        // ---- outputs (coalesced: lane = k), then the sentinel of codewords that need the exact path ----
+        uint32_t fl = c.flag;
+        fl |= __shfl_xor_sync(NPD_FULL, fl, 8);
+        fl |= __shfl_xor_sync(NPD_FULL, fl, 16);
+        __syncwarp();
+        for (int cc = 0; cc < nvalid; ++cc) {
+            float *dst = p.decoded + (cw0 + cc) * p.K;
+            for (int k = lane; k < p.K; k += 32) {
+                const int pos = __ldg(p.info + k);
+                dst[k] = ((US[(pos >> 5) * 8 + cc] >> (pos & 31)) & 1u) ? -1.0f : 1.0f;
+            }
+        }
+        __syncwarp();
+        if (ok && fl && sub == 0) p.decoded[cw * p.K] = __int_as_float(0x7fc00000);
+        __syncwarp();
+    }
+}
+
 int env_int(const char *name, int dflt)
 {
     const char *v = getenv(name);
@@ -708,6 +1001,37 @@ int launch_lane(const npd_code *code, ScParams p, cudaStream_t st)
     return NPD_OK;
 }
 
+int launch_quad(const npd_code *code, ScParams p, cudaStream_t st)
+{
+    DeviceProps dp;
+    if (npd_get_device_props(&dp)) return NPD_ECUDA;
+    const int n = code->n;
+    const size_t per_warp = quad_warp_smem_bytes(n);
+    const size_t budget = (size_t)dp.smem_optin;
+    if (per_warp + 1024 > budget) {
+        npd_set_error("SC quad kernel: N=%d needs %zu B of shared memory per warp", code->N, per_warp);
+        return NPD_EUNSUPPORTED;
+    }
+    int warps_per_sm = (int)((size_t)(228 * 1024) / (per_warp + 256));
+    int max_warps = env_int("NPD_SC_WARPS", 24);
+    if (warps_per_sm > max_warps) warps_per_sm = max_warps;
+    if (warps_per_sm < 1) warps_per_sm = 1;
+    int wpb = 1;
+    while (wpb < 4 && warps_per_sm >= wpb * 2 && per_warp * wpb * 2 + 1024 <= budget) wpb *= 2;
+    int blocks_per_sm = (int)((size_t)(228 * 1024) / (per_warp * wpb + 1024));
+    if (blocks_per_sm * wpb > max_warps) blocks_per_sm = max_warps / wpb;
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    const int64_t ngroups = (p.B + 7) / 8;
+    int64_t grid = (int64_t)dp.sm_count * blocks_per_sm;
+    const int64_t need = (ngroups + wpb - 1) / wpb;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    NPD_CHECK_CUDA(cudaFuncSetAttribute(sc_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpb)));
+    sc_quad_kernel<<<(unsigned)grid, 32 * wpb, per_warp * wpb, st>>>(p);
+    NPD_CHECK_CUDA(cudaGetLastError());
+    return NPD_OK;
+}
+
 template <bool PAC, bool EXTRAS>
 int dispatch_lane_blog(const npd_code *code, const ScParams &p, cudaStream_t st)
 {
@@ -729,7 +1053,9 @@ int dispatch(const npd_code *code, ScParams p, cudaStream_t st)
         return dispatch_group<PAC>(code, p, st);
     }
     const bool extras = p.use_gt != nullptr || p.leaf_llr != nullptr;
-    int rc = extras ? dispatch_lane_blog<PAC, true>(code, p, st) : dispatch_lane_blog<PAC, false>(code, p, st);
+    // decisions only, plain polar code, N >= 256: 4 lanes per codeword + simplified-SC pruning
+    const bool use_quad = !PAC && !extras && code->n >= 8 && env_int("NPD_SC_IMPL_LANE", 0) == 0;
+    int rc = use_quad ? launch_quad(code, p, st) : extras ? dispatch_lane_blog<PAC, true>(code, p, st) : dispatch_lane_blog<PAC, false>(code, p, st);
     if (rc) return rc;
     p.scan_flagged = 1;  // exact re-decode of codewords that hit sign(0) = 0
     return dispatch_group<PAC>(code, p, st);
