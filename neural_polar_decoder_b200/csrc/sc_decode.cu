@@ -708,71 +708,113 @@ __host__ __device__ inline size_t quad_warp_smem_bytes(int n)
     return (size_t)4 * 8 * ((2u << slog) - 64u) + (size_t)4 * 2 * ((1u << n) >> 5) * 8;
 }
 
-// Level slog = n-2 of the 8 codewords of the group for the quarter r of the code, from y: lane = element
-// (coalesced loads of y[j], y[j+h], y[j+2h], y[j+3h], h = N/4), level n-1 is folded in.
-template <int U>
-__device__ __forceinline__ void quad_top_phase(const ScParams &p, float *dst, const uint32_t *PS, int64_t cw0,
+// Level n-2 of the 8 codewords of the group for quarter r of the code, from y: lane = element (coalesced loads
+// of y[j], y[j+h], y[j+2h], y[j+3h], h = N/4, 32 loads in flight per lane), level n-1 folded in.  G1 / G0: the
+// level n-1 / n-2 node on the path is a right child (g with the partial sums of its left sibling) or not (f).
+template <int NLOG, bool G1, bool G0, bool FULL>
+__device__ __forceinline__ void quad_top_phase(const ScParams &p, float *dst, const uint32_t *PS, const float *ygrp,
                                                int nvalid, int r, int lane)
 {
-    const int n = p.n, N = 1 << n, hS = N >> 2;
-    const int ilog = n - 2 - 5;        // log2(32-element slices per codeword)
-    const int total = 8 << ilog;       // work items: (codeword, slice); codewords >= nvalid read row 0 of the group
-    const bool g1 = (r & 2) != 0, g0 = (r & 1) != 0;
-    const int b0base = (r - 1) * hS;   // level n-2 g: partial sums of the left sibling quarter
-    for (int it0 = 0; it0 < total; it0 += U) {
-        float v[U][4];
+    constexpr int N = 1 << NLOG, HS = N >> 2, SLICES = HS >> 5;
+    const int kx = (lane >> 2) & 7;  // swizzle key of element j = 32 slice + lane
+#pragma unroll 1
+    for (int slice = 0; slice < SLICES; ++slice) {
+        const float *yj = ygrp + slice * 32 + lane;
+        float v[8][4];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int it = it0 + u;
-            const int cc = it >> ilog;
-            const int j = ((it & ((1 << ilog) - 1)) << 5) + lane;
-            const float *yrow = p.y + (cw0 + (cc < nvalid ? cc : 0)) * N + j;
+        for (int cc = 0; cc < 8; ++cc) {
+            const float *row = yj + (FULL ? cc : min(cc, nvalid - 1)) * N;
 #pragma unroll
-            for (int t = 0; t < 4; ++t) v[u][t] = __ldg(yrow + t * hS);
+            for (int t = 0; t < 4; ++t) v[cc][t] = __ldg(row + t * HS);
         }
+        float *drow = dst + (slice * 32 + lane) * 8;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int it = it0 + u;
-            const int cc = it >> ilog;
-            const int j = ((it & ((1 << ilog) - 1)) << 5) + lane;
+        for (int cc = 0; cc < 8; ++cc) {
 #pragma unroll
-            for (int t = 0; t < 4; ++t) v[u][t] = p.scale * v[u][t];  // polar.py:468-469
-            float a0, a1;  // level n-1 elements j and j + hS
-            if (g1) {
-                const uint32_t w0 = PS[(j >> 5) * 8 + cc], w1 = PS[((j + hS) >> 5) * 8 + cc];
-                const uint32_t s0 = ((w0 >> (j & 31)) & 1u) << 31, s1 = ((w1 >> (j & 31)) & 1u) << 31;
-                a0 = __uint_as_float(__float_as_uint(v[u][0]) ^ s0) + v[u][2];
-                a1 = __uint_as_float(__float_as_uint(v[u][1]) ^ s1) + v[u][3];
+            for (int t = 0; t < 4; ++t) v[cc][t] = p.scale * v[cc][t];  // polar.py:468-469
+            float a0, a1;  // level n-1 elements j and j + HS
+            if (G1) {
+                const uint32_t s0 = ((PS[slice * 8 + cc] >> lane) & 1u) << 31;
+                const uint32_t s1 = ((PS[(slice + SLICES) * 8 + cc] >> lane) & 1u) << 31;
+                a0 = __uint_as_float(__float_as_uint(v[cc][0]) ^ s0) + v[cc][2];
+                a1 = __uint_as_float(__float_as_uint(v[cc][1]) ^ s1) + v[cc][3];
             } else {
-                a0 = npd_f_minsum(v[u][0], v[u][2]);
-                a1 = npd_f_minsum(v[u][1], v[u][3]);
+                a0 = npd_f_minsum(v[cc][0], v[cc][2]);
+                a1 = npd_f_minsum(v[cc][1], v[cc][3]);
             }
             float o;
-            if (g0) {
-                const int bit = b0base + j;
-                const uint32_t sg = ((PS[(bit >> 5) * 8 + cc] >> (bit & 31)) & 1u) << 31;
+            if (G0) {
+                const uint32_t sg = ((PS[((r - 1) * SLICES + slice) * 8 + cc] >> lane) & 1u) << 31;
                 o = __uint_as_float(__float_as_uint(a0) ^ sg) + a1;
             } else {
                 o = npd_f_minsum(a0, a1);
             }
-            dst[quad_idx(j, cc)] = o;
+            drow[cc ^ kx] = o;
         }
     }
 }
 
+// stored level LV+1 -> stored level LV; the lane quarter `sub` owns elements 4 i + sub, off[ii] = swizzled word
+// offset of element 4 ii + sub inside an aligned group of 32 elements
+template <int LV, bool G>
+__device__ __forceinline__ void quad_level(float *tree, const uint32_t *PSw, const int (&off)[8], int sub)
+{
+    constexpr int H = 1 << LV;
+    const float *par = tree + 8 * ((2 << LV) - 64);
+    float *ch = tree + 8 * ((1 << LV) - 64);
+#pragma unroll 2
+    for (int i0 = 0; i0 < H / 4; i0 += 8) {
+        uint32_t w = 0u;
+        if (G) w = PSw[i0] >> sub;  // word (i0 / 8) of the left sibling's partial sums, stride 8 words
+#pragma unroll
+        for (int ii = 0; ii < 8; ++ii) {
+            const int idx = 32 * i0 + off[ii];
+            const float a = par[idx], b = par[idx + 8 * H];
+            if (G) {
+                const uint32_t sg = ((w >> (4 * ii)) & 1u) << 31;
+                ch[idx] = __uint_as_float(__float_as_uint(a) ^ sg) + b;
+            } else {
+                ch[idx] = npd_f_minsum(a, b);
+            }
+        }
+    }
+}
+
+template <int LV>
+struct QuadLevelsDown {
+    static __device__ __forceinline__ void run(float *tree, const uint32_t *PS, const int (&off)[8], int sub, int cl, int top, int o)
+    {
+        if (LV <= top) {  // warp-uniform
+            if (LV == top) quad_level<LV, true>(tree, PS + ((o - (1 << LV)) >> 5) * 8 + cl, off, sub);
+            else quad_level<LV, false>(tree, nullptr, off, sub);
+        }
+        QuadLevelsDown<LV - 1>::run(tree, PS, off, sub, cl, top, o);
+    }
+};
+template <>
+struct QuadLevelsDown<5> {
+    static __device__ __forceinline__ void run(float *, const uint32_t *, const int (&)[8], int, int, int, int) {}
+};
+
+template <int NLOG>
 __global__ void __launch_bounds__(128) sc_quad_kernel(const ScParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int N = 1 << NLOG, NW = N >> 5, SLOG = NLOG - 2;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int wpb = blockDim.x >> 5;
-    const int n = p.n, N = 1 << n, NW = N >> 5, slog = n - 2;
     const int sub = lane >> 3, cl = lane & 7;
 
-    unsigned char *base = smem_raw + (size_t)warp * quad_warp_smem_bytes(n);
-    float *tree = reinterpret_cast<float *>(base);  // level lv (6 <= lv <= slog) at 8 * (2^lv - 64)
-    uint32_t *PS = reinterpret_cast<uint32_t *>(tree + (size_t)8 * ((2u << slog) - 64u));
+    unsigned char *base = smem_raw + (size_t)warp * quad_warp_smem_bytes(NLOG);
+    float *tree = reinterpret_cast<float *>(base);  // level lv (6 <= lv <= SLOG) at 8 * (2^lv - 64)
+    uint32_t *PS = reinterpret_cast<uint32_t *>(tree + 8 * ((2 << SLOG) - 64));
     uint32_t *US = PS + NW * 8;
+    float *top_dst = tree + 8 * ((1 << SLOG) - 64);
+
+    int off[8];
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) off[ii] = 32 * ii + 8 * sub + (cl ^ ii);
 
     QuadCtx c;
     c.sub = sub;
@@ -785,63 +827,46 @@ __global__ void __launch_bounds__(128) sc_quad_kernel(const ScParams p)
         const int64_t cw = cw0 + cl;
         const bool ok = cw < p.B;
         const int nvalid = (int)min((int64_t)8, p.B - cw0);
+        const float *ygrp = p.y + cw0 * N;
         c.flag = 0u;
 
-        const int nblocks = N >> 5;
-        for (int q = 0; q < nblocks; ++q) {
+#pragma unroll 1
+        for (int q = 0; q < NW; ++q) {
             const int o = q << 5;
-            const int top = (q == 0) ? n - 1 : (5 + __ffs(q) - 1);
-            if (top >= slog) {
+            const int top = (q == 0) ? NLOG - 1 : (5 + __ffs(q) - 1);
+            if (top >= SLOG) {
+                const int r = q >> (SLOG - 5);
                 __syncwarp();
-                quad_top_phase<4>(p, tree + (size_t)8 * ((1u << slog) - 64u), PS, cw0, nvalid, q >> (slog - 5), lane);
-                __syncwarp();
-            }
-            // stored level -> stored level: lane quarter `sub` owns elements 4 i + sub
-            for (int lv = min(top, slog - 1); lv >= 6; --lv) {
-                const int h = 1 << lv;
-                const float *par = tree + (size_t)8 * ((2u << lv) - 64u);
-                float *ch = tree + (size_t)8 * ((1u << lv) - 64u);
-                if (lv == top) {  // right child: g with the partial sums of leaves [o-h, o)
-                    const int wbase = (o - h) >> 5;
-                    for (int i0 = 0; i0 < h / 4; i0 += 8) {
-                        const uint32_t w = PS[(wbase + (i0 >> 3)) * 8 + cl] >> sub;
-#pragma unroll
-                        for (int ii = 0; ii < 8; ++ii) {
-                            const int idx = 32 * (i0 + ii) + 8 * sub + (cl ^ ii);
-                            const float a = par[idx], b = par[idx + 8 * h];
-                            const uint32_t sg = ((w >> (4 * ii)) & 1u) << 31;
-                            ch[idx] = __uint_as_float(__float_as_uint(a) ^ sg) + b;
-                        }
+                if (nvalid == 8) {
+                    switch (r) {
+                    case 0: quad_top_phase<NLOG, false, false, true>(p, top_dst, PS, ygrp, 8, r, lane); break;
+                    case 1: quad_top_phase<NLOG, false, true, true>(p, top_dst, PS, ygrp, 8, r, lane); break;
+                    case 2: quad_top_phase<NLOG, true, false, true>(p, top_dst, PS, ygrp, 8, r, lane); break;
+                    default: quad_top_phase<NLOG, true, true, true>(p, top_dst, PS, ygrp, 8, r, lane); break;
                     }
                 } else {
-                    for (int i0 = 0; i0 < h / 4; i0 += 8) {
-#pragma unroll
-                        for (int ii = 0; ii < 8; ++ii) {
-                            const int idx = 32 * (i0 + ii) + 8 * sub + (cl ^ ii);
-                            ch[idx] = npd_f_minsum(par[idx], par[idx + 8 * h]);
-                        }
+                    switch (r) {
+                    case 0: quad_top_phase<NLOG, false, false, false>(p, top_dst, PS, ygrp, nvalid, r, lane); break;
+                    case 1: quad_top_phase<NLOG, false, true, false>(p, top_dst, PS, ygrp, nvalid, r, lane); break;
+                    case 2: quad_top_phase<NLOG, true, false, false>(p, top_dst, PS, ygrp, nvalid, r, lane); break;
+                    default: quad_top_phase<NLOG, true, true, false>(p, top_dst, PS, ygrp, nvalid, r, lane); break;
                     }
                 }
+                __syncwarp();
             }
-            // level 5 straight into registers: L[i] = element 4 i + sub
+            QuadLevelsDown<SLOG - 1>::run(tree, PS, off, sub, cl, top, o);
+            // level 5 straight into registers: L[i] = element 4 i + sub (level 6 sits at offset 0)
             float L[8];
-            {
-                const float *par = tree;  // level 6 sits at offset 0
-                if (top == 5) {
-                    const uint32_t w = PS[(q - 1) * 8 + cl] >> sub;
+            if (top == 5) {
+                const uint32_t w = PS[(q - 1) * 8 + cl] >> sub;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int idx = 32 * i + 8 * sub + (cl ^ i);
-                        const uint32_t sg = ((w >> (4 * i)) & 1u) << 31;
-                        L[i] = __uint_as_float(__float_as_uint(par[idx]) ^ sg) + par[idx + 256];
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int idx = 32 * i + 8 * sub + (cl ^ i);
-                        L[i] = npd_f_minsum(par[idx], par[idx + 256]);
-                    }
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t sg = ((w >> (4 * i)) & 1u) << 31;
+                    L[i] = __uint_as_float(__float_as_uint(tree[off[i]]) ^ sg) + tree[off[i] + 256];
                 }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) L[i] = npd_f_minsum(tree[off[i]], tree[off[i] + 256]);
             }
             c.ps = 0u;
             c.us = 0u;
@@ -868,12 +893,14 @@ __global__ void __launch_bounds__(128) sc_quad_kernel(const ScParams p)
         fl |= __shfl_xor_sync(NPD_FULL, fl, 8);
         fl |= __shfl_xor_sync(NPD_FULL, fl, 16);
         __syncwarp();
-        for (int cc = 0; cc < nvalid; ++cc) {
-            float *dst = p.decoded + (cw0 + cc) * p.K;
-            for (int k = lane; k < p.K; k += 32) {
-                const int pos = __ldg(p.info + k);
-                dst[k] = ((US[(pos >> 5) * 8 + cc] >> (pos & 31)) & 1u) ? -1.0f : 1.0f;
-            }
+        float *dst0 = p.decoded + cw0 * p.K;
+        for (int k = lane; k < p.K; k += 32) {
+            const int pos = __ldg(p.info + k);
+            const uint32_t *w = US + (pos >> 5) * 8;
+            const int sh = pos & 31;
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc)
+                if (cc < nvalid) dst0[(size_t)cc * p.K + k] = ((w[cc] >> sh) & 1u) ? -1.0f : 1.0f;
         }
         __syncwarp();
         if (ok && fl && sub == 0) p.decoded[cw * p.K] = __int_as_float(0x7fc00000);
@@ -1026,8 +1053,17 @@ int launch_quad(const npd_code *code, ScParams p, cudaStream_t st)
     const int64_t need = (ngroups + wpb - 1) / wpb;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    NPD_CHECK_CUDA(cudaFuncSetAttribute(sc_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpb)));
-    sc_quad_kernel<<<(unsigned)grid, 32 * wpb, per_warp * wpb, st>>>(p);
+    void (*kern)(const ScParams) = nullptr;
+    switch (n) {
+    case 8: kern = sc_quad_kernel<8>; break;
+    case 9: kern = sc_quad_kernel<9>; break;
+    case 10: kern = sc_quad_kernel<10>; break;
+    case 11: kern = sc_quad_kernel<11>; break;
+    case 12: kern = sc_quad_kernel<12>; break;
+    default: npd_set_error("SC quad kernel: n=%d outside 8..12", n); return NPD_EUNSUPPORTED;
+    }
+    NPD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpb)));
+    kern<<<(unsigned)grid, 32 * wpb, per_warp * wpb, st>>>(p);
     NPD_CHECK_CUDA(cudaGetLastError());
     return NPD_OK;
 }
