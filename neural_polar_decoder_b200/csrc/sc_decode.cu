@@ -717,7 +717,7 @@ __device__ __forceinline__ void quad_top_phase(const ScParams &p, float *dst, co
 {
     constexpr int N = 1 << NLOG, HS = N >> 2, SLICES = HS >> 5;
     const int kx = (lane >> 2) & 7;  // swizzle key of element j = 32 slice + lane
-#pragma unroll 1
+#pragma unroll 2
     for (int slice = 0; slice < SLICES; ++slice) {
         const float *yj = ygrp + slice * 32 + lane;
         float v[8][4];
