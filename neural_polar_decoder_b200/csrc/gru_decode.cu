@@ -23,8 +23,8 @@
 //     the one-hot columns are per-thread constants, the GRU cell is thread-local, the new state of a
 //     layer is staged in registers until the layer's last MMA has read the old state, and the head
 //     dot product is a butterfly reduction across lanes.
-// Warp roles: warps 0-7 epilogue (TMEM lane quarter = warp % 4, column half = warp / 4), warp 8 = bulk
-// copy producer, warp 9 = MMA issuer + TMEM allocator.
+// Warp roles: warps 0-15 epilogue (TMEM lane quarter = warp % 4, 16-codeword column quarter = warp / 4), warp 16 =
+// bulk copy producer, warp 17 = MMA issuer + TMEM allocator.
 #include <cuda_fp16.h>
 
 #include <vector>
@@ -38,8 +38,12 @@ constexpr int JOB_UNITS = 128;     // hidden units per job (UMMA M)
 constexpr int A_TILE_BYTES = 128 * 128;  // 128 rows x 64 fp16
 constexpr int B_CHUNK_BYTES = TILE_B * 128;  // 64 rows x 64 fp16
 constexpr int NUM_STAGES = 5;
-constexpr int EPI_THREADS = 256;
-constexpr int NUM_THREADS = 320;
+constexpr int EPI_WARPS = 16;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int NUM_PRODUCERS = 1;  // bulk-copy producer warps (a second one changes nothing: the copies are not the limiter)
+constexpr int MMA_WARP = EPI_WARPS + NUM_PRODUCERS;
+constexpr int NUM_THREADS = (MMA_WARP + 1) * 32;
+constexpr int CW_PER_THREAD = TILE_B / (EPI_WARPS / 4);  // 16 codewords (accumulator columns) per epilogue thread
 
 // program entry (one per weight tile, in consumption order)
 //  bits 0-1 acc (0 R, 1 Z, 2 NI, 3 NH) | 2-3 bsrc (0 y, 1 h0, 2 h1) | 4-7 k chunk | 8 first (overwrite)
@@ -61,7 +65,8 @@ struct GruParams {
     float *decoded;              // [B,N]
     int64_t B;
     int N, H, KY, tiles_per_step;
-    int dbg;  // bench-only experiments: 1 = skip bulk copies, 2 = skip MMAs (results are garbage)
+    int dbg;  // bench-only experiments (results are garbage): 1 = no bulk copies, 2 = no MMAs, 4 = no per-tile work
+    int stages;  // ring stages in use (<= NUM_STAGES; bench-only knob NPD_GRU_STAGES)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -88,6 +93,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "@p bra DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// one non-blocking probe of a phase (the blocking wait costs ~90 cycles even when the phase is complete)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
@@ -119,6 +132,12 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr)
 {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// descriptor from its low word ((address & 0x3FFFF) >> 4): K steps and ring stages become plain adds on that word
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return (saddr & 0x3FFFF) >> 4; }
+__device__ __forceinline__ uint64_t umma_desc_from_lo(uint32_t lo)
+{
+    return (uint64_t)lo | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
 {
     uint32_t r[16];
@@ -139,7 +158,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8])
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 
 __device__ __forceinline__ float ex2_approx(float x)
 {
@@ -153,9 +172,15 @@ __device__ __forceinline__ float rcp_approx(float x)
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-// 2 MUFU + 2 FP32 ops each; relative error ~2^-22, exact limits at +-inf
-__device__ __forceinline__ float sigmoid_f(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
-__device__ __forceinline__ float tanh_f(float x) { return 1.0f - 2.0f * rcp_approx(1.0f + ex2_approx(2.8853900817779268f * x)); }
+// one MUFU.TANH per activation (max relative error 2^-11, the rounding the fp16 recurrent state gets anyway);
+// sigmoid(x) = 0.5 + 0.5 tanh(x / 2) takes the pre-halved argument
+__device__ __forceinline__ float tanh_f(float x)
+{
+    float r;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sigmoid_half_arg(float half_x) { return fmaf(tanh_f(half_x), 0.5f, 0.5f); }
 
 // byte offset of element (row c, k) inside a K-major SWIZZLE_128B operand buffer of 64-row chunks
 __device__ __forceinline__ uint32_t b_off(int c, int k)
@@ -210,7 +235,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
         s_bits[0] = 0xffffffffu;  // step 0 feeds back +1 (rnn_all.py:542-543)
         s_bits[1] = 0xffffffffu;
     }
-    if (warp == 9) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
@@ -229,57 +254,68 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
-    if (warp == 8) {
-        // ================= producer: stream the weight program, once per step =================
+    if (warp >= EPI_WARPS && warp < MMA_WARP) {
+        // ================= producers: stream the weight program, once per step; producer w copies tiles w, w + P, ... ==========
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (int step = 0; step < N; ++step) {
-                const unsigned char *src = p.wpack;
-                for (int t = 0; t < p.tiles_per_step; ++t, src += A_TILE_BYTES) {
-                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    if (p.dbg & 1) {
-                        mbar_arrive(bar_full + 8 * stage);
-                    } else {
-                        mbar_expect_tx(bar_full + 8 * stage, A_TILE_BYTES);
-                        bulk_g2s(smem_u32(s_ring + stage * A_TILE_BYTES), src, A_TILE_BYTES, bar_full + 8 * stage);
-                    }
-                    if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+            const uint32_t S = (uint32_t)p.stages, T = (uint32_t)p.tiles_per_step;
+            const uint32_t total = ((p.dbg & 4) ? 0u : (uint32_t)N) * T;
+            uint32_t g = (uint32_t)(warp - EPI_WARPS);
+            uint32_t t = g % T, stage = g % S, phase = (g / S) & 1u;
+            for (; g < total; g += NUM_PRODUCERS) {
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                if (p.dbg & 1) {
+                    mbar_arrive(bar_full + 8 * stage);
+                } else {
+                    mbar_expect_tx(bar_full + 8 * stage, A_TILE_BYTES);
+                    bulk_g2s(smem_u32(s_ring + stage * A_TILE_BYTES), p.wpack + (size_t)t * A_TILE_BYTES, A_TILE_BYTES, bar_full + 8 * stage);
                 }
+                t += NUM_PRODUCERS;
+                if (t >= T) t -= T;
+                stage += NUM_PRODUCERS;
+                while (stage >= S) { stage -= S; phase ^= 1; }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == MMA_WARP) {
+      {
         // ================= MMA issuer =================
         // The whole warp runs the (warp-uniform) schedule so that every address and flag lives in uniform
         // registers; one elected lane issues the tcgen05 instructions.  The tile order is the order in which
         // npd_gru_create packed the weight program.
         // M = 128, N = 64, fp16 x fp16 -> fp32 (a_format = b_format = 0), both operands K-major
         const uint32_t idesc = (1u << 4) | ((uint32_t)(TILE_B >> 3) << 17) | ((128u >> 4) << 24);
-        const uint32_t b_y = smem_u32(s_y), b_h0 = smem_u32(s_h0), b_h1 = smem_u32(s_h1);
-        const uint32_t ring0 = smem_u32(s_ring);
+        // descriptor low words: the issuing thread spends ~35 instead of ~70 instructions per 16 KB tile, which is what
+        // bounds this kernel (a tile is only 4 x 32 tensor-pipe cycles)
+        const uint32_t b_y = umma_desc_lo(smem_u32(s_y)), b_h0 = umma_desc_lo(smem_u32(s_h0)), b_h1 = umma_desc_lo(smem_u32(s_h1));
+        const uint32_t ring0 = umma_desc_lo(smem_u32(s_ring));
+        constexpr uint32_t B_CHUNK_LO = B_CHUNK_BYTES >> 4, A_TILE_LO = A_TILE_BYTES >> 4;
         const bool no_mma = (p.dbg & 2) != 0;
         uint32_t stage = 0, phase = 0;
         uint32_t job = 0;  // global job counter -> TMEM slot job & 1
         uint32_t hphase0 = 0, hphase1 = 0;
+        bool ready = false;  // early probe of the current stage's full barrier succeeded
 
-        // consume one weight tile: D[slot, acc] (+)= A(ring stage) * B(b_addr)^T over K = 64
-        auto tile = [&](uint32_t d_tmem, uint32_t b_addr, bool first) {
-            mbar_wait(bar_full + 8 * stage, phase);
+        // consume one weight tile: D[slot, acc] (+)= A(ring stage) * B(b_lo)^T over K = 64
+        auto tile = [&](uint32_t d_tmem, uint32_t b_lo, bool first) {
+            if (!ready) mbar_wait(bar_full + 8 * stage, phase);
             tc_fence_after();
-            const uint32_t a_addr = ring0 + stage * A_TILE_BYTES;
+            const uint32_t a_lo = ring0 + stage * A_TILE_LO;
+            const uint32_t cur = stage;
+            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+            ready = mbar_test(bar_full + 8 * stage, phase);  // overlaps the issue below
             if (elect_one()) {
                 if (!no_mma) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma_fp16(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), idesc,
+                        umma_fp16(d_tmem, umma_desc_from_lo(a_lo + k * 2), umma_desc_from_lo(b_lo + k * 2), idesc,
                                   (first && k == 0) ? 0u : 1u);
                 }
-                umma_commit(bar_empty + 8 * stage);  // frees the ring slot when these MMAs retire
+                umma_commit(bar_empty + 8 * cur);  // frees the ring slot when these MMAs retire
             }
             __syncwarp();
-            if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
         };
         auto run = [&](uint32_t d_tmem, uint32_t b_base, int nchunks, bool first) {
-            for (int kc = 0; kc < nchunks; ++kc) tile(d_tmem, b_base + kc * B_CHUNK_BYTES, first && kc == 0);
+            if (p.dbg & 4) return;  // experiment: no per-tile work at all
+            for (int kc = 0; kc < nchunks; ++kc) tile(d_tmem, b_base + kc * B_CHUNK_LO, first && kc == 0);
         };
 
         for (int step = 0; step < N; ++step) {
@@ -322,39 +358,45 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
                 __syncwarp();
             }
         }
+      }
     } else {
         // ================= epilogue warps: gate math, state update, head, feedback =================
-        const int q = warp & 3, half = warp >> 2;
-        const int col0 = half * 32;                       // this thread's 32 codewords
+        constexpr int CW = CW_PER_THREAD;                 // 16 codewords per thread
+        const int q = warp & 3, cq = warp >> 2;
+        const int col0 = cq * CW;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         uint32_t job = 0;
-        uint32_t staged[2 * 32];  // up to 4 jobs x 32 codewords, fp16 pairs (codeword 2i, 2i+1)
-        float head[32];
+        uint32_t staged[3 * (CW / 2)];  // all jobs but the last of a layer x 16 codewords, fp16 pairs (codeword 2i, 2i+1)
+        float head[CW];
         const uint32_t info0 = p.info_words[0], info1 = N > 32 ? p.info_words[1] : 0u,
                        info2 = N > 64 ? p.info_words[2] : 0u, info3 = N > 96 ? p.info_words[3] : 0u;
 
         for (int step = 0; step < N; ++step) {
-            const uint32_t bits = s_bits[half];
+            const uint32_t bits = s_bits[cq >> 1] >> ((cq & 1) * CW);
             for (int layer = 0; layer < 2; ++layer) {
                 unsigned char *s_h = layer ? s_h1 : s_h0;
                 if (layer == 1) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) head[i] = 0.0f;
+                    for (int i = 0; i < CW; ++i) head[i] = 0.0f;
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     if (j >= jobs_per_layer) break;
                     const int u = j * JOB_UNITS + q * 32 + lane;  // hidden unit of this thread
-                    float b_r, b_z, b_in, b_hn, cr0 = 0.f, cr1 = 0.f, cz0 = 0.f, cz1 = 0.f, cn0 = 0.f, cn1 = 0.f, wo = 0.f;
+                    // per-unit constants; sigmoid arguments are pre-halved (sigmoid(x) = 0.5 + 0.5 tanh(x / 2)) and the
+                    // one-hot input column of the previous decision is folded into the layer-0 biases
+                    float hr0, hr1, hz0, hz1, bn0, bn1, b_hn, wo = 0.f;
                     if (layer == 0) {
                         const float4 c0 = __ldg(reinterpret_cast<const float4 *>(p.consts0 + (size_t)u * 12));
                         const float4 c1 = __ldg(reinterpret_cast<const float4 *>(p.consts0 + (size_t)u * 12 + 4));
                         const float2 c2 = __ldg(reinterpret_cast<const float2 *>(p.consts0 + (size_t)u * 12 + 8));
-                        b_r = c0.x; b_z = c0.y; b_in = c0.z; b_hn = c0.w;
-                        cr0 = c1.x; cr1 = c1.y; cz0 = c1.z; cz1 = c1.w; cn0 = c2.x; cn1 = c2.y;
+                        hr0 = 0.5f * (c0.x + c1.x); hr1 = 0.5f * (c0.x + c1.y);
+                        hz0 = 0.5f * (c0.y + c1.z); hz1 = 0.5f * (c0.y + c1.w);
+                        bn0 = c0.z + c2.x; bn1 = c0.z + c2.y;
+                        b_hn = c0.w;
                     } else {
                         const float4 c0 = __ldg(reinterpret_cast<const float4 *>(p.consts1 + (size_t)u * 4));
-                        b_r = c0.x; b_z = c0.y; b_in = c0.z; b_hn = c0.w;
+                        hr0 = hr1 = 0.5f * c0.x; hz0 = hz1 = 0.5f * c0.y; bn0 = bn1 = c0.z; b_hn = c0.w;
                         wo = __ldg(p.w_out + u);
                     }
                     const uint32_t slot = job & 1;
@@ -362,45 +404,48 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
                     tc_fence_after();
                     const uint32_t t0 = tmem_base + lane_addr + slot * 256 + col0;
 #pragma unroll
-                    for (int cc = 0; cc < 32; cc += 8) {
+                    for (int cc = 0; cc < CW; cc += 8) {
                         float aR[8], aZ[8], aNI[8], aNH[8];
                         tmem_ld8(t0 + 0 * TILE_B + cc, aR);
                         tmem_ld8(t0 + 1 * TILE_B + cc, aZ);
                         tmem_ld8(t0 + 2 * TILE_B + cc, aNI);
                         tmem_ld8(t0 + 3 * TILE_B + cc, aNH);
                         tmem_ld_wait();
+                        if (cc + 8 == CW) {
+                            // all accumulators of this job are in registers: the MMA warp may refill the slot
+                            tc_fence_before();
+                            mbar_arrive(bar_tempty + 8 * slot);
+                        }
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            float gr = aR[i] + b_r, gz = aZ[i] + b_z, gn = aNI[i] + b_in;
-                            if (layer == 0) {
-                                const bool plus = (bits >> (cc + i)) & 1u;
-                                gr += plus ? cr1 : cr0;
-                                gz += plus ? cz1 : cz0;
-                                gn += plus ? cn1 : cn0;
-                            }
-                            const float r = sigmoid_f(gr), z = sigmoid_f(gz);
-                            const float nn = tanh_f(gn + r * (aNH[i] + b_hn));
+                            const bool plus = (layer == 0) && ((bits >> (cc + i)) & 1u);
+                            const float r = sigmoid_half_arg(fmaf(aR[i], 0.5f, plus ? hr1 : hr0));
+                            const float z = sigmoid_half_arg(fmaf(aZ[i], 0.5f, plus ? hz1 : hz0));
+                            const float nn = tanh_f(fmaf(r, aNH[i] + b_hn, aNI[i] + (plus ? bn1 : bn0)));
                             const float hold = __half2float(*reinterpret_cast<const __half *>(s_h + b_off(col0 + cc + i, u)));
-                            const float hnew = (1.0f - z) * nn + z * hold;
-                            if (layer == 1) head[cc + i] += wo * hnew;
-                            const uint32_t hb = (uint32_t)__half_as_ushort(__float2half_rn(hnew));
-                            const int si = j * 16 + ((cc + i) >> 1);
-                            if ((i & 1) == 0) staged[si] = hb; else staged[si] |= hb << 16;
+                            const float hnew = fmaf(z, hold - nn, nn);  // (1 - z) n + z h
+                            if (layer == 1) head[cc + i] = fmaf(wo, hnew, head[cc + i]);
+                            const unsigned short hb = __half_as_ushort(__float2half_rn(hnew));
+                            if (j == jobs_per_layer - 1) {
+                                // tmem_full of the layer's last job: every MMA reading the old state has retired
+                                *reinterpret_cast<unsigned short *>(s_h + b_off(col0 + cc + i, u)) = hb;
+                            } else {
+                                const int si = j * (CW / 2) + ((cc + i) >> 1);
+                                if ((i & 1) == 0) staged[si] = hb; else staged[si] |= (uint32_t)hb << 16;
+                            }
                         }
                     }
-                    tc_fence_before();
-                    mbar_arrive(bar_tempty + 8 * slot);
                     ++job;
                 }
                 // every MMA that reads the old state of this layer has retired (tmem_full of the last
                 // job): write the new state in place
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (j >= jobs_per_layer) break;
+                for (int j = 0; j < 3; ++j) {
+                    if (j >= jobs_per_layer - 1) break;
                     const int u = j * JOB_UNITS + q * 32 + lane;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const uint32_t pr = staged[j * 16 + i];
+                    for (int i = 0; i < CW / 2; ++i) {
+                        const uint32_t pr = staged[j * (CW / 2) + i];
                         *reinterpret_cast<unsigned short *>(s_h + b_off(col0 + 2 * i, u)) = (unsigned short)(pr & 0xffffu);
                         *reinterpret_cast<unsigned short *>(s_h + b_off(col0 + 2 * i + 1, u)) = (unsigned short)(pr >> 16);
                     }
@@ -409,9 +454,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
                 mbar_arrive(bar_hready + 8 * layer);
             }
 
-            // ---- head: logit[c] = w_out . h1[c] + b_out ; butterfly over the 32 lanes (units) ----
+            // ---- head: logit[c] = w_out . h1[c] + b_out ; transpose-reduce over the 32 lanes (units) ----
 #pragma unroll
-            for (int s = 16; s >= 1; s >>= 1) {
+            for (int s = CW / 2; s >= 1; s >>= 1) {
 #pragma unroll
                 for (int i = 0; i < s; ++i) {
                     const bool up = (lane & s) != 0;
@@ -420,7 +465,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
                     head[i] = keep + __shfl_xor_sync(NPD_FULL, send, s);
                 }
             }
-            s_red[q * TILE_B + col0 + lane] = head[0];  // lane l holds column col0 + l of this lane quarter
+            head[0] += __shfl_xor_sync(NPD_FULL, head[0], CW);  // lanes l and l ^ 16 hold the two halves of the units
+            if (lane < CW) s_red[q * TILE_B + col0 + lane] = head[0];  // lane l holds column col0 + l of this lane quarter
             epi_bar_sync();
             if (warp < 2) {
                 const int c = warp * 32 + lane;
@@ -446,7 +492,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
 }
 
 }  // namespace
@@ -631,6 +677,7 @@ NPD_API int npd_gru_decode(const npd_gru_t *g, const npd_code_t *code, const flo
     p.logits = logits; p.decoded = decoded; p.B = B; p.N = g->N; p.H = g->H; p.KY = g->KY;
     p.tiles_per_step = g->tiles_per_step;
     { const char *d = getenv("NPD_GRU_DBG"); p.dbg = d ? atoi(d) : 0; }
+    { const char *d = getenv("NPD_GRU_STAGES"); p.stages = d ? atoi(d) : NUM_STAGES; if (p.stages < 2 || p.stages > NUM_STAGES) p.stages = NUM_STAGES; }
     const int64_t grid = (B + TILE_B - 1) / TILE_B;
     gru_decode_kernel<<<(unsigned)grid, NUM_THREADS, g->smem_bytes, (cudaStream_t)stream>>>(p);
     NPD_CHECK_CUDA(cudaGetLastError());
