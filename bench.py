@@ -216,6 +216,9 @@ def main():
         return 1
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; keep stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def run_workload(name, wl):
