@@ -158,6 +158,25 @@ size_t npd_conv_workspace_bytes(const npd_conv_t *conv, int64_t B);
 int npd_conv_forward(const npd_conv_t *conv, const float *y, float *logits, float *in4, int64_t B,
                      void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- host-buffer entry points -------------------------------------------------------------------
+ * The same decoders for callers whose tensors live in HOST memory -- the reference's evaluation loops
+ * build the test set and draw the noise on the CPU (rnn_all.py:1771-1773, polar.py:204) and read the
+ * decisions back there (utils.py:41-45).  Every h_* argument is a HOST pointer with the shape of its
+ * device counterpart above (pinned memory for full PCIe speed; pageable memory works).  The batch is
+ * cut into chunks and chunk i+1's host->device copy, chunk i's kernels and chunk i-1's device->host
+ * copy overlap on three private streams of the current device; staging memory belongs to the library
+ * (grown on demand, reused across calls).  SYNCHRONOUS: outputs are complete on return.  Calls on the
+ * same device are serialised. */
+int npd_sc_decode_host(const npd_code_t *code, const float *h_y, float llr_scale,
+                       const float *h_use_gt, float *h_leaf_llr, float *h_decoded, int64_t B);
+int npd_pac_sc_decode_host(const npd_code_t *code, const float *h_y, float llr_scale,
+                           const float *h_use_gt_codeword, float *h_leaf_llr, float *h_v_hat,
+                           float *h_u_hat, int64_t B);
+int npd_gru_decode_host(const npd_gru_t *gru, const npd_code_t *code, const float *h_y,
+                        const float *h_forced, float *h_logits, float *h_decoded, int64_t B);
+int npd_conv_forward_host(const npd_conv_t *conv, const float *h_y, float *h_logits, float *h_in4,
+                          int64_t B);
+
 #ifdef __cplusplus
 }
 #endif

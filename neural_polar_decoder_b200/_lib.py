@@ -37,6 +37,10 @@ SIGNATURES = {
     "npd_conv_destroy": (_int, [_vp]),
     "npd_conv_workspace_bytes": (_sz, [_vp, _i64]),
     "npd_conv_forward": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
+    "npd_sc_decode_host": (_int, [_vp, _vp, _f32, _vp, _vp, _vp, _i64]),
+    "npd_pac_sc_decode_host": (_int, [_vp, _vp, _f32, _vp, _vp, _vp, _vp, _i64]),
+    "npd_gru_decode_host": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64]),
+    "npd_conv_forward_host": (_int, [_vp, _vp, _vp, _vp, _i64]),
 }
 
 _lib = None
@@ -101,6 +105,25 @@ def to_device_f32(t, device=None):
     if not t.is_cuda:
         t = t.to(device, non_blocking=True)
     return t.contiguous()
+
+
+def host_f32(t):
+    """Contiguous float32 HOST tensor for the npd_*_host entry points (no copy when it already is one)."""
+    if t is None:
+        return None
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(t)
+    assert not t.is_cuda
+    return t.to(torch.float32).contiguous()
+
+
+def host_out(shape, like):
+    """Fresh host output tensor; pinned when the caller's input is pinned (the copies are then truly async)."""
+    return torch.empty(shape, dtype=torch.float32, pin_memory=bool(like.is_pinned()))
+
+
+def hptr(t):
+    return _vp(0) if t is None else _vp(t.data_ptr())
 
 
 def to_host(t, like):

@@ -641,6 +641,12 @@ NPD_API int npd_conv_create(int N, int embed_dim, const float *h_params, size_t 
     return NPD_OK;
 }
 
+void npd_conv_dims(const npd_conv *cv, int *N, int *in4_channels)
+{
+    *N = cv->N;
+    *in4_channels = CC;
+}
+
 NPD_API int npd_conv_destroy(npd_conv_t *cv)
 {
     if (!cv) return NPD_OK;

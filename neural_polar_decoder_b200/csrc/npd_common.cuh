@@ -52,6 +52,9 @@ struct DeviceProps {
 };
 int npd_get_device_props(DeviceProps *p);
 
+// code length and channel count of forward()'s `in4` output of a convNet handle (conv_net.cu)
+void npd_conv_dims(const npd_conv *cv, int *N, int *in4_channels);
+
 // ---- device helpers ---------------------------------------------------------------------------
 #define NPD_FULL 0xffffffffu
 

@@ -143,11 +143,20 @@ class convNet(nn.Module):
 
     def _run(self, noisy_enc, want_in4):
         src = noisy_enc
+        if torch.is_tensor(src) and not src.is_cuda:
+            # host tensors: chunked copy/forward/copy pipeline inside the library (npd_conv_forward_host)
+            _lib.require_cuda()
+            yh = _lib.host_f32(src)
+            assert yh.dim() == 2 and yh.shape[1] == self.input_len
+            B = yh.shape[0]
+            logits = _lib.host_out((B, self.input_len), yh)
+            in4 = _lib.host_out((B, self.hidden_dim // 2, self.input_len), yh) if want_in4 else None
+            if B > 0:
+                _lib.check(_lib.load().npd_conv_forward_host(self.npd_handle().h, _lib.hptr(yh), _lib.hptr(logits),
+                                                             _lib.hptr(in4), B))
+            return logits, in4, src
         yd = _lib.to_device_f32(noisy_enc)
         assert yd.dim() == 2 and yd.shape[1] == self.input_len
         with torch.cuda.device(yd.device):
             logits, in4 = conv_forward(self.npd_handle(), yd, want_in4)
-        if src.device.type != "cuda":
-            logits = _lib.to_host(logits, src)
-            in4 = _lib.to_host(in4, src)
         return logits, in4, src

@@ -101,6 +101,20 @@ class PAC:
     def pac_sc_decode(self, corrupted_codewords, snr, use_gt_codeword=None):
         """reference pac_code.py:534-573 -> (leaf LLRs [B,N], v_hat[:, B] [B,K], u_hat [B,N])."""
         src_dev = corrupted_codewords.device
+        if src_dev.type != "cuda":
+            # host tensors: chunked copy/decode/copy pipeline inside the library (npd_pac_sc_decode_host)
+            _lib.require_cuda()
+            y = _lib.host_f32(corrupted_codewords)
+            assert y.dim() == 2 and y.shape[1] == self.N
+            Bn = y.shape[0]
+            gt = None if use_gt_codeword is None else _lib.host_f32(use_gt_codeword.cpu())
+            llr, v, u = (_lib.host_out((Bn, self.N), y), _lib.host_out((Bn, self.K), y),
+                         _lib.host_out((Bn, self.N), y))
+            if Bn > 0:
+                _lib.check(_lib.load().npd_pac_sc_decode_host(self._handle().h, _lib.hptr(y), llr_scale(snr),
+                                                              _lib.hptr(gt), _lib.hptr(llr), _lib.hptr(v),
+                                                              _lib.hptr(u), Bn))
+            return llr, v, u
         y = _lib.to_device_f32(corrupted_codewords)
         assert y.dim() == 2 and y.shape[1] == self.N
         Bn = y.shape[0]
@@ -114,6 +128,4 @@ class PAC:
                 _lib.check(_lib.load().npd_pac_sc_decode(h.h, _lib.ptr(y), llr_scale(snr), _lib.ptr(gt),
                                                          _lib.ptr(llr), _lib.ptr(v), _lib.ptr(u), Bn,
                                                          _lib.stream_ptr()))
-        if src_dev.type != "cuda":
-            llr, v, u = llr.to(src_dev), v.to(src_dev), u.to(src_dev)
         return llr, v, u

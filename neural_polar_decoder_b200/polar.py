@@ -106,7 +106,8 @@ class PolarCode:
         -> (leaf LLRs [B,N] incl. the +infty frozen prior, u_hat[:, info_positions] [B,K] in {-1,0,+1}).
         return_llr=False skips the LLR output (first element is None)."""
         src = corrupted_codewords
-        src_dev = src.device
+        if torch.is_tensor(src) and not src.is_cuda:
+            return self._sc_decode_host(src, snr, use_gt, return_llr)
         y = _lib.to_device_f32(corrupted_codewords)
         assert y.dim() == 2 and y.shape[1] == self.N, tuple(y.shape)
         B = y.shape[0]
@@ -118,6 +119,19 @@ class PolarCode:
             if B > 0:
                 _lib.check(_lib.load().npd_sc_decode(h.h, _lib.ptr(y), llr_scale(snr), _lib.ptr(gt),
                                                      _lib.ptr(llr), _lib.ptr(dec), B, _lib.stream_ptr()))
-        if src_dev.type != "cuda":
-            llr, dec = _lib.to_host(llr, src), _lib.to_host(dec, src)
+        return llr, dec
+
+    def _sc_decode_host(self, y, snr, use_gt, return_llr):
+        """Host tensors in, host tensors out: npd_sc_decode_host overlaps the chunked H2D copy, the
+        kernels and the D2H copy on the library's own streams (synchronous)."""
+        _lib.require_cuda()
+        y = _lib.host_f32(y)
+        assert y.dim() == 2 and y.shape[1] == self.N, tuple(y.shape)
+        B = y.shape[0]
+        gt = None if use_gt is None else _lib.host_f32(use_gt.cpu() if torch.is_tensor(use_gt) else use_gt)
+        llr = _lib.host_out((B, self.N), y) if return_llr else None
+        dec = _lib.host_out((B, self.K), y)
+        if B > 0:
+            _lib.check(_lib.load().npd_sc_decode_host(self._handle().h, _lib.hptr(y), llr_scale(snr), _lib.hptr(gt),
+                                                      _lib.hptr(llr), _lib.hptr(dec), B))
         return llr, dec

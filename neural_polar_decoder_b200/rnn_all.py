@@ -158,6 +158,19 @@ class RNN_decoder:
         if loss_inds is None:
             loss_inds = self.info_inds
         src = y
+        if torch.is_tensor(src) and not src.is_cuda and gt is None:
+            # host tensors: chunked copy/decode/copy pipeline inside the library (npd_gru_decode_host)
+            _lib.require_cuda()
+            yh = _lib.host_f32(src)
+            assert yh.dim() == 2 and yh.shape[1] == self.N
+            B = yh.shape[0]
+            decoded = _lib.host_out((B, self.N), yh)
+            logits = _lib.host_out((B, self.N), yh) if return_logits else None
+            if B > 0:
+                _lib.check(_lib.load().npd_gru_decode_host(net.npd_handle(self.N).h, self._loss_code(loss_inds).h,
+                                                           _lib.hptr(yh), None, _lib.hptr(logits),
+                                                           _lib.hptr(decoded), B))
+            return (decoded, logits) if return_logits else decoded
         yd = _lib.to_device_f32(y)
         assert yd.dim() == 2 and yd.shape[1] == self.N
         with torch.cuda.device(yd.device):
@@ -171,9 +184,6 @@ class RNN_decoder:
                 # realised as two passes when loss_inds is a strict subset.
                 raise NotImplementedError("genie-aided decode (gt=...) is listed under SURVEY.md 8(f)")
             decoded, logits = gru_decode(net, code, yd, forced, want_logits=return_logits)
-        if src.device.type != "cuda":
-            decoded = _lib.to_host(decoded, src)
-            logits = _lib.to_host(logits, src)
         return (decoded, logits) if return_logits else decoded
 
 
