@@ -51,6 +51,22 @@ def measured_peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")  # B200_PROFILING.md
 
 
+def ncu_traffic(workload, batch):
+    """DRAM bytes per launch of the workload's hot kernel, from the committed ncu capture (profiles/traffic.json),
+    scaled from the capture's batch to this launch's.  -> (bytes or None, note)"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            t = json.load(f).get(workload)
+    except Exception:
+        t = None
+    if not t:
+        return None, None
+    per_cw = (t["dram_read_bytes"] + t["dram_write_bytes"]) / float(t["capture_batch"])
+    return per_cw * batch, "ncu --set full, %s at %d codewords per launch (%s), scaled to this launch's batch" % (
+        t["kernel"], t["capture_batch"], t["source"])
+
+
 def make_code(w):
     from neural_polar_decoder_b200 import PolarCode, construct
     N, K = w["N"], w["K"]
@@ -358,6 +374,7 @@ def bench_sc(args, w, rank, world, local_rank):
     alg_bytes = (4 * N + 4 * K) * B  # fp32 y in + fp32 decisions out, per launch
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     cnt = counts.tolist()
+    traffic, traffic_src = ncu_traffic(args.workload, B)
     res = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
@@ -373,8 +390,8 @@ def bench_sc(args, w, rank, world, local_rank):
                        "decode / D2H pipeline on three streams)", "sampled_bit_errors": errs},
         "gpu_launches": 2 * args.steps,
         "roofline": {"kernel": "sc_quad_kernel" if N >= 256 else "sc_lane_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm"],
-                     "unit": "GB/s", "frac": achieved / peaks["hbm"], "traffic": None,
-                     "peak_source": peaks["src"], "kernel_ms": kern_ms, "count_kernel_ms": count_ms,
+                     "unit": "GB/s", "frac": achieved / peaks["hbm"], "traffic": traffic,
+                     "traffic_source": traffic_src, "peak_source": peaks["src"], "kernel_ms": kern_ms, "count_kernel_ms": count_ms,
                      "alg_bytes_per_launch": alg_bytes,
                      "llr_updates_per_s": N * int(np.log2(N)) * B / (kern_ms * 1e-3),
                      "note": "the decoder is instruction-issue bound, not HBM bound: N log2 N serial-by-level LLR updates "

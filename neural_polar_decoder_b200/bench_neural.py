@@ -42,6 +42,23 @@ def _setup(w, seed=11):
     return net, info
 
 
+def _traffic(workload, batch):
+    """roofline.traffic from the committed ncu capture (profiles/traffic.json; same helper as bench.py's)."""
+    import json
+    import os
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            t = json.load(f).get(workload)
+    except Exception:
+        t = None
+    if not t:
+        return None, None
+    per_cw = (t["dram_read_bytes"] + t["dram_write_bytes"]) / float(t["capture_batch"])
+    return per_cw * batch, "ncu --set full, %s at %d codewords per launch (%s), scaled to this launch's batch" % (
+        t["kernel"], t["capture_batch"], t["source"])
+
+
 def bench(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
     if w["kind"] == "conv":
         return bench_conv(args, w, rank, world, local_rank, ClockSampler, measured_peaks)
@@ -130,6 +147,7 @@ def bench_gru(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
     fl = flops_per_codeword(N) * B
     achieved = fl / (kern_ms * 1e-3) / 1e12
     cnt = counts.tolist()
+    traffic, traffic_src = _traffic(args.workload, B)
     return {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
@@ -147,7 +165,8 @@ def bench_gru(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
         "gpu_launches": 3 * args.steps,
         "roofline": {"kernel": "gru_decode_kernel", "bound": "tensor", "achieved": achieved,
                      "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
-                     "traffic": None, "peak_source": peaks["src"] + " (sustained 16-bit dense GEMM, cuBLAS bf16)", "kernel_ms": kern_ms,
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peaks["src"] + " (sustained 16-bit dense GEMM, cuBLAS bf16)", "kernel_ms": kern_ms,
                      "alg_flops_per_launch": fl, "flops_per_codeword": flops_per_codeword(N)},
         "ber": cnt[0] / float(world * B * args.steps * K), "bler": cnt[1] / float(world * B * args.steps),
         "frames": world * B * args.steps,
@@ -301,6 +320,7 @@ def bench_conv(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
     fl = CONV_FLOPS_PER_CODEWORD * B
     achieved = fl / (kern_ms * 1e-3) / 1e12
     cnt = counts.tolist()
+    traffic, traffic_src = _traffic(args.workload, B)
     return {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
@@ -320,7 +340,7 @@ def bench_conv(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
         "gpu_launches": (2 * chunks + 4) * args.steps,
         "roofline": {"kernel": "conv_stack_kernel + conv_fc_kernel (one npd_conv_forward call)", "bound": "tensor",
                      "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["bf16_sustained"], "traffic": None,
+                     "frac": achieved / peaks["bf16_sustained"], "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": peaks["src"] + " (sustained 16-bit dense GEMM, cuBLAS bf16)", "kernel_ms": kern_ms,
                      "alg_flops_per_launch": fl, "flops_per_codeword": CONV_FLOPS_PER_CODEWORD},
         "ber": cnt[0] / float(world * B * args.steps * K), "bler": cnt[1] / float(world * B * args.steps),
