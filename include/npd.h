@@ -131,14 +131,17 @@ int npd_gru_destroy(npd_gru_t *gru);
  * positions, +1 elsewhere.
  *   y       [B,N]          raw channel output (not LLR; rnn_all.py:533-534)
  *   forced  [B,N] or NULL  when given, step i feeds back forced[:, i-1] instead of the decoder's own
- *                          decision (logit parity under identical feedback; also the genie mode)
+ *                          decision: the teacher-forced pass of rnn_all.py:425-461 (logits = its output)
+ *   genie   [B,N] or NULL  when given, `decoded` starts as this tensor instead of ones (gt.clone(),
+ *                          rnn_all.py:519-522): positions outside the loss set keep and feed back their
+ *                          genie value, loss positions the decoder's own decision
  *   logits  [B,N] or NULL  head output of every step
  *   decoded [B,N]          +-1/0 decisions on `loss positions` (the code's info set), +1 elsewhere
  * workspace: device scratch of npd_gru_workspace_bytes(gru, B) bytes. */
 size_t npd_gru_workspace_bytes(const npd_gru_t *gru, int64_t B);
 int npd_gru_decode(const npd_gru_t *gru, const npd_code_t *code, const float *y,
-                   const float *forced, float *logits, float *decoded, int64_t B, void *workspace,
-                   size_t workspace_bytes, void *stream);
+                   const float *forced, const float *genie, float *logits, float *decoded, int64_t B,
+                   void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- convNet one-shot decoder ------------------------------------------------------------------
  * npd_conv_create / npd_conv_forward: convNet.forward (models.py:742-767; layers 701-740) with
@@ -173,7 +176,8 @@ int npd_pac_sc_decode_host(const npd_code_t *code, const float *h_y, float llr_s
                            const float *h_use_gt_codeword, float *h_leaf_llr, float *h_v_hat,
                            float *h_u_hat, int64_t B);
 int npd_gru_decode_host(const npd_gru_t *gru, const npd_code_t *code, const float *h_y,
-                        const float *h_forced, float *h_logits, float *h_decoded, int64_t B);
+                        const float *h_forced, const float *h_genie, float *h_logits,
+                        float *h_decoded, int64_t B);
 int npd_conv_forward_host(const npd_conv_t *conv, const float *h_y, float *h_logits, float *h_in4,
                           int64_t B);
 

@@ -32,14 +32,14 @@ SIGNATURES = {
     "npd_gru_create": (_int, [_int, _int] + [_vp] * 10 + [_c.POINTER(_vp)]),
     "npd_gru_destroy": (_int, [_vp]),
     "npd_gru_workspace_bytes": (_sz, [_vp, _i64]),
-    "npd_gru_decode": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
+    "npd_gru_decode": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
     "npd_conv_create": (_int, [_int, _int, _vp, _sz, _c.POINTER(_vp)]),
     "npd_conv_destroy": (_int, [_vp]),
     "npd_conv_workspace_bytes": (_sz, [_vp, _i64]),
     "npd_conv_forward": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
     "npd_sc_decode_host": (_int, [_vp, _vp, _f32, _vp, _vp, _vp, _i64]),
     "npd_pac_sc_decode_host": (_int, [_vp, _vp, _f32, _vp, _vp, _vp, _vp, _i64]),
-    "npd_gru_decode_host": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64]),
+    "npd_gru_decode_host": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
     "npd_conv_forward_host": (_int, [_vp, _vp, _vp, _vp, _i64]),
 }
 

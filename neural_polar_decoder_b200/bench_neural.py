@@ -90,7 +90,7 @@ def bench_gru(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
     dec_info = torch.empty(B, K, device=dev)
 
     def step():
-        _lib.check(lib.npd_gru_decode(gh.h, loss_code.h, _lib.ptr(y), None, None, _lib.ptr(decoded), B, None, 0, st))
+        _lib.check(lib.npd_gru_decode(gh.h, loss_code.h, _lib.ptr(y), None, None, None, _lib.ptr(decoded), B, None, 0, st))
 
     def sync():
         if world > 1:

@@ -60,6 +60,7 @@ struct GruParams {
     float b_out;
     const float *y;              // [B,N]
     const float *forced;         // [B,N] or null
+    const float *genie;          // [B,N] or null: decoded starts as this tensor (rnn_all.py:521-522)
     const uint32_t *info_words;  // bit i = position i is an info (loss) position
     float *logits;               // [B,N] or null
     float *decoded;              // [B,N]
@@ -473,14 +474,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
                 const float logit = ((s_red[c] + s_red[TILE_B + c]) + (s_red[2 * TILE_B + c] + s_red[3 * TILE_B + c])) + p.b_out;
                 const uint32_t iw = step < 32 ? info0 : step < 64 ? info1 : step < 96 ? info2 : info3;
                 const bool is_info = (iw >> (step & 31)) & 1u;
-                float dec = 1.0f;  // decoded = ones; only loss positions are overwritten (rnn_all.py:520, 546-547)
-                if (is_info) dec = (logit > 0.0f) ? 1.0f : ((logit < 0.0f) ? -1.0f : 0.0f);
                 const bool valid = cw0 + c < p.B;
+                // decoded = ones, or gt.clone() in genie mode; only loss positions are overwritten
+                // (rnn_all.py:519-522, 546-547)
+                float dec = (p.genie && valid) ? p.genie[(cw0 + c) * N + step] : 1.0f;
+                if (is_info) dec = (logit > 0.0f) ? 1.0f : ((logit < 0.0f) ? -1.0f : 0.0f);
                 if (valid) {
                     if (p.logits) p.logits[(cw0 + c) * N + step] = logit;
                     p.decoded[(cw0 + c) * N + step] = dec;
                 }
-                float prev = dec;  // next step feeds back sign(decoded[:, step]) ...
+                // next step feeds back sign(decoded[:, step]) (a genie value need not be +-1) ...
+                float prev = (dec > 0.0f) ? 1.0f : ((dec < 0.0f) ? -1.0f : 0.0f);
                 if (p.forced && valid) prev = p.forced[(cw0 + c) * N + step];  // ... or the forced sequence
                 // get_onehot (rnn_all.py:258-260): index = (0.5 + 0.5*prev).long() -> 1 only for prev = +1
                 const uint32_t m = __ballot_sync(NPD_FULL, prev >= 1.0f);
@@ -665,7 +669,8 @@ NPD_API int npd_gru_destroy(npd_gru_t *g)
 NPD_API size_t npd_gru_workspace_bytes(const npd_gru_t *, int64_t) { return 0; }
 
 NPD_API int npd_gru_decode(const npd_gru_t *g, const npd_code_t *code, const float *y, const float *forced,
-                           float *logits, float *decoded, int64_t B, void *, size_t, void *stream)
+                           const float *genie, float *logits, float *decoded, int64_t B, void *, size_t,
+                           void *stream)
 {
     NPD_REQUIRE(g && code && y && decoded, "npd_gru_decode: null argument");
     NPD_REQUIRE(B >= 0, "npd_gru_decode: negative batch");
@@ -673,7 +678,7 @@ NPD_API int npd_gru_decode(const npd_gru_t *g, const npd_code_t *code, const flo
     if (B == 0) return NPD_OK;
     GruParams p{};
     p.wpack = g->d_wpack; p.program = g->d_program; p.consts0 = g->d_consts0; p.consts1 = g->d_consts1;
-    p.w_out = g->d_w_out; p.b_out = g->b_out; p.y = y; p.forced = forced; p.info_words = code->d_info_words;
+    p.w_out = g->d_w_out; p.b_out = g->b_out; p.y = y; p.forced = forced; p.genie = genie; p.info_words = code->d_info_words;
     p.logits = logits; p.decoded = decoded; p.B = B; p.N = g->N; p.H = g->H; p.KY = g->KY;
     p.tiles_per_step = g->tiles_per_step;
     { const char *d = getenv("NPD_GRU_DBG"); p.dbg = d ? atoi(d) : 0; }

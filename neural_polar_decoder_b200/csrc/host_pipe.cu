@@ -185,7 +185,8 @@ NPD_API int npd_pac_sc_decode_host(const npd_code_t *code, const float *h_y, flo
 }
 
 NPD_API int npd_gru_decode_host(const npd_gru_t *gru, const npd_code_t *code, const float *h_y,
-                                const float *h_forced, float *h_logits, float *h_decoded, int64_t B)
+                                const float *h_forced, const float *h_genie, float *h_logits,
+                                float *h_decoded, int64_t B)
 {
     NPD_REQUIRE(gru && code && h_y && h_decoded, "npd_gru_decode_host: null argument");
     NPD_REQUIRE(B >= 0, "npd_gru_decode_host: B < 0");
@@ -197,17 +198,19 @@ NPD_API int npd_gru_decode_host(const npd_gru_t *gru, const npd_code_t *code, co
     const int64_t wave = (int64_t)64 * dp.sm_count;
     const int64_t chunk = pick_chunk(B, N * 4, 64, (size_t)wave * N * 4);
     const size_t ws = al256(npd_gru_workspace_bytes(gru, chunk));
-    const size_t per = al256(chunk * N * 4) * (2 + (h_forced ? 1 : 0) + (h_logits ? 1 : 0)) + ws;
+    const size_t per = al256(chunk * N * 4) * (2 + (h_forced ? 1 : 0) + (h_genie ? 1 : 0) + (h_logits ? 1 : 0)) + ws;
     return run_pipe(B, chunk, per, [&](char *arena, int64_t lo, int64_t n, cudaStream_t st) -> int {
         Carver cv(arena);
         float *d_y = cv.take(chunk * N * 4);
         float *d_dec = cv.take(chunk * N * 4);
         float *d_forced = cv.take(chunk * N * 4, h_forced != nullptr);
+        float *d_genie = cv.take(chunk * N * 4, h_genie != nullptr);
         float *d_logits = cv.take(chunk * N * 4, h_logits != nullptr);
         float *d_ws = cv.take(ws, ws != 0);
         H2D(d_y, h_y + lo * N, n * N * 4, st);
         if (d_forced) H2D(d_forced, h_forced + lo * N, n * N * 4, st);
-        int rc = npd_gru_decode(gru, code, d_y, d_forced, d_logits, d_dec, n, d_ws, ws, st);
+        if (d_genie) H2D(d_genie, h_genie + lo * N, n * N * 4, st);
+        int rc = npd_gru_decode(gru, code, d_y, d_forced, d_genie, d_logits, d_dec, n, d_ws, ws, st);
         if (rc) return rc;
         D2H(h_decoded + lo * N, d_dec, n * N * 4, st);
         if (d_logits) D2H(h_logits + lo * N, d_logits, n * N * 4, st);

@@ -12,7 +12,7 @@ NPD_API int npd_gru_create(int, int, const float *, const float *, const float *
 }
 NPD_API int npd_gru_destroy(npd_gru_t *) { return NPD_OK; }
 NPD_API size_t npd_gru_workspace_bytes(const npd_gru_t *, int64_t) { return 0; }
-NPD_API int npd_gru_decode(const npd_gru_t *, const npd_code_t *, const float *, const float *, float *,
+NPD_API int npd_gru_decode(const npd_gru_t *, const npd_code_t *, const float *, const float *, const float *, float *,
                            float *, int64_t, void *, size_t, void *)
 {
     npd_set_error("npd_gru_decode: GRU kernel not built into this libnpd.so");

@@ -6,6 +6,7 @@ Reference: rnn_all.py:258-260 (get_onehot), 294-398 (RNN_Model), 400-561 (RNN_de
 1015-1196 (get_code).  Out of scope: training branches, y_h0 / y_h0_out conditioning,
 LSTM / bidirectional / LayerNorm variants, the list decoder."""
 import ctypes
+import random
 
 import numpy as np
 import torch
@@ -111,15 +112,31 @@ class GruHandle:
             pass
 
 
-def gru_decode(net_or_handle, code_handle, y, forced=None, want_logits=False):
+def gru_decode(net_or_handle, code_handle, y, forced=None, want_logits=False, genie=None):
     """One fused launch: y [B,N] (device) -> (decoded [B,N], logits [B,N] or None)."""
     B, N = y.shape
     handle = net_or_handle if isinstance(net_or_handle, GruHandle) else net_or_handle.npd_handle(N)
     decoded = torch.empty(B, N, dtype=torch.float32, device=y.device)
     logits = torch.empty(B, N, dtype=torch.float32, device=y.device) if want_logits else None
     if B > 0:
-        _lib.check(_lib.load().npd_gru_decode(handle.h, code_handle.h, _lib.ptr(y), _lib.ptr(forced), _lib.ptr(logits),
-                                              _lib.ptr(decoded), B, None, 0, _lib.stream_ptr()))
+        _lib.check(_lib.load().npd_gru_decode(handle.h, code_handle.h, _lib.ptr(y), _lib.ptr(forced), _lib.ptr(genie),
+                                              _lib.ptr(logits), _lib.ptr(decoded), B, None, 0, _lib.stream_ptr()))
+    return decoded, logits
+
+
+def gru_decode_host(net_or_handle, code_handle, y, forced=None, want_logits=False, genie=None):
+    """Host tensors in / out through the library's chunked copy/decode/copy pipeline (npd_gru_decode_host)."""
+    _lib.require_cuda()
+    yh = _lib.host_f32(y)
+    B, N = yh.shape
+    handle = net_or_handle if isinstance(net_or_handle, GruHandle) else net_or_handle.npd_handle(N)
+    forced = None if forced is None else _lib.host_f32(forced.cpu())
+    genie = None if genie is None else _lib.host_f32(genie.cpu())
+    decoded = _lib.host_out((B, N), yh)
+    logits = _lib.host_out((B, N), yh) if want_logits else None
+    if B > 0:
+        _lib.check(_lib.load().npd_gru_decode_host(handle.h, code_handle.h, _lib.hptr(yh), _lib.hptr(forced),
+                                                   _lib.hptr(genie), _lib.hptr(logits), _lib.hptr(decoded), B))
     return decoded, logits
 
 
@@ -145,45 +162,47 @@ class RNN_decoder:
         return h
 
     def decode(self, net, train, y, gt=None, teacher_forcing_ratio=0., loss_inds=None, return_logits=False):
-        """Test branch of the reference (rnn_all.py:514-561) for decoding_type 'y_input' with one-hot
-        feedback: N autoregressive steps, hidden state from zero, decisions sign(logit) on loss_inds.
-        gt (genie decisions [B,N]) selects the reference's gt.clone() start: positions outside loss_inds
-        then feed back the genie value instead of +1."""
-        if train:
-            raise NotImplementedError("training branches (rnn_all.py:422-512) are out of scope of the B200 path")
+        """reference rnn_all.py:408-561 for decoding_type 'y_input' with one-hot feedback; all N autoregressive
+        steps are one kernel launch.
+
+        train=False (rnn_all.py:514-561): hidden state from zero, decisions sign(logit) on loss_inds (default: the
+        info positions), +1 elsewhere.  gt = genie tensor [B,N]: decoded starts as gt.clone(), so positions outside
+        loss_inds keep and feed back their genie value (rnn_all.py:519-522; the `loss_inds=code.loss_inds` call of
+        polar_RNN_full_test, 887).
+        train=True is served for EVALUATION only (no autograd graph; the reference's test_model(tf=True) calls it
+        under torch.no_grad(), rnn_all.py:982-984): teacher forcing (425-461) returns the raw outputs of all N
+        steps with gt fed back; student forcing (462-512) returns raw outputs on the info positions, 1 elsewhere.
+        Training itself (gradients) is out of scope of the B200 path."""
         if self.decoding_type != 'y_input' or not self.onehot or self.reverse_order:
             raise NotImplementedError("accelerated path: decoding_type='y_input', onehot=True, forward order")
         if getattr(net, "y_depth", 0) != 0:
             raise NotImplementedError("y_input with a y-MLP (y_depth > 0) is out of scope")
+        on_host = torch.is_tensor(y) and not y.is_cuda
+        run = gru_decode_host if on_host else gru_decode
+        yd = _lib.host_f32(y) if on_host else _lib.to_device_f32(y)
+        assert yd.dim() == 2 and yd.shape[1] == self.N
+        dev_ctx = torch.cuda.device(torch.cuda.current_device() if on_host else yd.device)
+
+        def like_y(t):
+            return None if t is None else (_lib.host_f32(t.cpu()) if on_host else _lib.to_device_f32(t, yd.device))
+
+        if train:
+            if torch.is_grad_enabled() and any(p.requires_grad for p in net.parameters()):
+                raise NotImplementedError("training (rnn_all.py:422-512 with gradients) is out of scope of the B200 "
+                                          "path; call under torch.no_grad() for teacher-/student-forced evaluation")
+            with dev_ctx:
+                if random.random() < teacher_forcing_ratio:  # rnn_all.py:425
+                    assert gt is not None and gt.shape[1] == self.N
+                    _, logits = run(net, self._loss_code(self.info_inds), yd, forced=like_y(gt), want_logits=True)
+                    return logits
+                decoded, logits = run(net, self._loss_code(self.info_inds), yd, want_logits=True)
+                mask = torch.zeros(self.N, dtype=torch.bool, device=logits.device)
+                mask[torch.as_tensor(np.asarray(self.info_inds), device=logits.device)] = True
+                return torch.where(mask.unsqueeze(0), logits, torch.ones_like(logits))
         if loss_inds is None:
             loss_inds = self.info_inds
-        src = y
-        if torch.is_tensor(src) and not src.is_cuda and gt is None:
-            # host tensors: chunked copy/decode/copy pipeline inside the library (npd_gru_decode_host)
-            _lib.require_cuda()
-            yh = _lib.host_f32(src)
-            assert yh.dim() == 2 and yh.shape[1] == self.N
-            B = yh.shape[0]
-            decoded = _lib.host_out((B, self.N), yh)
-            logits = _lib.host_out((B, self.N), yh) if return_logits else None
-            if B > 0:
-                _lib.check(_lib.load().npd_gru_decode_host(net.npd_handle(self.N).h, self._loss_code(loss_inds).h,
-                                                           _lib.hptr(yh), None, _lib.hptr(logits),
-                                                           _lib.hptr(decoded), B))
-            return (decoded, logits) if return_logits else decoded
-        yd = _lib.to_device_f32(y)
-        assert yd.dim() == 2 and yd.shape[1] == self.N
-        with torch.cuda.device(yd.device):
-            code = self._loss_code(loss_inds)
-            forced = None
-            if gt is not None:
-                # decoded starts as gt: a position outside loss_inds keeps (and feeds back) its gt value,
-                # a position inside feeds back the decoder's own decision.  Run once to get the decisions on
-                # the loss positions under that feedback: the kernel's `forced` stream is exact only when
-                # every position is forced, so genie mode = forced feedback on non-loss positions is
-                # realised as two passes when loss_inds is a strict subset.
-                raise NotImplementedError("genie-aided decode (gt=...) is listed under SURVEY.md 8(f)")
-            decoded, logits = gru_decode(net, code, yd, forced, want_logits=return_logits)
+        with dev_ctx:
+            decoded, logits = run(net, self._loss_code(loss_inds), yd, want_logits=return_logits, genie=like_y(gt))
         return (decoded, logits) if return_logits else decoded
 
 
@@ -224,3 +243,11 @@ def get_code(code_type, rate_profile, N, K, g=None, args=None):
     code.encode = code.encode_plotkin
     code.msg_indices = np.arange(K)
     return code
+
+
+if __name__ == '__main__':
+    # `python -m neural_polar_decoder_b200.rnn_all <run_crisp.sh flags> --test` (reference rnn_all.py:1198-1949,
+    # evaluation half; see cli.py)
+    import sys
+    from .cli import main
+    sys.exit(main())

@@ -194,6 +194,37 @@ def gru_cases():
     np.savez_compressed(os.path.join(OUT, "gru.npz"), **out)
 
 
+def gru_mode_cases():
+    """Genie-aided decode (gt / loss_inds, rnn_all.py:519-522, 887) and the teacher- / student-forced passes that
+    test_model(tf=True) runs under no_grad (rnn_all.py:982-984 -> 425-461, 462-512), from the live reference."""
+    ra = ref_shim.load("rnn_all")
+    ra.args = ref_shim.make_args(32, 16)
+    rs = np.random.RandomState(314)
+    out = {}
+    N, K, H, seed, gain, B = 32, 16, 512, 12, 8.0, 48
+    code = ref_shim.get_code("Polar", "polar", N, K)
+    sd = synth.gru_state_dict(seed, N, H, 2, head_gain=gain)
+    net = ra.RNN_Model("GRU", N + 2, H, 1, 2, N, 0, 0, out_linear_depth=1)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    dec = ra.RNN_decoder("y_input", N, code.info_positions, onehot=True)
+    msg = bpsk_msgs(rs, B, K)
+    x = code.encode_plotkin(torch.from_numpy(msg)).numpy()
+    y = torch.from_numpy(noisy(rs, x, 1.0))
+    gt = torch.ones(B, N)
+    gt[:, code.info_positions] = torch.from_numpy(msg)
+    loss_inds = np.asarray(code.info_positions)[-6:]          # the curriculum's "last bits only" (loss_only)
+    genie_sub = dec.decode(net, False, y, gt, loss_inds=loss_inds)
+    genie_all = dec.decode(net, False, y, gt)                   # loss_inds = info set: gt only matters on frozen (= +1)
+    with torch.no_grad():
+        tf = dec.decode(net, True, y, gt, 1)                    # teacher forced raw outputs, all N positions
+        sf = dec.decode(net, True, y, gt, 0)                    # student forced raw outputs on info positions
+    out.update(cfg=np.array([N, K, H, seed], dtype=np.int64), gain=np.float64(gain), y=y.numpy(), gt=gt.numpy(),
+               info=np.asarray(code.info_positions, dtype=np.int32), loss_inds=loss_inds.astype(np.int32),
+               genie_sub=genie_sub.numpy(), genie_all=genie_all.numpy(), teacher=tf.numpy(), student=sf.numpy())
+    np.savez_compressed(os.path.join(OUT, "gru_modes.npz"), **out)
+    print("gru modes: teacher |out| mean", float(tf.abs().mean()), flush=True)
+
+
 def conv_cases():
     import argparse as ap
     md = ref_shim.load("models")
@@ -252,7 +283,9 @@ if __name__ == "__main__":
     a = p.parse_args()
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    todo = a.only.split(",") if a.only else ["misc", "pac", "gru", "conv", "polar"]
+    todo = a.only.split(",") if a.only else ["misc", "pac", "gru", "gru_modes", "conv", "polar"]
+    if "gru_modes" in todo:
+        gru_mode_cases()
     if "misc" in todo:
         misc_cases()
     if "pac" in todo:

@@ -165,7 +165,7 @@ def gen_noise(seed, cw0, pt, B, N):
 # fp32 torch oracles for the floating-point decoders.
 # --------------------------------------------------------------------------------------------------
 
-def gru_decode(sd, y, N, info, forced=None, H=None, round_bf16=False):
+def gru_decode(sd, y, N, info, forced=None, H=None, round_bf16=False, genie=None):
     """fp32 restatement of RNN_decoder.decode(net, False, y) for decoding_type 'y_input', onehot,
     GRU (rnn_all.py:514-521, 532-547) with RNN_Model.forward (387-398) written out gate by gate
     (PyTorch nn.GRU gate order r,z,n).  The y-part of the layer-0 input projection is
@@ -175,6 +175,8 @@ def gru_decode(sd, y, N, info, forced=None, H=None, round_bf16=False):
     sd: state_dict-like mapping with the a7 key names (torch tensors or numpy arrays).
     forced: optional [B,N] of +-1: when given, step ii feeds back forced[:, ii-1] instead of the
             decoder's own decision (used for logit parity under identical feedback).
+    genie: optional [B,N]: decoded starts as this tensor instead of ones (gt.clone(), rnn_all.py:519-522), so
+            positions outside `info` (the loss positions) keep and feed back their genie value.
     round_bf16: emulate the kernel's operand rounding (weights, h and y operands to bf16, fp32
             accumulate) to size tolerances; not a parity target.
     -> (decoded[B,N] in {-1,0,+1} with +1 on non-info positions, logits[B,N])
@@ -201,7 +203,7 @@ def gru_decode(sd, y, N, info, forced=None, H=None, round_bf16=False):
     Hs = Whh[0].shape[1]
     info_set = set(int(i) for i in info)
     h = [torch.zeros(B, Hs) for _ in range(L)]
-    decoded = torch.ones(B, N)
+    decoded = torch.ones(B, N) if genie is None else T(genie).clone()
     logits = torch.zeros(B, N)
     Gy = rb(y) @ rb(Wih[0][:, :N]).t()  # hoisted y projection
     col_m1 = Wih[0][:, N]      # onehot(-1) = [1,0]  (rnn_all.py:258-260)

@@ -1,0 +1,110 @@
+"""CLI / checkpoint compatibility with the reference's rnn_all.py: argument surface, derived
+fields, the results-path scheme, checkpoint loading.  CPU tests use known answers taken from the reference
+(run_crisp.sh embeds the final-net file name its own first line produces; the results path was printed by
+the live reference during oracle/train_ref_checkpoint.py)."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from neural_polar_decoder_b200 import cli  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+# run_crisp.sh line 1 (reference), verbatim flags
+CRISP_LINE1 = ("--code Polar --rate_profile rev_polar --target_K 22 --N 64 --K 8 --decoding_type y_input "
+               "--rnn_feature_size 512 --y_hidden_size 128 --y_depth 3 --num_steps 10000 --batch_size 4096 --rnn_depth 2 "
+               "--model_save_per 10000 --tfr_min 1 --tfr_max 1 --dec_train_snr 0 --lr 0.001 --scheduler step "
+               "--lr_decay 2000 --lr_decay_gamma 0.95 --onehot --id run1 --test_codes y --test_bitwise --testing_snr 0 "
+               "--progressive_path Supervised_RNN_Polar_Results/progressive/N64_K22_H2E --test_snr_start -3 "
+               "--test_snr_end 3").split()
+# ... and the --load_path run_crisp.sh line 2 uses for the net that line 1 saved
+CRISP_LINE1_FINAL = ("./Supervised_RNN_Polar_Results/final_nets/Scheme_rev_polar_22/N64_K8_y_input_onehot_GRU_depth_2_"
+                     "fsize_512_y_depth_0_hsize_0_snr_0.0_bs_4096_tfr_1.0_activ_selu_init_He_optim_AdamW_lr_0.001_"
+                     "decay_2000_step_loss_MSE_run1.pt")
+
+
+def test_run_crisp_line_parses_and_derives_fields():
+    a = cli.get_args(CRISP_LINE1)
+    assert (a.N, a.K, a.target_K, a.rnn_feature_size, a.rnn_depth) == (64, 8, 22, 512, 2)
+    assert a.onehot is True and a.test_codes is True and a.test_bitwise is True
+    # y_input without --use_ynn zeroes the y-MLP sizes (rnn_all.py:251-254)
+    assert (a.y_depth, a.y_hidden_size) == (0, 0)
+    assert a.g == 91 and a.M == 6 and a.are_we_doing_ML is False and a.tfr_min == 1.0
+    assert cli.snr_grid(a) == [-3.0 + i for i in range(7)]
+
+
+def test_defaults_match_reference():
+    a = cli.get_args([])
+    assert (a.N, a.K, a.code, a.rate_profile, a.decoding_type) == (32, 12, "PAC", "RM", "y_h0")
+    assert a.target_K == 16 and a.g == 53 and a.test_size == 100000 and a.test_batch_size == 10000
+    assert (a.test_snr_start, a.test_snr_end, a.snr_points) == (-2.0, 4.0, 7)
+    assert a.run_dumer is True and a.tfr_min == 0.0
+    assert cli.get_args(["--K", "20", "--N", "32"]).target_K == 20
+
+
+def test_result_paths_match_reference_known_answers():
+    _, final = cli.result_paths(cli.get_args(CRISP_LINE1))
+    assert final == CRISP_LINE1_FINAL
+    a = cli.get_args("--code Polar --rate_profile polar --target_K 16 --N 32 --K 16 --decoding_type y_input "
+                     "--rnn_feature_size 128 --rnn_depth 2 --onehot --batch_size 1024 --tfr_min 1 --tfr_max 1 "
+                     "--dec_train_snr 0 --lr 0.001 --id npd_stage16".split())
+    results, _ = cli.result_paths(a)
+    assert results == ("./Supervised_RNN_Polar_Results/Polar_16_32/Scheme_polar/y_input_onehot/GRU_depth_2_fsize_128/"
+                       "y_depth_0_hsize_0/Dec_snr_0.0_bs_1024/tfr_1.0/Activ_selu_Init_He/Optim_AdamW_LR_0.001_loss_MSE/"
+                       "npd_stage16")
+
+
+def _trained():
+    names = [f[:-5] for f in os.listdir(GOLD) if f.startswith("crisp_gru_") and f.endswith(".json")]
+    if not names:
+        pytest.skip("no trained reference checkpoint fixture")
+    name = sorted(names)[0]
+    with open(os.path.join(GOLD, name + ".json")) as f:
+        return os.path.join(GOLD, name + ".pt"), json.load(f)
+
+
+def test_reference_checkpoint_loads_with_reference_keys():
+    path, meta = _trained()
+    ckpt = cli.load_checkpoint(path)
+    assert set(ckpt) == {"net", "step", "args"}
+    H, N = meta["H"], meta["N"]
+    assert tuple(ckpt["net"]["rnn.weight_ih_l0"].shape) == (3 * H, N + 2)
+    net, cargs, step = cli.net_from_checkpoint(path)  # strict load_state_dict: keys and shapes as in the reference
+    assert (cargs.N, cargs.K, cargs.rnn_feature_size) == (N, meta["K"], H) and step == ckpt["step"]
+    assert not net.training
+
+
+@pytest.mark.gpu
+def test_cli_test_mode_reproduces_reference_curve(capsys):
+    """`--test` through the drop-in on the reference-trained checkpoint: the GRU and SC BER/BLER curves must agree
+    with the curves the live reference printed for the same checkpoint within Monte-Carlo 95% confidence
+    intervals (independent noise on both sides)."""
+    path, meta = _trained()
+    argv = [a for a in meta["final_stage_argv"]]
+    for flag in ("--load_path", "--save_path"):
+        if flag in argv:
+            i = argv.index(flag)
+            del argv[i:i + 2]
+    argv += ["--test", "--test_load_path", path]
+    args = cli.get_args(argv)
+    torch.manual_seed(1)
+    res = cli.run_test(args)
+    printed = capsys.readouterr().out
+    assert "BERs of RNN:" in printed and "BERs of SC decoding:" in printed and "Model loaded at step" in printed
+    n = meta["test_size"]
+    K = meta["K"]
+    assert np.allclose(res["snr_range"], meta["snr_range"])
+    for ours, ref, per in ((res["bers_RNN"], meta["bers_RNN"], n), (res["bers_SC"], meta["bers_SC"], n),
+                           (res["blers_RNN"], meta["blers_RNN"], n), (res["blers_SC"], meta["blers_SC"], n)):
+        for a, b in zip(ours, ref):
+            p = 0.5 * (a + b)
+            # block errors are the independent events; a bit-error rate has at most K-fold correlated terms
+            sigma = np.sqrt(2 * max(p * (1 - p), 1e-9) / per) * (np.sqrt(K) if ours is res["bers_RNN"] or ours is res["bers_SC"] else 1.0)
+            assert abs(a - b) <= 4 * sigma + 2e-5, (a, b, sigma)

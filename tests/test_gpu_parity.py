@@ -256,6 +256,40 @@ def test_gru_vs_oracle_ragged_batch():
     assert (d.cpu().numpy()[:, [i for i in range(N) if i not in set(info.tolist())]] == 1).all()
 
 
+def test_gru_genie_and_forced_evaluation_modes(golden):
+    """RNN_decoder.decode with gt / loss_inds (genie, rnn_all.py:519-522, 887) and train=True under no_grad
+    (teacher- / student-forced evaluation, rnn_all.py:982-984) against the live-reference fixture."""
+    from neural_polar_decoder_b200.rnn_all import RNN_decoder
+    g = golden("gru_modes")
+    N, K, H, seed = [int(v) for v in g["cfg"]]
+    net, sd = _gru_net(N, H, seed, float(g["gain"]))
+    info = g["info"]
+    dec = RNN_decoder('y_input', N, info, onehot=True)
+    y, gt = torch.from_numpy(g["y"]).cuda(), torch.from_numpy(g["gt"]).cuda()
+    with torch.no_grad():
+        teacher = dec.decode(net, True, y, gt, 1).cpu().numpy()
+        student = dec.decode(net, True, y, gt, 0).cpu().numpy()
+    ref = g["teacher"]
+    err = np.abs(teacher - ref)
+    assert (err <= _gru_tol(ref)).all(), err.max()
+    # student forcing / genie: rows where no logit on a decided position is within the tolerance of zero
+    _, lg_free = oracle.gru_decode(sd, g["y"], N, info)
+    safe = (np.abs(lg_free[:, info]) > _gru_tol(lg_free)[:, info]).all(axis=1)
+    assert safe.sum() >= 8
+    assert (np.abs(student - g["student"])[safe] <= _gru_tol(g["student"])[safe]).all()
+    assert (student[:, [i for i in range(N) if i not in set(info.tolist())]] == 1).all()
+    for key, loss in (("genie_sub", g["loss_inds"]), ("genie_all", info)):
+        d = dec.decode(net, False, y, gt, loss_inds=loss).cpu().numpy()
+        _, lg = oracle.gru_decode(sd, g["y"], N, loss, genie=g["gt"])
+        safe = (np.abs(lg[:, loss]) > _gru_tol(lg)[:, loss]).all(axis=1)
+        assert safe.sum() >= 8
+        assert np.array_equal(d[safe], g[key][safe]), key
+        keep = [i for i in range(N) if i not in set(int(v) for v in loss)]
+        assert np.array_equal(d[:, keep], g["gt"][:, keep])  # positions outside the loss set keep their genie value
+    with pytest.raises(NotImplementedError):
+        dec.decode(net, True, y, gt, 1)  # gradients enabled = training: out of scope
+
+
 # ---------------------------------------------------------------------------------------------------
 # convNet one-shot decoder (fp16 tensor-core operands, fp32 accumulate, tanh-form GELU).  Parity is judged on
 # the LayerNorm output (the reference's `logits`): |d| <= 1e-2 * |ref| + 2e-3 (SURVEY.md 7: the absolute floor

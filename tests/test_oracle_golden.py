@@ -100,3 +100,26 @@ def test_conv_oracle_against_reference_fixtures(golden):
     N, K, E, seed = [int(v) for v in g["conv64_cfg"]]
     lg = oracle.conv_forward(synth.conv_state_dict(seed, N, E), g["conv64_y"])
     np.testing.assert_allclose(lg, g["conv64_logits"], rtol=0, atol=2e-5)
+
+
+def test_gru_oracle_modes_against_reference_fixture(golden):
+    """Genie-aided decode and the teacher- / student-forced evaluation passes (rnn_all.py:519-522, 425-512)."""
+    from neural_polar_decoder_b200 import synth
+    g = golden("gru_modes")
+    N, K, H, seed = [int(v) for v in g["cfg"]]
+    sd = synth.gru_state_dict(seed, N, H, 2, head_gain=float(g["gain"]))
+    y, gt, info = g["y"], g["gt"], g["info"]
+    # teacher forcing: every step is fed gt -> the raw head outputs are the logits under forced = gt
+    _, lg = oracle.gru_decode(sd, y, N, info, forced=gt)
+    np.testing.assert_allclose(lg, g["teacher"], rtol=0, atol=2e-5)
+    # student forcing: raw outputs on the info positions, ones elsewhere, own decisions fed back
+    dec, lg = oracle.gru_decode(sd, y, N, info)
+    student = np.where(np.isin(np.arange(N), info)[None, :], lg, 1.0)
+    safe_rows = (np.abs(lg[:, info]) > 1e-4).all(axis=1)
+    np.testing.assert_allclose(student[safe_rows], g["student"][safe_rows], rtol=0, atol=2e-5)
+    # genie: decoded starts as gt; only loss_inds are decided (and fed back as decided)
+    for key, loss in (("genie_sub", g["loss_inds"]), ("genie_all", info)):
+        dec, lg = oracle.gru_decode(sd, y, N, loss, genie=gt)
+        safe_rows = (np.abs(lg[:, loss]) > 1e-4).all(axis=1)
+        assert safe_rows.mean() > 0.9
+        assert np.array_equal(dec[safe_rows], g[key][safe_rows]), key
