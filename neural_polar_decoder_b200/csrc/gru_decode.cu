@@ -37,7 +37,7 @@ constexpr int TILE_B = 64;         // codewords per CTA
 constexpr int JOB_UNITS = 128;     // hidden units per job (UMMA M)
 constexpr int A_TILE_BYTES = 128 * 128;  // 128 rows x 64 fp16
 constexpr int B_CHUNK_BYTES = TILE_B * 128;  // 64 rows x 64 fp16
-constexpr int NUM_STAGES = 5;
+constexpr int NUM_STAGES = 6;  // 96 KB weight ring: the static MMA schedule needs 3*KH tiles to be whole ring passes
 constexpr int EPI_WARPS = 16;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int NUM_PRODUCERS = 1;  // bulk-copy producer warps (a second one changes nothing: the copies are not the limiter)
@@ -45,15 +45,9 @@ constexpr int MMA_WARP = EPI_WARPS + NUM_PRODUCERS;
 constexpr int NUM_THREADS = (MMA_WARP + 1) * 32;
 constexpr int CW_PER_THREAD = TILE_B / (EPI_WARPS / 4);  // 16 codewords (accumulator columns) per epilogue thread
 
-// program entry (one per weight tile, in consumption order)
-//  bits 0-1 acc (0 R, 1 Z, 2 NI, 3 NH) | 2-3 bsrc (0 y, 1 h0, 2 h1) | 4-7 k chunk | 8 first (overwrite)
-//  9 job_begin (wait tmem_empty) | 10 job_end (commit tmem_full) | 11 wait_h0 | 12 wait_h1
-constexpr uint32_t P_FIRST = 1u << 8, P_JOB_BEGIN = 1u << 9, P_JOB_END = 1u << 10, P_WAIT_H0 = 1u << 11,
-                   P_WAIT_H1 = 1u << 12;
-
 struct GruParams {
-    const unsigned char *wpack;  // tiles_per_step * 16 KB
-    const uint32_t *program;     // tiles_per_step entries
+    const unsigned char *wpack;  // tiles_per_step * 16 KB, in consumption order
+    const float *w_iyT;          // [N][3H] fp32: the y columns of weight_ih_l0, transposed (hoisted input projection)
     const float *consts0;        // [H][12]: b_r b_z b_in b_hn cr0 cr1 cz0 cz1 cn0 cn1 - -
     const float *consts1;        // [H][4] : b_r b_z b_in b_hn
     const float *w_out;          // [H]
@@ -65,10 +59,16 @@ struct GruParams {
     float *logits;               // [B,N] or null
     float *decoded;              // [B,N]
     int64_t B;
-    int N, H, KY, tiles_per_step;
+    int N, H, tiles_per_step;
     int dbg;  // bench-only experiments (results are garbage): 1 = no bulk copies, 2 = no MMAs, 4 = no per-tile work
-    int stages;  // ring stages in use (<= NUM_STAGES; bench-only knob NPD_GRU_STAGES)
+    long long *trace;  // bench-only (NPD_GRU_TRACE): [N][TRACE_SLOTS] clock64 stamps of CTA 0, or null
 };
+
+constexpr int TRACE_SLOTS = 100;  // per step: MMA warp 0..15 (job begin / issued), 16-17 (h_ready waits); epilogue 20..35, 36 step end
+__device__ __forceinline__ void trace_ev(const GruParams &p, int step, int slot)
+{
+    if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) p.trace[step * TRACE_SLOTS + slot] = clock64();
+}
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -107,6 +107,24 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// 2-CTA cluster plumbing: the two CTAs of a pair decode different codewords with the SAME weight stream, so every
+// weight tile is fetched from L2 once and multicast into both CTAs' rings (halves the L2 -> SM traffic, which is
+// what bounds the kernel once the MMA issue is lean: 16 KB per ~200 cycles per SM)
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint16_t mask)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ bool elect_one()
 {
@@ -194,28 +212,95 @@ struct Smem {
     static __host__ __device__ size_t ring() { return 0; }
     static __host__ __device__ size_t h0(int) { return (size_t)NUM_STAGES * A_TILE_BYTES; }
     static __host__ __device__ size_t h1(int H) { return h0(H) + (size_t)(H / 64) * B_CHUNK_BYTES; }
-    static __host__ __device__ size_t yb(int H) { return h1(H) + (size_t)(H / 64) * B_CHUNK_BYTES; }
-    static __host__ __device__ size_t red(int H, int KY) { return yb(H) + (size_t)KY * B_CHUNK_BYTES; }   // [4][64] floats
-    static __host__ __device__ size_t prog(int H, int KY) { return red(H, KY) + 4 * TILE_B * 4; }
-    static __host__ __device__ size_t bars(int H, int KY, int tiles) { return (prog(H, KY) + (size_t)tiles * 4 + 15) & ~(size_t)15; }
-    static __host__ __device__ size_t total(int H, int KY, int tiles) { return bars(H, KY, tiles) + 256; }
+    static __host__ __device__ size_t red(int H) { return h1(H) + (size_t)(H / 64) * B_CHUNK_BYTES; }   // [4][64] floats
+    static __host__ __device__ size_t bars(int H) { return red(H) + 4 * TILE_B * 4; }
+    static __host__ __device__ size_t total(int H) { return bars(H) + 256; }
 };
 
+// ---- MMA issue: one weight tile (4 K-steps) with the probe of the NEXT ring stage overlapped ----------------
+// The issuing thread is the throughput limit of this kernel (a tile is only 4 x 48 tensor-pipe cycles, measured by
+// tools/probe/umma_issue.cu), so its per-tile instruction stream is kept minimal: ring stage, barrier parity and all
+// descriptor offsets are compile-time constants (static schedule, see mma_block), and the ~150-cycle latency of the
+// barrier probe hides behind the four MMAs because its predicate is only consumed after they are issued (one asm
+// block keeps that order).  Returns 1 when the next stage's weights have already landed.
+__device__ __forceinline__ uint32_t tile_issue(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc0,
+                                               uint32_t bar_empty_cur, uint32_t bar_full_next, uint32_t parity_next,
+                                               bool no_mma)
+{
+    uint32_t ok;
+    const uint64_t a0 = umma_desc_from_lo(a_lo), b0 = umma_desc_from_lo(b_lo);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q, pacc, pone, pm;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 q, [%7], %8;\n\t"
+        "setp.ne.b32 pacc, %4, 0;\n\t"
+        "setp.eq.b32 pone, 0, 0;\n\t"
+        "setp.eq.b32 pm, %9, 0;\n\t"
+        "@pm tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %3, %5, pacc;\n\t"
+        "@pm tcgen05.mma.cta_group::1.kind::f16 [%1], %10, %11, %5, pone;\n\t"
+        "@pm tcgen05.mma.cta_group::1.kind::f16 [%1], %12, %13, %5, pone;\n\t"
+        "@pm tcgen05.mma.cta_group::1.kind::f16 [%1], %14, %15, %5, pone;\n\t"
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%6], %16;\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(d_tmem), "l"(a0), "l"(b0), "r"(acc0), "r"(idesc), "r"(bar_empty_cur), "r"(bar_full_next),
+          "r"(parity_next), "r"((uint32_t)no_mma), "l"(a0 + 2), "l"(b0 + 2), "l"(a0 + 4), "l"(b0 + 4), "l"(a0 + 6), "l"(b0 + 6),
+          "h"((uint16_t)3)  // the ring slot is released in BOTH CTAs of the pair (their empty barriers count 2 commits)
+        : "memory");
+    return ok;
+}
+
+// Three runs of KH tiles (= 3*KH tiles, a multiple of the 6 ring stages): every block starts at ring stage 0, so the
+// stage of tile t is t % 6 and its barrier parity ((t / 6) & 1) ^ pb with pb the block's starting parity.
+// Run r accumulates into TMEM columns d[r] from B operand chunks b[r] .. b[r] + KH - 1; first[r] = overwrite.
+struct MmaCtx {
+    uint32_t bar_full, bar_empty;  // shared addresses of full[0] / empty[0]
+    uint32_t ring_lo;              // descriptor low word of ring stage 0
+    uint32_t idesc;
+    uint32_t ok;                   // the current tile's weights are known to have landed
+    uint32_t pb;                   // barrier parity of the next block's first pass over the ring
+    bool no_mma;
+};
+
+template <int KH>
+__device__ __forceinline__ void mma_block(MmaCtx &c, uint32_t d0, uint32_t b0, bool f0, uint32_t d1, uint32_t b1, bool f1,
+                                          uint32_t d2, uint32_t b2, bool f2)
+{
+    constexpr uint32_t A_TILE_LO = A_TILE_BYTES >> 4, B_CHUNK_LO = B_CHUNK_BYTES >> 4;
+    constexpr int T = 3 * KH;
+    static_assert(T % NUM_STAGES == 0, "a block must be a whole number of ring passes");
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        const int r = t / KH, kc = t % KH;
+        const int stage = t % NUM_STAGES, pass = t / NUM_STAGES;
+        const int nstage = (t + 1) % NUM_STAGES, npass = (t + 1) / NUM_STAGES;  // t + 1 == T: stage 0 of the next block
+        const uint32_t d = r == 0 ? d0 : r == 1 ? d1 : d2;
+        const uint32_t b = (r == 0 ? b0 : r == 1 ? b1 : b2) + kc * B_CHUNK_LO;
+        const bool first = (r == 0 ? f0 : r == 1 ? f1 : f2) && kc == 0;
+        if (!c.ok) mbar_wait(c.bar_full + 8 * stage, (pass & 1) ^ c.pb);
+        c.ok = tile_issue(d, c.ring_lo + stage * A_TILE_LO, b, c.idesc, first ? 0u : 1u, c.bar_empty + 8 * stage,
+                          c.bar_full + 8 * nstage, (npass & 1) ^ c.pb, c.no_mma);
+    }
+    if ((T / NUM_STAGES) & 1) c.pb ^= 1;
+}
+
+template <int KH>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruParams p)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr int H = KH * 64, JOBS = H / JOB_UNITS;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int H = p.H, N = p.N, KY = p.KY, KH = H >> 6;
-    const int jobs_per_layer = H / JOB_UNITS;
+    const int N = p.N;
     const int64_t cw0 = (int64_t)blockIdx.x * TILE_B;
+    if (warp == 0) trace_ev(p, 0, 37);
 
     unsigned char *s_ring = smem + Smem::ring();
     unsigned char *s_h0 = smem + Smem::h0(H);
     unsigned char *s_h1 = smem + Smem::h1(H);
-    unsigned char *s_y = smem + Smem::yb(H);
-    float *s_red = reinterpret_cast<float *>(smem + Smem::red(H, KY));
-    uint64_t *s_bars = reinterpret_cast<uint64_t *>(smem + Smem::bars(H, KY, p.tiles_per_step));
-    // barriers: full[5], empty[5], tmem_full[2], tmem_empty[2], h_ready[2]
+    float *s_red = reinterpret_cast<float *>(smem + Smem::red(H));
+    uint64_t *s_bars = reinterpret_cast<uint64_t *>(smem + Smem::bars(H));
+    // barriers: full[S], empty[S], tmem_full[2], tmem_empty[2], h_ready[2]
     const uint32_t bar_full = smem_u32(s_bars), bar_empty = bar_full + 8 * NUM_STAGES,
                    bar_tfull = bar_empty + 8 * NUM_STAGES, bar_tempty = bar_tfull + 16, bar_hready = bar_tempty + 16;
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bars + 2 * NUM_STAGES + 6);
@@ -225,7 +310,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
     if (tid == 0) {
         for (int i = 0; i < NUM_STAGES; ++i) {
             mbar_init(bar_full + 8 * i, 1);
-            mbar_init(bar_empty + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, 2);  // this CTA's and the peer CTA's MMAs on the slot have retired
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_tfull + 8 * i, 1);
@@ -240,126 +325,134 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    // h0 = h1 = 0 (rnn_all.py:538); y tile: fp32 -> fp16, K padded to KY*64 with zeros
+    // h0 = h1 = 0 (rnn_all.py:538); the y tile goes, as fp32 [k][codeword], into the (still idle) ring memory for
+    // the input-projection prologue below
     for (int i = tid; i < (2 * KH * B_CHUNK_BYTES) / 16; i += NUM_THREADS)
         reinterpret_cast<uint4 *>(s_h0)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < TILE_B * KY * 64; i += NUM_THREADS) {
-        const int c = i / (KY * 64), k = i % (KY * 64);
-        float v = 0.0f;
-        if (k < N && cw0 + c < p.B) v = p.y[(cw0 + c) * N + k];
-        *reinterpret_cast<__half *>(s_y + b_off(c, k)) = __float2half_rn(v);
+    float *s_yT = reinterpret_cast<float *>(s_ring);
+    for (int i = tid; i < TILE_B * N; i += NUM_THREADS) {
+        const int c = i / N, k = i % N;
+        s_yT[k * TILE_B + c] = (cw0 + c < p.B) ? p.y[(cw0 + c) * N + k] : 0.0f;
     }
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
+    const uint32_t rank = cluster_ctarank();
+
+    // ---- input projection, hoisted out of the step loop: Gy = W_iy y is the same in all N steps.
+    // Every epilogue thread computes, in fp32, exactly the (unit, 16 codewords) entries it will add to its layer-0
+    // accumulators later and keeps them in thread-local memory (L1/L2-backed; 3 gates x JOBS x 16 floats).
+    float4 gy[JOBS * 3 * (CW_PER_THREAD / 4)];
+    if (warp < EPI_WARPS) {
+        const int q = warp & 3, col0 = (warp >> 2) * CW_PER_THREAD;
+        for (int jg = 0; jg < JOBS * 3; ++jg) {
+            const int j = jg / 3, g = jg % 3;
+            const int row = g * H + j * JOB_UNITS + q * 32 + lane;
+            float acc[CW_PER_THREAD];
+#pragma unroll
+            for (int i = 0; i < CW_PER_THREAD; ++i) acc[i] = 0.0f;
+#pragma unroll 8
+            for (int k = 0; k < N; ++k) {
+                const float w = __ldg(p.w_iyT + (size_t)k * (3 * H) + row);
+#pragma unroll
+                for (int i4 = 0; i4 < CW_PER_THREAD / 4; ++i4) {
+                    const float4 yv = *reinterpret_cast<const float4 *>(s_yT + k * TILE_B + col0 + 4 * i4);
+                    acc[4 * i4 + 0] = fmaf(w, yv.x, acc[4 * i4 + 0]);
+                    acc[4 * i4 + 1] = fmaf(w, yv.y, acc[4 * i4 + 1]);
+                    acc[4 * i4 + 2] = fmaf(w, yv.z, acc[4 * i4 + 2]);
+                    acc[4 * i4 + 3] = fmaf(w, yv.w, acc[4 * i4 + 3]);
+                }
+            }
+#pragma unroll
+            for (int i4 = 0; i4 < CW_PER_THREAD / 4; ++i4)
+                gy[jg * (CW_PER_THREAD / 4) + i4] = make_float4(acc[4 * i4], acc[4 * i4 + 1], acc[4 * i4 + 2], acc[4 * i4 + 3]);
+        }
+    }
+    // the ring memory (y tile) is free for the weight stream from here on, in both CTAs of the pair (the peer
+    // multicasts into this CTA's ring and arrives on its barriers)
+    cluster_sync_all();
+    if (warp == 0) trace_ev(p, 0, 38);
 
     if (warp >= EPI_WARPS && warp < MMA_WARP) {
-        // ================= producers: stream the weight program, once per step; producer w copies tiles w, w + P, ... ==========
+        // ================= producer: stream the weight program, once per step =================
         if (lane == 0) {
-            const uint32_t S = (uint32_t)p.stages, T = (uint32_t)p.tiles_per_step;
-            const uint32_t total = ((p.dbg & 4) ? 0u : (uint32_t)N) * T;
-            uint32_t g = (uint32_t)(warp - EPI_WARPS);
-            uint32_t t = g % T, stage = g % S, phase = (g / S) & 1u;
-            for (; g < total; g += NUM_PRODUCERS) {
-                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            const uint32_t T = (uint32_t)p.tiles_per_step;
+            const uint32_t total = (uint32_t)N * T;
+            uint32_t t = 0, stage = 0, phase = 0;
+            for (uint32_t g = 0; g < total; ++g) {
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1);  // both CTAs are done with the slot
                 if (p.dbg & 1) {
                     mbar_arrive(bar_full + 8 * stage);
                 } else {
                     mbar_expect_tx(bar_full + 8 * stage, A_TILE_BYTES);
-                    bulk_g2s(smem_u32(s_ring + stage * A_TILE_BYTES), p.wpack + (size_t)t * A_TILE_BYTES, A_TILE_BYTES, bar_full + 8 * stage);
+                    if ((g & 1u) == rank)  // the CTAs take turns fetching a tile for both
+                        bulk_g2s_multicast(smem_u32(s_ring + stage * A_TILE_BYTES), p.wpack + (size_t)t * A_TILE_BYTES,
+                                           A_TILE_BYTES, bar_full + 8 * stage, (uint16_t)3);
                 }
-                t += NUM_PRODUCERS;
-                if (t >= T) t -= T;
-                stage += NUM_PRODUCERS;
-                while (stage >= S) { stage -= S; phase ^= 1; }
+                if (++t == T) t = 0;
+                if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
             }
         }
+        __syncwarp();
     } else if (warp == MMA_WARP) {
-      {
-        // ================= MMA issuer =================
-        // The whole warp runs the (warp-uniform) schedule so that every address and flag lives in uniform
-        // registers; one elected lane issues the tcgen05 instructions.  The tile order is the order in which
-        // npd_gru_create packed the weight program.
+        // ================= MMA issuer: one thread runs the static schedule =================
         // M = 128, N = 64, fp16 x fp16 -> fp32 (a_format = b_format = 0), both operands K-major
-        const uint32_t idesc = (1u << 4) | ((uint32_t)(TILE_B >> 3) << 17) | ((128u >> 4) << 24);
-        // descriptor low words: the issuing thread spends ~35 instead of ~70 instructions per 16 KB tile, which is what
-        // bounds this kernel (a tile is only 4 x 32 tensor-pipe cycles)
-        const uint32_t b_y = umma_desc_lo(smem_u32(s_y)), b_h0 = umma_desc_lo(smem_u32(s_h0)), b_h1 = umma_desc_lo(smem_u32(s_h1));
-        const uint32_t ring0 = umma_desc_lo(smem_u32(s_ring));
-        constexpr uint32_t B_CHUNK_LO = B_CHUNK_BYTES >> 4, A_TILE_LO = A_TILE_BYTES >> 4;
-        const bool no_mma = (p.dbg & 2) != 0;
-        uint32_t stage = 0, phase = 0;
-        uint32_t job = 0;  // global job counter -> TMEM slot job & 1
-        uint32_t hphase0 = 0, hphase1 = 0;
-        bool ready = false;  // early probe of the current stage's full barrier succeeded
-
-        // consume one weight tile: D[slot, acc] (+)= A(ring stage) * B(b_lo)^T over K = 64
-        auto tile = [&](uint32_t d_tmem, uint32_t b_lo, bool first) {
-            if (!ready) mbar_wait(bar_full + 8 * stage, phase);
-            tc_fence_after();
-            const uint32_t a_lo = ring0 + stage * A_TILE_LO;
-            const uint32_t cur = stage;
-            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
-            ready = mbar_test(bar_full + 8 * stage, phase);  // overlaps the issue below
-            if (elect_one()) {
-                if (!no_mma) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_fp16(d_tmem, umma_desc_from_lo(a_lo + k * 2), umma_desc_from_lo(b_lo + k * 2), idesc,
-                                  (first && k == 0) ? 0u : 1u);
-                }
-                umma_commit(bar_empty + 8 * cur);  // frees the ring slot when these MMAs retire
-            }
-            __syncwarp();
-        };
-        auto run = [&](uint32_t d_tmem, uint32_t b_base, int nchunks, bool first) {
-            if (p.dbg & 4) return;  // experiment: no per-tile work at all
-            for (int kc = 0; kc < nchunks; ++kc) tile(d_tmem, b_base + kc * B_CHUNK_LO, first && kc == 0);
-        };
-
-        for (int step = 0; step < N; ++step) {
-            // ---- layer 0: R (h0, y), Z (h0, y), NI (y), NH (h0) ----
-            for (int j = 0; j < jobs_per_layer; ++j, ++job) {
-                const uint32_t slot = job & 1, d0 = tmem_base + slot * 256;
-                mbar_wait(bar_tempty + 8 * slot, ((job >> 1) & 1) ^ 1);
-                tc_fence_after();
-                run(d0 + 0 * TILE_B, b_h0, KH, true);
-                run(d0 + 0 * TILE_B, b_y, KY, false);
-                run(d0 + 1 * TILE_B, b_h0, KH, true);
-                run(d0 + 1 * TILE_B, b_y, KY, false);
-                run(d0 + 2 * TILE_B, b_y, KY, true);
-                run(d0 + 3 * TILE_B, b_h0, KH, true);
-                if (elect_one()) umma_commit(bar_tfull + 8 * slot);
-                __syncwarp();
-            }
-            // ---- layer 1: hidden-state stream first (previous step's h1), then this step's h0 ----
-            for (int j = 0; j < jobs_per_layer; ++j, ++job) {
-                const uint32_t slot = job & 1, d0 = tmem_base + slot * 256;
-                mbar_wait(bar_tempty + 8 * slot, ((job >> 1) & 1) ^ 1);
-                tc_fence_after();
-                if (j == 0 && step > 0) {
-                    mbar_wait(bar_hready + 8, hphase1);
-                    hphase1 ^= 1;
+        if (elect_one()) {
+            MmaCtx c;
+            c.bar_full = bar_full; c.bar_empty = bar_empty; c.ring_lo = umma_desc_lo(smem_u32(s_ring));
+            c.idesc = (1u << 4) | ((uint32_t)(TILE_B >> 3) << 17) | ((128u >> 4) << 24);
+            c.ok = 0; c.pb = 0; c.no_mma = (p.dbg & 2) != 0;
+            const uint32_t b_h0 = umma_desc_lo(smem_u32(s_h0)), b_h1 = umma_desc_lo(smem_u32(s_h1));
+            uint32_t job = 0;  // global job counter -> TMEM slot job & 1
+            uint32_t hphase0 = 0, hphase1 = 0;
+            for (int step = 0; step < N; ++step) {
+                // ---- layer 0: R, Z, NH from h0 (the y part of R, Z and all of NI are the hoisted Gy) ----
+                for (int j = 0; j < JOBS; ++j, ++job) {
+                    const uint32_t slot = job & 1, d0 = tmem_base + slot * 256;
+                    mbar_wait(bar_tempty + 8 * slot, ((job >> 1) & 1) ^ 1);
                     tc_fence_after();
+                    trace_ev(p, step, 2 * j);
+                    mma_block<KH>(c, d0 + 0 * TILE_B, b_h0, true, d0 + 1 * TILE_B, b_h0, true, d0 + 3 * TILE_B, b_h0, true);
+                    umma_commit(bar_tfull + 8 * slot);
+                    trace_ev(p, step, 2 * j + 1);
                 }
-                run(d0 + 3 * TILE_B, b_h1, KH, true);
-                run(d0 + 0 * TILE_B, b_h1, KH, true);
-                run(d0 + 1 * TILE_B, b_h1, KH, true);
-                if (j == 0) {
-                    mbar_wait(bar_hready + 0, hphase0);
-                    hphase0 ^= 1;
-                    tc_fence_after();
+                // ---- layer 1, two jobs at a time: both hidden-state streams first (they need only the previous
+                // step's h1 and cover the wait for layer 0's state update), then both input streams (this step's h0)
+                for (int jp = 0; jp < JOBS; jp += 2) {
+                    const int nj = (JOBS - jp) < 2 ? (JOBS - jp) : 2;
+                    for (int i = 0; i < nj; ++i) {
+                        const uint32_t jb = job + i, slot = jb & 1, d0 = tmem_base + slot * 256;
+                        mbar_wait(bar_tempty + 8 * slot, ((jb >> 1) & 1) ^ 1);
+                        tc_fence_after();
+                        trace_ev(p, step, 8 + 2 * (jp + i));
+                        if (jp == 0 && i == 0 && step > 0) {
+                            mbar_wait(bar_hready + 8, hphase1);
+                            hphase1 ^= 1;
+                            tc_fence_after();
+                            trace_ev(p, step, 17);
+                        }
+                        mma_block<KH>(c, d0 + 3 * TILE_B, b_h1, true, d0 + 0 * TILE_B, b_h1, true, d0 + 1 * TILE_B, b_h1, true);
+                    }
+                    if (jp == 0) {
+                        trace_ev(p, step, 18);
+                        mbar_wait(bar_hready + 0, hphase0);
+                        hphase0 ^= 1;
+                        tc_fence_after();
+                        trace_ev(p, step, 16);
+                    }
+                    for (int i = 0; i < nj; ++i) {
+                        const uint32_t jb = job + i, slot = jb & 1, d0 = tmem_base + slot * 256;
+                        mma_block<KH>(c, d0 + 0 * TILE_B, b_h0, false, d0 + 1 * TILE_B, b_h0, false, d0 + 2 * TILE_B, b_h0, true);
+                        umma_commit(bar_tfull + 8 * slot);
+                        trace_ev(p, step, 8 + 2 * (jp + i) + 1);
+                    }
+                    job += nj;
                 }
-                run(d0 + 0 * TILE_B, b_h0, KH, false);
-                run(d0 + 1 * TILE_B, b_h0, KH, false);
-                run(d0 + 2 * TILE_B, b_h0, KH, true);
-                if (elect_one()) umma_commit(bar_tfull + 8 * slot);
-                __syncwarp();
             }
         }
-      }
+        __syncwarp();
     } else {
         // ================= epilogue warps: gate math, state update, head, feedback =================
         constexpr int CW = CW_PER_THREAD;                 // 16 codewords per thread
@@ -381,8 +474,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
                     for (int i = 0; i < CW; ++i) head[i] = 0.0f;
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (j >= jobs_per_layer) break;
+                for (int j = 0; j < JOBS; ++j) {
                     const int u = j * JOB_UNITS + q * 32 + lane;  // hidden unit of this thread
                     // per-unit constants; sigmoid arguments are pre-halved (sigmoid(x) = 0.5 + 0.5 tanh(x / 2)) and the
                     // one-hot input column of the previous decision is folded into the layer-0 biases
@@ -403,19 +495,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
                     const uint32_t slot = job & 1;
                     mbar_wait(bar_tfull + 8 * slot, (job >> 1) & 1);
                     tc_fence_after();
+                    if (warp == 0) trace_ev(p, step, 20 + 2 * (layer * 4 + j));
                     const uint32_t t0 = tmem_base + lane_addr + slot * 256 + col0;
 #pragma unroll
                     for (int cc = 0; cc < CW; cc += 8) {
                         float aR[8], aZ[8], aNI[8], aNH[8];
                         tmem_ld8(t0 + 0 * TILE_B + cc, aR);
                         tmem_ld8(t0 + 1 * TILE_B + cc, aZ);
-                        tmem_ld8(t0 + 2 * TILE_B + cc, aNI);
+                        if (layer == 1) tmem_ld8(t0 + 2 * TILE_B + cc, aNI);
                         tmem_ld8(t0 + 3 * TILE_B + cc, aNH);
                         tmem_ld_wait();
                         if (cc + 8 == CW) {
                             // all accumulators of this job are in registers: the MMA warp may refill the slot
                             tc_fence_before();
                             mbar_arrive(bar_tempty + 8 * slot);
+                        }
+                        if (layer == 0) {
+                            // add the hoisted input projection of this (unit, codewords)
+#pragma unroll
+                            for (int h4 = 0; h4 < 2; ++h4) {
+                                const float4 gr = gy[(j * 3 + 0) * (CW / 4) + cc / 4 + h4];
+                                const float4 gz = gy[(j * 3 + 1) * (CW / 4) + cc / 4 + h4];
+                                const float4 gn = gy[(j * 3 + 2) * (CW / 4) + cc / 4 + h4];
+                                aR[4 * h4 + 0] += gr.x; aR[4 * h4 + 1] += gr.y; aR[4 * h4 + 2] += gr.z; aR[4 * h4 + 3] += gr.w;
+                                aZ[4 * h4 + 0] += gz.x; aZ[4 * h4 + 1] += gz.y; aZ[4 * h4 + 2] += gz.z; aZ[4 * h4 + 3] += gz.w;
+                                aNI[4 * h4 + 0] = gn.x; aNI[4 * h4 + 1] = gn.y; aNI[4 * h4 + 2] = gn.z; aNI[4 * h4 + 3] = gn.w;
+                            }
                         }
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -427,7 +532,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
                             const float hnew = fmaf(z, hold - nn, nn);  // (1 - z) n + z h
                             if (layer == 1) head[cc + i] = fmaf(wo, hnew, head[cc + i]);
                             const unsigned short hb = __half_as_ushort(__float2half_rn(hnew));
-                            if (j == jobs_per_layer - 1) {
+                            if (j == JOBS - 1) {
                                 // tmem_full of the layer's last job: every MMA reading the old state has retired
                                 *reinterpret_cast<unsigned short *>(s_h + b_off(col0 + cc + i, u)) = hb;
                             } else {
@@ -436,13 +541,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
                             }
                         }
                     }
+                    if (warp == 0) trace_ev(p, step, 21 + 2 * (layer * 4 + j));
                     ++job;
                 }
                 // every MMA that reads the old state of this layer has retired (tmem_full of the last
                 // job): write the new state in place
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    if (j >= jobs_per_layer - 1) break;
+                for (int j = 0; j < JOBS - 1; ++j) {
                     const int u = j * JOB_UNITS + q * 32 + lane;
 #pragma unroll
                     for (int i = 0; i < CW / 2; ++i) {
@@ -491,22 +596,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
                 if (lane == 0) s_bits[warp] = m;
             }
             epi_bar_sync();
+            if (warp == 0) trace_ev(p, step, 36);
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();  // the peer may still signal this CTA's barriers / write its ring until its own schedule ends
     if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
 }
 
 }  // namespace
 
 // ---- host side ----------------------------------------------------------------------------------
+static const void *gru_kernel_for(int H)
+{
+    switch (H) {
+    case 128: return (const void *)gru_decode_kernel<2>;
+    case 256: return (const void *)gru_decode_kernel<4>;
+    case 384: return (const void *)gru_decode_kernel<6>;
+    default: return (const void *)gru_decode_kernel<8>;
+    }
+}
+
 struct npd_gru {
-    int N, H, KY, tiles_per_step;
+    int N, H, tiles_per_step;
     float b_out;
     unsigned char *d_wpack;
-    uint32_t *d_program;
+    float *d_w_iyT;
     float *d_consts0, *d_consts1, *d_w_out;
     size_t smem_bytes;
 };
@@ -554,59 +670,38 @@ NPD_API int npd_gru_create(int N, int H, const float *w_ih0, const float *w_hh0,
                     return NPD_EUNSUPPORTED;
                 }
     }
-    const int KY = (N + 63) / 64, KH = H / 64, JOBS = H / 128, IN0 = N + 2;
+    const int KH = H / 64, JOBS = H / 128, IN0 = N + 2;
     std::vector<unsigned short> pack;
-    std::vector<uint32_t> prog;
-    auto emit = [&](uint32_t acc, uint32_t bsrc, uint32_t kc, uint32_t flags) { prog.push_back(acc | (bsrc << 2) | (kc << 4) | flags); };
-    // layer 0: per job R (h0 chunks, y chunks), Z (same), NI (y chunks), NH (h0 chunks)
+    int n_tiles = 0;
+    auto run = [&](const float *w, int gate, int j) {  // KH tiles: rows gate*H + j*128 .. +127 of a [3H, H] matrix
+        for (int kc = 0; kc < KH; ++kc, ++n_tiles)
+            pack_tile(pack, [&](int r, int kk) { return w[(size_t)(gate * H + j * 128 + r) * H + kc * 64 + kk]; });
+    };
+    // The order below is the MMA warp's static schedule (gru_decode_kernel): blocks of three runs.
+    // layer 0, per job: R, Z, NH from h0 (the y part of R and Z and all of NI come from the hoisted projection)
     for (int j = 0; j < JOBS; ++j) {
-        for (int g = 0; g < 2; ++g) {  // R, Z
-            for (int kc = 0; kc < KH; ++kc) {
-                pack_tile(pack, [&](int r, int kk) { return w_hh0[(size_t)(g * H + j * 128 + r) * H + kc * 64 + kk]; });
-                emit(g, 1, kc, (kc == 0 ? P_FIRST : 0) | ((g == 0 && kc == 0) ? P_JOB_BEGIN : 0));
-            }
-            for (int kc = 0; kc < KY; ++kc) {
-                pack_tile(pack, [&](int r, int kk) {
-                    const int k = kc * 64 + kk;
-                    return k < N ? w_ih0[(size_t)(g * H + j * 128 + r) * IN0 + k] : 0.0f;
-                });
-                emit(g, 0, kc, 0);
-            }
+        run(w_hh0, 0, j);
+        run(w_hh0, 1, j);
+        run(w_hh0, 2, j);
+    }
+    // layer 1, two jobs at a time: the hidden-state streams first (they need only the previous step's h1): NH, R_h,
+    // Z_h of both jobs; then the input streams (they need this step's h0): R_x, Z_x, NI of both jobs
+    for (int jp = 0; jp < JOBS; jp += 2) {
+        const int nj = (JOBS - jp) < 2 ? (JOBS - jp) : 2;
+        for (int i = 0; i < nj; ++i) {
+            run(w_hh1, 2, jp + i);
+            run(w_hh1, 0, jp + i);
+            run(w_hh1, 1, jp + i);
         }
-        for (int kc = 0; kc < KY; ++kc) {  // NI
-            pack_tile(pack, [&](int r, int kk) {
-                const int k = kc * 64 + kk;
-                return k < N ? w_ih0[(size_t)(2 * H + j * 128 + r) * IN0 + k] : 0.0f;
-            });
-            emit(2, 0, kc, kc == 0 ? P_FIRST : 0);
-        }
-        for (int kc = 0; kc < KH; ++kc) {  // NH
-            pack_tile(pack, [&](int r, int kk) { return w_hh0[(size_t)(2 * H + j * 128 + r) * H + kc * 64 + kk]; });
-            emit(3, 1, kc, (kc == 0 ? P_FIRST : 0) | (kc == KH - 1 ? P_JOB_END : 0));
+        for (int i = 0; i < nj; ++i) {
+            run(w_ih1, 0, jp + i);
+            run(w_ih1, 1, jp + i);
+            run(w_ih1, 2, jp + i);
         }
     }
-    // layer 1: per job the hidden-state stream first (needs only the previous step's h1), then the input
-    // stream (needs this step's h0): NH, R_h, Z_h, R_x, Z_x, NI
-    for (int j = 0; j < JOBS; ++j) {
-        for (int kc = 0; kc < KH; ++kc) {
-            pack_tile(pack, [&](int r, int kk) { return w_hh1[(size_t)(2 * H + j * 128 + r) * H + kc * 64 + kk]; });
-            emit(3, 2, kc, (kc == 0 ? (P_FIRST | P_JOB_BEGIN) : 0) | ((j == 0 && kc == 0) ? P_WAIT_H1 : 0));
-        }
-        for (int g = 0; g < 2; ++g)
-            for (int kc = 0; kc < KH; ++kc) {
-                pack_tile(pack, [&](int r, int kk) { return w_hh1[(size_t)(g * H + j * 128 + r) * H + kc * 64 + kk]; });
-                emit(g, 2, kc, kc == 0 ? P_FIRST : 0);
-            }
-        for (int g = 0; g < 2; ++g)
-            for (int kc = 0; kc < KH; ++kc) {
-                pack_tile(pack, [&](int r, int kk) { return w_ih1[(size_t)(g * H + j * 128 + r) * H + kc * 64 + kk]; });
-                emit(g, 1, kc, (j == 0 && g == 0 && kc == 0) ? P_WAIT_H0 : 0);
-            }
-        for (int kc = 0; kc < KH; ++kc) {
-            pack_tile(pack, [&](int r, int kk) { return w_ih1[(size_t)(2 * H + j * 128 + r) * H + kc * 64 + kk]; });
-            emit(2, 1, kc, (kc == 0 ? P_FIRST : 0) | (kc == KH - 1 ? P_JOB_END : 0));
-        }
-    }
+    std::vector<float> wiyT((size_t)N * 3 * H);
+    for (int k = 0; k < N; ++k)
+        for (int r = 0; r < 3 * H; ++r) wiyT[(size_t)k * 3 * H + r] = w_ih0[(size_t)r * IN0 + k];
     std::vector<float> c0((size_t)H * 12, 0.0f), c1((size_t)H * 4, 0.0f);
     for (int u = 0; u < H; ++u) {
         float *a = &c0[(size_t)u * 12];
@@ -626,25 +721,27 @@ NPD_API int npd_gru_create(int N, int H, const float *w_ih0, const float *w_hh0,
     }
     npd_gru *g = (npd_gru *)calloc(1, sizeof(npd_gru));
     if (!g) return NPD_ENOMEM;
-    g->N = N; g->H = H; g->KY = KY; g->tiles_per_step = (int)prog.size(); g->b_out = b_out[0];
-    g->smem_bytes = Smem::total(H, KY, g->tiles_per_step);
+    g->N = N; g->H = H; g->tiles_per_step = n_tiles; g->b_out = b_out[0];
+    g->smem_bytes = Smem::total(H);
     if (g->smem_bytes > (size_t)dp.smem_optin) {
         npd_set_error("npd_gru_create: needs %zu B of shared memory (limit %d)", g->smem_bytes, dp.smem_optin);
         free(g);
         return NPD_EUNSUPPORTED;
     }
     cudaError_t e = cudaMalloc(&g->d_wpack, pack.size() * 2);
-    if (e == cudaSuccess) e = cudaMalloc(&g->d_program, prog.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_w_iyT, wiyT.size() * 4);
     if (e == cudaSuccess) e = cudaMalloc(&g->d_consts0, c0.size() * 4);
     if (e == cudaSuccess) e = cudaMalloc(&g->d_consts1, c1.size() * 4);
     if (e == cudaSuccess) e = cudaMalloc(&g->d_w_out, (size_t)H * 4);
     if (e == cudaSuccess) e = cudaMemcpy(g->d_wpack, pack.data(), pack.size() * 2, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(g->d_program, prog.data(), prog.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(g->d_w_iyT, wiyT.data(), wiyT.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(g->d_consts0, c0.data(), c0.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(g->d_consts1, c1.data(), c1.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(g->d_w_out, w_out, (size_t)H * 4, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(gru_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bytes);
+    if (e == cudaSuccess) {
+        const void *kern = gru_kernel_for(H);
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bytes);
+    }
     if (e != cudaSuccess) {
         npd_set_error("npd_gru_create: %s", cudaGetErrorString(e));
         npd_gru_destroy(g);
@@ -658,7 +755,7 @@ NPD_API int npd_gru_destroy(npd_gru_t *g)
 {
     if (!g) return NPD_OK;
     cudaFree(g->d_wpack);
-    cudaFree(g->d_program);
+    cudaFree(g->d_w_iyT);
     cudaFree(g->d_consts0);
     cudaFree(g->d_consts1);
     cudaFree(g->d_w_out);
@@ -677,14 +774,42 @@ NPD_API int npd_gru_decode(const npd_gru_t *g, const npd_code_t *code, const flo
     NPD_REQUIRE(code->N == g->N, "npd_gru_decode: code length %d != decoder input length %d", code->N, g->N);
     if (B == 0) return NPD_OK;
     GruParams p{};
-    p.wpack = g->d_wpack; p.program = g->d_program; p.consts0 = g->d_consts0; p.consts1 = g->d_consts1;
+    p.wpack = g->d_wpack; p.w_iyT = g->d_w_iyT; p.consts0 = g->d_consts0; p.consts1 = g->d_consts1;
     p.w_out = g->d_w_out; p.b_out = g->b_out; p.y = y; p.forced = forced; p.genie = genie; p.info_words = code->d_info_words;
-    p.logits = logits; p.decoded = decoded; p.B = B; p.N = g->N; p.H = g->H; p.KY = g->KY;
+    p.logits = logits; p.decoded = decoded; p.B = B; p.N = g->N; p.H = g->H;
     p.tiles_per_step = g->tiles_per_step;
     { const char *d = getenv("NPD_GRU_DBG"); p.dbg = d ? atoi(d) : 0; }
-    { const char *d = getenv("NPD_GRU_STAGES"); p.stages = d ? atoi(d) : NUM_STAGES; if (p.stages < 2 || p.stages > NUM_STAGES) p.stages = NUM_STAGES; }
-    const int64_t grid = (B + TILE_B - 1) / TILE_B;
-    gru_decode_kernel<<<(unsigned)grid, NUM_THREADS, g->smem_bytes, (cudaStream_t)stream>>>(p);
+    const int64_t grid = ((B + 2 * TILE_B - 1) / (2 * TILE_B)) * 2;  // CTA pairs (clusters of 2); an odd tile count pads with an idle-data CTA
+    const char *trace_path = getenv("NPD_GRU_TRACE");  // bench-only: dump CTA 0's event clocks (synchronises!)
+    if (trace_path) NPD_CHECK_CUDA(cudaMalloc(&p.trace, sizeof(long long) * g->N * TRACE_SLOTS));
+    if (trace_path) NPD_CHECK_CUDA(cudaMemsetAsync(p.trace, 0, sizeof(long long) * g->N * TRACE_SLOTS, (cudaStream_t)stream));
+    void *args[] = {&p};
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = g->smem_bytes;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    NPD_CHECK_CUDA(cudaLaunchKernelExC(&cfg, gru_kernel_for(g->H), args));
     NPD_CHECK_CUDA(cudaGetLastError());
+    if (trace_path) {
+        std::vector<long long> h((size_t)g->N * TRACE_SLOTS);
+        NPD_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+        NPD_CHECK_CUDA(cudaMemcpy(h.data(), p.trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(p.trace);
+        if (FILE *f = fopen(trace_path, "w")) {
+            for (int s = 0; s < g->N; ++s) {
+                for (int k = 0; k < TRACE_SLOTS; ++k) fprintf(f, "%lld ", h[(size_t)s * TRACE_SLOTS + k]);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
     return NPD_OK;
 }

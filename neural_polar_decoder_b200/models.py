@@ -135,7 +135,8 @@ class convNet(nn.Module):
     def decode(self, noisy_enc, info_positions, mask, device, trg_seq=None):
         """-> (bits [B,N,1], mask); info_positions is ignored as in the reference (models.py:769-772)."""
         logits, _, _ = self._run(noisy_enc, want_in4=False)
-        return logits.squeeze().unsqueeze(-1).sign(), mask
+        # in place: `logits` is this call's own fresh tensor (no second [B,N] allocation on the host path)
+        return logits.sign_().squeeze().unsqueeze(-1), mask
 
     def logits(self, noisy_enc):
         """LayerNorm output [B,N] (what parity is judged on)."""
