@@ -95,6 +95,16 @@ int npd_pac_sc_decode(const npd_code_t *code, const float *y, float llr_scale,
                       const float *use_gt_codeword, float *leaf_llr, float *v_hat, float *u_hat,
                       int64_t B, void *stream);
 
+/* npd_scl_decode: PolarCode.scl_decode(y, snr, L, use_CRC=False) (polar.py:793-876 with pruneLists 777-791):
+ * SC-list decoding with L paths -- min-sum LLR recursion WITHOUT the frozen prior, path metric += |L| for every
+ * decision against sign(L), list pruned to the L smallest metrics (ascending list order), final pick = the
+ * surviving path whose re-encoded codeword is closest to y.  1 <= list_size <= 32.
+ *   leaf_llr [B,N] or NULL : llr_array[:,0,:] of the chosen path (frozen leaves include + infty)
+ *   decoded  [B,K]         : its u_hat[:, info_positions]
+ * The CRC-aided variant (use_CRC=True) needs the reference's per-codeword Python CRC and is not implemented. */
+int npd_scl_decode(const npd_code_t *code, const float *y, float llr_scale, int list_size,
+                   float *leaf_llr, float *decoded, int64_t B, void *stream);
+
 /* ---- error counting ----------------------------------------------------------------------------
  * npd_count_errors: numerators of errors_ber (utils.py:17-25) and errors_bler (utils.py:37-51):
  * counts[0] += #{round(a) != round(b)}, counts[1] += #rows with any mismatch, over a[B,K], b[B,K].
@@ -172,6 +182,8 @@ int npd_conv_forward(const npd_conv_t *conv, const float *y, float *logits, floa
  * same device are serialised. */
 int npd_sc_decode_host(const npd_code_t *code, const float *h_y, float llr_scale,
                        const float *h_use_gt, float *h_leaf_llr, float *h_decoded, int64_t B);
+int npd_scl_decode_host(const npd_code_t *code, const float *h_y, float llr_scale, int list_size,
+                        float *h_leaf_llr, float *h_decoded, int64_t B);
 int npd_pac_sc_decode_host(const npd_code_t *code, const float *h_y, float llr_scale,
                            const float *h_use_gt_codeword, float *h_leaf_llr, float *h_v_hat,
                            float *h_u_hat, int64_t B);

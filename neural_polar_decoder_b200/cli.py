@@ -10,7 +10,7 @@ What is mirrored
     reference training run left it; `--test_load_path` / `--model_iters` select a file as in 1749-1754;
   * checkpoint format {'net': state_dict, 'step': int, 'args': Namespace} (rnn_all.py:1471-1479);
   * the printed lines "Test SNRs :", "BERs of RNN:", "BERs of SC decoding:", "BERs of ML:", "Time taken".
-Not mirrored: training (raises unless --test), plotting, Fano / ML / list decoders (their lists print as zeros).
+Not mirrored: training (raises unless --test), plotting, Fano / ML / RNN-list decoders (their lists print as zeros).
 """
 import argparse
 import math
@@ -218,7 +218,7 @@ def run_test(args, out=print):
         out("BERs of Fano: {0}".format(res["bers_fano"]))
     else:
         r = sweep.polar_RNN_full_test(net, code, snr_range, loader, args.are_we_doing_ML, args.list_size is not None,
-                                      False, decoder=decoder)
+                                      False, decoder=decoder, list_size=args.list_size or 4)
         keys = ("bers_RNN", "blers_RNN", "bers_SC", "blers_SC", "bers_SCL", "blers_SCL", "bers_RNNL", "blers_RNNL",
                 "bers_ML", "blers_ML")
         res.update(dict(zip(keys, r)))

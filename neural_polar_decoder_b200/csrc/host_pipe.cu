@@ -154,6 +154,29 @@ NPD_API int npd_sc_decode_host(const npd_code_t *code, const float *h_y, float l
     });
 }
 
+NPD_API int npd_scl_decode_host(const npd_code_t *code, const float *h_y, float llr_scale, int list_size,
+                                float *h_leaf_llr, float *h_decoded, int64_t B)
+{
+    NPD_REQUIRE(code && h_y && h_decoded, "npd_scl_decode_host: null argument");
+    NPD_REQUIRE(B >= 0, "npd_scl_decode_host: B < 0");
+    if (B == 0) return NPD_OK;
+    const size_t N = code->N, K = code->K;
+    const int64_t chunk = pick_chunk(B, N * 4, 256, (size_t)4 << 20);
+    const size_t per = al256(chunk * N * 4) * (1 + (h_leaf_llr ? 1 : 0)) + al256(chunk * (K ? K : 1) * 4);
+    return run_pipe(B, chunk, per, [&](char *arena, int64_t lo, int64_t n, cudaStream_t st) -> int {
+        Carver cv(arena);
+        float *d_y = cv.take(chunk * N * 4);
+        float *d_llr = cv.take(chunk * N * 4, h_leaf_llr != nullptr);
+        float *d_dec = cv.take(chunk * (K ? K : 1) * 4);
+        H2D(d_y, h_y + lo * N, n * N * 4, st);
+        int rc = npd_scl_decode(code, d_y, llr_scale, list_size, d_llr, d_dec, n, st);
+        if (rc) return rc;
+        if (K) D2H(h_decoded + lo * K, d_dec, n * K * 4, st);
+        if (d_llr) D2H(h_leaf_llr + lo * N, d_llr, n * N * 4, st);
+        return NPD_OK;
+    });
+}
+
 NPD_API int npd_pac_sc_decode_host(const npd_code_t *code, const float *h_y, float llr_scale,
                                    const float *h_use_gt_codeword, float *h_leaf_llr, float *h_v_hat,
                                    float *h_u_hat, int64_t B)

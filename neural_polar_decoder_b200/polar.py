@@ -121,6 +121,37 @@ class PolarCode:
                                                      _lib.ptr(llr), _lib.ptr(dec), B, _lib.stream_ptr()))
         return llr, dec
 
+    def scl_decode(self, corrupted_codewords, snr, L=1, use_CRC=False, return_llr=True):
+        """reference polar.py:793-876: SC-list decoding with L paths and the ML pick among the list.
+        -> (leaf LLRs [B,N] of the chosen path, its u_hat[:, info_positions] [B,K]), on the caller's device.
+        use_CRC=True (the reference's per-codeword Python CRC check) is not on the accelerated path."""
+        if use_CRC:
+            raise NotImplementedError("CRC-aided list decoding (polar.py:738-775, 848-867) is out of scope of the B200 path")
+        src = corrupted_codewords
+        L = int(L)
+        if torch.is_tensor(src) and not src.is_cuda:
+            _lib.require_cuda()
+            y = _lib.host_f32(src)
+            assert y.dim() == 2 and y.shape[1] == self.N, tuple(y.shape)
+            B = y.shape[0]
+            llr = _lib.host_out((B, self.N), y) if return_llr else None
+            dec = _lib.host_out((B, self.K), y)
+            if B > 0:
+                _lib.check(_lib.load().npd_scl_decode_host(self._handle().h, _lib.hptr(y), llr_scale(snr), L,
+                                                           _lib.hptr(llr), _lib.hptr(dec), B))
+            return llr, dec
+        y = _lib.to_device_f32(src)
+        assert y.dim() == 2 and y.shape[1] == self.N, tuple(y.shape)
+        B = y.shape[0]
+        with torch.cuda.device(y.device):
+            h = self._handle()
+            llr = torch.empty(B, self.N, dtype=torch.float32, device=y.device) if return_llr else None
+            dec = torch.empty(B, self.K, dtype=torch.float32, device=y.device)
+            if B > 0:
+                _lib.check(_lib.load().npd_scl_decode(h.h, _lib.ptr(y), llr_scale(snr), L, _lib.ptr(llr), _lib.ptr(dec),
+                                                      B, _lib.stream_ptr()))
+        return llr, dec
+
     def _sc_decode_host(self, y, snr, use_gt, return_llr):
         """Host tensors in, host tensors out: npd_sc_decode_host overlaps the chunked H2D copy, the
         kernels and the D2H copy on the library's own streams (synchronous)."""

@@ -11,7 +11,8 @@ The reference loops read module globals (`args`, `code`, `decoder`, `device`); h
 arguments.  Semantics kept: the same codewords are re-noised for every SNR point, per-batch error RATES are
 averaged (`+= ber / num_test_batches`), results are Python lists indexed by SNR point.  Counters stay on the
 device and are read back once per call (the reference syncs with .item() after every decoder call).
-Decoders the hot path does not cover (SC-list, ML/MAP, RNN list, Fano) are skipped: their lists stay 0."""
+SC-list decoding (polar.scl_decode) is run where the reference runs it; decoders the hot path does not cover (ML/MAP,
+RNN list, Fano) are skipped: their lists stay 0."""
 import numpy as np
 import torch
 
@@ -42,7 +43,7 @@ def _rates(counts, sizes, K, n_snr, n_dec):
 
 
 def polar_RNN_full_test(net, polar, snr_range, Test_Data_Generator, run_ML=False, run_SCL=False, run_RNNL=False,
-                        decoder=None, device=None, seed=None):
+                        decoder=None, device=None, seed=None, list_size=4):
     """-> (bers_RNN, blers_RNN, bers_SC, blers_SC, bers_SCL, blers_SCL, bers_RNNL, blers_RNNL, bers_ML, blers_ML)."""
     assert decoder is not None, "pass the RNN_decoder (a module global in the reference)"
     _lib.require_cuda()
@@ -50,7 +51,7 @@ def polar_RNN_full_test(net, polar, snr_range, Test_Data_Generator, run_ML=False
     snr_range = list(snr_range)
     nb, ns = len(Test_Data_Generator), len(snr_range)
     info = torch.as_tensor(np.asarray(polar.info_positions), device=device)
-    counts = torch.zeros(nb, ns, 2, 2, dtype=torch.int64, device=device)
+    counts = torch.zeros(nb, ns, 3, 2, dtype=torch.int64, device=device)
     sizes, frame0 = [], 0
     seed = rng.get_seed() if seed is None else seed
     with torch.cuda.device(device):
@@ -62,13 +63,15 @@ def polar_RNN_full_test(net, polar, snr_range, Test_Data_Generator, run_ML=False
                 y = polar.channel(x, snr, point=(1 << 31) | si, cw_offset=frame0, seed=seed)
                 _, dec_sc = polar.sc_decode_new(y, snr, return_llr=False)
                 _count_into(counts[k, si, 1], msg, dec_sc)  # .sign() is the identity on {-1,0,+1}
+                if run_SCL:  # rnn_all.py:866-872 (args.list_size in the reference)
+                    _, dec_scl = polar.scl_decode(y, snr, list_size, False, return_llr=False)
+                    _count_into(counts[k, si, 2], msg, dec_scl)
                 dec = decoder.decode(net, False, y)
                 _count_into(counts[k, si, 0], msg, dec.index_select(1, info))
             frame0 += msg.shape[0]
-    (ber_r, bler_r), (ber_s, bler_s) = _rates(counts, sizes, polar.K, ns, 2)
+    (ber_r, bler_r), (ber_s, bler_s), (ber_l, bler_l) = _rates(counts, sizes, polar.K, ns, 3)
     zeros = [0. for _ in snr_range]
-    return (ber_r, bler_r, ber_s, bler_s, list(zeros), list(zeros), list(zeros), list(zeros), list(zeros),
-            list(zeros))
+    return (ber_r, bler_r, ber_s, bler_s, ber_l, bler_l, list(zeros), list(zeros), list(zeros), list(zeros))
 
 
 def test_full_data(net, code, snr_range, Test_Data_Generator, run_fano=False, run_dumer=True, decoder=None,
@@ -102,15 +105,16 @@ def test_full_data(net, code, snr_range, Test_Data_Generator, run_fano=False, ru
 
 
 def testXformer(net, polar, snr_range, Test_Data_Generator, device, Test_Data_Mask=None, run_ML=False,
-                bitwise_snr_idx=-1, seed=None):
+                bitwise_snr_idx=-1, seed=None, run_SCL=True, list_size=4):
     """One-shot decoders (net.decode(y, info_positions, mask, device) -> (bits[B,N,1], mask)).
-    -> the reference's 11 values; SCL / ML / bitwise-MAP entries stay 0 (out of the hot path)."""
+    -> the reference's 11 values; ML / bitwise-MAP entries stay 0 (out of the hot path); run_SCL=False skips the
+    list decoder the reference hard-wires at L = 4."""
     _lib.require_cuda()
     device = torch.device(device)
     snr_range = list(snr_range)
     nb, ns = len(Test_Data_Generator), len(snr_range)
     info = torch.as_tensor(np.asarray(polar.info_positions), device=device)
-    counts = torch.zeros(nb, ns, 2, 2, dtype=torch.int64, device=device)
+    counts = torch.zeros(nb, ns, 3, 2, dtype=torch.int64, device=device)
     bitwise = torch.zeros((1, polar.K), device=device)
     sizes, frame0 = [], 0
     seed = rng.get_seed() if seed is None else seed
@@ -123,16 +127,18 @@ def testXformer(net, polar, snr_range, Test_Data_Generator, device, Test_Data_Ma
                 y = polar.channel(x, snr, point=(1 << 31) | si, cw_offset=frame0, seed=seed)
                 _, dec_sc = polar.sc_decode_new(y, snr, return_llr=False)
                 _count_into(counts[k, si, 1], msg, dec_sc)
+                if run_SCL and not run_ML:  # run_models.py:328-333: list size 4 whenever the ML decoder is off
+                    _, dec_scl = polar.scl_decode(y, snr, list_size, False, return_llr=False)
+                    _count_into(counts[k, si, 2], msg, dec_scl)
                 bits, _ = net.decode(y, polar.info_positions, None, device)
                 dec = bits.reshape(bits.shape[0], -1).index_select(1, info)
                 _count_into(counts[k, si, 0], msg, dec)
                 if si == bitwise_snr_idx % ns and bitwise_snr_idx != -1:
                     bitwise += utils.errors_bitwise_ber(msg, dec.sign()).reshape(1, -1) / nb
             frame0 += msg.shape[0]
-    (ber_x, bler_x), (ber_s, bler_s) = _rates(counts, sizes, polar.K, ns, 2)
+    (ber_x, bler_x), (ber_s, bler_s), (ber_l, bler_l) = _rates(counts, sizes, polar.K, ns, 3)
     zeros = [0. for _ in snr_range]
-    return (ber_x, bler_x, ber_s, bler_s, list(zeros), list(zeros), list(zeros), list(zeros), bitwise, list(zeros),
-            list(zeros))
+    return (ber_x, bler_x, ber_s, bler_s, ber_l, bler_l, list(zeros), list(zeros), bitwise, list(zeros), list(zeros))
 
 
 # ---------------------------------------------------------------------------------------------------

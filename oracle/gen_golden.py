@@ -194,6 +194,32 @@ def gru_cases():
     np.savez_compressed(os.path.join(OUT, "gru.npz"), **out)
 
 
+def scl_cases():
+    """SC-list decoder (polar.py:793-876, use_CRC=False) on real-valued noise at several list sizes."""
+    rs = np.random.RandomState(2718)
+    out = {}
+    names = []
+    for N, K, L, B, snr in [(64, 22, 4, 160, 0.0), (64, 22, 8, 60, -1.0), (32, 16, 2, 120, 1.0), (32, 16, 4, 120, 0.0),
+                            (16, 8, 16, 80, 0.0), (8, 4, 32, 40, -2.0), (128, 64, 4, 40, 1.0), (256, 128, 2, 12, 2.0),
+                            (64, 22, 1, 50, 0.0)]:
+        code = ref_shim.get_code("Polar", "polar", N, K)
+        msg = bpsk_msgs(rs, B, K)
+        x = code.encode_plotkin(torch.from_numpy(msg)).numpy()
+        y = noisy(rs, x, snr)
+        llr, dec = code.scl_decode(torch.from_numpy(y), snr, L, use_CRC=False)
+        nm = "scl_%d_%d_L%d" % (N, K, L)
+        out[nm + "_y"] = y
+        out[nm + "_snr"] = np.float64(snr)
+        out[nm + "_info"] = np.asarray(code.info_positions, dtype=np.int32)
+        out[nm + "_msg"] = msg
+        out[nm + "_llr"] = llr.numpy()
+        out[nm + "_dec"] = dec.numpy()
+        names.append(nm)
+        print(nm, "BLER", float((dec.numpy() != msg).any(1).mean()), flush=True)
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, "scl.npz"), **out)
+
+
 def gru_mode_cases():
     """Genie-aided decode (gt / loss_inds, rnn_all.py:519-522, 887) and the teacher- / student-forced passes that
     test_model(tf=True) runs under no_grad (rnn_all.py:982-984 -> 425-461, 462-512), from the live reference."""
@@ -283,9 +309,11 @@ if __name__ == "__main__":
     a = p.parse_args()
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    todo = a.only.split(",") if a.only else ["misc", "pac", "gru", "gru_modes", "conv", "polar"]
+    todo = a.only.split(",") if a.only else ["misc", "pac", "gru", "gru_modes", "scl", "conv", "polar"]
     if "gru_modes" in todo:
         gru_mode_cases()
+    if "scl" in todo:
+        scl_cases()
     if "misc" in todo:
         misc_cases()
     if "pac" in todo:

@@ -179,6 +179,130 @@ NPDO_API int npdo_sc_decode(const float *y, int64_t B, int n, int K, const int32
     return fail ? -1 : 0;
 }
 
+/* polar.py:793-876 scl_decode(y, snr, L, use_CRC=False) with pruneLists (777-791), literal structure: every path
+ * owns its llr[n+1][N] / ps[n+1][N] arrays and its u_hat row; an information bit doubles the list (first copies take
+ * sign(L), second copies -sign(L) and pay |L|), a list longer than L is pruned to the L smallest metrics kept in
+ * ascending list-index order (torch.topk on -metric, then sort of the indices); a frozen bit pays |L| when
+ * sign(L) != +1 and stores L + infty; the final pick re-encodes every surviving path and takes the codeword closest
+ * to y in squared Euclidean distance (first minimum).  Priors are NOT part of the LLR recursion here (polar.py:801-803).
+ *   out: leaf_llr[B,N] = llr_array of the chosen path (row 0), decoded[B,K] = its u_hat[info].
+ * Ties: torch.topk's order among equal metrics and the float32 reduction order of the distance sum are
+ * implementation details of torch; this restatement breaks metric ties towards the lower list index and sums the
+ * distance in double precision.  Neither matters on real-valued noise (pinned on the fixtures). */
+typedef struct {
+    sc_work_t w;
+    float *u_hat;
+    float metric;
+} scl_path_t;
+
+static void scl_copy(scl_path_t *dst, const scl_path_t *src, int n)
+{
+    const int N = 1 << n;
+    memcpy(dst->w.llr, src->w.llr, sizeof(float) * (size_t)(n + 1) * N);
+    memcpy(dst->w.ps, src->w.ps, sizeof(float) * (size_t)(n + 1) * N);
+    memcpy(dst->u_hat, src->u_hat, sizeof(float) * N);
+    dst->metric = src->metric;
+}
+
+NPDO_API int npdo_scl_decode(const float *y, int64_t B, int n, int K, const int32_t *info,
+                             const uint8_t *frozen, float scale, float infty, int L,
+                             float *leaf_llr, float *decoded)
+{
+    const int N = 1 << n;
+    if (L < 1 || L > 64) return -1;
+    int fail = 0;
+#pragma omp parallel
+    {
+        /* two generations of up to 2L paths (before pruning) */
+        scl_path_t *cur = (scl_path_t *)calloc(2 * L, sizeof(scl_path_t));
+        scl_path_t *nxt = (scl_path_t *)calloc(2 * L, sizeof(scl_path_t));
+        float *x = (float *)calloc(N, sizeof(float));
+        int *order = (int *)calloc(2 * L, sizeof(int));
+        int bad = !cur || !nxt || !x || !order;
+        for (int i = 0; !bad && i < 2 * L; ++i) {
+            bad |= work_alloc(&cur[i].w, n) || work_alloc(&nxt[i].w, n);
+            cur[i].u_hat = (float *)calloc(N, sizeof(float));
+            nxt[i].u_hat = (float *)calloc(N, sizeof(float));
+            bad |= !cur[i].u_hat || !nxt[i].u_hat;
+        }
+        if (bad) {
+#pragma omp atomic write
+            fail = 1;
+        } else {
+#pragma omp for schedule(dynamic, 1)
+            for (int64_t b = 0; b < B; ++b) {
+                int np = 1;
+                memset(cur[0].w.llr, 0, sizeof(float) * (size_t)(n + 1) * N);
+                memset(cur[0].w.ps, 0, sizeof(float) * (size_t)(n + 1) * N);
+                memset(cur[0].u_hat, 0, sizeof(float) * N);
+                cur[0].metric = 0.0f;
+                for (int i = 0; i < N; ++i) cur[0].w.llr[(size_t)n * N + i] = scale * y[b * N + i];
+                for (int ii = 0; ii < N; ++ii) {
+                    for (int p = 0; p < np; ++p) update_llr(&cur[p].w, ii, NULL);
+                    if (frozen[ii]) {
+                        for (int p = 0; p < np; ++p) {
+                            const float Lv = cur[p].w.llr[ii];
+                            const float pen = fabsf(Lv) * ((sgnf(Lv) != 1.0f) ? 1.0f : 0.0f);
+                            cur[p].w.llr[ii] = Lv + infty * 1.0f;
+                            cur[p].u_hat[ii] = 1.0f;
+                            update_partial_sums(&cur[p].w, ii, cur[p].u_hat);
+                            cur[p].metric = cur[p].metric + pen;
+                        }
+                    } else {
+                        /* duplicate: slot p keeps sign(L), slot np + p takes -sign(L) and pays |L| */
+                        for (int p = 0; p < np; ++p) {
+                            const float Lv = cur[p].w.llr[ii];
+                            scl_copy(&cur[np + p], &cur[p], n);
+                            cur[p].u_hat[ii] = sgnf(Lv);
+                            cur[np + p].u_hat[ii] = -1.0f * sgnf(Lv);
+                            cur[np + p].metric = cur[p].metric + fabsf(Lv);
+                            update_partial_sums(&cur[p].w, ii, cur[p].u_hat);
+                            update_partial_sums(&cur[np + p].w, ii, cur[np + p].u_hat);
+                        }
+                        np *= 2;
+                        if (np > L) {
+                            /* pruneLists: the L smallest metrics, kept in ascending index order */
+                            int kept = 0;
+                            for (int i = 0; i < np; ++i) {
+                                int rank = 0;
+                                for (int j = 0; j < np; ++j)
+                                    rank += (cur[j].metric < cur[i].metric) || (cur[j].metric == cur[i].metric && j < i);
+                                if (rank < L) order[kept++] = i;
+                            }
+                            for (int j = 0; j < L; ++j) scl_copy(&nxt[j], &cur[order[j]], n);
+                            scl_path_t *t = cur; cur = nxt; nxt = t;
+                            np = L;
+                        }
+                    }
+                }
+                /* ML pick among the list (polar.py:869-874) */
+                int best = 0;
+                double best_d = 0.0;
+                for (int p = 0; p < np; ++p) {
+                    for (int i = 0; i < N; ++i) x[i] = 1.0f;
+                    for (int k = 0; k < K; ++k) x[info[k]] = cur[p].u_hat[info[k]];
+                    for (int d = 0; d < n; ++d) plotkin_stage(x, N, 1 << d);
+                    double dist = 0.0;
+                    for (int i = 0; i < N; ++i) {
+                        const float df = x[i] - y[b * N + i];
+                        dist += (double)(df * df);
+                    }
+                    if (p == 0 || dist < best_d) { best = p; best_d = dist; }
+                }
+                if (leaf_llr) memcpy(leaf_llr + b * N, cur[best].w.llr, sizeof(float) * N);
+                if (decoded)
+                    for (int k = 0; k < K; ++k) decoded[b * K + k] = cur[best].u_hat[info[k]];
+            }
+        }
+        for (int i = 0; cur && nxt && i < 2 * L; ++i) {
+            work_free(&cur[i].w); work_free(&nxt[i].w);
+            free(cur[i].u_hat); free(nxt[i].u_hat);
+        }
+        free(cur); free(nxt); free(x); free(order);
+    }
+    return fail ? -1 : 0;
+}
+
 /* pac_code.py:193-200 conv1bTrans_batch for one row.  g[M] holds +-1 (1 - 2*bit, MSB first,
  * pac_code.py:102-103); state[M-1] holds the previous inputs, newest first.
  * Returns u; writes next state into nxt (may alias neither). */

@@ -90,6 +90,23 @@ def sc_decode(y, snr_db, n, info, infty=1000.0, use_gt=None, scale=None):
     return leaf, uh, dec
 
 
+def scl_decode(y, snr_db, n, info, L, infty=1000.0, scale=None):
+    """-> (leaf_llr[B,N] of the chosen path, decoded[B,K]) following polar.py:793-876 (use_CRC=False)."""
+    y = _f32(y)
+    B, N = y.shape
+    assert N == 1 << n
+    info = np.ascontiguousarray(info, dtype=np.int32)
+    K = info.shape[0]
+    fr = frozen_mask(N, info)
+    leaf = np.empty((B, N), dtype=np.float32)
+    dec = np.empty((B, K), dtype=np.float32)
+    s = llr_scale(snr_db) if scale is None else np.float32(scale)
+    rc = lib().npdo_scl_decode(_ptr(y), ctypes.c_int64(B), n, K, _ptr(info, _i32p), _ptr(fr, _u8p),
+                               ctypes.c_float(s), ctypes.c_float(infty), int(L), _ptr(leaf), _ptr(dec))
+    assert rc == 0
+    return leaf, dec
+
+
 def pac_g_array(g: int):
     """pac_code.py:101-103: M = floor(log2 g)+1 bits, MSB first, mapped to 1-2*bit."""
     M = int(np.floor(np.log2(g))) + 1

@@ -123,3 +123,18 @@ def test_gru_oracle_modes_against_reference_fixture(golden):
         safe_rows = (np.abs(lg[:, loss]) > 1e-4).all(axis=1)
         assert safe_rows.mean() > 0.9
         assert np.array_equal(dec[safe_rows], g[key][safe_rows]), key
+
+
+def test_scl_oracle_against_reference_fixtures(golden):
+    """SC-list restatement vs the live reference's scl_decode (polar.py:793-876): chosen path's decisions and
+    leaf LLRs, bit for bit, at list sizes 1..32."""
+    g = golden("scl")
+    for nm in [str(s) for s in g["names"]]:
+        N, K, L = [int(v[1:]) if v.startswith("L") else int(v) for v in nm.split("_")[1:]]
+        n = int(np.log2(N))
+        llr, dec = oracle.scl_decode(g[nm + "_y"], float(g[nm + "_snr"]), n, g[nm + "_info"], L)
+        assert np.array_equal(dec, g[nm + "_dec"]), nm
+        assert np.array_equal(llr, g[nm + "_llr"]), nm
+        if L == 1:  # a list of one is the SC decoder (without the frozen prior in the recursion)
+            _, _, sc = oracle.sc_decode(g[nm + "_y"], float(g[nm + "_snr"]), n, g[nm + "_info"])
+            assert np.array_equal(dec, sc)
