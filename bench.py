@@ -32,6 +32,8 @@ WORKLOADS = {
                    desc="SC Polar(4096,2048), polarization-weight frozen set, AWGN 2 dB"),
     "sc64": dict(kind="sc", N=64, K=22, snr=0.0, batch=2097152,
                  desc="SC Polar(64,22), reference 'polar' profile, AWGN 0 dB"),
+    "scl64": dict(kind="sc", N=64, K=22, snr=0.0, batch=262144, L=4,
+                  desc="SC-list (L=4) Polar(64,22), reference 'polar' profile, AWGN 0 dB"),
     "gru64": dict(kind="gru", N=64, K=22, snr=0.0, batch=37888,
                   desc="CRISP GRU(2x512, y_input, onehot) Polar(64,22), AWGN 0 dB, synthetic weights"),
     "gru32": dict(kind="gru", N=32, K=16, snr=0.0, batch=37888,
@@ -150,7 +152,10 @@ def cpu_rate_sc(w, seconds, threads, rng_seed=0):
 
     def run(y):
         t0 = time.perf_counter()
-        oracle.run_threaded(lambda lo, hi: oracle.sc_decode(y[lo:hi], w["snr"], n, info), y.shape[0], threads)
+        if w.get("L"):
+            oracle.run_threaded(lambda lo, hi: oracle.scl_decode(y[lo:hi], w["snr"], n, info, w["L"]), y.shape[0], threads)
+        else:
+            oracle.run_threaded(lambda lo, hi: oracle.sc_decode(y[lo:hi], w["snr"], n, info), y.shape[0], threads)
         return time.perf_counter() - t0
 
     probe = max(threads, 8)
@@ -307,9 +312,16 @@ def bench_sc(args, w, rank, world, local_rank):
     _lib.check(lib.npd_gen_encode_awgn(h.h, _lib.ptr(msg), None, _lib.ptr(y), B, sigma, seed, 0, rank * B,
                                        _lib.stream_ptr()))
     st = _lib.stream_ptr()
+    L = int(w.get("L", 0))
+
+    def decode_call():
+        if L:
+            _lib.check(lib.npd_scl_decode(h.h, _lib.ptr(y), scale, L, None, _lib.ptr(dec), B, st))
+        else:
+            _lib.check(lib.npd_sc_decode(h.h, _lib.ptr(y), scale, None, None, _lib.ptr(dec), B, st))
 
     def step():
-        _lib.check(lib.npd_sc_decode(h.h, _lib.ptr(y), scale, None, None, _lib.ptr(dec), B, st))
+        decode_call()
         _lib.check(lib.npd_count_errors(_lib.ptr(msg), _lib.ptr(dec), B, K, _lib._vp(counts.data_ptr()), st))
 
     def sync():
@@ -331,7 +343,7 @@ def bench_sc(args, w, rank, world, local_rank):
     t_start.record()
     for i in range(args.steps):
         ev[i][0].record()
-        _lib.check(lib.npd_sc_decode(h.h, _lib.ptr(y), scale, None, None, _lib.ptr(dec), B, st))
+        decode_call()
         ev[i][1].record()
         _lib.check(lib.npd_count_errors(_lib.ptr(msg), _lib.ptr(dec), B, K, _lib._vp(counts.data_ptr()), st))
         ev[i][2].record()
@@ -354,14 +366,19 @@ def bench_sc(args, w, rank, world, local_rank):
     y_host = y[:e2e_B].cpu().pin_memory()
     msg_host = msg[:e2e_B:61].cpu()
     e2e_steps = max(3, min(args.steps, 10))
+    def host_call():
+        if L:
+            return code.scl_decode(y_host, snr, L, False, return_llr=False)
+        return code.sc_decode_new(y_host, snr, return_llr=False)
+
     d_host = None
     for _ in range(3):  # warm-up holds the previous result like the timed loop does (pinned-pool steady state)
-        _, d_host = code.sc_decode_new(y_host, snr, return_llr=False)
+        _, d_host = host_call()
     sync()
     t0 = time.perf_counter()
     errs = 0
     for _ in range(e2e_steps):
-        _, d_host = code.sc_decode_new(y_host, snr, return_llr=False)  # returns host tensors
+        _, d_host = host_call()  # returns host tensors
         errs += int((d_host[::61] != msg_host).sum())                  # the step's result is read on the host (every 61st frame checked here)
     torch.cuda.synchronize()
     e2e_dt = time.perf_counter() - t0
@@ -389,7 +406,7 @@ def bench_sc(args, w, rank, world, local_rank):
                 "api": "PolarCode.sc_decode_new(pinned host y, snr) -> host decisions (npd_sc_decode_host: chunked H2D / "
                        "decode / D2H pipeline on three streams)", "sampled_bit_errors": errs},
         "gpu_launches": 2 * args.steps,
-        "roofline": {"kernel": "sc_quad_kernel" if N >= 256 else "sc_lane_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm"],
+        "roofline": {"kernel": "scl_kernel" if L else ("sc_quad_kernel" if N >= 256 else "sc_lane_kernel"), "bound": "hbm", "achieved": achieved, "peak": peaks["hbm"],
                      "unit": "GB/s", "frac": achieved / peaks["hbm"], "traffic": traffic,
                      "traffic_source": traffic_src, "peak_source": peaks["src"], "kernel_ms": kern_ms, "count_kernel_ms": count_ms,
                      "alg_bytes_per_launch": alg_bytes,

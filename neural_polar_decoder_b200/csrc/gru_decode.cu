@@ -199,6 +199,15 @@ __device__ __forceinline__ float tanh_f(float x)
     asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+__device__ __forceinline__ uint32_t pack_h2(float a, float b)
+{
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t w)
+{
+    return __half22float2(*reinterpret_cast<const __half2 *>(&w));
+}
 __device__ __forceinline__ float sigmoid_half_arg(float half_x) { return fmaf(tanh_f(half_x), 0.5f, 0.5f); }
 
 // byte offset of element (row c, k) inside a K-major SWIZZLE_128B operand buffer of 64-row chunks
@@ -343,8 +352,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
 
     // ---- input projection, hoisted out of the step loop: Gy = W_iy y is the same in all N steps.
     // Every epilogue thread computes, in fp32, exactly the (unit, 16 codewords) entries it will add to its layer-0
-    // accumulators later and keeps them in thread-local memory (L1/L2-backed; 3 gates x JOBS x 16 floats).
-    float4 gy[JOBS * 3 * (CW_PER_THREAD / 4)];
+    // accumulators later and keeps them, rounded to fp16, in thread-local memory (3 gates x JOBS x 16 halves = 384 B
+    // per thread, 29 MB for a full wave: L2-resident; as fp32 the wave's 58 MB fell out of L2 -- ncu showed 7 GB of
+    // DRAM traffic per launch).
+    uint4 gy[JOBS * 3 * (CW_PER_THREAD / 8)];
     if (warp < EPI_WARPS) {
         const int q = warp & 3, col0 = (warp >> 2) * CW_PER_THREAD;
         for (int jg = 0; jg < JOBS * 3; ++jg) {
@@ -366,8 +377,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
                 }
             }
 #pragma unroll
-            for (int i4 = 0; i4 < CW_PER_THREAD / 4; ++i4)
-                gy[jg * (CW_PER_THREAD / 4) + i4] = make_float4(acc[4 * i4], acc[4 * i4 + 1], acc[4 * i4 + 2], acc[4 * i4 + 3]);
+            for (int i8 = 0; i8 < CW_PER_THREAD / 8; ++i8)
+                gy[jg * (CW_PER_THREAD / 8) + i8] =
+                    make_uint4(pack_h2(acc[8 * i8 + 0], acc[8 * i8 + 1]), pack_h2(acc[8 * i8 + 2], acc[8 * i8 + 3]),
+                               pack_h2(acc[8 * i8 + 4], acc[8 * i8 + 5]), pack_h2(acc[8 * i8 + 6], acc[8 * i8 + 7]));
         }
     }
     // the ring memory (y tile) is free for the weight stream from here on, in both CTAs of the pair (the peer
@@ -512,14 +525,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
                         }
                         if (layer == 0) {
                             // add the hoisted input projection of this (unit, codewords)
+                            const uint4 gr = gy[(j * 3 + 0) * (CW / 8) + cc / 8];
+                            const uint4 gz = gy[(j * 3 + 1) * (CW / 8) + cc / 8];
+                            const uint4 gn = gy[(j * 3 + 2) * (CW / 8) + cc / 8];
+                            const uint32_t wr[4] = {gr.x, gr.y, gr.z, gr.w}, wz[4] = {gz.x, gz.y, gz.z, gz.w},
+                                           wn[4] = {gn.x, gn.y, gn.z, gn.w};
 #pragma unroll
-                            for (int h4 = 0; h4 < 2; ++h4) {
-                                const float4 gr = gy[(j * 3 + 0) * (CW / 4) + cc / 4 + h4];
-                                const float4 gz = gy[(j * 3 + 1) * (CW / 4) + cc / 4 + h4];
-                                const float4 gn = gy[(j * 3 + 2) * (CW / 4) + cc / 4 + h4];
-                                aR[4 * h4 + 0] += gr.x; aR[4 * h4 + 1] += gr.y; aR[4 * h4 + 2] += gr.z; aR[4 * h4 + 3] += gr.w;
-                                aZ[4 * h4 + 0] += gz.x; aZ[4 * h4 + 1] += gz.y; aZ[4 * h4 + 2] += gz.z; aZ[4 * h4 + 3] += gz.w;
-                                aNI[4 * h4 + 0] = gn.x; aNI[4 * h4 + 1] = gn.y; aNI[4 * h4 + 2] = gn.z; aNI[4 * h4 + 3] = gn.w;
+                            for (int h2 = 0; h2 < 4; ++h2) {
+                                const float2 fr = unpack_h2(wr[h2]), fz = unpack_h2(wz[h2]), fn = unpack_h2(wn[h2]);
+                                aR[2 * h2] += fr.x; aR[2 * h2 + 1] += fr.y;
+                                aZ[2 * h2] += fz.x; aZ[2 * h2 + 1] += fz.y;
+                                aNI[2 * h2] = fn.x; aNI[2 * h2 + 1] = fn.y;
                             }
                         }
 #pragma unroll
