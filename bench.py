@@ -238,6 +238,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; keep stdout to the one JSON line
+        # (the banner is printed at every level from VERSION up): send NCCL's own log to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
