@@ -48,6 +48,8 @@ constexpr int CW_PER_THREAD = TILE_B / (EPI_WARPS / 4);  // 16 codewords (accumu
 struct GruParams {
     const unsigned char *wpack;  // tiles_per_step * 16 KB, in consumption order
     const float *w_iyT;          // [N][3H] fp32: the y columns of weight_ih_l0, transposed (hoisted input projection)
+    const unsigned char *wpack2; // CTA-pair kernel: [2 ranks][tiles_per_step2] 16 KB half-tiles, or null
+    int tiles_per_step2;
     const float *consts0;        // [H][12]: b_r b_z b_in b_hn cr0 cr1 cz0 cz1 cn0 cn1 - -
     const float *consts1;        // [H][4] : b_r b_z b_in b_hn
     const float *w_out;          // [H]
@@ -64,7 +66,18 @@ struct GruParams {
     long long *trace;  // bench-only (NPD_GRU_TRACE): [N][TRACE_SLOTS] clock64 stamps of CTA 0, or null
 };
 
-constexpr int TRACE_SLOTS = 100;  // per step: MMA warp 0..15 (job begin / issued), 16-17 (h_ready waits); epilogue 20..35, 36 step end
+constexpr int TRACE_SLOTS = 360;  // per step: MMA warp 0..15 (job begin / issued), 16-17 (h_ready waits); epilogue 20..35, 36 step end
+__device__ __forceinline__ long long gtime_ns()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// bench-only: wall-clock (ns) stamp of cluster 0's two CTAs, for the ring round-trip breakdown of the pair kernel
+__device__ __forceinline__ void trace_ns(const GruParams &p, int step, int slot)
+{
+    if (p.trace && (blockIdx.x >> 1) == 0 && slot < TRACE_SLOTS) p.trace[step * TRACE_SLOTS + slot] = gtime_ns();
+}
 __device__ __forceinline__ void trace_ev(const GruParams &p, int step, int slot)
 {
     if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) p.trace[step * TRACE_SLOTS + slot] = clock64();
@@ -270,6 +283,9 @@ struct MmaCtx {
     uint32_t ok;                   // the current tile's weights are known to have landed
     uint32_t pb;                   // barrier parity of the next block's first pass over the ring
     bool no_mma;
+    int trace_tile, trace_step;    // bench-only: per-tile clock stamps (slots 40..) of one job per step
+    int tile_in_step;
+    const GruParams *prm;
 };
 
 template <int KH>
@@ -416,7 +432,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
             MmaCtx c;
             c.bar_full = bar_full; c.bar_empty = bar_empty; c.ring_lo = umma_desc_lo(smem_u32(s_ring));
             c.idesc = (1u << 4) | ((uint32_t)(TILE_B >> 3) << 17) | ((128u >> 4) << 24);
-            c.ok = 0; c.pb = 0; c.no_mma = (p.dbg & 2) != 0;
+            c.ok = 0; c.pb = 0; c.no_mma = (p.dbg & 2) != 0; c.trace_tile = -1; c.trace_step = 0; c.prm = &p; c.tile_in_step = 1 << 30;
             const uint32_t b_h0 = umma_desc_lo(smem_u32(s_h0)), b_h1 = umma_desc_lo(smem_u32(s_h1));
             uint32_t job = 0;  // global job counter -> TMEM slot job & 1
             uint32_t hphase0 = 0, hphase1 = 0;
@@ -621,9 +637,533 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
     if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
 }
 
+// =====================================================================================================================
+// CTA-pair kernel (cta_group::2): M = 256 hidden units x N = 128 codewords per tcgen05.mma
+// =====================================================================================================================
+// tools/probe/umma_issue.cu / umma2_probe.cu measured what bounds the single-CTA kernel above: an M=128 N=64 MMA costs
+// 48 cycles (its 6 KB of operand reads at the 128 B/clk shared-memory port) against 32 at the tensor rate, while one
+// M=256 N=128 cta_group::2 MMA takes 64 cycles for four times the work -- each SM reads its 128-unit half of the
+// weight tile once for 128 codewords.  Here a cluster of two CTAs decodes 128 codewords:
+//   * CTA r keeps the hidden states of its own 64 codewords (the B operand rows 64r .. 64r+63) and streams only the
+//     unit rows 256J + 128r .. + 127 of every weight tile (its half of the A operand): half the L2 traffic per SM;
+//   * the leader CTA's elected thread issues every MMA and commits (multicast) to both CTAs' barriers; the peer's MMA
+//     warp relays "my half of the tile has landed" to the leader's full barriers;
+//   * CTA r's TMEM receives D rows = its 128 units x ALL 128 codewords; a job's four accumulators (R, Z, NI, NH) x
+//     128 columns fill TMEM, so the hand-off between MMA and epilogue is per accumulator (4 full / 4 empty barriers):
+//     R and Z are drained as soon as they complete, while the MMAs of the later accumulators still run;
+//   * an epilogue thread owns one unit and 32 codewords; half of the warps update codewords whose state lives in the
+//     peer CTA: they read the old and write the new state through distributed shared memory, and every CTA sends its
+//     partial head sums (over its 256 units) to the peer so that both compute identical decisions for all 128
+//     codewords (the one-hot feedback is needed by both CTAs' layer-0 epilogues).
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// a pure signal (no data published through it): a release at cluster scope costs the arriving thread ~0.8 us
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP_C:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_C;\n\t"
+        "bra WAIT_LOOP_C;\n\t"
+        "DONE_C:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void st_cluster_u16(uint32_t addr, unsigned short v)
+{
+    asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+__device__ __forceinline__ unsigned short ld_cluster_u16(uint32_t addr)
+{
+    unsigned short v;
+    asm volatile("ld.shared::cluster.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v)
+{
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void umma_commit2(uint32_t bar)  // arrives on the same barrier of BOTH CTAs
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+// one weight tile (4 K-steps of M=256 N=128) + probe of the next ring stage; see tile_issue
+__device__ __forceinline__ uint32_t tile_issue2(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc0,
+                                                uint32_t bar_empty_cur, uint32_t bar_full_next, uint32_t parity_next,
+                                                uint32_t skip_mma)
+{
+    uint32_t ok;
+    const uint64_t a0 = umma_desc_from_lo(a_lo), b0 = umma_desc_from_lo(b_lo);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q, pacc, pone, pm;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 q, [%7], %8;\n\t"
+        "setp.ne.b32 pacc, %4, 0;\n\t"
+        "setp.eq.b32 pone, 0, 0;\n\t"
+        "setp.eq.b32 pm, %16, 0;\n\t"
+        "@pm tcgen05.mma.cta_group::2.kind::f16 [%1], %2, %3, %5, pacc;\n\t"
+        "@pm tcgen05.mma.cta_group::2.kind::f16 [%1], %9, %10, %5, pone;\n\t"
+        "@pm tcgen05.mma.cta_group::2.kind::f16 [%1], %11, %12, %5, pone;\n\t"
+        "@pm tcgen05.mma.cta_group::2.kind::f16 [%1], %13, %14, %5, pone;\n\t"
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%6], %15;\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(d_tmem), "l"(a0), "l"(b0), "r"(acc0), "r"(idesc), "r"(bar_empty_cur), "r"(bar_full_next), "r"(parity_next),
+          "l"(a0 + 2), "l"(b0 + 2), "l"(a0 + 4), "l"(b0 + 4), "l"(a0 + 6), "l"(b0 + 6), "h"((uint16_t)3), "r"(skip_mma)
+        : "memory");
+    return ok;
+}
+
+// run RUN (0..2) of a 3-run block: KH tiles accumulating into TMEM columns d from B chunks b .. b + KH - 1
+template <int KH, int RUN>
+__device__ __forceinline__ void mma_run2(MmaCtx &c, uint32_t d, uint32_t b, bool first)
+{
+    constexpr uint32_t A_TILE_LO = A_TILE_BYTES >> 4, B_CHUNK_LO = B_CHUNK_BYTES >> 4;
+#pragma unroll
+    for (int kc = 0; kc < KH; ++kc) {
+        const int t = RUN * KH + kc;
+        const int stage = t % NUM_STAGES, pass = t / NUM_STAGES;
+        const int nstage = (t + 1) % NUM_STAGES, npass = (t + 1) / NUM_STAGES;
+        // (cluster-scope acquires cost ~1000 cycles each; the issuing thread reads none of the data itself -- each SM's
+        // tensor core reads its own shared memory, which the bulk copy completed before signalling)
+        if (!c.ok && !c.no_mma) mbar_wait(c.bar_full + 8 * stage, (pass & 1) ^ c.pb);
+        if (c.tile_in_step < 48) trace_ns(*c.prm, c.trace_step, 100 + c.tile_in_step);        // leader: data of both halves seen
+        c.ok = tile_issue2(d, c.ring_lo + stage * A_TILE_LO, b + kc * B_CHUNK_LO, c.idesc, (first && kc == 0) ? 0u : 1u,
+                           c.bar_empty + 8 * stage, c.bar_full + 8 * nstage, (npass & 1) ^ c.pb, (uint32_t)(c.prm->dbg & 32));
+        if (c.trace_tile >= 0 && c.trace_tile < 48 && c.prm->trace) c.prm->trace[c.trace_step * TRACE_SLOTS + 40 + c.trace_tile++] = clock64();
+        if (c.tile_in_step < 48) trace_ns(*c.prm, c.trace_step, 150 + c.tile_in_step);        // leader: MMAs + commit issued
+        ++c.tile_in_step;
+    }
+    if (RUN == 2 && ((3 * KH / NUM_STAGES) & 1)) c.pb ^= 1;
+}
+
+constexpr int PAIR_CW = 2 * TILE_B;   // codewords per cluster
+constexpr int CW3 = PAIR_CW / 4;      // 32 accumulator columns (codewords) per epilogue thread
+
+struct Smem3 {
+    static __host__ __device__ size_t ring() { return 0; }
+    static __host__ __device__ size_t h0(int) { return (size_t)NUM_STAGES * A_TILE_BYTES; }
+    static __host__ __device__ size_t h1(int H) { return h0(H) + (size_t)(H / 64) * B_CHUNK_BYTES; }
+    static __host__ __device__ size_t headacc(int H) { return h1(H) + (size_t)(H / 64) * B_CHUNK_BYTES; }  // [4][128] floats
+    static __host__ __device__ size_t part(int H) { return headacc(H) + 4 * PAIR_CW * 4; }                  // [128] floats: the peer's partial logits
+    static __host__ __device__ size_t bars(int H) { return part(H) + PAIR_CW * 4; }
+    static __host__ __device__ size_t total(int H) { return bars(H) + 256; }
+};
+
+template <int KH>
+__global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruParams p)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr int H = KH * 64, JOBS2 = H / 256;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = p.N;
+    const uint32_t rank = cluster_ctarank();
+    const int64_t pair0 = (int64_t)(blockIdx.x >> 1) * PAIR_CW;  // first codeword of the pair
+    const int64_t cw0 = pair0 + rank * TILE_B;                   // first codeword whose state lives in this CTA
+
+    unsigned char *s_ring = smem + Smem3::ring();
+    unsigned char *s_h0 = smem + Smem3::h0(H);
+    unsigned char *s_h1 = smem + Smem3::h1(H);
+    float *s_headacc = reinterpret_cast<float *>(smem + Smem3::headacc(H));
+    float *s_part = reinterpret_cast<float *>(smem + Smem3::part(H));
+    uint64_t *s_bars = reinterpret_cast<uint64_t *>(smem + Smem3::bars(H));
+    // barriers: full[S], empty[S], acc_full[4], acc_empty[4] (leader's are used), h_ready[2] (leader's), head[1]
+    const uint32_t bar_full = smem_u32(s_bars), bar_empty = bar_full + 8 * NUM_STAGES,
+                   bar_afull = bar_empty + 8 * NUM_STAGES, bar_aempty = bar_afull + 32, bar_hready = bar_aempty + 32,
+                   bar_head = bar_hready + 16;
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bars + 2 * NUM_STAGES + 11);
+    uint32_t *s_bits = s_tmem + 1;  // [4]: feedback bits of the pair's 128 codewords (1 = previous decision was +1)
+
+    if (tid == 0) {
+        for (int i = 0; i < NUM_STAGES; ++i) {
+            mbar_init(bar_full + 8 * i, rank == 0 ? 2 : 1);  // leader: own copy + the peer's relay
+            mbar_init(bar_empty + 8 * i, 1);
+        }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(bar_afull + 8 * i, 1);
+            mbar_init(bar_aempty + 8 * i, 2 * EPI_WARPS);  // one arrive per epilogue warp of both CTAs
+        }
+        for (int i = 0; i < 2; ++i) mbar_init(bar_hready + 8 * i, 2 * EPI_WARPS);
+        mbar_init(bar_head, 4);  // the peer's four warps that send partial logits
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int i = 0; i < 4; ++i) s_bits[i] = 0xffffffffu;  // step 0 feeds back +1 (rnn_all.py:542-543)
+    }
+    // h0 = h1 = 0 (rnn_all.py:538); y of all 128 codewords of the pair as fp32 [k][codeword] in the idle ring memory
+    for (int i = tid; i < (2 * KH * B_CHUNK_BYTES) / 16; i += NUM_THREADS)
+        reinterpret_cast<uint4 *>(s_h0)[i] = make_uint4(0, 0, 0, 0);
+    float *s_yT = reinterpret_cast<float *>(s_ring);
+    for (int i = tid; i < PAIR_CW * N; i += NUM_THREADS) {
+        const int c = i / N, k = i % N;
+        s_yT[k * PAIR_CW + c] = (pair0 + c < p.B) ? p.y[(pair0 + c) * N + k] : 0.0f;
+    }
+    fence_async_smem();
+    __syncthreads();
+    cluster_sync_all();  // both CTAs' barriers exist before any cross-CTA signal; TMEM allocation is pair-wide
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    // ---- hoisted input projection for (this thread's unit) x (its 32 codeword columns), fp16 in local memory ----
+    uint4 gy[JOBS2 * 3 * (CW3 / 8)];
+    if (warp < EPI_WARPS) {
+        const int q = warp & 3, col0 = (warp >> 2) * CW3;
+        for (int jg = 0; jg < JOBS2 * 3; ++jg) {
+            const int j = jg / 3, g = jg % 3;
+            const int row = g * H + j * 256 + (int)rank * 128 + q * 32 + lane;
+            float acc[CW3];
+#pragma unroll
+            for (int i = 0; i < CW3; ++i) acc[i] = 0.0f;
+#pragma unroll 4
+            for (int k = 0; k < N; ++k) {
+                const float w = __ldg(p.w_iyT + (size_t)k * (3 * H) + row);
+#pragma unroll
+                for (int i4 = 0; i4 < CW3 / 4; ++i4) {
+                    const float4 yv = *reinterpret_cast<const float4 *>(s_yT + k * PAIR_CW + col0 + 4 * i4);
+                    acc[4 * i4 + 0] = fmaf(w, yv.x, acc[4 * i4 + 0]);
+                    acc[4 * i4 + 1] = fmaf(w, yv.y, acc[4 * i4 + 1]);
+                    acc[4 * i4 + 2] = fmaf(w, yv.z, acc[4 * i4 + 2]);
+                    acc[4 * i4 + 3] = fmaf(w, yv.w, acc[4 * i4 + 3]);
+                }
+            }
+#pragma unroll
+            for (int i8 = 0; i8 < CW3 / 8; ++i8)
+                gy[jg * (CW3 / 8) + i8] =
+                    make_uint4(pack_h2(acc[8 * i8 + 0], acc[8 * i8 + 1]), pack_h2(acc[8 * i8 + 2], acc[8 * i8 + 3]),
+                               pack_h2(acc[8 * i8 + 4], acc[8 * i8 + 5]), pack_h2(acc[8 * i8 + 6], acc[8 * i8 + 7]));
+        }
+    }
+    cluster_sync_all();  // the ring memory (y tile) of both CTAs is free for the weight stream from here on
+
+    const uint32_t lead_aempty = mapa_u32(bar_aempty, 0), lead_hready = mapa_u32(bar_hready, 0);
+
+    if (warp >= EPI_WARPS && warp < MMA_WARP) {
+        // ================= producer: this CTA's half of every weight tile =================
+        if (lane == 0) {
+            const uint32_t T = (uint32_t)p.tiles_per_step2;
+            const uint32_t total = (p.dbg & 1) ? 0u : (uint32_t)N * T;
+            const unsigned char *src = p.wpack2 + (size_t)rank * T * A_TILE_BYTES;
+            uint32_t t = 0, stage = 0, phase = 0;
+            for (uint32_t g = 0; g < total; ++g) {
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                if (t < 48) trace_ns(p, (int)(g / T), (rank ? 250 : 200) + (int)t);  // producer: slot free, copy goes out
+                mbar_expect_tx(bar_full + 8 * stage, A_TILE_BYTES);
+                bulk_g2s(smem_u32(s_ring + stage * A_TILE_BYTES), src + (size_t)t * A_TILE_BYTES, A_TILE_BYTES, bar_full + 8 * stage);
+                if (++t == T) t = 0;
+                if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == MMA_WARP) {
+        if (elect_one()) {
+            if (rank != 0) {
+                // ================= peer: relay "my half has landed" to the leader's full barriers =================
+                const uint32_t total = (p.dbg & 1) ? 0u : (uint32_t)N * (uint32_t)p.tiles_per_step2;
+                const uint32_t lead_full = mapa_u32(bar_full, 0);
+                uint32_t stage = 0, phase = 0;
+                const uint32_t T = (uint32_t)p.tiles_per_step2;
+                for (uint32_t g = 0; g < total; ++g) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    if (g % T < 48) trace_ns(p, (int)(g / T), 300 + (int)(g % T));  // relay: the peer's half has landed
+                    mbar_arrive_cluster_relaxed(lead_full + 8 * stage);
+                    if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+                }
+            } else {
+                // ================= leader: the static MMA schedule for both SMs =================
+                MmaCtx c;
+                c.bar_full = bar_full; c.bar_empty = bar_empty; c.ring_lo = umma_desc_lo(smem_u32(s_ring));
+                c.idesc = (1u << 4) | ((uint32_t)(PAIR_CW >> 3) << 17) | ((256u >> 4) << 24);  // M = 256, N = 128
+                c.ok = 0; c.pb = 0; c.no_mma = (p.dbg & 17) != 0;  /* bench-only: 1 = no weight stream at all, 16 = stream runs but is not waited for */ c.trace_tile = -1; c.trace_step = 0; c.prm = &p; c.tile_in_step = 0;
+                const uint32_t b_h0 = umma_desc_lo(smem_u32(s_h0)), b_h1 = umma_desc_lo(smem_u32(s_h1));
+                const uint32_t dR = tmem_base, dZ = tmem_base + PAIR_CW, dNI = tmem_base + 2 * PAIR_CW, dNH = tmem_base + 3 * PAIR_CW;
+                uint32_t use[4] = {0, 0, 0, 0};  // how often each accumulator region has been filled
+                uint32_t hphase0 = 0, hphase1 = 0;
+                auto acquire = [&](int a) {  // TMEM write-after-read only: no data flows through this wait
+                    mbar_wait(bar_aempty + 8 * a, (use[a] & 1) ^ 1);
+                    tc_fence_after();
+                };
+                auto publish = [&](int a) {
+                    umma_commit2(bar_afull + 8 * a);
+                    ++use[a];
+                };
+                for (int step = 0; step < N; ++step) {
+                    c.tile_in_step = 0; c.trace_step = step;
+                    for (int j = 0; j < JOBS2; ++j) {  // layer 0: R, Z, NH from h0
+                        trace_ev(p, step, 2 * j);
+                        acquire(0); mma_run2<KH, 0>(c, dR, b_h0, true); publish(0);
+                        acquire(1); mma_run2<KH, 1>(c, dZ, b_h0, true); publish(1);
+                        acquire(3); mma_run2<KH, 2>(c, dNH, b_h0, true); publish(3);
+                        trace_ev(p, step, 2 * j + 1);
+                    }
+                    for (int j = 0; j < JOBS2; ++j) {  // layer 1: R, Z, NH from h1 (previous step), then R, Z, NI from h0
+                        trace_ev(p, step, 8 + 2 * j);
+                        c.trace_tile = (j == JOBS2 - 1) ? 0 : -1;
+                        c.trace_step = step;
+                        if (j == 0 && step > 0) {
+                            mbar_wait_cluster(bar_hready + 8, hphase1);
+                            hphase1 ^= 1;
+                            tc_fence_after();
+                        }
+                        acquire(0); mma_run2<KH, 0>(c, dR, b_h1, true);
+                        acquire(1); mma_run2<KH, 1>(c, dZ, b_h1, true);
+                        acquire(3); mma_run2<KH, 2>(c, dNH, b_h1, true); publish(3);
+                        if (j == 0) {
+                            trace_ev(p, step, 18);
+                            mbar_wait_cluster(bar_hready + 0, hphase0);
+                            hphase0 ^= 1;
+                            tc_fence_after();
+                            trace_ev(p, step, 16);
+                        }
+                        mma_run2<KH, 0>(c, dR, b_h0, false); publish(0);
+                        mma_run2<KH, 1>(c, dZ, b_h0, false); publish(1);
+                        acquire(2); mma_run2<KH, 2>(c, dNI, b_h0, true); publish(2);
+                        trace_ev(p, step, 8 + 2 * j + 1);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= epilogue warps =================
+        const int q = warp & 3, cq = warp >> 2;
+        const int col0 = cq * CW3;                       // first of this thread's 32 codeword columns (pair index)
+        const uint32_t owner = (uint32_t)(cq >> 1);      // CTA that holds these codewords' hidden states
+        const int row0 = col0 & (TILE_B - 1);            // their rows in the owner's B-operand buffers
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        // bench-only experiment (results are garbage): dbg & 8 = every state access goes to this CTA's own memory
+        const uint32_t h0_owner = mapa_u32(smem_u32(s_h0), (p.dbg & 8) ? rank : owner),
+                       h1_owner = mapa_u32(smem_u32(s_h1), (p.dbg & 8) ? rank : owner);
+        const uint32_t peer = rank ^ 1u;
+        const uint32_t part_peer = mapa_u32(smem_u32(s_part), peer), head_peer = mapa_u32(bar_head, peer);
+        const uint32_t bits_peer = mapa_u32(smem_u32(s_bits), peer);
+        uint32_t use[4] = {0, 0, 0, 0};
+        uint32_t staged[(JOBS2 > 1 ? JOBS2 - 1 : 1) * (CW3 / 2)];
+        const uint32_t info0 = p.info_words[0], info1 = N > 32 ? p.info_words[1] : 0u,
+                       info2 = N > 64 ? p.info_words[2] : 0u, info3 = N > 96 ? p.info_words[3] : 0u;
+
+        // drain accumulator a (32 columns) into v[], then hand the region back to the leader's MMA thread
+        auto wait_acc = [&](int a) {
+            mbar_wait(bar_afull + 8 * a, use[a] & 1);
+            ++use[a];
+            tc_fence_after();
+        };
+        auto release_acc = [&](int a) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster_relaxed(lead_aempty + 8 * a);
+        };
+
+        for (int step = 0; step < N; ++step) {
+            const uint32_t bits = s_bits[cq];
+            for (int layer = 0; layer < 2; ++layer) {
+                const uint32_t h_owner = layer ? h1_owner : h0_owner;
+                if (layer == 1 && lane < 8) {
+#pragma unroll
+                    for (int c8 = 0; c8 < CW3 / 8; ++c8) s_headacc[q * PAIR_CW + col0 + c8 * 8 + lane] = 0.0f;
+                }
+#pragma unroll
+                for (int j = 0; j < JOBS2; ++j) {
+                    const int u = j * 256 + (int)rank * 128 + q * 32 + lane;  // hidden unit of this thread
+                    float hr0, hr1, hz0, hz1, bn0, bn1, b_hn, wo = 0.f;
+                    if (layer == 0) {
+                        const float4 c0 = __ldg(reinterpret_cast<const float4 *>(p.consts0 + (size_t)u * 12));
+                        const float4 c1 = __ldg(reinterpret_cast<const float4 *>(p.consts0 + (size_t)u * 12 + 4));
+                        const float2 c2 = __ldg(reinterpret_cast<const float2 *>(p.consts0 + (size_t)u * 12 + 8));
+                        hr0 = 0.5f * (c0.x + c1.x); hr1 = 0.5f * (c0.x + c1.y);
+                        hz0 = 0.5f * (c0.y + c1.z); hz1 = 0.5f * (c0.y + c1.w);
+                        bn0 = c0.z + c2.x; bn1 = c0.z + c2.y;
+                        b_hn = c0.w;
+                    } else {
+                        const float4 c0 = __ldg(reinterpret_cast<const float4 *>(p.consts1 + (size_t)u * 4));
+                        hr0 = hr1 = 0.5f * c0.x; hz0 = hz1 = 0.5f * c0.y; bn0 = bn1 = c0.z; b_hn = c0.w;
+                        wo = __ldg(p.w_out + u);
+                    }
+                    const uint32_t t0 = tmem_base + lane_addr + col0;
+                    uint32_t rp[CW3 / 2], zp[CW3 / 2];  // r and z of the 32 columns as fp16 pairs
+                    // ---- R, then Z: drained as soon as they complete ----
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        wait_acc(a);
+#pragma unroll
+                        for (int cc = 0; cc < CW3; cc += 8) {
+                            float v[8];
+                            tmem_ld8(t0 + a * PAIR_CW + cc, v);
+                            tmem_ld_wait();
+                            if (cc + 8 == CW3) release_acc(a);
+                            if (layer == 0) {
+                                const uint4 g4 = gy[(j * 3 + a) * (CW3 / 8) + cc / 8];
+                                const uint32_t w4[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+                                for (int h2 = 0; h2 < 4; ++h2) {
+                                    const float2 f = unpack_h2(w4[h2]);
+                                    v[2 * h2] += f.x; v[2 * h2 + 1] += f.y;
+                                }
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; i += 2) {
+                                const bool p0 = (layer == 0) && ((bits >> (cc + i)) & 1u), p1 = (layer == 0) && ((bits >> (cc + i + 1)) & 1u);
+                                const float s0 = sigmoid_half_arg(fmaf(v[i], 0.5f, a == 0 ? (p0 ? hr1 : hr0) : (p0 ? hz1 : hz0)));
+                                const float s1 = sigmoid_half_arg(fmaf(v[i + 1], 0.5f, a == 0 ? (p1 ? hr1 : hr0) : (p1 ? hz1 : hz0)));
+                                (a == 0 ? rp : zp)[(cc + i) >> 1] = pack_h2(s0, s1);
+                            }
+                        }
+                    }
+                    // ---- the job's last accumulators: NH (layer 0; NI is the hoisted projection), NH + NI (layer 1) ----
+                    if (warp == 0) trace_ev(p, step, 19 + 0 * (layer * 4 + j));
+                    wait_acc(3);
+                    if (layer == 1) wait_acc(2);
+                    if (warp == 0) trace_ev(p, step, 20 + 2 * (layer * 4 + j));
+#pragma unroll
+                    for (int cc = 0; cc < CW3; cc += 8) {
+                        float aNH[8], aNI[8];
+                        unsigned short hold[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) hold[i] = ld_cluster_u16(h_owner + b_off(row0 + cc + i, u));
+                        tmem_ld8(t0 + 3 * PAIR_CW + cc, aNH);
+                        if (layer == 1) tmem_ld8(t0 + 2 * PAIR_CW + cc, aNI);
+                        tmem_ld_wait();
+                        if (cc + 8 == CW3) {
+                            release_acc(3);
+                            if (layer == 1) release_acc(2);
+                        }
+                        if (layer == 0) {
+                            const uint4 g4 = gy[(j * 3 + 2) * (CW3 / 8) + cc / 8];
+                            const uint32_t w4[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+                            for (int h2 = 0; h2 < 4; ++h2) {
+                                const float2 f = unpack_h2(w4[h2]);
+                                aNI[2 * h2] = f.x; aNI[2 * h2 + 1] = f.y;
+                            }
+                        }
+                        float hsum[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const bool plus = (layer == 0) && ((bits >> (cc + i)) & 1u);
+                            const float2 r2 = unpack_h2(rp[(cc + i) >> 1]), z2 = unpack_h2(zp[(cc + i) >> 1]);
+                            const float r = (i & 1) ? r2.y : r2.x, z = (i & 1) ? z2.y : z2.x;
+                            const float nn = tanh_f(fmaf(r, aNH[i] + b_hn, aNI[i] + (plus ? bn1 : bn0)));
+                            const float ho = __half2float(__ushort_as_half(hold[i]));
+                            const float hnew = fmaf(z, ho - nn, nn);  // (1 - z) n + z h
+                            hsum[i] = wo * hnew;
+                            const unsigned short hb = __half_as_ushort(__float2half_rn(hnew));
+                            if (j == JOBS2 - 1) {
+                                // the last accumulator of the layer's last job is full: every MMA reading the old state retired
+                                st_cluster_u16(h_owner + b_off(row0 + cc + i, u), hb);
+                            } else {
+                                const int si = j * (CW3 / 2) + ((cc + i) >> 1);
+                                if ((i & 1) == 0) staged[si] = hb; else staged[si] |= (uint32_t)hb << 16;
+                            }
+                        }
+                        if (layer == 1) {
+                            // head: reduce the 8 columns over the warp's 32 units; lane l < 8 ends with column cc + l
+#pragma unroll
+                            for (int s = 4; s >= 1; s >>= 1) {
+#pragma unroll
+                                for (int i = 0; i < s; ++i) {
+                                    const bool up = (lane & s) != 0;
+                                    const float send = up ? hsum[i] : hsum[i + s];
+                                    const float keep = up ? hsum[i + s] : hsum[i];
+                                    hsum[i] = keep + __shfl_xor_sync(NPD_FULL, send, s);
+                                }
+                            }
+                            hsum[0] += __shfl_xor_sync(NPD_FULL, hsum[0], 8);
+                            hsum[0] += __shfl_xor_sync(NPD_FULL, hsum[0], 16);
+                            if (lane < 8) s_headacc[q * PAIR_CW + col0 + cc + lane] += hsum[0];
+                        }
+                    }
+                    if (warp == 0) trace_ev(p, step, 21 + 2 * (layer * 4 + j));
+                }
+#pragma unroll
+                for (int j = 0; j < JOBS2 - 1; ++j) {
+                    const int u = j * 256 + (int)rank * 128 + q * 32 + lane;
+#pragma unroll
+                    for (int i = 0; i < CW3 / 2; ++i) {
+                        const uint32_t pr = staged[j * (CW3 / 2) + i];
+                        st_cluster_u16(h_owner + b_off(row0 + 2 * i, u), (unsigned short)(pr & 0xffffu));
+                        st_cluster_u16(h_owner + b_off(row0 + 2 * i + 1, u), (unsigned short)(pr >> 16));
+                    }
+                }
+                // the state rows (in either CTA) are read by the tensor cores of both SMs: make the stores visible to
+                // the async proxy, then one release-arrive per warp on the leader's barrier
+                asm volatile("fence.proxy.async;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    if (owner == rank) {
+                        // the state rows this warp wrote live in this CTA: order them locally, then a plain signal
+                        asm volatile("fence.acq_rel.cta;" ::: "memory");
+                        mbar_arrive_cluster_relaxed(lead_hready + 8 * layer);
+                    } else {
+                        mbar_arrive_cluster(lead_hready + 8 * layer);  // remote rows: release at cluster scope (~0.8 us)
+                    }
+                }
+            }
+
+            // ---- head: this CTA's partial logits (over its 256 units) go to both CTAs ----
+            epi_bar_sync();
+            float part = 0.0f;
+            if (warp < 4) {
+                const int c = warp * 32 + lane;  // codeword of the pair
+                part = (s_headacc[c] + s_headacc[PAIR_CW + c]) + (s_headacc[2 * PAIR_CW + c] + s_headacc[3 * PAIR_CW + c]);
+                st_cluster_f32(part_peer + c * 4, part);
+            }
+            if (warp < 4) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(head_peer);  // release: the partial logits above are visible to the peer
+                mbar_wait_cluster(bar_head, step & 1);
+                const int c = warp * 32 + lane;
+                const float logit = (part + s_part[c]) + p.b_out;  // a + b == b + a: both CTAs get the same logit
+                const uint32_t iw = step < 32 ? info0 : step < 64 ? info1 : step < 96 ? info2 : info3;
+                const bool is_info = (iw >> (step & 31)) & 1u;
+                const bool valid = pair0 + c < p.B;
+                const bool mine = (uint32_t)(c >> 6) == rank;  // the owner CTA writes the outputs
+                float dec = (p.genie && valid) ? p.genie[(pair0 + c) * N + step] : 1.0f;
+                if (is_info) dec = (logit > 0.0f) ? 1.0f : ((logit < 0.0f) ? -1.0f : 0.0f);
+                if (valid && mine) {
+                    if (p.logits) p.logits[(pair0 + c) * N + step] = logit;
+                    p.decoded[(pair0 + c) * N + step] = dec;
+                }
+                float prev = (dec > 0.0f) ? 1.0f : ((dec < 0.0f) ? -1.0f : 0.0f);
+                if (p.forced && valid) prev = p.forced[(pair0 + c) * N + step];
+                const uint32_t m = __ballot_sync(NPD_FULL, prev >= 1.0f);
+                if (lane == 0) s_bits[warp] = m;  // both CTAs compute all 128 decisions identically
+            }
+            epi_bar_sync();
+            if (warp == 0) trace_ev(p, step, 36);
+        }
+        (void)bits_peer;
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+
 }  // namespace
 
 // ---- host side ----------------------------------------------------------------------------------
+static const void *gru_kernel3_for(int H)
+{
+    return H == 256 ? (const void *)gru_decode_kernel3<4> : (const void *)gru_decode_kernel3<8>;
+}
+
 static const void *gru_kernel_for(int H)
 {
     switch (H) {
@@ -637,7 +1177,9 @@ static const void *gru_kernel_for(int H)
 struct npd_gru {
     int N, H, tiles_per_step;
     float b_out;
-    unsigned char *d_wpack;
+    unsigned char *d_wpack, *d_wpack2;
+    int tiles_per_step2;
+    size_t smem_bytes3;
     float *d_w_iyT;
     float *d_consts0, *d_consts1, *d_w_out;
     size_t smem_bytes;
@@ -715,6 +1257,25 @@ NPD_API int npd_gru_create(int N, int H, const float *w_ih0, const float *w_hh0,
             run(w_ih1, 2, jp + i);
         }
     }
+    // CTA-pair kernel (H a multiple of 256): rank r streams the unit rows 256 J + 128 r .. + 127 of every pair tile.
+    // layer 0 per job: R, Z, NH (w_hh0); layer 1 per job: R, Z, NH (w_hh1, previous step's h1), then R, Z, NI (w_ih1)
+    std::vector<unsigned short> pack2;
+    int n_tiles2 = 0;
+    if (H % 256 == 0) {
+        for (int r = 0; r < 2; ++r) {
+            int cnt = 0;
+            auto run2 = [&](const float *w, int gate, int J) {
+                for (int kc = 0; kc < KH; ++kc, ++cnt)
+                    pack_tile(pack2, [&](int row, int kk) { return w[(size_t)(gate * H + J * 256 + r * 128 + row) * H + kc * 64 + kk]; });
+            };
+            for (int J = 0; J < H / 256; ++J) { run2(w_hh0, 0, J); run2(w_hh0, 1, J); run2(w_hh0, 2, J); }
+            for (int J = 0; J < H / 256; ++J) {
+                run2(w_hh1, 0, J); run2(w_hh1, 1, J); run2(w_hh1, 2, J);
+                run2(w_ih1, 0, J); run2(w_ih1, 1, J); run2(w_ih1, 2, J);
+            }
+            n_tiles2 = cnt;
+        }
+    }
     std::vector<float> wiyT((size_t)N * 3 * H);
     for (int k = 0; k < N; ++k)
         for (int r = 0; r < 3 * H; ++r) wiyT[(size_t)k * 3 * H + r] = w_ih0[(size_t)r * IN0 + k];
@@ -739,6 +1300,8 @@ NPD_API int npd_gru_create(int N, int H, const float *w_ih0, const float *w_hh0,
     if (!g) return NPD_ENOMEM;
     g->N = N; g->H = H; g->tiles_per_step = n_tiles; g->b_out = b_out[0];
     g->smem_bytes = Smem::total(H);
+    g->tiles_per_step2 = n_tiles2;
+    g->smem_bytes3 = Smem3::total(H);
     if (g->smem_bytes > (size_t)dp.smem_optin) {
         npd_set_error("npd_gru_create: needs %zu B of shared memory (limit %d)", g->smem_bytes, dp.smem_optin);
         free(g);
@@ -746,6 +1309,10 @@ NPD_API int npd_gru_create(int N, int H, const float *w_ih0, const float *w_hh0,
     }
     cudaError_t e = cudaMalloc(&g->d_wpack, pack.size() * 2);
     if (e == cudaSuccess) e = cudaMalloc(&g->d_w_iyT, wiyT.size() * 4);
+    if (e == cudaSuccess && n_tiles2) e = cudaMalloc(&g->d_wpack2, pack2.size() * 2);
+    if (e == cudaSuccess && n_tiles2) e = cudaMemcpy(g->d_wpack2, pack2.data(), pack2.size() * 2, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && n_tiles2)
+        e = cudaFuncSetAttribute(gru_kernel3_for(H), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bytes3);
     if (e == cudaSuccess) e = cudaMalloc(&g->d_consts0, c0.size() * 4);
     if (e == cudaSuccess) e = cudaMalloc(&g->d_consts1, c1.size() * 4);
     if (e == cudaSuccess) e = cudaMalloc(&g->d_w_out, (size_t)H * 4);
@@ -772,6 +1339,7 @@ NPD_API int npd_gru_destroy(npd_gru_t *g)
     if (!g) return NPD_OK;
     cudaFree(g->d_wpack);
     cudaFree(g->d_w_iyT);
+    cudaFree(g->d_wpack2);
     cudaFree(g->d_consts0);
     cudaFree(g->d_consts1);
     cudaFree(g->d_w_out);
@@ -794,6 +1362,10 @@ NPD_API int npd_gru_decode(const npd_gru_t *g, const npd_code_t *code, const flo
     p.w_out = g->d_w_out; p.b_out = g->b_out; p.y = y; p.forced = forced; p.genie = genie; p.info_words = code->d_info_words;
     p.logits = logits; p.decoded = decoded; p.B = B; p.N = g->N; p.H = g->H;
     p.tiles_per_step = g->tiles_per_step;
+    p.wpack2 = g->d_wpack2; p.tiles_per_step2 = g->tiles_per_step2;
+    // CTA-pair kernel (cta_group::2) when the weights were packed for it; NPD_GRU_PAIR=0 selects the single-CTA kernel
+    bool use_pair = g->d_wpack2 != nullptr;
+    { const char *d = getenv("NPD_GRU_PAIR"); if (d) use_pair = use_pair && atoi(d) != 0; }
     { const char *d = getenv("NPD_GRU_DBG"); p.dbg = d ? atoi(d) : 0; }
     const int64_t grid = ((B + 2 * TILE_B - 1) / (2 * TILE_B)) * 2;  // CTA pairs (clusters of 2); an odd tile count pads with an idle-data CTA
     const char *trace_path = getenv("NPD_GRU_TRACE");  // bench-only: dump CTA 0's event clocks (synchronises!)
@@ -803,7 +1375,7 @@ NPD_API int npd_gru_decode(const npd_gru_t *g, const npd_code_t *code, const flo
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = g->smem_bytes;
+    cfg.dynamicSmemBytes = use_pair ? g->smem_bytes3 : g->smem_bytes;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -812,7 +1384,7 @@ NPD_API int npd_gru_decode(const npd_gru_t *g, const npd_code_t *code, const flo
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    NPD_CHECK_CUDA(cudaLaunchKernelExC(&cfg, gru_kernel_for(g->H), args));
+    NPD_CHECK_CUDA(cudaLaunchKernelExC(&cfg, use_pair ? gru_kernel3_for(g->H) : gru_kernel_for(g->H), args));
     NPD_CHECK_CUDA(cudaGetLastError());
     if (trace_path) {
         std::vector<long long> h((size_t)g->N * TRACE_SLOTS);

@@ -28,8 +28,10 @@ if t[0, 37] and t[0, 38]:
 per_step = np.diff(t[:, 0])
 print("cycles per step: median %d  min %d max %d" % (np.median(per_step[2:]), per_step[2:].min(), per_step[2:].max()))
 if t.shape[1] > 40 and t[s0, 41] > 0:
+    import os
+    ref_slot = int(os.environ.get('TRACE_REF_SLOT', '10'))
     for s in range(s0, s0 + ns):
         tl = t[s, 40:88]
-        d = np.diff(np.concatenate([[t[s, 10]], tl]))
+        d = np.diff(np.concatenate([[t[s, ref_slot]], tl]))
         print("step %d: L1j1 per-tile issue-thread cycles: %s" % (s, " ".join(str(int(x)) for x in d)))
         print("   EPI L1j0 math window: %d..%d relative to L1j1 begin" % (t[s, 20 + 8] - t[s, 10], t[s, 21 + 8] - t[s, 10]))
