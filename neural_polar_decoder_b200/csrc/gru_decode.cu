@@ -1105,7 +1105,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
                 // the async proxy, then one release-arrive per warp on the leader's barrier
                 asm volatile("fence.proxy.async;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) {
+                // layer 1's state is first read by the NEXT step's layer-1 MMAs: its (slow) release is deferred until the
+                // head exchange below is on its way
+                if (layer == 0 && lane == 0) {
                     if (owner == rank) {
                         // the state rows this warp wrote live in this CTA: order them locally, then a plain signal
                         asm volatile("fence.acq_rel.cta;" ::: "memory");
@@ -1118,6 +1120,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
 
             // ---- head: this CTA's partial logits (over its 256 units) go to both CTAs ----
             epi_bar_sync();
+            auto publish_h1 = [&]() {
+                if (lane == 0) {
+                    if (owner == rank) {
+                        asm volatile("fence.acq_rel.cta;" ::: "memory");
+                        mbar_arrive_cluster_relaxed(lead_hready + 8);
+                    } else {
+                        mbar_arrive_cluster(lead_hready + 8);
+                    }
+                }
+            };
+            if (warp >= 4) publish_h1();
             float part = 0.0f;
             if (warp < 4) {
                 const int c = warp * 32 + lane;  // codeword of the pair
@@ -1144,6 +1157,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
                 if (p.forced && valid) prev = p.forced[(pair0 + c) * N + step];
                 const uint32_t m = __ballot_sync(NPD_FULL, prev >= 1.0f);
                 if (lane == 0) s_bits[warp] = m;  // both CTAs compute all 128 decisions identically
+                publish_h1();
             }
             epi_bar_sync();
             if (warp == 0) trace_ev(p, step, 36);

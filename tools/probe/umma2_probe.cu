@@ -137,5 +137,9 @@ int main()
     CK(cudaMemcpy(h, dC, 16, cudaMemcpyDeviceToHost));
     printf("back-to-back: issue %.1f cyc/MMA, complete %.1f cyc/MMA (M=256 N=128 K=16 per MMA = 2 x (128x128x16) per SM pair)\n",
            h[0] / (8.0 * 1000), h[1] / (8.0 * 1000));
+    // latency: 8 MMAs (two tiles) issued once, then commit (multicast) -> wait
+    for (int it = 0; it < 2; ++it) { probe<<<2 * pairs, 128, smem>>>(dA, dB, dD, 1, dC); CK(cudaDeviceSynchronize()); }
+    CK(cudaMemcpy(h, dC, 16, cudaMemcpyDeviceToHost));
+    printf("8 MMAs: issued after %lld cycles, commit observed after %lld cycles (8 x 64 = 512 of them are execution)\n", h[0], h[1]);
     return 0;
 }
