@@ -865,6 +865,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
             for (uint32_t g = 0; g < total; ++g) {
                 mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                 if (t < 48) trace_ns(p, (int)(g / T), (rank ? 250 : 200) + (int)t);  // producer: slot free, copy goes out
+                // every CTA's copy signals its OWN barrier: a bulk copy whose mbarrier operand points into the other CTA
+                // never completes (tried: the kernel hangs), hence the relay in the peer's MMA warp
                 mbar_expect_tx(bar_full + 8 * stage, A_TILE_BYTES);
                 bulk_g2s(smem_u32(s_ring + stage * A_TILE_BYTES), src + (size_t)t * A_TILE_BYTES, A_TILE_BYTES, bar_full + 8 * stage);
                 if (++t == T) t = 0;
