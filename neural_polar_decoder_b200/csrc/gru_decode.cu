@@ -25,6 +25,7 @@
 //     dot product is a butterfly reduction across lanes.
 // Warp roles: warps 0-15 epilogue (TMEM lane quarter = warp % 4, 16-codeword column quarter = warp / 4), warp 16 =
 // bulk copy producer, warp 17 = MMA issuer + TMEM allocator.
+#include <cuda.h>  // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint; libcuda is not linked)
 #include <cuda_fp16.h>
 
 #include <vector>
@@ -50,6 +51,7 @@ struct GruParams {
     const float *w_iyT;          // [N][3H] fp32: the y columns of weight_ih_l0, transposed (hoisted input projection)
     const unsigned char *wpack2; // CTA-pair kernel: [2 ranks][tiles_per_step2] 16 KB half-tiles, or null
     int tiles_per_step2;
+    int use_tmap;                // pair kernel: weight halves arrive by 2-SM tensor copies that signal the leader directly
     const float *consts0;        // [H][12]: b_r b_z b_in b_hn cr0 cr1 cz0 cz1 cn0 cn1 - -
     const float *consts1;        // [H][4] : b_r b_z b_in b_hn
     const float *w_out;          // [H]
@@ -764,8 +766,16 @@ struct Smem3 {
     static __host__ __device__ size_t total(int H) { return bars(H) + 256; }
 };
 
+// 2-SM tensor copy of one 16 KB half-tile ([128 rows][128 B] box of the pre-swizzled weight stream) into THIS CTA's
+// ring; its transaction bytes complete on the LEADER CTA's barrier (peer bit of the shared::cluster address cleared)
+__device__ __forceinline__ void tmap_g2s_pair(uint32_t dst, const CUtensorMap *tmap, int row, uint32_t bar_local)
+{
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_local & 0xFEFFFFFFu), "r"(0), "r"(row) : "memory");
+}
+
 template <int KH>
-__global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruParams p)
+__global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruParams p, const __grid_constant__ CUtensorMap tmap)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int H = KH * 64, JOBS2 = H / 256;
@@ -790,7 +800,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
 
     if (tid == 0) {
         for (int i = 0; i < NUM_STAGES; ++i) {
-            mbar_init(bar_full + 8 * i, rank == 0 ? 2 : 1);  // leader: own copy + the peer's relay
+            // relay variant: leader = own copy + the peer's relay; tensor-copy variant: one expect_tx of both halves
+            mbar_init(bar_full + 8 * i, (rank == 0 && !p.use_tmap) ? 2 : 1);
             mbar_init(bar_empty + 8 * i, 1);
         }
         for (int i = 0; i < 4; ++i) {
@@ -865,10 +876,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
             for (uint32_t g = 0; g < total; ++g) {
                 mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                 if (t < 48) trace_ns(p, (int)(g / T), (rank ? 250 : 200) + (int)t);  // producer: slot free, copy goes out
-                // every CTA's copy signals its OWN barrier: a bulk copy whose mbarrier operand points into the other CTA
-                // never completes (tried: the kernel hangs), hence the relay in the peer's MMA warp
-                mbar_expect_tx(bar_full + 8 * stage, A_TILE_BYTES);
-                bulk_g2s(smem_u32(s_ring + stage * A_TILE_BYTES), src + (size_t)t * A_TILE_BYTES, A_TILE_BYTES, bar_full + 8 * stage);
+                if (p.use_tmap) {
+                    // both halves complete on the leader's barrier: no relay, the leader expects 2 x 16 KB
+                    if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * A_TILE_BYTES);
+                    tmap_g2s_pair(smem_u32(s_ring + stage * A_TILE_BYTES), &tmap, (int)((rank * T + t) * 128), bar_full + 8 * stage);
+                } else {
+                    // every CTA's copy signals its OWN barrier (a plain bulk copy whose mbarrier operand points into the
+                    // other CTA never completes -- tried: the kernel hangs), hence the relay in the peer's MMA warp
+                    mbar_expect_tx(bar_full + 8 * stage, A_TILE_BYTES);
+                    bulk_g2s(smem_u32(s_ring + stage * A_TILE_BYTES), src + (size_t)t * A_TILE_BYTES, A_TILE_BYTES, bar_full + 8 * stage);
+                }
                 if (++t == T) t = 0;
                 if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
             }
@@ -878,7 +895,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
         if (elect_one()) {
             if (rank != 0) {
                 // ================= peer: relay "my half has landed" to the leader's full barriers =================
-                const uint32_t total = (p.dbg & 1) ? 0u : (uint32_t)N * (uint32_t)p.tiles_per_step2;
+                const uint32_t total = ((p.dbg & 1) || p.use_tmap) ? 0u : (uint32_t)N * (uint32_t)p.tiles_per_step2;
                 const uint32_t lead_full = mapa_u32(bar_full, 0);
                 uint32_t stage = 0, phase = 0;
                 const uint32_t T = (uint32_t)p.tiles_per_step2;
@@ -1194,6 +1211,8 @@ struct npd_gru {
     int N, H, tiles_per_step;
     float b_out;
     unsigned char *d_wpack, *d_wpack2;
+    CUtensorMap tmap2;   // [2 * tiles_per_step2 * 128 rows][128 B] view of d_wpack2 for the 2-SM tensor copies
+    int have_tmap2;
     int tiles_per_step2;
     size_t smem_bytes3;
     float *d_w_iyT;
@@ -1329,6 +1348,26 @@ NPD_API int npd_gru_create(int N, int H, const float *w_ih0, const float *w_hh0,
     if (e == cudaSuccess && n_tiles2) e = cudaMemcpy(g->d_wpack2, pack2.data(), pack2.size() * 2, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && n_tiles2)
         e = cudaFuncSetAttribute(gru_kernel3_for(H), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bytes3);
+    if (e == cudaSuccess && n_tiles2) {
+        // tensor map over the half-tile stream; without the driver entry point the pair kernel uses its relay variant
+        typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
+            qres == cudaDriverEntryPointSuccess) {
+            const cuuint64_t gdim[2] = {128, (cuuint64_t)2 * n_tiles2 * 128};
+            const cuuint64_t gstride[1] = {128};
+            const cuuint32_t box[2] = {128, 128}, estride[2] = {1, 1};
+            const CUresult r = ((EncodeFn)fn)(&g->tmap2, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, g->d_wpack2, gdim, gstride, box, estride,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            g->have_tmap2 = (r == CUDA_SUCCESS);
+        } else {
+            (void)cudaGetLastError();
+        }
+    }
     if (e == cudaSuccess) e = cudaMalloc(&g->d_consts0, c0.size() * 4);
     if (e == cudaSuccess) e = cudaMalloc(&g->d_consts1, c1.size() * 4);
     if (e == cudaSuccess) e = cudaMalloc(&g->d_w_out, (size_t)H * 4);
@@ -1382,12 +1421,17 @@ NPD_API int npd_gru_decode(const npd_gru_t *g, const npd_code_t *code, const flo
     // CTA-pair kernel (cta_group::2) when the weights were packed for it; NPD_GRU_PAIR=0 selects the single-CTA kernel
     bool use_pair = g->d_wpack2 != nullptr;
     { const char *d = getenv("NPD_GRU_PAIR"); if (d) use_pair = use_pair && atoi(d) != 0; }
+    // the 2-SM tensor-copy variant (no relay) works but measures slower than relay + linear bulk copies (12.4 vs 11.4 ms
+    // per 37888 codewords): opt-in with NPD_GRU_TMAP=1
+    p.use_tmap = 0;
+    { const char *d = getenv("NPD_GRU_TMAP"); if (d) p.use_tmap = g->have_tmap2 && atoi(d) != 0; }
     { const char *d = getenv("NPD_GRU_DBG"); p.dbg = d ? atoi(d) : 0; }
     const int64_t grid = ((B + 2 * TILE_B - 1) / (2 * TILE_B)) * 2;  // CTA pairs (clusters of 2); an odd tile count pads with an idle-data CTA
     const char *trace_path = getenv("NPD_GRU_TRACE");  // bench-only: dump CTA 0's event clocks (synchronises!)
     if (trace_path) NPD_CHECK_CUDA(cudaMalloc(&p.trace, sizeof(long long) * g->N * TRACE_SLOTS));
     if (trace_path) NPD_CHECK_CUDA(cudaMemsetAsync(p.trace, 0, sizeof(long long) * g->N * TRACE_SLOTS, (cudaStream_t)stream));
-    void *args[] = {&p};
+    CUtensorMap tm = g->tmap2;
+    void *args[] = {&p, &tm};  // the single-CTA kernel takes only the first
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(NUM_THREADS);
