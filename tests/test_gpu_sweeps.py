@@ -118,3 +118,17 @@ def test_mc_decoder_sweep_gru_statistics():
     full = mc_decoder_sweep(code, fn, [0.0], 3000, chunk=1024, seed=4, rank=0, world=1)[3]
     parts = [mc_decoder_sweep(code, fn, [0.0], 3000, chunk=999, seed=4, rank=r, world=2)[3] for r in range(2)]
     assert torch.equal(full, parts[0] + parts[1]) and int(full[0, 2]) == 3000
+
+
+@pytest.mark.gpu
+def test_mc_sweep_cli(capsys):
+    """`python -m neural_polar_decoder_b200.mc_sweep` (BASELINE config 5 call pattern): SC and SC-list sweeps print one
+    JSON line; the SC-list curve lies below the SC curve and the frame count is what was asked for."""
+    import json
+    from neural_polar_decoder_b200 import mc_sweep
+    assert mc_sweep.main(["--N", "256", "--K", "128", "--snr", "1.5", "2.5", "--frames", "200000"]) == 0
+    sc = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert sc["frames"] == [200000, 200000] and sc["bler"][0] > sc["bler"][1] > 0
+    assert mc_sweep.main(["--N", "256", "--K", "128", "--snr", "1.5", "2.5", "--frames", "200000", "--list_size", "4"]) == 0
+    scl = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert scl["decoder"] == "SCL-4" and all(l < s for l, s in zip(scl["bler"], sc["bler"]))
