@@ -170,6 +170,10 @@ int npd_conv_destroy(npd_conv_t *conv);
 size_t npd_conv_workspace_bytes(const npd_conv_t *conv, int64_t B);
 int npd_conv_forward(const npd_conv_t *conv, const float *y, float *logits, float *in4, int64_t B,
                      void *workspace, size_t workspace_bytes, void *stream);
+/* npd_conv_decode: convNet.decode (models.py:769-772): bits[B,N] = sign(logits) (torch.sign: -1, 0, +1), same
+ * kernels, the sign taken in the last kernel's epilogue. */
+int npd_conv_decode(const npd_conv_t *conv, const float *y, float *bits, int64_t B, void *workspace,
+                    size_t workspace_bytes, void *stream);
 
 /* ---- host-buffer entry points -------------------------------------------------------------------
  * The same decoders for callers whose tensors live in HOST memory -- the reference's evaluation loops
@@ -192,6 +196,7 @@ int npd_gru_decode_host(const npd_gru_t *gru, const npd_code_t *code, const floa
                         float *h_decoded, int64_t B);
 int npd_conv_forward_host(const npd_conv_t *conv, const float *h_y, float *h_logits, float *h_in4,
                           int64_t B);
+int npd_conv_decode_host(const npd_conv_t *conv, const float *h_y, float *h_bits, int64_t B);
 
 #ifdef __cplusplus
 }

@@ -43,6 +43,8 @@ SIGNATURES = {
     "npd_pac_sc_decode_host": (_int, [_vp, _vp, _f32, _vp, _vp, _vp, _vp, _i64]),
     "npd_gru_decode_host": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
     "npd_conv_forward_host": (_int, [_vp, _vp, _vp, _vp, _i64]),
+    "npd_conv_decode": (_int, [_vp, _vp, _vp, _i64, _vp, _sz, _vp]),
+    "npd_conv_decode_host": (_int, [_vp, _vp, _vp, _i64]),
 }
 
 _lib = None

@@ -316,6 +316,7 @@ struct FcParams {
     const unsigned char *act, *w1, *w23;
     const float *consts;  // b1[256] b2[64] b3[64] lnw[64] lnb[64]
     float *logits;        // [B,64]
+    int sign_out;         // store sign(logit) instead of the logit (convNet.decode, models.py:769-772)
     int64_t B, n_tiles;
 };
 
@@ -487,12 +488,14 @@ __global__ void __launch_bounds__(FC_THREADS, 1) conv_fc_kernel(const FcParams p
             const float rstd = rsqrtf(var * (1.0f / CN) + 1e-6f);
             if (cw < p.B) {
                 float4 *dst = reinterpret_cast<float4 *>(p.logits + cw * CN);
+                const bool sg = p.sign_out != 0;
+                auto out = [&](float v) { return sg ? (float)((v > 0.0f) - (v < 0.0f)) : v; };  // torch.sign
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
-                    dst[i / 4] = make_float4(x0[i] * rstd * lnw[i] + lnb[i], x0[i + 1] * rstd * lnw[i + 1] + lnb[i + 1],
-                                             x0[i + 2] * rstd * lnw[i + 2] + lnb[i + 2], x0[i + 3] * rstd * lnw[i + 3] + lnb[i + 3]);
-                    dst[8 + i / 4] = make_float4(x1[i] * rstd * lnw[32 + i] + lnb[32 + i], x1[i + 1] * rstd * lnw[33 + i] + lnb[33 + i],
-                                                 x1[i + 2] * rstd * lnw[34 + i] + lnb[34 + i], x1[i + 3] * rstd * lnw[35 + i] + lnb[35 + i]);
+                    dst[i / 4] = make_float4(out(x0[i] * rstd * lnw[i] + lnb[i]), out(x0[i + 1] * rstd * lnw[i + 1] + lnb[i + 1]),
+                                             out(x0[i + 2] * rstd * lnw[i + 2] + lnb[i + 2]), out(x0[i + 3] * rstd * lnw[i + 3] + lnb[i + 3]));
+                    dst[8 + i / 4] = make_float4(out(x1[i] * rstd * lnw[32 + i] + lnb[32 + i]), out(x1[i + 1] * rstd * lnw[33 + i] + lnb[33 + i]),
+                                                 out(x1[i + 2] * rstd * lnw[34 + i] + lnb[34 + i]), out(x1[i + 3] * rstd * lnw[35 + i] + lnb[35 + i]));
                 }
             }
         }
@@ -669,8 +672,23 @@ NPD_API size_t npd_conv_workspace_bytes(const npd_conv_t *cv, int64_t B)
     return (size_t)tiles * FC_KC * FC_A_BYTES;
 }
 
+static int conv_forward_impl(const npd_conv_t *cv, const float *y, float *logits, float *in4, int64_t B, void *workspace,
+                             size_t workspace_bytes, void *stream, int sign_out);
+
 NPD_API int npd_conv_forward(const npd_conv_t *cv, const float *y, float *logits, float *in4, int64_t B,
                              void *workspace, size_t workspace_bytes, void *stream)
+{
+    return conv_forward_impl(cv, y, logits, in4, B, workspace, workspace_bytes, stream, 0);
+}
+
+NPD_API int npd_conv_decode(const npd_conv_t *cv, const float *y, float *bits, int64_t B, void *workspace,
+                            size_t workspace_bytes, void *stream)
+{
+    return conv_forward_impl(cv, y, bits, nullptr, B, workspace, workspace_bytes, stream, 1);
+}
+
+static int conv_forward_impl(const npd_conv_t *cv, const float *y, float *logits, float *in4, int64_t B, void *workspace,
+                             size_t workspace_bytes, void *stream, int sign_out)
 {
     NPD_REQUIRE(cv && y && logits, "npd_conv_forward: null argument");
     NPD_REQUIRE(B >= 0, "npd_conv_forward: negative batch");
@@ -694,7 +712,7 @@ NPD_API int npd_conv_forward(const npd_conv_t *cv, const float *y, float *logits
         NPD_CHECK_CUDA(cudaGetLastError());
         FcParams fp{};
         fp.act = (const unsigned char *)workspace; fp.w1 = cv->d_w1; fp.w23 = cv->d_w23; fp.consts = cv->d_consts;
-        fp.logits = logits + b0 * CN; fp.B = nb; fp.n_tiles = (nb + 127) / 128;
+        fp.logits = logits + b0 * CN; fp.sign_out = sign_out; fp.B = nb; fp.n_tiles = (nb + 127) / 128;
         const unsigned g2 = (unsigned)(fp.n_tiles < cv->sm_count ? fp.n_tiles : cv->sm_count);
         conv_fc_kernel<<<g2, FC_THREADS, FC_SMEM, st>>>(fp);
         NPD_CHECK_CUDA(cudaGetLastError());

@@ -868,12 +868,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
 
     if (warp >= EPI_WARPS && warp < MMA_WARP) {
         // ================= producer: this CTA's half of every weight tile =================
-        if (lane == 0) {
+        // PRODUCER_LANES threads take the ring stages in turn (stage = tile % 6, so each lane owns fixed stages): one
+        // thread's wake-up + issue latency per tile is otherwise what the ring round trip waits for
+        constexpr int PRODUCER_LANES = 2;
+        static_assert(NUM_STAGES % PRODUCER_LANES == 0, "each producer lane owns fixed ring stages");
+        if (lane < PRODUCER_LANES) {
             const uint32_t T = (uint32_t)p.tiles_per_step2;
             const uint32_t total = (p.dbg & 1) ? 0u : (uint32_t)N * T;
             const unsigned char *src = p.wpack2 + (size_t)rank * T * A_TILE_BYTES;
-            uint32_t t = 0, stage = 0, phase = 0;
-            for (uint32_t g = 0; g < total; ++g) {
+            uint32_t t = (uint32_t)lane, stage = (uint32_t)lane, phase = 0;
+            for (uint32_t g = (uint32_t)lane; g < total; g += PRODUCER_LANES) {
                 mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                 if (t < 48) trace_ns(p, (int)(g / T), (rank ? 250 : 200) + (int)t);  // producer: slot free, copy goes out
                 if (p.use_tmap) {
@@ -886,8 +890,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
                     mbar_expect_tx(bar_full + 8 * stage, A_TILE_BYTES);
                     bulk_g2s(smem_u32(s_ring + stage * A_TILE_BYTES), src + (size_t)t * A_TILE_BYTES, A_TILE_BYTES, bar_full + 8 * stage);
                 }
-                if (++t == T) t = 0;
-                if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+                t += PRODUCER_LANES;
+                if (t >= T) t -= T;
+                stage += PRODUCER_LANES;
+                if (stage >= NUM_STAGES) { stage -= NUM_STAGES; phase ^= 1; }
             }
         }
         __syncwarp();

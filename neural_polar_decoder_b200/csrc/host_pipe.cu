@@ -241,8 +241,20 @@ NPD_API int npd_gru_decode_host(const npd_gru_t *gru, const npd_code_t *code, co
     });
 }
 
+static int conv_host_impl(const npd_conv_t *conv, const float *h_y, float *h_logits, float *h_in4, int64_t B, int sign_out);
+
 NPD_API int npd_conv_forward_host(const npd_conv_t *conv, const float *h_y, float *h_logits,
                                   float *h_in4, int64_t B)
+{
+    return conv_host_impl(conv, h_y, h_logits, h_in4, B, 0);
+}
+
+NPD_API int npd_conv_decode_host(const npd_conv_t *conv, const float *h_y, float *h_bits, int64_t B)
+{
+    return conv_host_impl(conv, h_y, h_bits, nullptr, B, 1);
+}
+
+static int conv_host_impl(const npd_conv_t *conv, const float *h_y, float *h_logits, float *h_in4, int64_t B, int sign_out)
 {
     NPD_REQUIRE(conv && h_y && h_logits, "npd_conv_forward_host: null argument");
     NPD_REQUIRE(B >= 0, "npd_conv_forward_host: B < 0");
@@ -260,7 +272,8 @@ NPD_API int npd_conv_forward_host(const npd_conv_t *conv, const float *h_y, floa
         float *d_in4 = cv.take(chunk * c4 * n_ * 4, h_in4 != nullptr);
         float *d_ws = cv.take(ws, ws != 0);
         H2D(d_y, h_y + lo * n_, n * n_ * 4, st);
-        int rc = npd_conv_forward(conv, d_y, d_logits, d_in4, n, d_ws, ws, st);
+        int rc = sign_out ? npd_conv_decode(conv, d_y, d_logits, n, d_ws, ws, st)
+                          : npd_conv_forward(conv, d_y, d_logits, d_in4, n, d_ws, ws, st);
         if (rc) return rc;
         D2H(h_logits + lo * n_, d_logits, n * n_ * 4, st);
         if (d_in4) D2H(h_in4 + lo * c4 * n_, d_in4, n * c4 * n_ * 4, st);

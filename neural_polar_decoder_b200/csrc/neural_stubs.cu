@@ -28,6 +28,11 @@ NPD_API int npd_conv_create(int, int, const float *, size_t, npd_conv_t **)
 }
 NPD_API int npd_conv_destroy(npd_conv_t *) { return NPD_OK; }
 NPD_API size_t npd_conv_workspace_bytes(const npd_conv_t *, int64_t) { return 0; }
+NPD_API int npd_conv_decode(const npd_conv_t *, const float *, float *, int64_t, void *, size_t, void *)
+{
+    npd_set_error("npd_conv_decode: conv kernel not built into this libnpd.so");
+    return NPD_EUNSUPPORTED;
+}
 NPD_API int npd_conv_forward(const npd_conv_t *, const float *, float *, float *, int64_t, void *, size_t, void *)
 {
     npd_set_error("npd_conv_forward: conv kernel not built into this libnpd.so");

@@ -71,15 +71,19 @@ class ConvHandle:
             pass
 
 
-def conv_forward(handle, y, want_in4=False):
+def conv_forward(handle, y, want_in4=False, sign=False):
     """Two fused launches per chunk: y [B,N] (device fp32) -> (logits [B,N], in4 [B,C,N] or None)."""
     B, N = y.shape
     logits = torch.empty(B, N, dtype=torch.float32, device=y.device)
     in4 = torch.empty(B, handle.embed_dim // 2, N, dtype=torch.float32, device=y.device) if want_in4 else None
     if B > 0:
         ws = handle.workspace(B, y.device)
-        _lib.check(_lib.load().npd_conv_forward(handle.h, _lib.ptr(y), _lib.ptr(logits), _lib.ptr(in4), B,
-                                                ctypes.c_void_p(ws.data_ptr()), ws.numel(), _lib.stream_ptr()))
+        if sign:  # convNet.decode: bits = sign(logits), taken in the kernel's epilogue
+            _lib.check(_lib.load().npd_conv_decode(handle.h, _lib.ptr(y), _lib.ptr(logits), B,
+                                                   ctypes.c_void_p(ws.data_ptr()), ws.numel(), _lib.stream_ptr()))
+        else:
+            _lib.check(_lib.load().npd_conv_forward(handle.h, _lib.ptr(y), _lib.ptr(logits), _lib.ptr(in4), B,
+                                                    ctypes.c_void_p(ws.data_ptr()), ws.numel(), _lib.stream_ptr()))
     return logits, in4
 
 
@@ -134,15 +138,14 @@ class convNet(nn.Module):
 
     def decode(self, noisy_enc, info_positions, mask, device, trg_seq=None):
         """-> (bits [B,N,1], mask); info_positions is ignored as in the reference (models.py:769-772)."""
-        logits, _, _ = self._run(noisy_enc, want_in4=False)
-        # in place: `logits` is this call's own fresh tensor (no second [B,N] allocation on the host path)
-        return logits.sign_().squeeze().unsqueeze(-1), mask
+        bits, _, _ = self._run(noisy_enc, want_in4=False, sign=True)  # npd_conv_decode: sign taken on the device
+        return bits.squeeze().unsqueeze(-1), mask
 
     def logits(self, noisy_enc):
         """LayerNorm output [B,N] (what parity is judged on)."""
         return self._run(noisy_enc, want_in4=False)[0]
 
-    def _run(self, noisy_enc, want_in4):
+    def _run(self, noisy_enc, want_in4, sign=False):
         src = noisy_enc
         if torch.is_tensor(src) and not src.is_cuda:
             # host tensors: chunked copy/forward/copy pipeline inside the library (npd_conv_forward_host)
@@ -152,12 +155,14 @@ class convNet(nn.Module):
             B = yh.shape[0]
             logits = _lib.host_out((B, self.input_len), yh)
             in4 = _lib.host_out((B, self.hidden_dim // 2, self.input_len), yh) if want_in4 else None
-            if B > 0:
+            if B > 0 and sign:
+                _lib.check(_lib.load().npd_conv_decode_host(self.npd_handle().h, _lib.hptr(yh), _lib.hptr(logits), B))
+            elif B > 0:
                 _lib.check(_lib.load().npd_conv_forward_host(self.npd_handle().h, _lib.hptr(yh), _lib.hptr(logits),
                                                              _lib.hptr(in4), B))
             return logits, in4, src
         yd = _lib.to_device_f32(noisy_enc)
         assert yd.dim() == 2 and yd.shape[1] == self.input_len
         with torch.cuda.device(yd.device):
-            logits, in4 = conv_forward(self.npd_handle(), yd, want_in4)
+            logits, in4 = conv_forward(self.npd_handle(), yd, want_in4, sign=sign)
         return logits, in4, src

@@ -95,3 +95,20 @@ def test_conv_host_equals_device(monkeypatch):
     out_h = net.forward(y, None, None, torch.device("cuda"))
     assert torch.equal(out_h[3], out_d[3].cpu()) and torch.equal(out_h[4], out_d[4].cpu())
     assert torch.equal(out_h[1], out_d[1].cpu())
+
+
+def test_conv_decode_is_sign_of_forward():
+    """convNet.decode (npd_conv_decode: the sign is taken in the kernel's epilogue) == sign of forward()'s logits,
+    device and host paths."""
+    import argparse
+    from neural_polar_decoder_b200 import synth
+    from neural_polar_decoder_b200.models import convNet
+    net = convNet(argparse.Namespace(embed_dim=128, max_len=64, N=64, dont_use_bias=False, dropout=0.1))
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in synth.conv_state_dict(2, 64, 128).items()})
+    net.eval()
+    y = torch.randn(333, 64, generator=torch.Generator().manual_seed(4))
+    logits = net.forward(y.cuda(), None, None, torch.device("cuda"))[3]
+    bits_d, _ = net.decode(y.cuda(), None, None, torch.device("cuda"))
+    bits_h, _ = net.decode(y, None, None, torch.device("cuda"))
+    assert bits_d.shape == (333, 64, 1) and torch.equal(bits_d, logits.sign())
+    assert not bits_h.is_cuda and torch.equal(bits_h, logits.sign().cpu())
