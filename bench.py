@@ -413,6 +413,12 @@ def bench_sc(args, w, rank, world, local_rank):
                      "traffic_source": traffic_src, "peak_source": peaks["src"], "kernel_ms": kern_ms, "count_kernel_ms": count_ms,
                      "alg_bytes_per_launch": alg_bytes,
                      "llr_updates_per_s": N * int(np.log2(N)) * B / (kern_ms * 1e-3),
+                     "smem_roofline": {"bound": "smem", "unit": "codewords/s",
+                                       "achieved": B / (kern_ms * 1e-3),
+                                       "peak": 37.2e12 / (12.0 * N * int(np.log2(N))),
+                                       "frac": (B / (kern_ms * 1e-3)) / (37.2e12 / (12.0 * N * int(np.log2(N)))),
+                                       "note": "SURVEY.md 8(d) second bound: N log2 N LLR updates x 12 B of shared-memory traffic "
+                                               "each at 37.2 TB/s chip-wide (148 SMs x 128 B/clk x 1.965 GHz)"},
                      "note": "the decoder is instruction-issue bound, not HBM bound: N log2 N serial-by-level LLR updates "
                              "per codeword against 4N+4K bytes (DESIGN.md 4.1)"},
         "ber": cnt[0] / float(world * B * args.steps * K), "bler": cnt[1] / float(world * B * args.steps),
