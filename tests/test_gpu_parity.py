@@ -256,6 +256,28 @@ def test_gru_vs_oracle_ragged_batch():
     assert (d.cpu().numpy()[:, [i for i in range(N) if i not in set(info.tolist())]] == 1).all()
 
 
+@pytest.mark.parametrize("N,K,H,B", [(16, 8, 128, 70), (128, 64, 384, 130), (64, 22, 256, 129), (32, 16, 512, 257)])
+def test_gru_shapes_vs_oracle(N, K, H, B):
+    """Every kernel instantiation: H = 128 / 384 (single-CTA kernel), 256 / 512 (CTA-pair kernel), N from 16 to 128,
+    batches that leave a CTA pair half empty; logits under forced (= oracle) feedback within tolerance."""
+    from neural_polar_decoder_b200 import construct
+    from neural_polar_decoder_b200.rnn_all import RNN_decoder, gru_decode
+    net, sd = _gru_net(N, H, 100 + H + N, 6.0)
+    rs = construct.reference_rs256()
+    info = np.sort(rs[rs < N][:K])
+    dec = RNN_decoder('y_input', N, info, onehot=True)
+    rng = np.random.RandomState(N + H)
+    y = (rng.choice([-1.0, 1.0], size=(B, N)) + 0.8 * rng.randn(B, N)).astype(np.float32)
+    do, lo = oracle.gru_decode(sd, y, N, info)
+    d, lg = gru_decode(net, dec._loss_code(info), torch.from_numpy(y).cuda(), forced=torch.from_numpy(do).cuda(),
+                       want_logits=True)
+    err = np.abs(lg.cpu().numpy() - lo)
+    assert (err <= _gru_tol(lo)).all(), (err.max(), (err / _gru_tol(lo)).max())
+    dfree = dec.decode(net, False, torch.from_numpy(y).cuda()).cpu().numpy()
+    risky_before = np.cumsum(np.abs(lo) <= _gru_tol(lo), axis=1) > 0
+    assert not ((dfree != do) & ~risky_before).any()
+
+
 def test_gru_genie_and_forced_evaluation_modes(golden):
     """RNN_decoder.decode with gt / loss_inds (genie, rnn_all.py:519-522, 887) and train=True under no_grad
     (teacher- / student-forced evaluation, rnn_all.py:982-984) against the live-reference fixture."""
