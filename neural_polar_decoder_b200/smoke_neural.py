@@ -12,8 +12,13 @@ from .rnn_all import RNN_Model, RNN_decoder, gru_decode
 
 def run(oracle):
     rng = np.random.RandomState(0)
-    # ---- CRISP GRU, Polar(32,16), H = 256, ragged batch ----
-    N, K, H, B = 32, 16, 256, 100
+    # ---- CRISP GRU: the flagship shape Polar(64,22), H = 512 (CTA-pair kernel), then Polar(32,16), H = 256, ragged ----
+    for N, K, H, B in ((64, 22, 512, 192), (32, 16, 256, 100)):
+        _gru(oracle, rng, N, K, H, B)
+    _conv(oracle, rng)
+
+
+def _gru(oracle, rng, N, K, H, B):
     sd = synth.gru_state_dict(3, N, H, 2, head_gain=6.0)
     net = RNN_Model('GRU', N + 2, H, 1, 2, N, 0, 0)
     net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
@@ -28,6 +33,9 @@ def run(oracle):
     tol = 1e-2 * (np.abs(lo) + np.sqrt((lo ** 2).mean()))
     assert (err <= tol).all(), "GRU logits differ from the oracle: max err %.3e" % err.max()
     print("smoke: GRU(2x%d) Polar(%d,%d) logits within tolerance on %d frames (max err %.2e)" % (H, N, K, B, err.max()))
+
+
+def _conv(oracle, rng):
     # ---- convNet, Polar(64,22) ----
     N, E, B = 64, 128, 50
     sd = synth.conv_state_dict(4, N, E)
