@@ -126,7 +126,8 @@ int npd_mc_sc_sweep(const npd_code_t *code, int64_t B, int64_t chunk, float sigm
 /* ---- CRISP GRU sequential decoder --------------------------------------------------------------
  * npd_gru_create: repack the parameters of RNN_Model('GRU', N+2, H, 1, L=2, ...) (rnn_all.py:294-343;
  * state_dict keys rnn.weight_ih_l{0,1}, rnn.weight_hh_l{0,1}, rnn.bias_*, linear.weight/bias) from
- * host fp32 into the kernel's bf16 layouts.  h_* are host pointers, PyTorch layouts:
+ * host fp32 into the kernel's fp16 tile streams (pre-swizzled 16 KB weight tiles in consumption order, one stream per
+ * kernel variant).  h_* are host pointers, PyTorch layouts:
  *   w_ih0[3H, N+2], w_hh0[3H,H], b_ih0[3H], b_hh0[3H], w_ih1[3H,H], w_hh1[3H,H], b_ih1[3H],
  *   b_hh1[3H], w_out[H], b_out[1].  Gate order r,z,n. */
 int npd_gru_create(int N, int H, const float *h_w_ih0, const float *h_w_hh0, const float *h_b_ih0,

@@ -78,7 +78,7 @@ class RNN_Model(nn.Module):
 
 
 class GruHandle:
-    """Owns an npd_gru_t (bf16 weight program in HBM)."""
+    """Owns an npd_gru_t (fp16 weight tile streams in HBM)."""
 
     def __init__(self, N, H, sd):
         _lib.require_cuda()
