@@ -29,6 +29,8 @@
 
 #include <vector>
 
+#include <type_traits>
+
 #include "npd_common.cuh"
 #include "tc_common.cuh"
 
@@ -89,8 +91,17 @@ struct ConvParams {
     float *in4;                  // optional [B,64,64]
     int64_t B, n_pass;
     int dbg;  // bench-only experiments (NPD_CONV_DBG): 1 = no MMAs, 2 = no epilogue math, 4 = no weight copies
+    long long *trace;  // bench-only (NPD_CONV_TRACE): clock64 stamps of CTA 0's third pass, [layer][group][4], or null
     LayerDesc layers[CV_LAYERS];
 };
+
+// slot k of (layer L, group g): 0 = MMA warp: activations ready, 1 = MMA warp: all slots issued + committed,
+// 2 = epilogue warp 0: accumulators seen, 3 = epilogue warp 0: next layer's operand rows written
+__device__ __forceinline__ void cv_trace(const ConvParams &p, int64_t ps, int L, int g, int k)
+{
+    if (p.trace && blockIdx.x == 0 && ps == 2 * (int64_t)gridDim.x && (threadIdx.x & 31) == 0)
+        p.trace[(L * 2 + g) * 4 + k] = clock64();
+}
 
 // One epilogue block: 32 accumulator columns [c, c+32) of the thread's TMEM lane -> + bias (fp32) -> GELU on fp16
 // pairs (-> + residual row, in place) -> four 16-byte chunks of the K-major SWIZZLE_128B operand row `orow`
@@ -127,6 +138,68 @@ __device__ __forceinline__ void epi_block(uint32_t taddr, int c, const float *bi
             }
         }
         if (store) *dst = pk;
+    }
+}
+
+// All MMAs of one weight slot of a layer whose shape is known at compile time (the clock-stamp trace showed the MMA warp
+// issuing for 92 % of a pass at 75 cycles per N = 64 MMA against the 48-cycle operand-read floor: runtime layer
+// descriptors made every MMA pay descriptor arithmetic and branches).  Here tap, chunk, K step and row tile are
+// compile-time, so every descriptor is one add of an immediate to a_in0 / a_in1 / b_slot.
+//   COUT 64: two taps per slot (rows 0-63 / 64-127 of the slot); COUT 128: one (tap, 64-channel input chunk) per slot
+template <int COUT, int KSTEPS, int CHUNKS, int DIL, int J>
+__device__ __forceinline__ void conv_issue_slot(uint32_t d0, uint32_t a_in0, uint32_t a_in1, uint32_t b_slot, uint32_t idesc)
+{
+    constexpr int NENT = COUT == 64 ? 2 : 1;
+#pragma unroll
+    for (int e = 0; e < NENT; ++e) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int tap = COUT == 64 ? 2 * J + e : (CHUNKS == 1 ? J : J >> 1);
+        const int chunk = (COUT == 64 || CHUNKS == 1) ? 0 : (J & 1);
+        if (tap >= 7) break;
+        const uint32_t a_lo = (chunk ? a_in1 : a_in0) + (uint32_t)(((CV_HALO + (tap - 3) * DIL) * 128) >> 4);
+        const uint32_t b_lo = b_slot + (uint32_t)((e * 8192) >> 4);
+#pragma unroll
+        for (int m = 0; m < CV_TILES; ++m)
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k)
+                umma_f16(d0 + m * 128, umma_desc_from_lo(a_lo + m * 1024 + k * 2), umma_desc_from_lo(b_lo + k * 2), idesc,
+                         (J | e | k) ? 1u : 0u);
+    }
+}
+
+struct ConvIssue {
+    uint32_t bar_full, bar_empty, ring_lo;
+    uint32_t st, ph;
+    bool no_mma;
+};
+
+// every slot of one (layer, group): wait for the slot's weights, issue its MMAs, release it unless the other group re-uses it
+template <int COUT, int KSTEPS, int CHUNKS, int DIL, int NSLOTS>
+__device__ __forceinline__ void conv_issue_group(ConvIssue &c, uint32_t d0, uint32_t a_in0, uint32_t a_in1, bool hold)
+{
+    constexpr uint32_t idesc = umma_idesc_f16(128, COUT);
+    auto slot = [&](auto jc) {
+        constexpr int J = decltype(jc)::value;
+        mbar_wait(c.bar_full + 8 * c.st, c.ph);
+        tc_fence_after();
+        if (elect_one()) {
+            if (!c.no_mma) conv_issue_slot<COUT, KSTEPS, CHUNKS, DIL, J>(d0, a_in0, a_in1, c.ring_lo + c.st * (CV_SLOT >> 4), idesc);
+            if (!hold) umma_commit(c.bar_empty + 8 * c.st);
+        }
+        __syncwarp();
+        if (++c.st == CV_STAGES) { c.st = 0; c.ph ^= 1; }
+    };
+    // NSLOTS is 4, 7 or 14
+    slot(std::integral_constant<int, 0>{}); slot(std::integral_constant<int, 1>{}); slot(std::integral_constant<int, 2>{});
+    slot(std::integral_constant<int, 3>{});
+    if constexpr (NSLOTS > 4) {
+        slot(std::integral_constant<int, 4>{}); slot(std::integral_constant<int, 5>{}); slot(std::integral_constant<int, 6>{});
+    }
+    if constexpr (NSLOTS > 7) {
+        slot(std::integral_constant<int, 7>{}); slot(std::integral_constant<int, 8>{}); slot(std::integral_constant<int, 9>{});
+        slot(std::integral_constant<int, 10>{}); slot(std::integral_constant<int, 11>{}); slot(std::integral_constant<int, 12>{});
+        slot(std::integral_constant<int, 13>{});
     }
 }
 
@@ -187,60 +260,42 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_stack_kernel(const ConvPar
         }
     } else if (warp == CV_EPI_WARPS + 1) {
         // ================= MMA issuer (warp-uniform schedule, one elected lane issues) =================
-        const uint32_t ring0 = smem_u32(smem + CV_OFF_RING), bufs0 = smem_u32(s_bufs);
-        uint32_t stage = 0, phase = 0, nact0 = 0, nact1 = 0;
-        for (int64_t ps = blockIdx.x; ps < p.n_pass; ps += gridDim.x)
+        // layer shapes are compile-time (models.py:701-730: (C_out, C_in, dilation) = kConvShape); the ring stage, the
+        // activation buffers of the group and the TMEM base are the only runtime terms of a descriptor
+        const uint32_t bufs0 = umma_desc_lo(smem_u32(s_bufs));
+        constexpr uint32_t BUF_LO = CV_BUF >> 4;
+        ConvIssue c;
+        c.bar_full = bar_full; c.bar_empty = bar_empty; c.ring_lo = umma_desc_lo(smem_u32(smem + CV_OFF_RING));
+        c.st = 0; c.ph = 0; c.no_mma = (p.dbg & 1) != 0;
+        uint32_t nact0 = 0, nact1 = 0;
+        for (int64_t ps = blockIdx.x; ps < p.n_pass; ps += gridDim.x) {
+#pragma unroll
             for (int L = 0; L < CV_LAYERS; ++L) {
-                const LayerDesc ld = p.layers[L];
-                const uint32_t idesc = umma_idesc_f16(128, ld.cout);
+                uint32_t st0 = c.st, ph0 = c.ph;
+#pragma unroll
                 for (int g = 0; g < 2; ++g) {
-                    const bool hold = ld.cout == 64 && g == 0;  // group 1 re-uses and then releases the slots
+                    const bool hold = (L < 8) && g == 0;  // 64-channel layers: group 1 re-uses and then releases the slots
                     uint32_t &nact = g ? nact1 : nact0;
                     mbar_wait(bar_act + 8 * g, nact & 1);
                     ++nact;
                     tc_fence_after();
-                    const uint32_t bx = bufs0 + (g * 2) * CV_BUF, bt = bx + CV_BUF;
+                    cv_trace(p, ps, L, g, 0);
+                    const uint32_t bx = bufs0 + (g * 2) * BUF_LO, bt = bx + BUF_LO;
                     const uint32_t in0 = (L & 1) ? bt : bx, in1 = bx;
                     const uint32_t d0 = tmem_base + (uint32_t)(g * 2) * 128;
-                    uint32_t st = stage, ph = phase;
-                    for (int j = 0; j < ld.nslots; ++j) {
-                        mbar_wait(bar_full + 8 * st, ph);
-                        tc_fence_after();
-                        const uint32_t slot = ring0 + st * CV_SLOT;
-                        if (elect_one()) {
-                            const int nent = ld.cout == 64 ? 2 : 1;
-                            for (int e = 0; e < nent && !(p.dbg & 1); ++e) {
-                                int tap, chunk = 0;
-                                if (ld.cout == 64) tap = 2 * j + e;
-                                else if (ld.chunks == 1) tap = j;
-                                else { tap = j >> 1; chunk = j & 1; }
-                                if (tap >= 7) break;
-                                const uint32_t b_lo = umma_desc_lo(slot + e * 8192);
-                                const uint32_t a_lo = umma_desc_lo((chunk ? in1 : in0) + (uint32_t)((CV_HALO + (tap - 3) * ld.dil) * 128));
-                                if (ld.ksteps == 4) {
-#pragma unroll
-                                    for (int m = 0; m < CV_TILES; ++m)
-#pragma unroll
-                                        for (int k = 0; k < 4; ++k)
-                                            umma_f16(d0 + m * 128, umma_desc_from_lo(a_lo + m * 1024 + k * 2),
-                                                     umma_desc_from_lo(b_lo + k * 2), idesc, (j | e | k) ? 1u : 0u);
-                                } else {
-#pragma unroll
-                                    for (int m = 0; m < CV_TILES; ++m)
-                                        umma_f16(d0 + m * 128, umma_desc_from_lo(a_lo + m * 1024), umma_desc_from_lo(b_lo), idesc,
-                                                 (j | e) ? 1u : 0u);
-                                }
-                            }
-                            if (!hold) umma_commit(bar_empty + 8 * st);
-                        }
-                        __syncwarp();
-                        if (++st == CV_STAGES) { st = 0; ph ^= 1; }
-                    }
-                    if (!hold) { stage = st; phase = ph; }
+                    if (L < 8 && g == 1) { c.st = st0; c.ph = ph0; }  // the slots are still resident from group 0
+                    if (L == 0) conv_issue_group<64, 1, 1, 1, 4>(c, d0, in0, in1, hold);
+                    else if (L == 1 || L == 4 || L == 7) conv_issue_group<64, 4, 1, 2, 4>(c, d0, in0, in1, hold);
+                    else if (L == 2 || L == 5) conv_issue_group<64, 4, 1, 4, 4>(c, d0, in0, in1, hold);
+                    else if (L == 3 || L == 6) conv_issue_group<64, 4, 1, 1, 4>(c, d0, in0, in1, hold);
+                    else if (L == 8) conv_issue_group<128, 4, 1, 4, 7>(c, d0, in0, in1, hold);
+                    else conv_issue_group<128, 4, 2, 1, 14>(c, d0, in0, in1, hold);
                     if (elect_one()) umma_commit(bar_acc + 8 * g);
                     __syncwarp();
+                    cv_trace(p, ps, L, g, 1);
                 }
             }
+        }
     } else {
         // ================= epilogue warps: one thread = one row (position) of one tile, half its channels ===========
         const int q = warp & 3, m = (warp >> 2) & 1, hc = warp >> 3;
@@ -271,6 +326,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_stack_kernel(const ConvPar
                     mbar_wait(bar_acc + 8 * g, nacc & 1);
                     ++nacc;
                     tc_fence_after();
+                    if (warp == 0) cv_trace(p, ps, L, g, 2);
                     const int64_t cw = ps * CV_CW + g * CV_G + gi;
                     const bool valid = in_cw && cw < p.B;
                     unsigned char *bx = s_bufs + (g * 2) * CV_BUF, *bt = bx + CV_BUF;
@@ -302,6 +358,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_stack_kernel(const ConvPar
                         fence_async_smem();
                         mbar_arrive(bar_act + 8 * g);
                     }
+                    if (warp == 0) cv_trace(p, ps, L, g, 3);
                 }
             }
         }
@@ -707,9 +764,24 @@ static int conv_forward_impl(const npd_conv_t *cv, const float *y, float *logits
         cp.B = nb; cp.n_pass = (nb + CV_CW - 1) / CV_CW;
         memcpy(cp.layers, cv->layers, sizeof(cp.layers));
         { const char *d = getenv("NPD_CONV_DBG"); cp.dbg = d ? atoi(d) : 0; }
+        const char *trace_path = (b0 == 0) ? getenv("NPD_CONV_TRACE") : nullptr;  // bench-only (synchronises!)
+        if (trace_path) {
+            NPD_CHECK_CUDA(cudaMalloc(&cp.trace, sizeof(long long) * CV_LAYERS * 8));
+            NPD_CHECK_CUDA(cudaMemsetAsync(cp.trace, 0, sizeof(long long) * CV_LAYERS * 8, st));
+        }
         const unsigned g1 = (unsigned)(cp.n_pass < cv->sm_count ? cp.n_pass : cv->sm_count);
         conv_stack_kernel<<<g1, CV_THREADS, CV_SMEM, st>>>(cp);
         NPD_CHECK_CUDA(cudaGetLastError());
+        if (trace_path) {
+            long long h[CV_LAYERS * 8];
+            NPD_CHECK_CUDA(cudaStreamSynchronize(st));
+            NPD_CHECK_CUDA(cudaMemcpy(h, cp.trace, sizeof(h), cudaMemcpyDeviceToHost));
+            cudaFree(cp.trace);
+            if (FILE *f = fopen(trace_path, "w")) {
+                for (int i = 0; i < CV_LAYERS * 2; ++i) fprintf(f, "%lld %lld %lld %lld\n", h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+                fclose(f);
+            }
+        }
         FcParams fp{};
         fp.act = (const unsigned char *)workspace; fp.w1 = cv->d_w1; fp.w23 = cv->d_w23; fp.consts = cv->d_consts;
         fp.logits = logits + b0 * CN; fp.sign_out = sign_out; fp.B = nb; fp.n_tiles = (nb + 127) / 128;
