@@ -32,6 +32,8 @@ WORKLOADS = {
                    desc="SC Polar(4096,2048), polarization-weight frozen set, AWGN 2 dB"),
     "sc64": dict(kind="sc", N=64, K=22, snr=0.0, batch=2097152,
                  desc="SC Polar(64,22), reference 'polar' profile, AWGN 0 dB"),
+    "enc1024": dict(kind="enc", N=1024, K=512, snr=2.0, batch=131072,
+                    desc="message generation + Plotkin encoder + BPSK/AWGN channel, Polar(1024,512), 2 dB (Philox noise)"),
     "scl64": dict(kind="sc", N=64, K=22, snr=0.0, batch=262144, L=4,
                   desc="SC-list (L=4) Polar(64,22), reference 'polar' profile, AWGN 0 dB"),
     "gru64": dict(kind="gru", N=64, K=22, snr=0.0, batch=37888,
@@ -247,6 +249,8 @@ def main():
     def run_workload(name, wl):
         a = argparse.Namespace(**vars(args))
         a.workload = name
+        if wl["kind"] == "enc":
+            return bench_enc(a, wl, rank, world, local_rank)
         if wl["kind"] == "sc":
             r = bench_sc(a, wl, rank, world, local_rank)
         else:
@@ -290,6 +294,65 @@ def default_workload():
     except Exception:
         pass
     return "sc1024"
+
+
+def bench_enc(args, w, rank, world, local_rank):
+    """Subsystem (1): fused message generation + encoder + channel (npd_gen_encode_awgn), HBM-write roofline."""
+    import torch
+    import torch.distributed as dist
+    from neural_polar_decoder_b200 import _lib, utils
+    lib = _lib.load()
+    N, K, B, snr = w["N"], w["K"], w["batch"], w["snr"]
+    code = make_code(w)
+    h = code._handle()
+    dev = torch.device("cuda", local_rank)
+    sigma = float(np.float32(utils.snr_db2sigma(snr)))
+    msg = torch.empty(B, K, device=dev)
+    y = torch.empty(B, N, device=dev)
+    st = _lib.stream_ptr()
+
+    def step(i):
+        _lib.check(lib.npd_gen_encode_awgn(h.h, _lib.ptr(msg), None, _lib.ptr(y), B, sigma, 2026, i, rank * B, st))
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0.record()
+    for i in range(args.steps):
+        step(i)
+    t1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = t0.elapsed_time(t1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    kern_ms = ms / args.steps
+    peaks = measured_peaks()
+    alg_bytes = (4 * N + 4 * K) * B  # y and msg written once
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    return {
+        "metric": "generated + encoded + noised codewords/sec", "value": world * B * args.steps / (ms * 1e-3), "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": kern_ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": w["desc"], "N": N, "K": K, "snr_db": snr, "batch_per_gpu": B,
+                   "l2_policy": "outputs larger than L2 (y = %d MB per GPU)" % (B * N * 4 >> 20)},
+        "clocks": clocks, "gpu_launches": args.steps,
+        "e2e": {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "note": "the generator has no host-side input; its output feeds the decoders on the device"},
+        "roofline": {"kernel": "encode_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm"], "traffic": None, "peak_source": peaks["src"], "kernel_ms": kern_ms,
+                     "alg_bytes_per_launch": alg_bytes},
+    }
 
 
 def bench_sc(args, w, rank, world, local_rank):

@@ -53,13 +53,18 @@ __global__ void __launch_bounds__(128) encode_kernel(const EncParams p)
         for (int i = lane; i < 2 * NW; i += 32) W[i] = 0u;
         __syncwarp();
         // rate profile: u[info] = msg, 0-bits (+1) elsewhere (polar.py:137-138, pac_code.py:171-172)
+        uint4 rnd = make_uint4(0, 0, 0, 0);
+        int rnd_block = -1;  // one Philox block serves 128 message bits: a lane's k = lane + 32 i stays in it for 4 turns
         for (int k = lane; k < K; k += 32) {
             uint32_t bit;
             if (p.msg_in) {
                 bit = p.msg_in[r * K + k] < 0.0f;
             } else {
-                uint4 rnd = npd_philox4x32_10(
-                    make_uint4((uint32_t)cw, (uint32_t)(cw >> 32), (uint32_t)(k >> 7), NPD_STREAM_MSG), key);
+                if ((k >> 7) != rnd_block) {
+                    rnd_block = k >> 7;
+                    rnd = npd_philox4x32_10(
+                        make_uint4((uint32_t)cw, (uint32_t)(cw >> 32), (uint32_t)rnd_block, NPD_STREAM_MSG), key);
+                }
                 const uint32_t wsel = (k >> 5) & 3;
                 const uint32_t word = wsel == 0 ? rnd.x : wsel == 1 ? rnd.y : wsel == 2 ? rnd.z : rnd.w;
                 bit = (word >> (k & 31)) & 1u;
