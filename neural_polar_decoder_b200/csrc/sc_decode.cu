@@ -349,6 +349,42 @@ __device__ __forceinline__ void lane_leaf(float L, LaneCtx<BLOG, PAC, EXTRAS> &c
 template <int S, int O, int BLOG, bool PAC, bool EXTRAS>
 __device__ __forceinline__ void lane_node(const float (&L)[S], LaneCtx<BLOG, PAC, EXTRAS> &c)
 {
+    if constexpr (!PAC && !EXTRAS && S >= 4) {
+        // simplified SC (see the quad kernel): subtrees that are entirely frozen / entirely information are not walked.
+        // The frozen pattern is the same for all 32 codewords of the warp, so the branch is warp-uniform; a codeword
+        // that violates a shortcut's condition is flagged (c.tie) and re-decoded by the exact path.
+        constexpr uint32_t M = (S >= 32) ? 0xffffffffu : ((1u << S) - 1u);
+        const uint32_t fm = (c.frozen >> O) & M;
+        if (fm == M) {
+            // rate-0: every leaf satisfies |L| <= sum |alpha_i| < infty, so sign(L + infty) = +1 (polar.py:399, 471-472)
+            float sm = fabsf(L[0]);
+#pragma unroll
+            for (int j = 1; j < S; ++j) sm += fabsf(L[j]);
+            c.tie |= !(sm < 0.99f * c.infty);
+            return;
+        }
+        if (fm == 0u) {
+            // rate-1: partial sums = hard decisions of the node's LLRs, u = x F^(x)s (exact unless an LLR is 0)
+            uint32_t x = 0u;
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                x |= (__float_as_uint(L[j]) >> 31) << j;
+                c.tie |= (L[j] == 0.0f);
+            }
+            uint32_t u = x;
+#pragma unroll
+            for (int h = 1; h < S; h <<= 1) {
+                uint32_t mk = 0u;
+#pragma unroll
+                for (int b = 0; b < S; ++b)
+                    if (!(b & h)) mk |= 1u << b;
+                u ^= (u >> h) & mk;
+            }
+            c.ps |= x << O;
+            c.us |= u << O;
+            return;
+        }
+    }
     if constexpr (S == 1) {
         lane_leaf<O>(L[0], c);
     } else {
