@@ -131,7 +131,7 @@ int64_t pick_chunk(int64_t B, size_t row_bytes, int64_t granule, size_t target_b
 NPD_API int npd_sc_decode_host(const npd_code_t *code, const float *h_y, float llr_scale,
                                const float *h_use_gt, float *h_leaf_llr, float *h_decoded, int64_t B)
 {
-    NPD_REQUIRE(code && h_y && h_decoded, "npd_sc_decode_host: null argument");
+    NPD_REQUIRE(code && h_y && (h_decoded || code->K == 0), "npd_sc_decode_host: null argument");
     NPD_REQUIRE(B >= 0, "npd_sc_decode_host: B < 0");
     if (B == 0) return NPD_OK;
     const size_t N = code->N, K = code->K;
@@ -157,7 +157,7 @@ NPD_API int npd_sc_decode_host(const npd_code_t *code, const float *h_y, float l
 NPD_API int npd_scl_decode_host(const npd_code_t *code, const float *h_y, float llr_scale, int list_size,
                                 float *h_leaf_llr, float *h_decoded, int64_t B)
 {
-    NPD_REQUIRE(code && h_y && h_decoded, "npd_scl_decode_host: null argument");
+    NPD_REQUIRE(code && h_y && (h_decoded || code->K == 0), "npd_scl_decode_host: null argument");
     NPD_REQUIRE(B >= 0, "npd_scl_decode_host: B < 0");
     if (B == 0) return NPD_OK;
     const size_t N = code->N, K = code->K;

@@ -1139,7 +1139,7 @@ NPD_API int npd_sc_decode(const npd_code_t *code, const float *y, float llr_scal
                           const float *use_gt, float *leaf_llr, float *decoded, int64_t B,
                           void *stream)
 {
-    NPD_REQUIRE(code && y && decoded, "npd_sc_decode: null argument");
+    NPD_REQUIRE(code && y && (decoded || code->K == 0), "npd_sc_decode: null argument");
     NPD_REQUIRE(B >= 0, "npd_sc_decode: negative batch");
     NPD_REQUIRE(code->pac_g == 0, "npd_sc_decode: PAC code object; use npd_pac_sc_decode");
     if (B == 0) return NPD_OK;

@@ -331,7 +331,7 @@ int launch_scl(const npd_code *code, const SclParams &p, cudaStream_t st)
 NPD_API int npd_scl_decode(const npd_code_t *code, const float *y, float llr_scale, int list_size, float *leaf_llr,
                            float *decoded, int64_t B, void *stream)
 {
-    NPD_REQUIRE(code && y && decoded, "npd_scl_decode: null argument");
+    NPD_REQUIRE(code && y && (decoded || code->K == 0), "npd_scl_decode: null argument");
     NPD_REQUIRE(B >= 0, "npd_scl_decode: negative batch");
     NPD_REQUIRE(code->pac_g == 0, "npd_scl_decode: polar code objects only");
     NPD_REQUIRE(list_size >= 1, "npd_scl_decode: list size %d < 1", list_size);

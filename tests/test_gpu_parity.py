@@ -399,3 +399,16 @@ def test_conv_chunked_workspace_and_envelope():
     hh = ctypes.c_void_p()
     blob = np.zeros(16, dtype=np.float32)
     assert lib.npd_conv_create(32, 128, ctypes.c_void_p(blob.ctypes.data), 16, ctypes.byref(hh)) == _lib.NPD_EUNSUPPORTED
+
+
+def test_sc_code_without_information_bits():
+    """K = 0 (every position frozen): the leaf LLRs are still the reference's, decoded is [B, 0]."""
+    from neural_polar_decoder_b200 import PolarCode
+    code = PolarCode(4, 0, None, F=np.arange(16))
+    r = np.random.RandomState(3)
+    y = (1.0 + 0.9 * r.randn(100, 16)).astype(np.float32)
+    llr, dec = code.sc_decode_new(torch.from_numpy(y).cuda(), 1.0)
+    lo, _, do = oracle.sc_decode(y, 1.0, 4, code.info_positions)
+    assert dec.shape == (100, 0) and np.array_equal(llr.cpu().numpy(), lo)
+    llr_h, dec_h = code.sc_decode_new(torch.from_numpy(y), 1.0)
+    assert dec_h.shape == (100, 0) and np.array_equal(llr_h.numpy(), lo)

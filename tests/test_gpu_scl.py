@@ -100,3 +100,19 @@ def test_sweeps_run_the_list_decoder():
     assert all(0 < l <= s for l, s in zip(blers_scl, blers_sc)) and blers_scl[1] < blers_scl[0]
     out0 = sweep.polar_RNN_full_test(net, code, [0.0, 2.0], loader, False, False, False, decoder=dec, seed=1)
     assert out0[4] == [0.0, 0.0] and out0[2] == bers_sc
+
+
+@pytest.mark.parametrize("N,K", [(16, 16), (16, 1), (8, 0), (2, 1)])
+def test_scl_degenerate_codes(N, K):
+    """All-information, single-information-bit, no-information and two-bit codes against the oracle."""
+    from neural_polar_decoder_b200 import PolarCode
+    n = int(np.log2(N))
+    frozen = np.arange(N - K)  # the K last positions carry information
+    code = PolarCode(n, K, None, F=frozen)
+    r = np.random.RandomState(N * 7 + K)
+    y = (r.choice([-1.0, 1.0], size=(300, N)) + 0.9 * r.randn(300, N)).astype(np.float32)
+    for L in (1, 4):
+        llr_o, dec_o = oracle.scl_decode(y, 1.0, n, code.info_positions, L)
+        llr, dec = code.scl_decode(torch.from_numpy(y).cuda(), 1.0, L)
+        assert dec.shape == (300, K)
+        assert np.array_equal(dec.cpu().numpy(), dec_o) and np.array_equal(llr.cpu().numpy(), llr_o)
