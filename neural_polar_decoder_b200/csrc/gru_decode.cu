@@ -996,11 +996,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
             if (lane == 0) mbar_arrive_cluster_relaxed(lead_aempty + 8 * a);
         };
 
+        uint32_t head_phase = 0;  // phases of bar_head consumed so far (not every step exchanges partial logits)
         for (int step = 0; step < N; ++step) {
             const uint32_t bits = s_bits[cq];
+            // a position outside the loss set decides +1 (or its genie value) whatever the logit: unless the caller
+            // wants the logits, the head reduction and the cross-CTA exchange are skipped on those steps
+            const uint32_t iw_step = step < 32 ? info0 : step < 64 ? info1 : step < 96 ? info2 : info3;
+            const bool need_head = ((iw_step >> (step & 31)) & 1u) || p.logits != nullptr;
             for (int layer = 0; layer < 2; ++layer) {
                 const uint32_t h_owner = layer ? h1_owner : h0_owner;
-                if (layer == 1 && lane < 8) {
+                if (layer == 1 && need_head && lane < 8) {
 #pragma unroll
                     for (int c8 = 0; c8 < CW3 / 8; ++c8) s_headacc[q * PAIR_CW + col0 + c8 * 8 + lane] = 0.0f;
                 }
@@ -1097,7 +1102,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
                                 if ((i & 1) == 0) staged[si] = hb; else staged[si] |= (uint32_t)hb << 16;
                             }
                         }
-                        if (layer == 1) {
+                        if (layer == 1 && need_head) {
                             // head: reduce the 8 columns over the warp's 32 units; lane l < 8 ends with column cc + l
 #pragma unroll
                             for (int s = 4; s >= 1; s >>= 1) {
@@ -1144,7 +1149,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
             }
 
             // ---- head: this CTA's partial logits (over its 256 units) go to both CTAs ----
-            epi_bar_sync();
+            if (need_head) epi_bar_sync();
             auto publish_h1 = [&]() {
                 if (lane == 0) {
                     if (owner == rank) {
@@ -1157,19 +1162,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
             };
             if (warp >= 4) publish_h1();
             float part = 0.0f;
-            if (warp < 4) {
+            if (warp < 4 && need_head) {
                 const int c = warp * 32 + lane;  // codeword of the pair
                 part = (s_headacc[c] + s_headacc[PAIR_CW + c]) + (s_headacc[2 * PAIR_CW + c] + s_headacc[3 * PAIR_CW + c]);
                 st_cluster_f32(part_peer + c * 4, part);
             }
             if (warp < 4) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(head_peer);  // release: the partial logits above are visible to the peer
-                mbar_wait_cluster(bar_head, step & 1);
+                float logit = 0.0f;
+                if (need_head) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(head_peer);  // release: the partial logits above are visible to the peer
+                    mbar_wait_cluster(bar_head, head_phase & 1);
+                    logit = (part + s_part[warp * 32 + lane]) + p.b_out;  // a + b == b + a: both CTAs get the same logit
+                }
                 const int c = warp * 32 + lane;
-                const float logit = (part + s_part[c]) + p.b_out;  // a + b == b + a: both CTAs get the same logit
-                const uint32_t iw = step < 32 ? info0 : step < 64 ? info1 : step < 96 ? info2 : info3;
-                const bool is_info = (iw >> (step & 31)) & 1u;
+                const bool is_info = (iw_step >> (step & 31)) & 1u;
                 const bool valid = pair0 + c < p.B;
                 const bool mine = (uint32_t)(c >> 6) == rank;  // the owner CTA writes the outputs
                 float dec = (p.genie && valid) ? p.genie[(pair0 + c) * N + step] : 1.0f;
@@ -1184,6 +1191,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
                 if (lane == 0) s_bits[warp] = m;  // both CTAs compute all 128 decisions identically
                 publish_h1();
             }
+            if (need_head) ++head_phase;
             epi_bar_sync();
             if (warp == 0) trace_ev(p, step, 36);
         }
