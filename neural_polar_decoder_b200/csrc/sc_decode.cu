@@ -39,6 +39,7 @@ struct ScParams {
     uint32_t pac_taps, pac_state_mask;
     int scan_flagged;      // group kernel: 1 = only codewords whose decoded[cw][0] is the NaN sentinel
     int slog;              // lane kernel: highest stored level
+    long long *trace;      // bench-only (NPD_SC_TRACE): cycles of warp 0 / block 0's second group: top, levels, block, merge, output, total
 };
 
 template <int G>
@@ -753,16 +754,16 @@ __device__ __forceinline__ void quad_top_phase(const ScParams &p, float *dst, co
 {
     constexpr int N = 1 << NLOG, HS = N >> 2, SLICES = HS >> 5;
     const int kx = (lane >> 2) & 7;  // swizzle key of element j = 32 slice + lane
-#pragma unroll 2
-    for (int slice = 0; slice < SLICES; ++slice) {
+    auto load = [&](float (&v)[8][4], int slice) {
         const float *yj = ygrp + slice * 32 + lane;
-        float v[8][4];
 #pragma unroll
         for (int cc = 0; cc < 8; ++cc) {
             const float *row = yj + (FULL ? cc : min(cc, nvalid - 1)) * N;
 #pragma unroll
             for (int t = 0; t < 4; ++t) v[cc][t] = __ldg(row + t * HS);
         }
+    };
+    auto reduce = [&](float (&v)[8][4], int slice) {
         float *drow = dst + (slice * 32 + lane) * 8;
 #pragma unroll
         for (int cc = 0; cc < 8; ++cc) {
@@ -787,6 +788,16 @@ __device__ __forceinline__ void quad_top_phase(const ScParams &p, float *dst, co
             }
             drow[cc ^ kx] = o;
         }
+    };
+    // explicit two-deep software pipeline: the 32 loads of the next slice are in flight while this one is reduced
+    float va[8][4], vb[8][4];
+    load(va, 0);
+#pragma unroll 1
+    for (int slice = 0; slice < SLICES; slice += 2) {
+        load(vb, slice + 1);
+        reduce(va, slice);
+        if (slice + 2 < SLICES) load(va, slice + 2);
+        reduce(vb, slice + 1);
     }
 }
 
@@ -832,7 +843,7 @@ struct QuadLevelsDown<5> {
     static __device__ __forceinline__ void run(float *, const uint32_t *, const int (&)[8], int, int, int, int) {}
 };
 
-template <int NLOG>
+template <int NLOG, bool TRACE = false>
 __global__ void __launch_bounds__(128) sc_quad_kernel(const ScParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -865,11 +876,14 @@ __global__ void __launch_bounds__(128) sc_quad_kernel(const ScParams p)
         const int nvalid = (int)min((int64_t)8, p.B - cw0);
         const float *ygrp = p.y + cw0 * N;
         c.flag = 0u;
+        const bool tr = TRACE && p.trace && blockIdx.x == 0 && warp == 0 && grp == (int64_t)gridDim.x * wpb;
+        long long t_top = 0, t_lev = 0, t_blk = 0, t_mrg = 0, t_a = 0, t_b, t_start = tr ? clock64() : 0;
 
 #pragma unroll 1
         for (int q = 0; q < NW; ++q) {
             const int o = q << 5;
             const int top = (q == 0) ? NLOG - 1 : (5 + __ffs(q) - 1);
+            if (tr) t_a = clock64();
             if (top >= SLOG) {
                 const int r = q >> (SLOG - 5);
                 __syncwarp();
@@ -890,7 +904,9 @@ __global__ void __launch_bounds__(128) sc_quad_kernel(const ScParams p)
                 }
                 __syncwarp();
             }
+            if (tr) { t_b = clock64(); t_top += t_b - t_a; t_a = t_b; }
             QuadLevelsDown<SLOG - 1>::run(tree, PS, off, sub, cl, top, o);
+            if (tr) { t_b = clock64(); t_lev += t_b - t_a; t_a = t_b; }
             // level 5 straight into registers: L[i] = element 4 i + sub (level 6 sits at offset 0)
             float L[8];
             if (top == 5) {
@@ -914,6 +930,7 @@ __global__ void __launch_bounds__(128) sc_quad_kernel(const ScParams p)
                 US[q * 8 + cl] = c.us;
             }
             __syncwarp();
+            if (tr) { t_b = clock64(); t_blk += t_b - t_a; t_a = t_b; }
             // word-level merges: every trailing one of q completes a block of 2^(5+j+1) leaves
             const int m = __ffs(~q) - 1;
             for (int j = 0; j < m; ++j) {
@@ -922,7 +939,9 @@ __global__ void __launch_bounds__(128) sc_quad_kernel(const ScParams p)
                 for (int i = sub; i < nw; i += 4) PS[(wl + i) * 8 + cl] ^= PS[(wl + nw + i) * 8 + cl];
                 __syncwarp();
             }
+            if (tr) { t_b = clock64(); t_mrg += t_b - t_a; }
         }
+        const long long t_loop_end = tr ? clock64() : 0;
 
         // ---- outputs (coalesced: lane = k), then the sentinel of codewords that need the exact path ----
         uint32_t fl = c.flag;
@@ -941,6 +960,11 @@ __global__ void __launch_bounds__(128) sc_quad_kernel(const ScParams p)
         __syncwarp();
         if (ok && fl && sub == 0) p.decoded[cw * p.K] = __int_as_float(0x7fc00000);
         __syncwarp();
+        if (tr && lane == 0) {
+            const long long t_end = clock64();
+            p.trace[0] = t_top; p.trace[1] = t_lev; p.trace[2] = t_blk; p.trace[3] = t_mrg;
+            p.trace[4] = t_end - t_loop_end; p.trace[5] = t_end - t_start;
+        }
     }
 }
 
@@ -1090,17 +1114,36 @@ int launch_quad(const npd_code *code, ScParams p, cudaStream_t st)
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     void (*kern)(const ScParams) = nullptr;
+    const char *trace_path = getenv("NPD_SC_TRACE");  // bench-only (synchronises!): phase cycles of one group, N = 1024
+    if (trace_path && n != 10) trace_path = nullptr;
     switch (n) {
     case 8: kern = sc_quad_kernel<8>; break;
     case 9: kern = sc_quad_kernel<9>; break;
-    case 10: kern = sc_quad_kernel<10>; break;
+    case 10: kern = trace_path ? sc_quad_kernel<10, true> : sc_quad_kernel<10>; break;
     case 11: kern = sc_quad_kernel<11>; break;
     case 12: kern = sc_quad_kernel<12>; break;
     default: npd_set_error("SC quad kernel: n=%d outside 8..12", n); return NPD_EUNSUPPORTED;
     }
     NPD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpb)));
+    if (trace_path) {
+        NPD_CHECK_CUDA(cudaMalloc(&p.trace, 6 * sizeof(long long)));
+        NPD_CHECK_CUDA(cudaMemsetAsync(p.trace, 0, 6 * sizeof(long long), st));
+    }
     kern<<<(unsigned)grid, 32 * wpb, per_warp * wpb, st>>>(p);
     NPD_CHECK_CUDA(cudaGetLastError());
+    if (trace_path) {
+        long long h[6];
+        NPD_CHECK_CUDA(cudaStreamSynchronize(st));
+        NPD_CHECK_CUDA(cudaMemcpy(h, p.trace, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(p.trace);
+        if (h[5] == 0) return NPD_OK;  // this launch was too small to reach the traced group
+        if (FILE *f = fopen(trace_path, "w")) {
+            fprintf(f, "quad kernel, one group of 8 codewords on one warp (%d warps per SM): top phase %lld, stored levels %lld, "
+                       "32-leaf blocks %lld, partial-sum merges %lld, output %lld, total %lld cycles\n",
+                    blocks_per_sm * wpb, h[0], h[1], h[2], h[3], h[4], h[5]);
+            fclose(f);
+        }
+    }
     return NPD_OK;
 }
 
