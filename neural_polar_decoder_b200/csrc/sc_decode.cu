@@ -949,13 +949,25 @@ __global__ void __launch_bounds__(128) sc_quad_kernel(const ScParams p)
         fl |= __shfl_xor_sync(NPD_FULL, fl, 16);
         __syncwarp();
         float *dst0 = p.decoded + cw0 * p.K;
-        for (int k = lane; k < p.K; k += 32) {
-            const int pos = __ldg(p.info + k);
-            const uint32_t *w = US + (pos >> 5) * 8;
-            const int sh = pos & 31;
+        for (int k0 = 0; k0 < p.K; k0 += 32 * 16) {
+            // the info positions of 16 rounds are fetched together (they were 16 exposed L2 round trips per group)
+            int pos[16];
 #pragma unroll
-            for (int cc = 0; cc < 8; ++cc)
-                if (cc < nvalid) dst0[(size_t)cc * p.K + k] = ((w[cc] >> sh) & 1u) ? -1.0f : 1.0f;
+            for (int i = 0; i < 16; ++i) {
+                const int k = k0 + 32 * i + lane;
+                pos[i] = k < p.K ? __ldg(p.info + k) : 0;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int k = k0 + 32 * i + lane;
+                if (k < p.K) {
+                    const uint32_t *w = US + (pos[i] >> 5) * 8;
+                    const int sh = pos[i] & 31;
+#pragma unroll
+                    for (int cc = 0; cc < 8; ++cc)
+                        if (cc < nvalid) dst0[(size_t)cc * p.K + k] = ((w[cc] >> sh) & 1u) ? -1.0f : 1.0f;
+                }
+            }
         }
         __syncwarp();
         if (ok && fl && sub == 0) p.decoded[cw * p.K] = __int_as_float(0x7fc00000);
