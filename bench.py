@@ -396,6 +396,8 @@ def bench_sc(args, w, rank, world, local_rank):
 
     for _ in range(args.warmup):
         step()
+    if world > 1:
+        dist.all_reduce(counts)  # warm-up of the collective too (its first call sets up NCCL channels)
     sync()
     counts.zero_()
     sampler = ClockSampler(local_rank)

@@ -99,6 +99,9 @@ def bench_gru(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
 
     for _ in range(args.warmup):
         step()
+    if world > 1:
+        dist.all_reduce(counts)  # warm-up of the collective too (its first call sets up NCCL channels)
+        counts.zero_()
     sync()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -273,6 +276,9 @@ def bench_conv(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
 
     for _ in range(args.warmup):
         step()
+    if world > 1:
+        dist.all_reduce(counts)  # warm-up of the collective too (its first call sets up NCCL channels)
+        counts.zero_()
     sync()
     sampler = ClockSampler(local_rank)
     sampler.start()
