@@ -594,25 +594,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
                 mbar_arrive(bar_hready + 8 * layer);
             }
 
-            // ---- head: logit[c] = w_out . h1[c] + b_out ; transpose-reduce over the 32 lanes (units) ----
+            // ---- head: logit[c] = w_out . h1[c] + b_out ; transpose-reduce over the 32 lanes (units).  A position
+            // outside the loss set decides +1 (or its genie value) whatever the logit: skipped unless logits are wanted.
+            const uint32_t iw = step < 32 ? info0 : step < 64 ? info1 : step < 96 ? info2 : info3;
+            const bool is_info = (iw >> (step & 31)) & 1u;
+            const bool need_head = is_info || p.logits != nullptr;
+            if (need_head) {
 #pragma unroll
-            for (int s = CW / 2; s >= 1; s >>= 1) {
+                for (int s = CW / 2; s >= 1; s >>= 1) {
 #pragma unroll
-                for (int i = 0; i < s; ++i) {
-                    const bool up = (lane & s) != 0;
-                    const float send = up ? head[i] : head[i + s];
-                    const float keep = up ? head[i + s] : head[i];
-                    head[i] = keep + __shfl_xor_sync(NPD_FULL, send, s);
+                    for (int i = 0; i < s; ++i) {
+                        const bool up = (lane & s) != 0;
+                        const float send = up ? head[i] : head[i + s];
+                        const float keep = up ? head[i + s] : head[i];
+                        head[i] = keep + __shfl_xor_sync(NPD_FULL, send, s);
+                    }
                 }
+                head[0] += __shfl_xor_sync(NPD_FULL, head[0], CW);  // lanes l and l ^ 16 hold the two halves of the units
+                if (lane < CW) s_red[q * TILE_B + col0 + lane] = head[0];  // lane l holds column col0 + l of this lane quarter
+                epi_bar_sync();
             }
-            head[0] += __shfl_xor_sync(NPD_FULL, head[0], CW);  // lanes l and l ^ 16 hold the two halves of the units
-            if (lane < CW) s_red[q * TILE_B + col0 + lane] = head[0];  // lane l holds column col0 + l of this lane quarter
-            epi_bar_sync();
             if (warp < 2) {
                 const int c = warp * 32 + lane;
-                const float logit = ((s_red[c] + s_red[TILE_B + c]) + (s_red[2 * TILE_B + c] + s_red[3 * TILE_B + c])) + p.b_out;
-                const uint32_t iw = step < 32 ? info0 : step < 64 ? info1 : step < 96 ? info2 : info3;
-                const bool is_info = (iw >> (step & 31)) & 1u;
+                const float logit = need_head ? ((s_red[c] + s_red[TILE_B + c]) + (s_red[2 * TILE_B + c] + s_red[3 * TILE_B + c])) + p.b_out : 0.0f;
                 const bool valid = cw0 + c < p.B;
                 // decoded = ones, or gt.clone() in genie mode; only loss positions are overwritten
                 // (rnn_all.py:519-522, 546-547)
