@@ -117,7 +117,8 @@ int npd_count_errors(const float *a, const float *b, int64_t B, int K, uint64_t 
  * round trip: generate B messages (global indices cw_offset..cw_offset+B), encode, add noise,
  * SC-decode, count.  counts (device uint64[3]) accumulates bit errors, block errors, frames.
  * `workspace` is caller-owned device scratch of at least npd_mc_sc_workspace_bytes(code, chunk)
- * bytes; the batch is processed in chunks of `chunk` codewords. */
+ * bytes (two chunks: one is generated on a library-owned second stream while the other is decoded and
+ * counted on `stream`); the batch is processed in chunks of `chunk` codewords. */
 size_t npd_mc_sc_workspace_bytes(const npd_code_t *code, int64_t chunk);
 int npd_mc_sc_sweep(const npd_code_t *code, int64_t B, int64_t chunk, float sigma, float llr_scale,
                     uint64_t seed, uint32_t point, uint64_t cw_offset, void *workspace,

@@ -3,6 +3,8 @@
 // Replaces errors_ber / errors_bler (reference utils.py:17-25, 37-51: round() both tensors, count
 // mismatching elements and rows with any mismatch; the reference goes through CPU numpy for BLER) and
 // the per-SNR inner loop of polar.py:1258-1291 / rnn_all.py:843-856.
+#include <mutex>
+
 #include "npd_common.cuh"
 
 namespace {
@@ -59,12 +61,27 @@ NPD_API int npd_count_errors(const float *a, const float *b, int64_t B, int K, u
     return launch_count(a, b, B, K, counts, 0, (cudaStream_t)stream);
 }
 
+namespace {
+// one chunk's scratch: msg[chunk,K] + decoded[chunk,K] + y[chunk,N], each region 256-byte aligned
+size_t mc_slot_bytes(const npd_code_t *code, int64_t chunk)
+{
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    return al((size_t)chunk * code->K * 4) * 2 + al((size_t)chunk * code->N * 4);
+}
+
+// second stream + events of the sweep's two-deep pipeline, one set per device (created on first use)
+struct SweepPipe {
+    std::mutex mu;  // the enqueue of one sweep call is atomic with respect to other host threads on the device
+    cudaStream_t gen = nullptr;
+    cudaEvent_t generated[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr}, start = nullptr;
+};
+SweepPipe g_sweep[64];
+}  // namespace
+
 NPD_API size_t npd_mc_sc_workspace_bytes(const npd_code_t *code, int64_t chunk)
 {
     if (!code || chunk <= 0) return 0;
-    // msg[chunk,K] + y[chunk,N] + decoded[chunk,K], each region 256-byte aligned
-    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    return al((size_t)chunk * code->K * 4) * 2 + al((size_t)chunk * code->N * 4);
+    return 2 * mc_slot_bytes(code, chunk);  // two chunks in flight: one being generated, one being decoded
 }
 
 NPD_API int npd_mc_sc_sweep(const npd_code_t *code, int64_t B, int64_t chunk, float sigma,
@@ -77,19 +94,46 @@ NPD_API int npd_mc_sc_sweep(const npd_code_t *code, int64_t B, int64_t chunk, fl
     NPD_REQUIRE(workspace_bytes >= npd_mc_sc_workspace_bytes(code, chunk),
                 "npd_mc_sc_sweep: workspace too small (%zu < %zu)", workspace_bytes,
                 npd_mc_sc_workspace_bytes(code, chunk));
+    // Two chunks in flight: chunk i+1 is generated (message bits, encoder, channel) on a second stream while chunk i
+    // is decoded and counted on the caller's stream -- the generator (Philox / Box-Muller, issue-bound, little shared
+    // memory) and the SC kernel (shared-memory-bound occupancy, 12 warps per SM) fill different resources of an SM.
+    int dev = 0;
+    NPD_CHECK_CUDA(cudaGetDevice(&dev));
+    NPD_REQUIRE(dev < 64, "npd_mc_sc_sweep: device index %d not supported", dev);
+    SweepPipe &sp = g_sweep[dev];
+    std::lock_guard<std::mutex> lk(sp.mu);
+    if (!sp.gen) {
+        NPD_CHECK_CUDA(cudaStreamCreateWithFlags(&sp.gen, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            NPD_CHECK_CUDA(cudaEventCreateWithFlags(&sp.generated[i], cudaEventDisableTiming));
+            NPD_CHECK_CUDA(cudaEventCreateWithFlags(&sp.consumed[i], cudaEventDisableTiming));
+        }
+        NPD_CHECK_CUDA(cudaEventCreateWithFlags(&sp.start, cudaEventDisableTiming));
+    }
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    char *ws = (char *)workspace;
-    float *msg = (float *)ws;
-    float *dec = (float *)(ws + al((size_t)chunk * code->K * 4));
-    float *y = (float *)(ws + 2 * al((size_t)chunk * code->K * 4));
-    for (int64_t done = 0; done < B; done += chunk) {
+    const size_t slot_bytes = mc_slot_bytes(code, chunk);
+    cudaStream_t main_st = (cudaStream_t)stream;
+    // the generator stream starts after whatever the caller queued before this call (e.g. zeroing the counters)
+    NPD_CHECK_CUDA(cudaEventRecord(sp.start, main_st));
+    NPD_CHECK_CUDA(cudaStreamWaitEvent(sp.gen, sp.start, 0));
+    int64_t n_chunks = 0;
+    for (int64_t done = 0; done < B; done += chunk, ++n_chunks) {
+        const int slot = (int)(n_chunks & 1);
         const int64_t b = (B - done < chunk) ? (B - done) : chunk;
-        int rc = npd_gen_encode_awgn(code, msg, nullptr, y, b, sigma, seed, point, cw_offset + done, stream);
+        char *ws = (char *)workspace + slot * slot_bytes;
+        float *msg = (float *)ws;
+        float *dec = (float *)(ws + al((size_t)chunk * code->K * 4));
+        float *y = (float *)(ws + 2 * al((size_t)chunk * code->K * 4));
+        if (n_chunks >= 2) NPD_CHECK_CUDA(cudaStreamWaitEvent(sp.gen, sp.consumed[slot], 0));  // slot's previous chunk counted
+        int rc = npd_gen_encode_awgn(code, msg, nullptr, y, b, sigma, seed, point, cw_offset + done, sp.gen);
         if (rc) return rc;
-        rc = npd_sc_decode(code, y, llr_scale, nullptr, nullptr, dec, b, stream);
+        NPD_CHECK_CUDA(cudaEventRecord(sp.generated[slot], sp.gen));
+        NPD_CHECK_CUDA(cudaStreamWaitEvent(main_st, sp.generated[slot], 0));
+        rc = npd_sc_decode(code, y, llr_scale, nullptr, nullptr, dec, b, main_st);
         if (rc) return rc;
-        rc = launch_count(msg, dec, b, code->K, counts, (uint64_t)b, (cudaStream_t)stream);
+        rc = launch_count(msg, dec, b, code->K, counts, (uint64_t)b, main_st);
         if (rc) return rc;
+        NPD_CHECK_CUDA(cudaEventRecord(sp.consumed[slot], main_st));
     }
     return NPD_OK;
 }
