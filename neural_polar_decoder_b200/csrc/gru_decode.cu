@@ -52,6 +52,7 @@ struct GruParams {
     const unsigned char *wpack2; // CTA-pair kernel: [2 ranks][tiles_per_step2] 16 KB half-tiles, or null
     int tiles_per_step2;
     int use_tmap;                // pair kernel: weight halves arrive by 2-SM tensor copies that signal the leader directly
+    int quad;                    // pair kernel: clusters of 4 = two pairs that share every half-tile by multicast
     const float *consts0;        // [H][12]: b_r b_z b_in b_hn cr0 cr1 cz0 cz1 cn0 cn1 - -
     const float *consts1;        // [H][4] : b_r b_z b_in b_hn
     const float *w_out;          // [H]
@@ -287,6 +288,7 @@ struct MmaCtx {
     bool no_mma;
     int trace_tile, trace_step;    // bench-only: per-tile clock stamps (slots 40..) of one job per step
     int tile_in_step;
+    uint16_t empty_mask;           // pair kernel: CTAs whose ring slot a tile's completion releases
     const GruParams *prm;
 };
 
@@ -434,7 +436,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
             MmaCtx c;
             c.bar_full = bar_full; c.bar_empty = bar_empty; c.ring_lo = umma_desc_lo(smem_u32(s_ring));
             c.idesc = (1u << 4) | ((uint32_t)(TILE_B >> 3) << 17) | ((128u >> 4) << 24);
-            c.ok = 0; c.pb = 0; c.no_mma = (p.dbg & 2) != 0; c.trace_tile = -1; c.trace_step = 0; c.prm = &p; c.tile_in_step = 1 << 30;
+            c.ok = 0; c.pb = 0; c.no_mma = (p.dbg & 2) != 0; c.trace_tile = -1; c.trace_step = 0; c.prm = &p; c.tile_in_step = 1 << 30; c.empty_mask = 3;
             const uint32_t b_h0 = umma_desc_lo(smem_u32(s_h0)), b_h1 = umma_desc_lo(smem_u32(s_h1));
             uint32_t job = 0;  // global job counter -> TMEM slot job & 1
             uint32_t hphase0 = 0, hphase1 = 0;
@@ -700,16 +702,16 @@ __device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v)
 {
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
-__device__ __forceinline__ void umma_commit2(uint32_t bar)  // arrives on the same barrier of BOTH CTAs
+__device__ __forceinline__ void umma_commit2(uint32_t bar, uint16_t mask)  // arrives on the same barrier of every CTA in mask
 {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+                 ::"r"(bar), "h"(mask) : "memory");
 }
 
 // one weight tile (4 K-steps of M=256 N=128) + probe of the next ring stage; see tile_issue
 __device__ __forceinline__ uint32_t tile_issue2(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc0,
                                                 uint32_t bar_empty_cur, uint32_t bar_full_next, uint32_t parity_next,
-                                                uint32_t skip_mma)
+                                                uint32_t skip_mma, uint16_t empty_mask)
 {
     uint32_t ok;
     const uint64_t a0 = umma_desc_from_lo(a_lo), b0 = umma_desc_from_lo(b_lo);
@@ -729,7 +731,7 @@ __device__ __forceinline__ uint32_t tile_issue2(uint32_t d_tmem, uint32_t a_lo, 
         "}"
         : "=r"(ok)
         : "r"(d_tmem), "l"(a0), "l"(b0), "r"(acc0), "r"(idesc), "r"(bar_empty_cur), "r"(bar_full_next), "r"(parity_next),
-          "l"(a0 + 2), "l"(b0 + 2), "l"(a0 + 4), "l"(b0 + 4), "l"(a0 + 6), "l"(b0 + 6), "h"((uint16_t)3), "r"(skip_mma)
+          "l"(a0 + 2), "l"(b0 + 2), "l"(a0 + 4), "l"(b0 + 4), "l"(a0 + 6), "l"(b0 + 6), "h"(empty_mask), "r"(skip_mma)
         : "memory");
     return ok;
 }
@@ -749,7 +751,8 @@ __device__ __forceinline__ void mma_run2(MmaCtx &c, uint32_t d, uint32_t b, bool
         if (!c.ok && !c.no_mma) mbar_wait(c.bar_full + 8 * stage, (pass & 1) ^ c.pb);
         if (c.tile_in_step < 48) trace_ns(*c.prm, c.trace_step, 100 + c.tile_in_step);        // leader: data of both halves seen
         c.ok = tile_issue2(d, c.ring_lo + stage * A_TILE_LO, b + kc * B_CHUNK_LO, c.idesc, (first && kc == 0) ? 0u : 1u,
-                           c.bar_empty + 8 * stage, c.bar_full + 8 * nstage, (npass & 1) ^ c.pb, (uint32_t)(c.prm->dbg & 32));
+                           c.bar_empty + 8 * stage, c.bar_full + 8 * nstage, (npass & 1) ^ c.pb, (uint32_t)(c.prm->dbg & 32),
+                           c.empty_mask);
         if (c.trace_tile >= 0 && c.trace_tile < 48 && c.prm->trace) c.prm->trace[c.trace_step * TRACE_SLOTS + 40 + c.trace_tile++] = clock64();
         if (c.tile_in_step < 48) trace_ns(*c.prm, c.trace_step, 150 + c.tile_in_step);        // leader: MMAs + commit issued
         ++c.tile_in_step;
@@ -785,7 +788,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
     constexpr int H = KH * 64, JOBS2 = H / 256;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = p.N;
-    const uint32_t rank = cluster_ctarank();
+    const uint32_t crank = cluster_ctarank();  // rank in the cluster (2 CTAs = one pair, or 4 = two pairs sharing weights)
+    const uint32_t rank = crank & 1u;          // rank in the MMA pair: 0 = leader
+    const uint32_t lead = crank & ~1u, sibling = crank ^ 2u;
+    const uint16_t pair_mask = (uint16_t)(3u << lead);
     const int64_t pair0 = (int64_t)(blockIdx.x >> 1) * PAIR_CW;  // first codeword of the pair
     const int64_t cw0 = pair0 + rank * TILE_B;                   // first codeword whose state lives in this CTA
 
@@ -806,7 +812,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
         for (int i = 0; i < NUM_STAGES; ++i) {
             // relay variant: leader = own copy + the peer's relay; tensor-copy variant: one expect_tx of both halves
             mbar_init(bar_full + 8 * i, (rank == 0 && !p.use_tmap) ? 2 : 1);
-            mbar_init(bar_empty + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, p.quad ? 2 : 1);  // both pairs' MMAs on a shared (multicast) slot have retired
         }
         for (int i = 0; i < 4; ++i) {
             mbar_init(bar_afull + 8 * i, 1);
@@ -868,7 +874,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
     }
     cluster_sync_all();  // the ring memory (y tile) of both CTAs is free for the weight stream from here on
 
-    const uint32_t lead_aempty = mapa_u32(bar_aempty, 0), lead_hready = mapa_u32(bar_hready, 0);
+    const uint32_t lead_aempty = mapa_u32(bar_aempty, lead), lead_hready = mapa_u32(bar_hready, lead);
 
     if (warp >= EPI_WARPS && warp < MMA_WARP) {
         // ================= producer: this CTA's half of every weight tile =================
@@ -892,7 +898,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
                     // every CTA's copy signals its OWN barrier (a plain bulk copy whose mbarrier operand points into the
                     // other CTA never completes -- tried: the kernel hangs), hence the relay in the peer's MMA warp
                     mbar_expect_tx(bar_full + 8 * stage, A_TILE_BYTES);
-                    bulk_g2s(smem_u32(s_ring + stage * A_TILE_BYTES), src + (size_t)t * A_TILE_BYTES, A_TILE_BYTES, bar_full + 8 * stage);
+                    if (!p.quad)
+                        bulk_g2s(smem_u32(s_ring + stage * A_TILE_BYTES), src + (size_t)t * A_TILE_BYTES, A_TILE_BYTES, bar_full + 8 * stage);
+                    else if (((g & 1u) << 1 | rank) == crank)  // the two CTAs with this pair rank take turns fetching for both
+                        bulk_g2s_multicast(smem_u32(s_ring + stage * A_TILE_BYTES), src + (size_t)t * A_TILE_BYTES, A_TILE_BYTES,
+                                           bar_full + 8 * stage, (uint16_t)((1u << crank) | (1u << sibling)));
                 }
                 t += PRODUCER_LANES;
                 if (t >= T) t -= T;
@@ -906,7 +916,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
             if (rank != 0) {
                 // ================= peer: relay "my half has landed" to the leader's full barriers =================
                 const uint32_t total = ((p.dbg & 1) || p.use_tmap) ? 0u : (uint32_t)N * (uint32_t)p.tiles_per_step2;
-                const uint32_t lead_full = mapa_u32(bar_full, 0);
+                const uint32_t lead_full = mapa_u32(bar_full, lead);
                 uint32_t stage = 0, phase = 0;
                 const uint32_t T = (uint32_t)p.tiles_per_step2;
                 for (uint32_t g = 0; g < total; ++g) {
@@ -921,6 +931,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
                 c.bar_full = bar_full; c.bar_empty = bar_empty; c.ring_lo = umma_desc_lo(smem_u32(s_ring));
                 c.idesc = (1u << 4) | ((uint32_t)(PAIR_CW >> 3) << 17) | ((256u >> 4) << 24);  // M = 256, N = 128
                 c.ok = 0; c.pb = 0; c.no_mma = (p.dbg & 17) != 0;  /* bench-only: 1 = no weight stream at all, 16 = stream runs but is not waited for */ c.trace_tile = -1; c.trace_step = 0; c.prm = &p; c.tile_in_step = 0;
+                c.empty_mask = p.quad ? (uint16_t)0xF : pair_mask;
                 const uint32_t b_h0 = umma_desc_lo(smem_u32(s_h0)), b_h1 = umma_desc_lo(smem_u32(s_h1));
                 const uint32_t dR = tmem_base, dZ = tmem_base + PAIR_CW, dNI = tmem_base + 2 * PAIR_CW, dNH = tmem_base + 3 * PAIR_CW;
                 uint32_t use[4] = {0, 0, 0, 0};  // how often each accumulator region has been filled
@@ -930,7 +941,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
                     tc_fence_after();
                 };
                 auto publish = [&](int a) {
-                    umma_commit2(bar_afull + 8 * a);
+                    umma_commit2(bar_afull + 8 * a, pair_mask);
                     ++use[a];
                 };
                 for (int step = 0; step < N; ++step) {
@@ -974,13 +985,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
         // ================= epilogue warps =================
         const int q = warp & 3, cq = warp >> 2;
         const int col0 = cq * CW3;                       // first of this thread's 32 codeword columns (pair index)
-        const uint32_t owner = (uint32_t)(cq >> 1);      // CTA that holds these codewords' hidden states
+        const uint32_t owner = (uint32_t)(cq >> 1);      // CTA of the pair that holds these codewords' hidden states
         const int row0 = col0 & (TILE_B - 1);            // their rows in the owner's B-operand buffers
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         // bench-only experiment (results are garbage): dbg & 8 = every state access goes to this CTA's own memory
-        const uint32_t h0_owner = mapa_u32(smem_u32(s_h0), (p.dbg & 8) ? rank : owner),
-                       h1_owner = mapa_u32(smem_u32(s_h1), (p.dbg & 8) ? rank : owner);
-        const uint32_t peer = rank ^ 1u;
+        const uint32_t h0_owner = mapa_u32(smem_u32(s_h0), lead + ((p.dbg & 8) ? rank : owner)),
+                       h1_owner = mapa_u32(smem_u32(s_h1), lead + ((p.dbg & 8) ? rank : owner));
+        const uint32_t peer = crank ^ 1u;
         const uint32_t part_peer = mapa_u32(smem_u32(s_part), peer), head_peer = mapa_u32(bar_head, peer);
         const uint32_t bits_peer = mapa_u32(smem_u32(s_bits), peer);
         uint32_t use[4] = {0, 0, 0, 0};
@@ -1441,10 +1452,18 @@ NPD_API int npd_gru_decode(const npd_gru_t *g, const npd_code_t *code, const flo
     { const char *d = getenv("NPD_GRU_PAIR"); if (d) use_pair = use_pair && atoi(d) != 0; }
     // the 2-SM tensor-copy variant (no relay) works but measures slower than relay + linear bulk copies (12.4 vs 11.4 ms
     // per 37888 codewords): opt-in with NPD_GRU_TMAP=1
+    // NPD_GRU_QUAD=1: clusters of four (two MMA pairs that take turns fetching every half-tile and multicast it to the CTA
+    // with the same pair rank in the other pair: half the L2 reads). Measured 12.7 ms against 10.95 ms for plain pairs at
+    // 37888 codewords -- a ring slot then frees only when BOTH pairs have consumed it, which couples their schedules --
+    // so plain pairs stay the default.
+    p.quad = 0;
+    { const char *d = getenv("NPD_GRU_QUAD"); if (d) p.quad = use_pair && atoi(d) != 0; }
     p.use_tmap = 0;
     { const char *d = getenv("NPD_GRU_TMAP"); if (d) p.use_tmap = g->have_tmap2 && atoi(d) != 0; }
+    if (p.use_tmap) p.quad = 0;
     { const char *d = getenv("NPD_GRU_DBG"); p.dbg = d ? atoi(d) : 0; }
-    const int64_t grid = ((B + 2 * TILE_B - 1) / (2 * TILE_B)) * 2;  // CTA pairs (clusters of 2); an odd tile count pads with an idle-data CTA
+    int64_t grid = ((B + 2 * TILE_B - 1) / (2 * TILE_B)) * 2;  // CTA pairs (clusters of 2); an odd tile count pads with an idle-data CTA
+    if (p.quad) grid = (grid + 3) / 4 * 4;
     const char *trace_path = getenv("NPD_GRU_TRACE");  // bench-only: dump CTA 0's event clocks (synchronises!)
     if (trace_path) NPD_CHECK_CUDA(cudaMalloc(&p.trace, sizeof(long long) * g->N * TRACE_SLOTS));
     if (trace_path) NPD_CHECK_CUDA(cudaMemsetAsync(p.trace, 0, sizeof(long long) * g->N * TRACE_SLOTS, (cudaStream_t)stream));
@@ -1457,7 +1476,7 @@ NPD_API int npd_gru_decode(const npd_gru_t *g, const npd_code_t *code, const flo
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.x = p.quad ? 4 : 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
