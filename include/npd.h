@@ -155,6 +155,15 @@ int npd_gru_decode(const npd_gru_t *gru, const npd_code_t *code, const float *y,
                    const float *forced, const float *genie, float *logits, float *decoded, int64_t B,
                    void *workspace, size_t workspace_bytes, void *stream);
 
+/* npd_gru_decode_h0: the same loop started from a caller-supplied hidden state -- decoding_type 'y_h0'
+ * (rnn_all.py:523-531): hidden = net.get_h0(y) (RNN_Model.get_h0, 362-375: the y-MLP reshaped to [L,B,H]) and the
+ * step input is only the previous decision, i.e. a decoder created with all-zero y columns in w_ih0.
+ *   h0      [2,B,H] or NULL  initial hidden state of both layers, fp32 (NULL = zeros = npd_gru_decode)
+ * every other argument as npd_gru_decode. */
+int npd_gru_decode_h0(const npd_gru_t *gru, const npd_code_t *code, const float *y, const float *h0,
+                      const float *forced, const float *genie, float *logits, float *decoded, int64_t B,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- convNet one-shot decoder ------------------------------------------------------------------
  * npd_conv_create / npd_conv_forward: convNet.forward (models.py:742-767; layers 701-740) with
  * embed_dim = 2*C (C = 64), max_len = N: ten dilated k=7 Conv1d + GELU with three residual adds,

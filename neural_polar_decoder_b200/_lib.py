@@ -35,6 +35,7 @@ SIGNATURES = {
     "npd_gru_destroy": (_int, [_vp]),
     "npd_gru_workspace_bytes": (_sz, [_vp, _i64]),
     "npd_gru_decode": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
+    "npd_gru_decode_h0": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
     "npd_conv_create": (_int, [_int, _int, _vp, _sz, _c.POINTER(_vp)]),
     "npd_conv_destroy": (_int, [_vp]),
     "npd_conv_workspace_bytes": (_sz, [_vp, _i64]),

@@ -159,7 +159,12 @@ def build_net(args):
                          args.y_hidden_size if args.out_linear_depth > 1 else 0, 0, args.activation, args.dropout,
                          args.use_skip, out_linear_depth=args.out_linear_depth, bidirectional=args.bidirectional,
                          use_layernorm=args.use_layernorm)
-    raise NotImplementedError("decoding_type %r: the B200 path covers 'y_input' (run_crisp.sh)" % args.decoding_type)
+    if args.decoding_type == "y_h0":  # the reference's default: initial state from the y-MLP (rnn_all.py:1316-1317)
+        return RNN_Model(args.rnn_type, 1 + onehot, args.rnn_feature_size, 1, args.rnn_depth, args.N,
+                         args.y_hidden_size, args.y_depth, args.activation, args.dropout, args.use_skip,
+                         bidirectional=args.bidirectional, use_layernorm=args.use_layernorm)
+    # 'y_h0_out' (rnn_all.py:1323-1324) cannot run in the reference: its head is built for H inputs and fed [Fy | out]
+    raise NotImplementedError("decoding_type %r: the B200 path covers 'y_input' and 'y_h0'" % args.decoding_type)
 
 
 def net_from_checkpoint(path_or_ckpt):

@@ -60,6 +60,7 @@ struct GruParams {
     const float *y;              // [B,N]
     const float *forced;         // [B,N] or null
     const float *genie;          // [B,N] or null: decoded starts as this tensor (rnn_all.py:521-522)
+    const float *h0;             // [2][B][H] or null: initial hidden state (decoding_type 'y_h0', rnn_all.py:523-524)
     const uint32_t *info_words;  // bit i = position i is an info (loss) position
     float *logits;               // [B,N] or null
     float *decoded;              // [B,N]
@@ -354,10 +355,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    // h0 = h1 = 0 (rnn_all.py:538); the y tile goes, as fp32 [k][codeword], into the (still idle) ring memory for
-    // the input-projection prologue below
-    for (int i = tid; i < (2 * KH * B_CHUNK_BYTES) / 16; i += NUM_THREADS)
-        reinterpret_cast<uint4 *>(s_h0)[i] = make_uint4(0, 0, 0, 0);
+    // h0 = h1 = 0 (rnn_all.py:538) or the caller's initial state (net.get_h0(y), 523-524); the y tile goes, as fp32
+    // [k][codeword], into the (still idle) ring memory for the input-projection prologue below
+    if (p.h0 == nullptr) {
+        for (int i = tid; i < (2 * KH * B_CHUNK_BYTES) / 16; i += NUM_THREADS)
+            reinterpret_cast<uint4 *>(s_h0)[i] = make_uint4(0, 0, 0, 0);
+    } else {
+        for (int i = tid; i < 2 * TILE_B * H; i += NUM_THREADS) {
+            const int layer = i / (TILE_B * H), c = (i / H) % TILE_B, u = i % H;
+            const float v = (cw0 + c < p.B) ? p.h0[((size_t)layer * p.B + cw0 + c) * H + u] : 0.0f;
+            *reinterpret_cast<__half *>((layer ? s_h1 : s_h0) + b_off(c, u)) = __float2half_rn(v);
+        }
+    }
     float *s_yT = reinterpret_cast<float *>(s_ring);
     for (int i = tid; i < TILE_B * N; i += NUM_THREADS) {
         const int c = i / N, k = i % N;
@@ -823,9 +832,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int i = 0; i < 4; ++i) s_bits[i] = 0xffffffffu;  // step 0 feeds back +1 (rnn_all.py:542-543)
     }
-    // h0 = h1 = 0 (rnn_all.py:538); y of all 128 codewords of the pair as fp32 [k][codeword] in the idle ring memory
-    for (int i = tid; i < (2 * KH * B_CHUNK_BYTES) / 16; i += NUM_THREADS)
-        reinterpret_cast<uint4 *>(s_h0)[i] = make_uint4(0, 0, 0, 0);
+    // h0 = h1 = 0 (rnn_all.py:538) or the caller's initial state of this CTA's 64 codewords (net.get_h0(y), 523-524);
+    // y of all 128 codewords of the pair as fp32 [k][codeword] in the idle ring memory
+    if (p.h0 == nullptr) {
+        for (int i = tid; i < (2 * KH * B_CHUNK_BYTES) / 16; i += NUM_THREADS)
+            reinterpret_cast<uint4 *>(s_h0)[i] = make_uint4(0, 0, 0, 0);
+    } else {
+        for (int i = tid; i < 2 * TILE_B * H; i += NUM_THREADS) {
+            const int layer = i / (TILE_B * H), c = (i / H) % TILE_B, u = i % H;
+            const float v = (cw0 + c < p.B) ? p.h0[((size_t)layer * p.B + cw0 + c) * H + u] : 0.0f;
+            *reinterpret_cast<__half *>((layer ? s_h1 : s_h0) + b_off(c, u)) = __float2half_rn(v);
+        }
+    }
     float *s_yT = reinterpret_cast<float *>(s_ring);
     for (int i = tid; i < PAIR_CW * N; i += NUM_THREADS) {
         const int c = i / N, k = i % N;
@@ -1434,8 +1452,15 @@ NPD_API int npd_gru_destroy(npd_gru_t *g)
 NPD_API size_t npd_gru_workspace_bytes(const npd_gru_t *, int64_t) { return 0; }
 
 NPD_API int npd_gru_decode(const npd_gru_t *g, const npd_code_t *code, const float *y, const float *forced,
-                           const float *genie, float *logits, float *decoded, int64_t B, void *, size_t,
+                           const float *genie, float *logits, float *decoded, int64_t B, void *ws, size_t ws_bytes,
                            void *stream)
+{
+    return npd_gru_decode_h0(g, code, y, nullptr, forced, genie, logits, decoded, B, ws, ws_bytes, stream);
+}
+
+NPD_API int npd_gru_decode_h0(const npd_gru_t *g, const npd_code_t *code, const float *y, const float *h0,
+                              const float *forced, const float *genie, float *logits, float *decoded, int64_t B, void *,
+                              size_t, void *stream)
 {
     NPD_REQUIRE(g && code && y && decoded, "npd_gru_decode: null argument");
     NPD_REQUIRE(B >= 0, "npd_gru_decode: negative batch");
@@ -1443,7 +1468,7 @@ NPD_API int npd_gru_decode(const npd_gru_t *g, const npd_code_t *code, const flo
     if (B == 0) return NPD_OK;
     GruParams p{};
     p.wpack = g->d_wpack; p.w_iyT = g->d_w_iyT; p.consts0 = g->d_consts0; p.consts1 = g->d_consts1;
-    p.w_out = g->d_w_out; p.b_out = g->b_out; p.y = y; p.forced = forced; p.genie = genie; p.info_words = code->d_info_words;
+    p.w_out = g->d_w_out; p.b_out = g->b_out; p.y = y; p.h0 = h0; p.forced = forced; p.genie = genie; p.info_words = code->d_info_words;
     p.logits = logits; p.decoded = decoded; p.B = B; p.N = g->N; p.H = g->H;
     p.tiles_per_step = g->tiles_per_step;
     p.wpack2 = g->d_wpack2; p.tiles_per_step2 = g->tiles_per_step2;

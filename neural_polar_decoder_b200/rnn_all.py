@@ -1,16 +1,17 @@
 """Drop-in for the hot-path half of the reference's rnn_all.py / rnn.py: RNN_Model (parameter
-container with the reference's state_dict keys), RNN_decoder.decode (test branch, 'y_input', onehot) and
+container with the reference's state_dict keys), RNN_decoder.decode ('y_input' and 'y_h0') and
 get_code.  The N-step autoregressive decode is ONE libnpd.so launch (csrc/gru_decode.cu).
 
 Reference: rnn_all.py:258-260 (get_onehot), 294-398 (RNN_Model), 400-561 (RNN_decoder),
-1015-1196 (get_code).  Out of scope: training branches, y_h0 / y_h0_out conditioning,
-LSTM / bidirectional / LayerNorm variants, the list decoder."""
+1015-1196 (get_code).  Out of scope: training branches (gradients), MLP heads
+(out_linear_depth > 1), LSTM / bidirectional / LayerNorm variants, the GRU list decoder."""
 import ctypes
 import random
 
 import numpy as np
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import _lib, construct
 from .pac_code import PAC
@@ -48,11 +49,46 @@ class RNN_Model(nn.Module):
                                          batch_first=True)
         self.drop = nn.Dropout(dropout)
         self.layernorm = nn.LayerNorm(feature_size) if use_layernorm else nn.Identity()
-        if out_linear_depth != 1 or (y_hidden_size > 0 and y_depth > 0):
-            raise NotImplementedError("only the run_crisp.sh configuration (y_input: y_depth=0, "
-                                      "out_linear_depth=1) is on the accelerated path")
-        self.linear = nn.Linear((int(bidirectional) + 1) * feature_size, output_size)
+        D = int(bidirectional) + 1
+        self.y_output_size = D * num_rnn_layers * feature_size if y_output_size is None else y_output_size
+        if y_hidden_size > 0 and y_depth > 0:  # the y-MLP of 'y_h0' / use_ynn (rnn_all.py:323-329), same parameter names
+            self.y_linears = nn.ModuleList([nn.Linear(y_size, y_hidden_size, bias=True)])
+            self.y_linears.extend([nn.Linear(y_hidden_size, y_hidden_size, bias=True) for _ in range(1, y_depth - 1)])
+            self.y_linears.append(nn.Linear(y_hidden_size, self.y_output_size - (y_size if skip else 0), bias=True))
+        if out_linear_depth == 1:
+            self.linear = nn.Linear(D * feature_size, output_size)
+        else:  # rnn_all.py:335-343; loads reference checkpoints, but the fused kernel has no MLP head (_supported)
+            layers = [nn.Linear(D * feature_size, y_hidden_size)]
+            for _ in range(1, out_linear_depth - 1):
+                layers += [nn.SELU(), nn.Linear(y_hidden_size, y_hidden_size)]
+            layers += [nn.SELU(), nn.Linear(y_hidden_size, output_size)]
+            self.linear = nn.Sequential(*layers)
         self._npd = None  # (key, handle)
+
+    def act(self, inputs):
+        """rnn_all.py:346-360 (unknown names fall through to identity there too)."""
+        fn = {'tanh': torch.tanh, 'elu': F.elu, 'relu': F.relu, 'selu': F.selu, 'sigmoid': torch.sigmoid}
+        return fn.get(self.activation, lambda x: x)(inputs)
+
+    def get_Fy(self, y):
+        """rnn_all.py:377-384: the y-MLP.  The reference skips the activation only for `ii == y_depth`, which with
+        y_depth layers (y_depth >= 2) never happens -- the last layer is activated too -- and with y_depth == 1 (two
+        layers) hits the second one.  A small dense MLP run once per batch: torch (cuBLAS) on y's device."""
+        x = y
+        for ii, layer in enumerate(self.y_linears):
+            x = F.linear(x, layer.weight.to(y.device), layer.bias.to(y.device))
+            if ii != self.y_depth:
+                x = self.act(x)
+        return x
+
+    def get_h0(self, y):
+        """rnn_all.py:362-375: y-MLP output [B, L*H] read as [B, H, L] and permuted to [L, B, H]."""
+        x = self.get_Fy(y)
+        if self.skip:
+            x = torch.cat([y, x], 1)
+        x = x.reshape(-1, self.feature_size, (int(self.bidirectional) + 1) * self.num_rnn_layers).permute(2, 0, 1)
+        x = x.contiguous()
+        return x if self.rnn_type == 'GRU' else (x, x)
 
     def forward(self, input, hidden, Fy=None):
         out, hidden = self.rnn(input, hidden)
@@ -65,14 +101,15 @@ class RNN_Model(nn.Module):
         return (self.rnn_type == 'GRU' and self.num_rnn_layers == 2 and not self.bidirectional and
                 not self.use_layernorm and self.output_size == 1 and self.out_linear_depth == 1)
 
-    def npd_handle(self, N):
+    def npd_handle(self, N, onehot=True, y_in=True):
         if not self._supported():
-            raise NotImplementedError("fused decode supports GRU, 2 layers, unidirectional, no LayerNorm, 1 output")
+            raise NotImplementedError("fused decode supports GRU, 2 layers, unidirectional, no LayerNorm, 1 output, "
+                                      "out_linear_depth 1")
         sd = self.state_dict()
-        key = (N, torch.cuda.current_device()) + tuple((k, v._version, v.data_ptr()) for k, v in sd.items())
+        key = (N, onehot, y_in, torch.cuda.current_device()) + tuple((k, v._version, v.data_ptr()) for k, v in sd.items())
         if self._npd is not None and self._npd[0] == key:
             return self._npd[1]
-        handle = GruHandle(N, self.feature_size, sd)
+        handle = GruHandle(N, self.feature_size, sd, onehot=onehot, y_in=y_in)
         self._npd = (key, handle)
         return handle
 
@@ -80,7 +117,10 @@ class RNN_Model(nn.Module):
 class GruHandle:
     """Owns an npd_gru_t (fp16 weight tile streams in HBM)."""
 
-    def __init__(self, N, H, sd):
+    def __init__(self, N, H, sd, onehot=True, y_in=True):
+        """onehot / y_in describe the columns of rnn.weight_ih_l0: [y (N, when y_in) | feedback (2 one-hot, else 1)].
+        The library takes the run_crisp.sh form [3H, N+2]; the other forms are widened to it exactly: absent y
+        columns are zeros ('y_h0', rnn_all.py:526-528), a scalar +-1 feedback column w is the one-hot pair [-w, +w]."""
         _lib.require_cuda()
         lib = _lib.load()
 
@@ -90,8 +130,11 @@ class GruHandle:
             assert tuple(t.shape) == tuple(shape), (name, tuple(t.shape), shape)
             return t
 
+        w_in = host("rnn.weight_ih_l0", (3 * H, (N if y_in else 0) + (2 if onehot else 1)))
+        wy = w_in[:, :N] if y_in else torch.zeros(3 * H, N)
+        fb = w_in[:, -2:] if onehot else torch.cat([-w_in[:, -1:], w_in[:, -1:]], 1)
         self._keep = [
-            host("rnn.weight_ih_l0", (3 * H, N + 2)), host("rnn.weight_hh_l0", (3 * H, H)),
+            torch.cat([wy, fb], 1).contiguous(), host("rnn.weight_hh_l0", (3 * H, H)),
             host("rnn.bias_ih_l0", (3 * H,)), host("rnn.bias_hh_l0", (3 * H,)),
             host("rnn.weight_ih_l1", (3 * H, H)), host("rnn.weight_hh_l1", (3 * H, H)),
             host("rnn.bias_ih_l1", (3 * H,)), host("rnn.bias_hh_l1", (3 * H,)),
@@ -112,15 +155,19 @@ class GruHandle:
             pass
 
 
-def gru_decode(net_or_handle, code_handle, y, forced=None, want_logits=False, genie=None):
-    """One fused launch: y [B,N] (device) -> (decoded [B,N], logits [B,N] or None)."""
+def gru_decode(net_or_handle, code_handle, y, forced=None, want_logits=False, genie=None, h0=None):
+    """One fused launch: y [B,N] (device) -> (decoded [B,N], logits [B,N] or None).  h0 [2,B,H]: initial state."""
     B, N = y.shape
     handle = net_or_handle if isinstance(net_or_handle, GruHandle) else net_or_handle.npd_handle(N)
     decoded = torch.empty(B, N, dtype=torch.float32, device=y.device)
     logits = torch.empty(B, N, dtype=torch.float32, device=y.device) if want_logits else None
+    if h0 is not None:
+        h0 = h0.float().contiguous()
+        assert tuple(h0.shape) == (2, B, handle.H) and h0.device == y.device, (tuple(h0.shape), h0.device)
     if B > 0:
-        _lib.check(_lib.load().npd_gru_decode(handle.h, code_handle.h, _lib.ptr(y), _lib.ptr(forced), _lib.ptr(genie),
-                                              _lib.ptr(logits), _lib.ptr(decoded), B, None, 0, _lib.stream_ptr()))
+        _lib.check(_lib.load().npd_gru_decode_h0(handle.h, code_handle.h, _lib.ptr(y), _lib.ptr(h0), _lib.ptr(forced),
+                                                 _lib.ptr(genie), _lib.ptr(logits), _lib.ptr(decoded), B, None, 0,
+                                                 _lib.stream_ptr()))
     return decoded, logits
 
 
@@ -162,48 +209,76 @@ class RNN_decoder:
         return h
 
     def decode(self, net, train, y, gt=None, teacher_forcing_ratio=0., loss_inds=None, return_logits=False):
-        """reference rnn_all.py:408-561 for decoding_type 'y_input' with one-hot feedback; all N autoregressive
-        steps are one kernel launch.
+        """reference rnn_all.py:408-561 for decoding_type 'y_input' (zero initial state, step input [Fy | feedback],
+        Fy = y or the y-MLP net.get_Fy(y) under use_ynn, 532-547) and 'y_h0' (initial state net.get_h0(y), step input
+        = feedback only, 523-531), feedback one-hot or the scalar +-1, forward or reverse order; all N autoregressive
+        steps are one kernel launch.  ('y_h0_out' cannot run in the reference either: forward() concatenates
+        [Fy (L*H) | out (H)] into a head built for H inputs, rnn_all.py:334-343, 393-396.)
 
-        train=False (rnn_all.py:514-561): hidden state from zero, decisions sign(logit) on loss_inds (default: the
-        info positions), +1 elsewhere.  gt = genie tensor [B,N]: decoded starts as gt.clone(), so positions outside
-        loss_inds keep and feed back their genie value (rnn_all.py:519-522; the `loss_inds=code.loss_inds` call of
-        polar_RNN_full_test, 887).
+        train=False (rnn_all.py:514-561): decisions sign(logit) on loss_inds (default: the info positions), +1
+        elsewhere.  gt = genie tensor [B,N]: decoded starts as gt.clone(), so positions outside loss_inds keep and
+        feed back their genie value (rnn_all.py:519-522; the `loss_inds=code.loss_inds` call of
+        polar_RNN_full_test, 887).  reverse_order: step ii handles position N-1-ii (gt flipped on entry, 417-419,
+        result flipped back, 558-561).
         train=True is served for EVALUATION only (no autograd graph; the reference's test_model(tf=True) calls it
         under torch.no_grad(), rnn_all.py:982-984): teacher forcing (425-461) returns the raw outputs of all N
-        steps with gt fed back; student forcing (462-512) returns raw outputs on the info positions, 1 elsewhere.
-        Training itself (gradients) is out of scope of the B200 path."""
-        if self.decoding_type != 'y_input' or not self.onehot or self.reverse_order:
-            raise NotImplementedError("accelerated path: decoding_type='y_input', onehot=True, forward order")
-        if getattr(net, "y_depth", 0) != 0:
-            raise NotImplementedError("y_input with a y-MLP (y_depth > 0) is out of scope")
+        steps with gt fed back; student forcing (462-512) returns raw outputs on the steps `ii in info_inds`, 1
+        elsewhere.  Training itself (gradients) is out of scope of the B200 path.
+        One deviation, on a measure-zero input: a scalar (non-one-hot) feedback of exactly 0 (sign of a zero logit or
+        of a zero genie value) enters the reference as 0 * w and this path as -w, the one-hot convention (258-260)."""
+        if self.decoding_type not in ('y_input', 'y_h0'):
+            raise NotImplementedError("decoding_type %r: the accelerated path serves 'y_input' and 'y_h0'"
+                                      % (self.decoding_type,))
+        N = self.N
+        y_h0 = self.decoding_type == 'y_h0'
+        ynn = (not y_h0) and getattr(net, "y_depth", 0) != 0
         on_host = torch.is_tensor(y) and not y.is_cuda
-        run = gru_decode_host if on_host else gru_decode
-        yd = _lib.host_f32(y) if on_host else _lib.to_device_f32(y)
-        assert yd.dim() == 2 and yd.shape[1] == self.N
-        dev_ctx = torch.cuda.device(torch.cuda.current_device() if on_host else yd.device)
+        pipe = on_host and not (y_h0 or ynn)   # the library's chunked host pipeline; the y-MLP variants go via the device
+        run = gru_decode_host if pipe else gru_decode
+        yd = _lib.host_f32(y) if pipe else _lib.to_device_f32(y)
+        assert yd.dim() == 2 and yd.shape[1] == N
+        dev_ctx = torch.cuda.device(torch.cuda.current_device() if pipe else yd.device)
+        handle = net.npd_handle(N, onehot=bool(self.onehot), y_in=not y_h0)
+        flip = (lambda t: t.flip(1)) if self.reverse_order else (lambda t: t)
 
         def like_y(t):
-            return None if t is None else (_lib.host_f32(t.cpu()) if on_host else _lib.to_device_f32(t, yd.device))
+            return None if t is None else (_lib.host_f32(t.cpu()) if pipe else _lib.to_device_f32(t, yd.device))
 
-        if train:
-            if torch.is_grad_enabled() and any(p.requires_grad for p in net.parameters()):
-                raise NotImplementedError("training (rnn_all.py:422-512 with gradients) is out of scope of the B200 "
-                                          "path; call under torch.no_grad() for teacher-/student-forced evaluation")
-            with dev_ctx:
-                if random.random() < teacher_forcing_ratio:  # rnn_all.py:425
-                    assert gt is not None and gt.shape[1] == self.N
-                    _, logits = run(net, self._loss_code(self.info_inds), yd, forced=like_y(gt), want_logits=True)
-                    return logits
-                decoded, logits = run(net, self._loss_code(self.info_inds), yd, want_logits=True)
-                mask = torch.zeros(self.N, dtype=torch.bool, device=logits.device)
-                mask[torch.as_tensor(np.asarray(self.info_inds), device=logits.device)] = True
-                return torch.where(mask.unsqueeze(0), logits, torch.ones_like(logits))
-        if loss_inds is None:
-            loss_inds = self.info_inds
+        def back(t):
+            t = flip(t)
+            return t.cpu() if (on_host and not pipe) else t
+
+        kw = {}
+        if gt is not None:
+            gt = flip(gt)
         with dev_ctx:
-            decoded, logits = run(net, self._loss_code(loss_inds), yd, want_logits=return_logits, genie=like_y(gt))
-        return (decoded, logits) if return_logits else decoded
+            if y_h0:
+                with torch.no_grad():
+                    kw["h0"] = net.get_h0(yd)
+            elif ynn:
+                with torch.no_grad():
+                    yd = net.get_Fy(yd).contiguous()
+                assert yd.shape[1] == N, "use_ynn: the y-MLP must emit N values (y_output_size = N, rnn_all.py:1320)"
+            if train:
+                if torch.is_grad_enabled() and any(p.requires_grad for p in net.parameters()):
+                    raise NotImplementedError("training (rnn_all.py:422-512 with gradients) is out of scope of the "
+                                              "B200 path; call under torch.no_grad() for teacher-/student-forced "
+                                              "evaluation")
+                if random.random() < teacher_forcing_ratio:  # rnn_all.py:425
+                    assert gt is not None and gt.shape[1] == N
+                    _, logits = run(handle, self._loss_code(self.info_inds), yd, forced=like_y(gt), want_logits=True, **kw)
+                    return back(logits)
+                _, logits = run(handle, self._loss_code(self.info_inds), yd, want_logits=True, **kw)
+                mask = torch.zeros(N, dtype=torch.bool, device=logits.device)
+                mask[torch.as_tensor(np.asarray(self.info_inds), device=logits.device)] = True  # `ii in info_inds`
+                return back(torch.where(mask.unsqueeze(0), logits, torch.ones_like(logits)))
+            if loss_inds is None:
+                loss_inds = self.info_inds
+            steps = np.asarray(loss_inds, dtype=np.int64)
+            if self.reverse_order:
+                steps = N - 1 - steps  # `jj in loss_inds` with jj = N-1-ii (rnn_all.py:416, 546)
+            decoded, logits = run(handle, self._loss_code(steps), yd, want_logits=return_logits, genie=like_y(gt), **kw)
+        return (back(decoded), back(logits)) if return_logits else back(decoded)
 
 
 def get_code(code_type, rate_profile, N, K, g=None, args=None):

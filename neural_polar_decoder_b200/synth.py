@@ -25,6 +25,21 @@ def gru_state_dict(seed, N, H=512, layers=2, head_gain=1.0):
     return sd
 
 
+def gru_y_state_dict(seed, N, H, in_size, y_hidden, y_depth, y_out, head_gain=1.0):
+    """state_dict of RNN_Model('GRU', in_size, H, 1, 2, N, y_hidden, y_depth, y_output_size=y_out) (reference
+    rnn_all.py:1317 'y_h0': in_size = 1 + onehot, y_out = 2H; 1320 use_ynn: in_size = N + 1 + onehot, y_out = N):
+    the GRU and head of gru_state_dict with a first layer of in_size columns, plus the y-MLP y_linears.{i}
+    (rnn_all.py:323-329)."""
+    sd = gru_state_dict(seed, in_size - 2, H, 2, head_gain)
+    rs = np.random.RandomState(seed + 7919)
+    dims = [(y_hidden, N)] + [(y_hidden, y_hidden)] * max(0, y_depth - 2) + [(y_out, y_hidden)]
+    for i, (o, n_in) in enumerate(dims):
+        k = 1.0 / np.sqrt(n_in)
+        sd["y_linears.%d.weight" % i] = rs.uniform(-k, k, (o, n_in)).astype(np.float32)
+        sd["y_linears.%d.bias" % i] = rs.uniform(-k, k, (o,)).astype(np.float32)
+    return sd
+
+
 CONV_LAYERS = [  # (name, C_out, C_in) in state_dict order (reference models.py:701-730)
     ("layers1.0", 64, 1), ("layers1.2", 64, 64), ("layers2.0", 64, 64), ("layers2.2", 64, 64),
     ("layers3.0", 64, 64), ("layers3.2", 64, 64), ("layers4.0", 64, 64), ("layers4.2", 64, 64),

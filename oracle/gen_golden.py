@@ -251,6 +251,59 @@ def gru_mode_cases():
     print("gru modes: teacher |out| mean", float(tf.abs().mean()), flush=True)
 
 
+GRU_COND = [  # name, decoding_type, onehot, reverse, y_hidden, y_depth, activation, H, seed
+    ("h0_onehot", "y_h0", True, False, 48, 2, "selu", 512, 31),
+    ("h0_scalar", "y_h0", False, False, 40, 1, "relu", 256, 32),
+    ("h0_reverse", "y_h0", True, True, 48, 3, "tanh", 256, 33),
+    ("ynn_onehot", "y_input", True, False, 48, 2, "relu", 256, 34),
+    ("yin_scalar_rev", "y_input", False, True, 0, 0, "relu", 256, 35),
+]
+
+
+def gru_cond_cases():
+    """The decoder's other conditionings, from the live reference: 'y_h0' (initial state = y-MLP, input = feedback only,
+    rnn_all.py:523-531, model of 1317), 'y_input' through the y-MLP (use_ynn, 1320), scalar instead of one-hot
+    feedback (410-411), reverse order (414-419, 558-561).  Per case: free-running decode, genie decode on the last
+    six info positions, teacher-forced raw outputs (train=True under no_grad)."""
+    ra = ref_shim.load("rnn_all")
+    ra.args = ref_shim.make_args(32, 16)
+    rs = np.random.RandomState(2718)
+    N, K, B, gain = 32, 16, 40, 6.0
+    code = ref_shim.get_code("Polar", "polar", N, K)
+    info = np.asarray(code.info_positions)
+    out = {"names": np.array([c[0] for c in GRU_COND]), "info": info.astype(np.int32), "gain": np.float64(gain)}
+    for name, dtype, onehot, rev, yh, yd, act, H, seed in GRU_COND:
+        y_h0 = dtype == "y_h0"
+        in_size = (0 if y_h0 else N) + 1 + int(onehot)
+        if yd > 0:
+            sd = synth.gru_y_state_dict(seed, N, H, in_size, yh, yd, 2 * H if y_h0 else N, head_gain=gain)
+            net = ra.RNN_Model("GRU", in_size, H, 1, 2, N, yh, yd, act, y_output_size=None if y_h0 else N)
+        else:
+            sd = synth.gru_state_dict(seed, in_size - 2, H, 2, head_gain=gain)
+            net = ra.RNN_Model("GRU", in_size, H, 1, 2, N, 0, 0, act)
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        dec = ra.RNN_decoder(dtype, N, info, onehot=onehot, reverse_order=rev)
+        msg = bpsk_msgs(rs, B, K)
+        x = code.encode_plotkin(torch.from_numpy(msg)).numpy()
+        y = torch.from_numpy(noisy(rs, x, 1.0))
+        gt = torch.ones(B, N)
+        gt[:, info] = torch.from_numpy(msg)
+        free = dec.decode(net, False, y)
+        genie = dec.decode(net, False, y, gt, loss_inds=info[-6:])
+        with torch.no_grad():
+            teacher = dec.decode(net, True, y, gt, 1)
+        out[name + "_cfg"] = np.array([H, seed, yh, yd, int(onehot), int(rev)], dtype=np.int64)
+        out[name + "_type"] = np.array(dtype)
+        out[name + "_act"] = np.array(act)
+        out[name + "_y"] = y.numpy()
+        out[name + "_gt"] = gt.numpy()
+        out[name + "_free"] = free.numpy()
+        out[name + "_genie"] = genie.numpy()
+        out[name + "_teacher"] = teacher.numpy()
+        print("gru cond", name, "teacher |out| mean", float(teacher.abs().mean()), flush=True)
+    np.savez_compressed(os.path.join(OUT, "gru_cond.npz"), **out)
+
+
 def conv_cases():
     import argparse as ap
     md = ref_shim.load("models")
@@ -309,7 +362,9 @@ if __name__ == "__main__":
     a = p.parse_args()
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    todo = a.only.split(",") if a.only else ["misc", "pac", "gru", "gru_modes", "scl", "conv", "polar"]
+    todo = a.only.split(",") if a.only else ["misc", "pac", "gru", "gru_modes", "gru_cond", "scl", "conv", "polar"]
+    if "gru_cond" in todo:
+        gru_cond_cases()
     if "gru_modes" in todo:
         gru_mode_cases()
     if "scl" in todo:

@@ -182,7 +182,34 @@ def gen_noise(seed, cw0, pt, B, N):
 # fp32 torch oracles for the floating-point decoders.
 # --------------------------------------------------------------------------------------------------
 
-def gru_decode(sd, y, N, info, forced=None, H=None, round_bf16=False, genie=None):
+def y_mlp(sd, y, y_depth, activation="relu"):
+    """RNN_Model.get_Fy (rnn_all.py:377-384): Linear layers y_linears.{i}; the activation (act, 346-360) follows every
+    layer whose index differs from y_depth -- i.e. all of them when there are y_depth layers (y_depth >= 2), and only
+    the first of the two layers that y_depth == 1 builds (323-329)."""
+    import torch
+    import torch.nn.functional as F
+    act = {"tanh": torch.tanh, "elu": F.elu, "relu": F.relu, "selu": F.selu, "sigmoid": torch.sigmoid}.get(
+        activation, lambda t: t)
+    x = torch.as_tensor(np.asarray(y)).float()
+    ii = 0
+    while ("y_linears.%d.weight" % ii) in sd:
+        W = torch.as_tensor(np.asarray(sd["y_linears.%d.weight" % ii])).float()
+        b = torch.as_tensor(np.asarray(sd["y_linears.%d.bias" % ii])).float()
+        x = x @ W.t() + b
+        if ii != y_depth:
+            x = act(x)
+        ii += 1
+    return x
+
+
+def gru_h0(sd, y, y_depth, H, L=2, activation="relu"):
+    """RNN_Model.get_h0 (rnn_all.py:362-375, skip=False): the y-MLP output [B, L*H] is READ AS [B, H, L] and permuted
+    to [L, B, H] -- layer l's state is the stride-L slice x[:, l::L]."""
+    x = y_mlp(sd, y, y_depth, activation)
+    return x.reshape(-1, H, L).permute(2, 0, 1).contiguous().numpy()
+
+
+def gru_decode(sd, y, N, info, forced=None, H=None, round_bf16=False, genie=None, h0=None, onehot=True, y_in=True):
     """fp32 restatement of RNN_decoder.decode(net, False, y) for decoding_type 'y_input', onehot,
     GRU (rnn_all.py:514-521, 532-547) with RNN_Model.forward (387-398) written out gate by gate
     (PyTorch nn.GRU gate order r,z,n).  The y-part of the layer-0 input projection is
@@ -194,6 +221,9 @@ def gru_decode(sd, y, N, info, forced=None, H=None, round_bf16=False, genie=None
             decoder's own decision (used for logit parity under identical feedback).
     genie: optional [B,N]: decoded starts as this tensor instead of ones (gt.clone(), rnn_all.py:519-522), so
             positions outside `info` (the loss positions) keep and feed back their genie value.
+    h0: optional [L,B,H] initial state (decoding_type 'y_h0': net.get_h0(y), rnn_all.py:523-524; default zeros, 538).
+    y_in: False when the step input carries no y part ('y_h0', 526-528: input = feedback only).
+    onehot: False = the feedback enters as the scalar prev (RNN_decoder onehot=False, onehot_fn = identity, 410-411).
     round_bf16: emulate the kernel's operand rounding (weights, h and y operands to bf16, fp32
             accumulate) to size tolerances; not a parity target.
     -> (decoded[B,N] in {-1,0,+1} with +1 on non-info positions, logits[B,N])
@@ -219,12 +249,16 @@ def gru_decode(sd, y, N, info, forced=None, H=None, round_bf16=False, genie=None
     bo = T(sd["linear.bias"])
     Hs = Whh[0].shape[1]
     info_set = set(int(i) for i in info)
-    h = [torch.zeros(B, Hs) for _ in range(L)]
+    h = [torch.zeros(B, Hs) for _ in range(L)] if h0 is None else [T(h0)[l].clone() for l in range(L)]
     decoded = torch.ones(B, N) if genie is None else T(genie).clone()
     logits = torch.zeros(B, N)
-    Gy = rb(y) @ rb(Wih[0][:, :N]).t()  # hoisted y projection
-    col_m1 = Wih[0][:, N]      # onehot(-1) = [1,0]  (rnn_all.py:258-260)
-    col_p1 = Wih[0][:, N + 1]  # onehot(+1) = [0,1]
+    ny = N if y_in else 0
+    Gy = rb(y) @ rb(Wih[0][:, :N]).t() if y_in else torch.zeros(B, 3 * Hs)  # hoisted y projection
+    if onehot:
+        col_m1 = Wih[0][:, ny]      # onehot(-1) = [1,0]  (rnn_all.py:258-260)
+        col_p1 = Wih[0][:, ny + 1]  # onehot(+1) = [0,1]
+    else:
+        col_fb = Wih[0][:, ny]      # scalar feedback column
     for ii in range(N):
         if ii == 0:
             prev = torch.ones(B)
@@ -232,8 +266,11 @@ def gru_decode(sd, y, N, info, forced=None, H=None, round_bf16=False, genie=None
             prev = T(forced)[:, ii - 1]
         else:
             prev = decoded[:, ii - 1].sign()
-        sel = (0.5 + 0.5 * prev).long()  # 0 -> column N, 1 -> column N+1 (sign 0 maps to 0)
-        gi = Gy + torch.where(sel[:, None] == 1, col_p1[None, :], col_m1[None, :]) + bih[0]
+        if onehot:
+            sel = (0.5 + 0.5 * prev).long()  # 0 -> column N, 1 -> column N+1 (sign 0 maps to 0)
+            gi = Gy + torch.where(sel[:, None] == 1, col_p1[None, :], col_m1[None, :]) + bih[0]
+        else:
+            gi = Gy + prev[:, None] * col_fb[None, :] + bih[0]
         x = None
         for l in range(L):
             if l > 0:

@@ -312,6 +312,70 @@ def test_gru_genie_and_forced_evaluation_modes(golden):
         dec.decode(net, True, y, gt, 1)  # gradients enabled = training: out of scope
 
 
+@pytest.mark.parametrize("nm", ["h0_onehot", "h0_scalar", "h0_reverse", "ynn_onehot", "yin_scalar_rev"])
+def test_gru_conditionings_vs_reference_fixture(golden, nm):
+    """RNN_decoder.decode for decoding_type 'y_h0' (initial state = the y-MLP, rnn_all.py:523-531), 'y_input' through
+    the y-MLP (use_ynn), scalar feedback and reverse order, against outputs of the live reference: teacher-forced raw
+    outputs within the logit tolerance; free-running and genie decisions equal on rows with no near-zero logit."""
+    from neural_polar_decoder_b200.rnn_all import RNN_Model, RNN_decoder
+    from test_oracle_golden import _cond_case
+    g = golden("gru_cond")
+    info = g["info"]
+    H, seed, yh, yd, onehot, rev = [int(v) for v in g[nm + "_cfg"]]
+    dtype, act = str(g[nm + "_type"]), str(g[nm + "_act"])
+    sd, kw, y_k, _ = _cond_case(g, nm)
+    N = y_k.shape[1]
+    in_size = (0 if dtype == "y_h0" else N) + 1 + onehot
+    net = RNN_Model('GRU', in_size, H, 1, 2, N, yh, yd, act, y_output_size=None if dtype == "y_h0" else N)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    dec = RNN_decoder(dtype, N, info, onehot=bool(onehot), reverse_order=bool(rev))
+    y, gt = torch.from_numpy(g[nm + "_y"]).cuda(), torch.from_numpy(g[nm + "_gt"]).cuda()
+    with torch.no_grad():
+        teacher = dec.decode(net, True, y, gt, 1).cpu().numpy()
+    ref = g[nm + "_teacher"]
+    err = np.abs(teacher - ref)
+    print("%s: teacher-forced err max %.3e, worst err/tol %.2f" % (nm, err.max(), (err / _gru_tol(ref)).max()))
+    assert (err <= _gru_tol(ref)).all(), err.max()
+    fl = (lambda a: np.ascontiguousarray(a[:, ::-1])) if rev else (lambda a: a)
+    for key, loss, genie in (("_free", info, None), ("_genie", info[-6:], gt)):
+        steps = N - 1 - loss if rev else loss
+        _, lg = oracle.gru_decode(sd, y_k, N, steps, genie=None if genie is None else fl(g[nm + "_gt"]), **kw)
+        safe = (np.abs(lg[:, steps]) > _gru_tol(lg)[:, steps]).all(axis=1)
+        assert safe.sum() >= 8
+        d = dec.decode(net, False, y, genie, loss_inds=None if genie is None else loss).cpu().numpy()
+        assert np.array_equal(d[safe], g[nm + key][safe]), (nm, key)
+    # host tensors in -> host tensors out
+    d = dec.decode(net, False, y.cpu())
+    assert not d.is_cuda and np.array_equal(d.numpy()[safe], dec.decode(net, False, y).cpu().numpy()[safe])
+
+
+def test_gru_h0_ragged_batch_both_kernels():
+    """npd_gru_decode_h0 at a batch that is not a multiple of the tile, H = 256 (CTA-pair kernel) and H = 128
+    (single-CTA kernel), against the fp32 oracle under forced feedback."""
+    from neural_polar_decoder_b200 import construct, synth
+    from neural_polar_decoder_b200.rnn_all import RNN_Model, RNN_decoder, gru_decode
+    N, K, B = 32, 16, 333
+    rs = construct.reference_rs256()
+    info = np.sort(rs[rs < N][:K])
+    rng = np.random.RandomState(9)
+    y = (rng.choice([-1.0, 1.0], size=(B, N)) + 0.8 * rng.randn(B, N)).astype(np.float32)
+    for H in (256, 128):
+        sd = synth.gru_y_state_dict(40 + H, N, H, 2, 32, 2, 2 * H, head_gain=6.0)
+        net = RNN_Model('GRU', 2, H, 1, 2, N, 32, 2, 'tanh')
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        h0 = oracle.gru_h0(sd, y, 2, H, activation='tanh')
+        do, lo = oracle.gru_decode(sd, y, N, info, h0=h0, y_in=False)
+        dec = RNN_decoder('y_h0', N, info, onehot=True)
+        yd = torch.from_numpy(y).cuda()
+        with torch.no_grad():
+            h0d = net.get_h0(yd)
+        assert np.allclose(h0d.cpu().numpy(), h0, atol=1e-5)
+        _, lg = gru_decode(net.npd_handle(N, True, False), dec._loss_code(info), yd, forced=torch.from_numpy(do).cuda(),
+                           want_logits=True, h0=h0d)
+        err = np.abs(lg.cpu().numpy() - lo)
+        assert (err <= _gru_tol(lo)).all(), (H, err.max())
+
+
 # ---------------------------------------------------------------------------------------------------
 # convNet one-shot decoder (fp16 tensor-core operands, fp32 accumulate, tanh-form GELU).  Parity is judged on
 # the LayerNorm output (the reference's `logits`): |d| <= 1e-2 * |ref| + 2e-3 (SURVEY.md 7: the absolute floor

@@ -125,6 +125,50 @@ def test_gru_oracle_modes_against_reference_fixture(golden):
         assert np.array_equal(dec[safe_rows], g[key][safe_rows]), key
 
 
+def _cond_case(g, nm):
+    """(state_dict, decode kwargs, y as the kernel sees it, loss-step helper) of one gru_cond.npz case."""
+    from neural_polar_decoder_b200 import synth
+    H, seed, yh, yd, onehot, rev = [int(v) for v in g[nm + "_cfg"]]
+    y_h0 = str(g[nm + "_type"]) == "y_h0"
+    N = g[nm + "_y"].shape[1]
+    in_size = (0 if y_h0 else N) + 1 + onehot
+    gain = float(g["gain"])
+    if yd > 0:
+        sd = synth.gru_y_state_dict(seed, N, H, in_size, yh, yd, 2 * H if y_h0 else N, head_gain=gain)
+    else:
+        sd = synth.gru_state_dict(seed, in_size - 2, H, 2, head_gain=gain)
+    kw = dict(onehot=bool(onehot), y_in=not y_h0)
+    y = g[nm + "_y"]
+    if y_h0:
+        kw["h0"] = oracle.gru_h0(sd, y, yd, H, activation=str(g[nm + "_act"]))
+    elif yd > 0:
+        y = oracle.y_mlp(sd, y, yd, str(g[nm + "_act"])).numpy()
+    return sd, kw, y, bool(rev)
+
+
+def test_gru_oracle_conditionings_against_reference_fixture(golden):
+    """'y_h0' (initial state from the y-MLP), use_ynn, scalar feedback and reverse order (rnn_all.py:410-419,
+    523-531, 1317-1320) against the live reference: teacher-forced raw outputs, free-running and genie decodes."""
+    g = golden("gru_cond")
+    info = g["info"]
+    for nm in [str(s) for s in g["names"]]:
+        sd, kw, y, rev = _cond_case(g, nm)
+        N = y.shape[1]
+        fl = (lambda a: np.ascontiguousarray(a[:, ::-1])) if rev else (lambda a: a)
+        gt = fl(g[nm + "_gt"])                       # the reference flips gt on entry (417-419) ...
+        _, lg = oracle.gru_decode(sd, y, N, info, forced=gt, **kw)
+        np.testing.assert_allclose(fl(lg), g[nm + "_teacher"], rtol=0, atol=2e-5, err_msg=nm)  # ... and its result on exit
+        steps = N - 1 - info if rev else info        # `jj in loss_inds`, jj = N-1-ii
+        dec, lg = oracle.gru_decode(sd, y, N, steps, **kw)
+        safe = (np.abs(lg[:, steps]) > 1e-4).all(axis=1)
+        assert safe.mean() > 0.9 and np.array_equal(fl(dec)[safe], g[nm + "_free"][safe]), nm
+        loss = info[-6:]
+        steps = N - 1 - loss if rev else loss
+        dec, lg = oracle.gru_decode(sd, y, N, steps, genie=gt, **kw)
+        safe = (np.abs(lg[:, steps]) > 1e-4).all(axis=1)
+        assert safe.mean() > 0.9 and np.array_equal(fl(dec)[safe], g[nm + "_genie"][safe]), nm
+
+
 def test_scl_oracle_against_reference_fixtures(golden):
     """SC-list restatement vs the live reference's scl_decode (polar.py:793-876): chosen path's decisions and
     leaf LLRs, bit for bit, at list sizes 1..32."""
