@@ -137,6 +137,14 @@ int npd_gru_create(int N, int H, const float *h_w_ih0, const float *h_w_hh0, con
                    const float *h_b_out, npd_gru_t **out);
 int npd_gru_destroy(npd_gru_t *gru);
 
+/* npd_gru_set_head_mlp: replace the Linear(H,1) head by the MLP head RNN_Model builds for out_linear_depth > 1
+ * (rnn_all.py:335-343): Linear(H,Yh) SELU [Linear(Yh,Yh) SELU] x (depth-2) Linear(Yh,1), Yh = y_hidden_size.
+ * h_params: host fp32 blob in state_dict order of `linear.*`: weight [Yh,H], bias [Yh], then (depth-2) x
+ * (weight [Yh,Yh], bias [Yh]), then weight [1,Yh], bias [1].  Create the decoder with w_out = zeros first.
+ * A decoder with an MLP head needs npd_gru_workspace_bytes(gru, B) > 0 bytes of workspace per decode call.
+ * Envelope: 2 <= depth <= 8, Yh a multiple of 16 in [16, 1024]; NPD_EUNSUPPORTED otherwise. */
+int npd_gru_set_head_mlp(npd_gru_t *gru, int depth, int y_hidden_size, const float *h_params);
+
 /* npd_gru_decode: RNN_decoder.decode(net, False, y) test branch, decoding_type 'y_input', onehot
  * (rnn_all.py:514-521, 532-547) with RNN_Model.forward (387-398): N autoregressive steps, hidden
  * state zero-initialised, input [y | onehot(prev decision)], decision = sign(logit) on info

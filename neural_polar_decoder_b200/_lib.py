@@ -33,6 +33,7 @@ SIGNATURES = {
     "npd_mc_sc_sweep": (_int, [_vp, _i64, _i64, _f32, _f32, _u64, _u32, _u64, _vp, _sz, _vp, _vp]),
     "npd_gru_create": (_int, [_int, _int] + [_vp] * 10 + [_c.POINTER(_vp)]),
     "npd_gru_destroy": (_int, [_vp]),
+    "npd_gru_set_head_mlp": (_int, [_vp, _int, _int, _vp]),
     "npd_gru_workspace_bytes": (_sz, [_vp, _i64]),
     "npd_gru_decode": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
     "npd_gru_decode_h0": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),

@@ -61,6 +61,14 @@ struct GruParams {
     const float *forced;         // [B,N] or null
     const float *genie;          // [B,N] or null: decoded starts as this tensor (rnn_all.py:521-522)
     const float *h0;             // [2][B][H] or null: initial hidden state (decoding_type 'y_h0', rnn_all.py:523-524)
+    // MLP head (out_linear_depth > 1, rnn_all.py:335-343): Linear(H,Yh) SELU [Linear(Yh,Yh) SELU]* Linear(Yh,1).
+    // Single-CTA kernel only; head_depth <= 1 means the plain Linear(H,1) head (w_out / b_out).
+    int head_depth, head_yh;
+    const __half *head_w1;       // [Yh][H]
+    const __half *head_wh;       // [head_depth - 2][Yh][Yh]
+    const float *head_b;         // [head_depth - 1][Yh]
+    const float *head_wl;        // [Yh]; its bias is b_out
+    __half *head_act;            // workspace: [CTA][2][64][Yh] activations (L2-resident ping-pong)
     const uint32_t *info_words;  // bit i = position i is an info (loss) position
     float *logits;               // [B,N] or null
     float *decoded;              // [B,N]
@@ -231,6 +239,58 @@ __device__ __forceinline__ float sigmoid_half_arg(float half_x) { return fmaf(ta
 __device__ __forceinline__ uint32_t b_off(int c, int k)
 {
     return (uint32_t)((k >> 6) * B_CHUNK_BYTES + c * 128 + ((((k & 63) >> 3) ^ (c & 7)) << 4) + (k & 7) * 2);
+}
+
+// ---- MLP head on the legacy warp-level tensor-core path: 0.13 MFLOP per codeword and step (2.8 % of the step's GRU
+// work), so plain mma.sync from the epilogue warps is enough and leaves the tcgen05 schedule untouched ----
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float selu_f(float x)  // torch.nn.SELU
+{
+    return 1.0507009873554805f * (fmaxf(x, 0.0f) + fminf(1.6732632423543772f * expm1f(x), 0.0f));
+}
+// out[c][j] = selu(sum_k W[j][k] in[c][k] + bias[j]) for the CTA's 64 codewords c, j < M; in(c, k) returns the fp16 pair
+// (k, k+1) of codeword c; all 16 epilogue warps call it, a warp item = 16 units x 32 codewords
+template <class LoadPair>
+__device__ __forceinline__ void head_layer(int warp, int lane, const __half *W, const float *bias, int M, int K, LoadPair in,
+                                           __half *out)
+{
+    const int g = lane >> 2, t = lane & 3;
+    for (int item = warp; item < (M / 16) * 2; item += EPI_WARPS) {
+        const int j0 = (item >> 1) * 16, c0 = (item & 1) * 32;
+        float acc[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[nt][i] = 0.0f;
+        const __half *w_lo = W + (size_t)(j0 + g) * K + 2 * t, *w_hi = w_lo + (size_t)8 * K;
+        for (int k0 = 0; k0 < K; k0 += 16) {
+            uint32_t a[4];
+            a[0] = __ldg(reinterpret_cast<const uint32_t *>(w_lo + k0));
+            a[1] = __ldg(reinterpret_cast<const uint32_t *>(w_hi + k0));
+            a[2] = __ldg(reinterpret_cast<const uint32_t *>(w_lo + k0 + 8));
+            a[3] = __ldg(reinterpret_cast<const uint32_t *>(w_hi + k0 + 8));
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int c = c0 + nt * 8 + g;
+                mma16816(acc[nt], a, in(c, k0 + 2 * t), in(c, k0 + 2 * t + 8));
+            }
+        }
+        const float b_lo = __ldg(bias + j0 + g), b_hi = __ldg(bias + j0 + g + 8);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const int c = c0 + nt * 8 + 2 * t;
+            __half *o = out + (size_t)c * M + j0 + g;
+            o[0] = __float2half_rn(selu_f(acc[nt][0] + b_lo));
+            o[M] = __float2half_rn(selu_f(acc[nt][1] + b_lo));
+            o[8] = __float2half_rn(selu_f(acc[nt][2] + b_hi));
+            o[M + 8] = __float2half_rn(selu_f(acc[nt][3] + b_hi));
+        }
+    }
 }
 
 struct Smem {
@@ -610,7 +670,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
             const uint32_t iw = step < 32 ? info0 : step < 64 ? info1 : step < 96 ? info2 : info3;
             const bool is_info = (iw >> (step & 31)) & 1u;
             const bool need_head = is_info || p.logits != nullptr;
-            if (need_head) {
+            if (need_head && p.head_depth > 1) {
+                // MLP head: h1 of this step is complete in shared memory once every epilogue thread has passed here
+                epi_bar_sync();
+                const int Yh = p.head_yh;
+                __half *act0 = p.head_act + (size_t)blockIdx.x * 2 * TILE_B * Yh, *act1 = act0 + (size_t)TILE_B * Yh;
+                head_layer(warp, lane, p.head_w1, p.head_b, Yh, H,
+                           [&](int c, int k) { return *reinterpret_cast<const uint32_t *>(s_h1 + b_off(c, k)); }, act0);
+                epi_bar_sync();
+                for (int l = 0; l < p.head_depth - 2; ++l) {
+                    const __half *src = act0;
+                    head_layer(warp, lane, p.head_wh + (size_t)l * Yh * Yh, p.head_b + (size_t)(l + 1) * Yh, Yh, Yh,
+                               [&](int c, int k) { return __ldcg(reinterpret_cast<const uint32_t *>(src + (size_t)c * Yh + k)); },
+                               act1);
+                    epi_bar_sync();
+                    __half *tmp = act0; act0 = act1; act1 = tmp;
+                }
+#pragma unroll
+                for (int i = 0; i < TILE_B / EPI_WARPS; ++i) {
+                    const int c = warp * (TILE_B / EPI_WARPS) + i;
+                    float sacc = 0.0f;
+                    for (int j = lane; j < Yh; j += 32)
+                        sacc = fmaf(__ldg(p.head_wl + j), __half2float(__ldcg(act0 + (size_t)c * Yh + j)), sacc);
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1) sacc += __shfl_xor_sync(NPD_FULL, sacc, o);
+                    if (lane < 4) s_red[lane * TILE_B + c] = lane == 0 ? sacc : 0.0f;
+                }
+                epi_bar_sync();
+            } else if (need_head) {
 #pragma unroll
                 for (int s = CW / 2; s >= 1; s >>= 1) {
 #pragma unroll
@@ -1265,6 +1352,9 @@ struct npd_gru {
     float *d_w_iyT;
     float *d_consts0, *d_consts1, *d_w_out;
     size_t smem_bytes;
+    int head_depth, head_yh;   // MLP head (npd_gru_set_head_mlp); depth 0 = the Linear(H,1) head of npd_gru_create
+    __half *d_head_w1, *d_head_wh;
+    float *d_head_b, *d_head_wl;
 };
 
 namespace {
@@ -1445,11 +1535,59 @@ NPD_API int npd_gru_destroy(npd_gru_t *g)
     cudaFree(g->d_consts0);
     cudaFree(g->d_consts1);
     cudaFree(g->d_w_out);
+    cudaFree(g->d_head_w1); cudaFree(g->d_head_wh); cudaFree(g->d_head_b); cudaFree(g->d_head_wl);
     free(g);
     return NPD_OK;
 }
 
-NPD_API size_t npd_gru_workspace_bytes(const npd_gru_t *, int64_t) { return 0; }
+NPD_API int npd_gru_set_head_mlp(npd_gru_t *g, int depth, int Yh, const float *h_params)
+{
+    NPD_REQUIRE(g && h_params, "npd_gru_set_head_mlp: null argument");
+    if (depth < 2 || depth > 8 || Yh < 16 || Yh > 1024 || (Yh % 16) != 0) {
+        npd_set_error("npd_gru_set_head_mlp: supported envelope is 2 <= depth <= 8, y_hidden_size a multiple of 16 in "
+                      "[16, 1024] (got depth=%d, y_hidden_size=%d)", depth, Yh);
+        return NPD_EUNSUPPORTED;
+    }
+    const int H = g->H;
+    const size_t y = (size_t)Yh;
+    std::vector<__half> w1(y * H), wh((size_t)(depth - 2) * y * y + 1);
+    std::vector<float> b((size_t)(depth - 1) * y);
+    const float *q = h_params;
+    for (size_t i = 0; i < y * H; ++i) w1[i] = __float2half_rn(q[i]);
+    q += y * H;
+    for (size_t i = 0; i < y; ++i) b[i] = q[i];
+    q += y;
+    for (int l = 0; l < depth - 2; ++l) {
+        for (size_t i = 0; i < y * y; ++i) wh[(size_t)l * y * y + i] = __float2half_rn(q[i]);
+        q += y * y;
+        for (size_t i = 0; i < y; ++i) b[(size_t)(l + 1) * y + i] = q[i];
+        q += y;
+    }
+    cudaFree(g->d_head_w1); cudaFree(g->d_head_wh); cudaFree(g->d_head_b); cudaFree(g->d_head_wl);
+    g->d_head_w1 = g->d_head_wh = nullptr; g->d_head_b = g->d_head_wl = nullptr;
+    g->head_depth = 0;
+    cudaError_t e = cudaMalloc(&g->d_head_w1, w1.size() * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_head_wh, wh.size() * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_head_b, b.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_head_wl, y * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(g->d_head_w1, w1.data(), w1.size() * 2, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(g->d_head_wh, wh.data(), wh.size() * 2, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(g->d_head_b, b.data(), b.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(g->d_head_wl, q, y * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        npd_set_error("npd_gru_set_head_mlp: %s", cudaGetErrorString(e));
+        return NPD_ECUDA;
+    }
+    g->b_out = q[y];
+    g->head_depth = depth; g->head_yh = Yh;
+    return NPD_OK;
+}
+
+NPD_API size_t npd_gru_workspace_bytes(const npd_gru_t *g, int64_t B)
+{
+    if (!g || g->head_depth <= 1 || B <= 0) return 0;
+    return (size_t)((B + TILE_B - 1) / TILE_B + 1) * 2 * TILE_B * g->head_yh * sizeof(__half);  // +1: the padding CTA of a cluster
+}
 
 NPD_API int npd_gru_decode(const npd_gru_t *g, const npd_code_t *code, const float *y, const float *forced,
                            const float *genie, float *logits, float *decoded, int64_t B, void *ws, size_t ws_bytes,
@@ -1459,8 +1597,8 @@ NPD_API int npd_gru_decode(const npd_gru_t *g, const npd_code_t *code, const flo
 }
 
 NPD_API int npd_gru_decode_h0(const npd_gru_t *g, const npd_code_t *code, const float *y, const float *h0,
-                              const float *forced, const float *genie, float *logits, float *decoded, int64_t B, void *,
-                              size_t, void *stream)
+                              const float *forced, const float *genie, float *logits, float *decoded, int64_t B, void *ws,
+                              size_t ws_bytes, void *stream)
 {
     NPD_REQUIRE(g && code && y && decoded, "npd_gru_decode: null argument");
     NPD_REQUIRE(B >= 0, "npd_gru_decode: negative batch");
@@ -1474,6 +1612,14 @@ NPD_API int npd_gru_decode_h0(const npd_gru_t *g, const npd_code_t *code, const 
     p.wpack2 = g->d_wpack2; p.tiles_per_step2 = g->tiles_per_step2;
     // CTA-pair kernel (cta_group::2) when the weights were packed for it; NPD_GRU_PAIR=0 selects the single-CTA kernel
     bool use_pair = g->d_wpack2 != nullptr;
+    if (g->head_depth > 1) {
+        const size_t need = npd_gru_workspace_bytes(g, B);
+        NPD_REQUIRE(ws && ws_bytes >= need, "npd_gru_decode: a decoder with an MLP head needs %zu bytes of workspace (got %zu)",
+                    need, ws ? ws_bytes : (size_t)0);
+        use_pair = false;  // the MLP head lives in the single-CTA kernel
+        p.head_depth = g->head_depth; p.head_yh = g->head_yh; p.head_w1 = g->d_head_w1; p.head_wh = g->d_head_wh;
+        p.head_b = g->d_head_b; p.head_wl = g->d_head_wl; p.head_act = (__half *)ws;
+    }
     { const char *d = getenv("NPD_GRU_PAIR"); if (d) use_pair = use_pair && atoi(d) != 0; }
     // the 2-SM tensor-copy variant (no relay) works but measures slower than relay + linear bulk copies (12.4 vs 11.4 ms
     // per 37888 codewords): opt-in with NPD_GRU_TMAP=1

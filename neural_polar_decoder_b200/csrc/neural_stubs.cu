@@ -11,6 +11,17 @@ NPD_API int npd_gru_create(int, int, const float *, const float *, const float *
     return NPD_EUNSUPPORTED;
 }
 NPD_API int npd_gru_destroy(npd_gru_t *) { return NPD_OK; }
+NPD_API int npd_gru_set_head_mlp(npd_gru_t *, int, int, const float *)
+{
+    npd_set_error("npd_gru_set_head_mlp: GRU kernel not built into this libnpd.so");
+    return NPD_EUNSUPPORTED;
+}
+NPD_API int npd_gru_decode_h0(const npd_gru_t *, const npd_code_t *, const float *, const float *, const float *, const float *,
+                              float *, float *, int64_t, void *, size_t, void *)
+{
+    npd_set_error("npd_gru_decode_h0: GRU kernel not built into this libnpd.so");
+    return NPD_EUNSUPPORTED;
+}
 NPD_API size_t npd_gru_workspace_bytes(const npd_gru_t *, int64_t) { return 0; }
 NPD_API int npd_gru_decode(const npd_gru_t *, const npd_code_t *, const float *, const float *, const float *, float *,
                            float *, int64_t, void *, size_t, void *)

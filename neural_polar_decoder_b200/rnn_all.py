@@ -99,17 +99,17 @@ class RNN_Model(nn.Module):
     # ---- libnpd handle (weights repacked once per parameter version) ----
     def _supported(self):
         return (self.rnn_type == 'GRU' and self.num_rnn_layers == 2 and not self.bidirectional and
-                not self.use_layernorm and self.output_size == 1 and self.out_linear_depth == 1)
+                not self.use_layernorm and self.output_size == 1 and self.out_linear_depth >= 1)
 
     def npd_handle(self, N, onehot=True, y_in=True):
         if not self._supported():
-            raise NotImplementedError("fused decode supports GRU, 2 layers, unidirectional, no LayerNorm, 1 output, "
-                                      "out_linear_depth 1")
+            raise NotImplementedError("fused decode supports GRU, 2 layers, unidirectional, no LayerNorm, 1 output")
         sd = self.state_dict()
         key = (N, onehot, y_in, torch.cuda.current_device()) + tuple((k, v._version, v.data_ptr()) for k, v in sd.items())
         if self._npd is not None and self._npd[0] == key:
             return self._npd[1]
-        handle = GruHandle(N, self.feature_size, sd, onehot=onehot, y_in=y_in)
+        handle = GruHandle(N, self.feature_size, sd, onehot=onehot, y_in=y_in, head_depth=self.out_linear_depth,
+                           y_hidden=self.y_hidden_size)
         self._npd = (key, handle)
         return handle
 
@@ -117,7 +117,7 @@ class RNN_Model(nn.Module):
 class GruHandle:
     """Owns an npd_gru_t (fp16 weight tile streams in HBM)."""
 
-    def __init__(self, N, H, sd, onehot=True, y_in=True):
+    def __init__(self, N, H, sd, onehot=True, y_in=True, head_depth=1, y_hidden=0):
         """onehot / y_in describe the columns of rnn.weight_ih_l0: [y (N, when y_in) | feedback (2 one-hot, else 1)].
         The library takes the run_crisp.sh form [3H, N+2]; the other forms are widened to it exactly: absent y
         columns are zeros ('y_h0', rnn_all.py:526-528), a scalar +-1 feedback column w is the one-hot pair [-w, +w]."""
@@ -138,13 +138,22 @@ class GruHandle:
             host("rnn.bias_ih_l0", (3 * H,)), host("rnn.bias_hh_l0", (3 * H,)),
             host("rnn.weight_ih_l1", (3 * H, H)), host("rnn.weight_hh_l1", (3 * H, H)),
             host("rnn.bias_ih_l1", (3 * H,)), host("rnn.bias_hh_l1", (3 * H,)),
-            host("linear.weight", (1, H)), host("linear.bias", (1,)),
         ]
+        mlp = None
+        if head_depth == 1:
+            self._keep += [host("linear.weight", (1, H)), host("linear.bias", (1,))]
+        else:  # nn.Sequential head (rnn_all.py:335-343): Linear at indices 0, 2, 4, ... with SELU in between
+            self._keep += [torch.zeros(1, H), torch.zeros(1)]
+            dims = [(y_hidden, H)] + [(y_hidden, y_hidden)] * (head_depth - 2) + [(1, y_hidden)]
+            mlp = torch.cat([t.reshape(-1) for i, (o, n_in) in enumerate(dims)
+                             for t in (host("linear.%d.weight" % (2 * i), (o, n_in)), host("linear.%d.bias" % (2 * i), (o,)))])
         h = ctypes.c_void_p()
         _lib.check(lib.npd_gru_create(int(N), int(H), *[ctypes.c_void_p(t.data_ptr()) for t in self._keep],
                                       ctypes.byref(h)))
         self.h, self.N, self.H = h, N, H
         self._keep = None
+        if mlp is not None:
+            _lib.check(lib.npd_gru_set_head_mlp(h, int(head_depth), int(y_hidden), ctypes.c_void_p(mlp.data_ptr())))
 
     def __del__(self):
         try:
@@ -165,9 +174,12 @@ def gru_decode(net_or_handle, code_handle, y, forced=None, want_logits=False, ge
         h0 = h0.float().contiguous()
         assert tuple(h0.shape) == (2, B, handle.H) and h0.device == y.device, (tuple(h0.shape), h0.device)
     if B > 0:
-        _lib.check(_lib.load().npd_gru_decode_h0(handle.h, code_handle.h, _lib.ptr(y), _lib.ptr(h0), _lib.ptr(forced),
-                                                 _lib.ptr(genie), _lib.ptr(logits), _lib.ptr(decoded), B, None, 0,
-                                                 _lib.stream_ptr()))
+        lib = _lib.load()
+        ws_bytes = int(lib.npd_gru_workspace_bytes(handle.h, B))  # non-zero only for MLP heads
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=y.device) if ws_bytes else None
+        _lib.check(lib.npd_gru_decode_h0(handle.h, code_handle.h, _lib.ptr(y), _lib.ptr(h0), _lib.ptr(forced),
+                                         _lib.ptr(genie), _lib.ptr(logits), _lib.ptr(decoded), B, _lib.ptr(ws), ws_bytes,
+                                         _lib.stream_ptr()))
     return decoded, logits
 
 

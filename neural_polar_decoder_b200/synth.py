@@ -40,6 +40,19 @@ def gru_y_state_dict(seed, N, H, in_size, y_hidden, y_depth, y_out, head_gain=1.
     return sd
 
 
+def with_mlp_head(sd, seed, H, y_hidden, depth, head_gain=1.0):
+    """Replace the Linear(H,1) head of a GRU state_dict by the nn.Sequential head of out_linear_depth = depth > 1
+    (reference rnn_all.py:335-343): linear.{0,2,...}: Linear(H,Yh) SELU [Linear(Yh,Yh) SELU]* Linear(Yh,1)."""
+    sd = OrderedDict((k, v) for k, v in sd.items() if not k.startswith("linear."))
+    rs = np.random.RandomState(seed + 104729)
+    dims = [(y_hidden, H)] + [(y_hidden, y_hidden)] * (depth - 2) + [(1, y_hidden)]
+    for i, (o, n_in) in enumerate(dims):
+        k = (head_gain if i == len(dims) - 1 else 2.0) / np.sqrt(n_in)
+        sd["linear.%d.weight" % (2 * i)] = rs.uniform(-k, k, (o, n_in)).astype(np.float32)
+        sd["linear.%d.bias" % (2 * i)] = rs.uniform(-k, k, (o,)).astype(np.float32)
+    return sd
+
+
 CONV_LAYERS = [  # (name, C_out, C_in) in state_dict order (reference models.py:701-730)
     ("layers1.0", 64, 1), ("layers1.2", 64, 64), ("layers2.0", 64, 64), ("layers2.2", 64, 64),
     ("layers3.0", 64, 64), ("layers3.2", 64, 64), ("layers4.0", 64, 64), ("layers4.2", 64, 64),

@@ -251,12 +251,15 @@ def gru_mode_cases():
     print("gru modes: teacher |out| mean", float(tf.abs().mean()), flush=True)
 
 
-GRU_COND = [  # name, decoding_type, onehot, reverse, y_hidden, y_depth, activation, H, seed
-    ("h0_onehot", "y_h0", True, False, 48, 2, "selu", 512, 31),
-    ("h0_scalar", "y_h0", False, False, 40, 1, "relu", 256, 32),
-    ("h0_reverse", "y_h0", True, True, 48, 3, "tanh", 256, 33),
-    ("ynn_onehot", "y_input", True, False, 48, 2, "relu", 256, 34),
-    ("yin_scalar_rev", "y_input", False, True, 0, 0, "relu", 256, 35),
+GRU_COND = [  # name, decoding_type, onehot, reverse, y_hidden, y_depth, activation, H, seed, out_linear_depth
+    ("h0_onehot", "y_h0", True, False, 48, 2, "selu", 512, 31, 1),
+    ("h0_scalar", "y_h0", False, False, 40, 1, "relu", 256, 32, 1),
+    ("h0_reverse", "y_h0", True, True, 48, 3, "tanh", 256, 33, 1),
+    ("ynn_onehot", "y_input", True, False, 48, 2, "relu", 256, 34, 1),
+    ("yin_scalar_rev", "y_input", False, True, 0, 0, "relu", 256, 35, 1),
+    ("yin_head3", "y_input", True, False, 128, 0, "relu", 512, 36, 3),   # rnn_all.py:1322 with --out_linear_depth 3
+    ("yin_head2", "y_input", True, False, 48, 0, "relu", 256, 37, 2),
+    ("h0_head4", "y_h0", True, False, 64, 2, "selu", 128, 38, 4),
 ]
 
 
@@ -272,15 +275,17 @@ def gru_cond_cases():
     code = ref_shim.get_code("Polar", "polar", N, K)
     info = np.asarray(code.info_positions)
     out = {"names": np.array([c[0] for c in GRU_COND]), "info": info.astype(np.int32), "gain": np.float64(gain)}
-    for name, dtype, onehot, rev, yh, yd, act, H, seed in GRU_COND:
+    for name, dtype, onehot, rev, yh, yd, act, H, seed, od in GRU_COND:
         y_h0 = dtype == "y_h0"
         in_size = (0 if y_h0 else N) + 1 + int(onehot)
         if yd > 0:
             sd = synth.gru_y_state_dict(seed, N, H, in_size, yh, yd, 2 * H if y_h0 else N, head_gain=gain)
-            net = ra.RNN_Model("GRU", in_size, H, 1, 2, N, yh, yd, act, y_output_size=None if y_h0 else N)
         else:
             sd = synth.gru_state_dict(seed, in_size - 2, H, 2, head_gain=gain)
-            net = ra.RNN_Model("GRU", in_size, H, 1, 2, N, 0, 0, act)
+        if od > 1:
+            sd = synth.with_mlp_head(sd, seed, H, yh, od, head_gain=gain)
+        net = ra.RNN_Model("GRU", in_size, H, 1, 2, N, yh, yd, act, out_linear_depth=od,
+                           y_output_size=None if (y_h0 or yd == 0) else N)
         net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
         dec = ra.RNN_decoder(dtype, N, info, onehot=onehot, reverse_order=rev)
         msg = bpsk_msgs(rs, B, K)
@@ -292,7 +297,7 @@ def gru_cond_cases():
         genie = dec.decode(net, False, y, gt, loss_inds=info[-6:])
         with torch.no_grad():
             teacher = dec.decode(net, True, y, gt, 1)
-        out[name + "_cfg"] = np.array([H, seed, yh, yd, int(onehot), int(rev)], dtype=np.int64)
+        out[name + "_cfg"] = np.array([H, seed, yh, yd, int(onehot), int(rev), od], dtype=np.int64)
         out[name + "_type"] = np.array(dtype)
         out[name + "_act"] = np.array(act)
         out[name + "_y"] = y.numpy()

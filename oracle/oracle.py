@@ -245,8 +245,13 @@ def gru_decode(sd, y, N, info, forced=None, H=None, round_bf16=False, genie=None
     Whh = [T(sd["rnn.weight_hh_l%d" % l]) for l in range(L)]
     bih = [T(sd["rnn.bias_ih_l%d" % l]) for l in range(L)]
     bhh = [T(sd["rnn.bias_hh_l%d" % l]) for l in range(L)]
-    Wo = T(sd["linear.weight"])
-    bo = T(sd["linear.bias"])
+    if "linear.weight" in sd:
+        Wo, bo, head = T(sd["linear.weight"]), T(sd["linear.bias"]), None
+    else:  # out_linear_depth > 1 (rnn_all.py:335-343): nn.Sequential of Linear (even indices) with SELU in between
+        head, i = [], 0
+        while ("linear.%d.weight" % i) in sd:
+            head.append((T(sd["linear.%d.weight" % i]), T(sd["linear.%d.bias" % i])))
+            i += 2
     Hs = Whh[0].shape[1]
     info_set = set(int(i) for i in info)
     h = [torch.zeros(B, Hs) for _ in range(L)] if h0 is None else [T(h0)[l].clone() for l in range(L)]
@@ -281,7 +286,15 @@ def gru_decode(sd, y, N, info, forced=None, H=None, round_bf16=False, genie=None
             n = torch.tanh(gi[:, 2 * Hs:] + r * gh[:, 2 * Hs:])
             h[l] = (1 - z) * n + z * h[l]
             x = h[l]
-        out = (rb(x) @ rb(Wo).t() + bo).view(-1) if round_bf16 else (x @ Wo.t() + bo).view(-1)
+        if head is not None:
+            out = x
+            for li, (Wl, bl) in enumerate(head):
+                out = out @ Wl.t() + bl
+                if li + 1 < len(head):
+                    out = torch.nn.functional.selu(out)
+            out = out.view(-1)
+        else:
+            out = (rb(x) @ rb(Wo).t() + bo).view(-1) if round_bf16 else (x @ Wo.t() + bo).view(-1)
         logits[:, ii] = out
         if ii in info_set:
             decoded[:, ii] = out.sign()

@@ -312,21 +312,23 @@ def test_gru_genie_and_forced_evaluation_modes(golden):
         dec.decode(net, True, y, gt, 1)  # gradients enabled = training: out of scope
 
 
-@pytest.mark.parametrize("nm", ["h0_onehot", "h0_scalar", "h0_reverse", "ynn_onehot", "yin_scalar_rev"])
+@pytest.mark.parametrize("nm", ["h0_onehot", "h0_scalar", "h0_reverse", "ynn_onehot", "yin_scalar_rev", "yin_head3",
+                                "yin_head2", "h0_head4"])
 def test_gru_conditionings_vs_reference_fixture(golden, nm):
     """RNN_decoder.decode for decoding_type 'y_h0' (initial state = the y-MLP, rnn_all.py:523-531), 'y_input' through
-    the y-MLP (use_ynn), scalar feedback and reverse order, against outputs of the live reference: teacher-forced raw
+    the y-MLP (use_ynn), scalar feedback, reverse order and MLP heads (out_linear_depth > 1, 335-343), against outputs of the live reference: teacher-forced raw
     outputs within the logit tolerance; free-running and genie decisions equal on rows with no near-zero logit."""
     from neural_polar_decoder_b200.rnn_all import RNN_Model, RNN_decoder
     from test_oracle_golden import _cond_case
     g = golden("gru_cond")
     info = g["info"]
-    H, seed, yh, yd, onehot, rev = [int(v) for v in g[nm + "_cfg"]]
+    H, seed, yh, yd, onehot, rev, od = [int(v) for v in g[nm + "_cfg"]]
     dtype, act = str(g[nm + "_type"]), str(g[nm + "_act"])
     sd, kw, y_k, _ = _cond_case(g, nm)
     N = y_k.shape[1]
     in_size = (0 if dtype == "y_h0" else N) + 1 + onehot
-    net = RNN_Model('GRU', in_size, H, 1, 2, N, yh, yd, act, y_output_size=None if dtype == "y_h0" else N)
+    net = RNN_Model('GRU', in_size, H, 1, 2, N, yh, yd, act, out_linear_depth=od,
+                    y_output_size=None if (dtype == "y_h0" or yd == 0) else N)
     net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
     dec = RNN_decoder(dtype, N, info, onehot=bool(onehot), reverse_order=bool(rev))
     y, gt = torch.from_numpy(g[nm + "_y"]).cuda(), torch.from_numpy(g[nm + "_gt"]).cuda()

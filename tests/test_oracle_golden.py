@@ -128,7 +128,7 @@ def test_gru_oracle_modes_against_reference_fixture(golden):
 def _cond_case(g, nm):
     """(state_dict, decode kwargs, y as the kernel sees it, loss-step helper) of one gru_cond.npz case."""
     from neural_polar_decoder_b200 import synth
-    H, seed, yh, yd, onehot, rev = [int(v) for v in g[nm + "_cfg"]]
+    H, seed, yh, yd, onehot, rev, od = [int(v) for v in g[nm + "_cfg"]]
     y_h0 = str(g[nm + "_type"]) == "y_h0"
     N = g[nm + "_y"].shape[1]
     in_size = (0 if y_h0 else N) + 1 + onehot
@@ -137,6 +137,8 @@ def _cond_case(g, nm):
         sd = synth.gru_y_state_dict(seed, N, H, in_size, yh, yd, 2 * H if y_h0 else N, head_gain=gain)
     else:
         sd = synth.gru_state_dict(seed, in_size - 2, H, 2, head_gain=gain)
+    if od > 1:
+        sd = synth.with_mlp_head(sd, seed, H, yh, od, head_gain=gain)
     kw = dict(onehot=bool(onehot), y_in=not y_h0)
     y = g[nm + "_y"]
     if y_h0:
@@ -147,8 +149,8 @@ def _cond_case(g, nm):
 
 
 def test_gru_oracle_conditionings_against_reference_fixture(golden):
-    """'y_h0' (initial state from the y-MLP), use_ynn, scalar feedback and reverse order (rnn_all.py:410-419,
-    523-531, 1317-1320) against the live reference: teacher-forced raw outputs, free-running and genie decodes."""
+    """'y_h0' (initial state from the y-MLP), use_ynn, scalar feedback, reverse order and MLP heads (rnn_all.py:335-343,
+    410-419, 523-531, 1317-1322) against the live reference: teacher-forced raw outputs, free-running and genie decodes."""
     g = golden("gru_cond")
     info = g["info"]
     for nm in [str(s) for s in g["names"]]:
