@@ -46,6 +46,10 @@ def polar_RNN_full_test(net, polar, snr_range, Test_Data_Generator, run_ML=False
                         decoder=None, device=None, seed=None, list_size=4):
     """-> (bers_RNN, blers_RNN, bers_SC, blers_SC, bers_SCL, blers_SCL, bers_RNNL, blers_RNNL, bers_ML, blers_ML)."""
     assert decoder is not None, "pass the RNN_decoder (a module global in the reference)"
+    if run_ML or run_RNNL:
+        # run_RNNL is hard-wired False at the reference's only call site (rnn_all.py:1897); run_ML is a 2^K brute-force
+        # search (892-930).  Neither is on the B200 path: fail instead of returning silent zero curves.
+        raise NotImplementedError("polar_RNN_full_test: run_ML / run_RNNL are not on the accelerated path")
     _lib.require_cuda()
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     snr_range = list(snr_range)
