@@ -55,6 +55,31 @@ __global__ void __launch_bounds__(128) encode_kernel(const EncParams p)
         // rate profile: u[info] = msg, 0-bits (+1) elsewhere (polar.py:137-138, pac_code.py:171-172)
         uint4 rnd = make_uint4(0, 0, 0, 0);
         int rnd_block = -1;  // one Philox block serves 128 message bits: a lane's k = lane + 32 i stays in it for 4 turns
+        if (!p.msg_in && (K & 3) == 0 && K <= 4096) {
+            // generated messages, four bits per lane and turn (the per-bit loop below cost 2/3 of the kernel's
+            // instructions at K = 512): bits 4q..4q+3 sit in one word of Philox block q >> 5, which is the same block
+            // for the whole warp -- lane b draws block b once, every turn broadcasts its block -- and msg_out / info
+            // move as 16-byte vectors
+            const uint4 mine = npd_philox4x32_10(make_uint4((uint32_t)cw, (uint32_t)(cw >> 32), (uint32_t)lane, NPD_STREAM_MSG), key);
+            for (int q0 = 0; q0 < (K >> 2); q0 += 32) {  // whole-warp turns: the shuffles need every lane
+                const int q = q0 + lane, k0 = q << 2, src = q0 >> 5;
+                rnd = make_uint4(__shfl_sync(NPD_FULL, mine.x, src), __shfl_sync(NPD_FULL, mine.y, src),
+                                 __shfl_sync(NPD_FULL, mine.z, src), __shfl_sync(NPD_FULL, mine.w, src));
+                if (q >= (K >> 2)) continue;
+                const uint32_t wsel = (k0 >> 5) & 3;
+                const uint32_t word = wsel == 0 ? rnd.x : wsel == 1 ? rnd.y : wsel == 2 ? rnd.z : rnd.w;
+                const uint32_t nib = (word >> (k0 & 31)) & 0xFu;
+                if (p.msg_out)
+                    *reinterpret_cast<float4 *>(p.msg_out + r * K + k0) =
+                        make_float4((nib & 1u) ? -1.0f : 1.0f, (nib & 2u) ? -1.0f : 1.0f, (nib & 4u) ? -1.0f : 1.0f,
+                                    (nib & 8u) ? -1.0f : 1.0f);
+                const int4 pos = __ldg(reinterpret_cast<const int4 *>(p.info + k0));
+                if (nib & 1u) atomicOr(&V[pos.x >> 5], 1u << (pos.x & 31));
+                if (nib & 2u) atomicOr(&V[pos.y >> 5], 1u << (pos.y & 31));
+                if (nib & 4u) atomicOr(&V[pos.z >> 5], 1u << (pos.z & 31));
+                if (nib & 8u) atomicOr(&V[pos.w >> 5], 1u << (pos.w & 31));
+            }
+        } else
         for (int k = lane; k < K; k += 32) {
             uint32_t bit;
             if (p.msg_in) {
@@ -116,10 +141,10 @@ __global__ void __launch_bounds__(128) encode_kernel(const EncParams p)
                         make_uint4((uint32_t)cw, (uint32_t)(cw >> 32), (uint32_t)q, NPD_STREAM_NOISE + p.point), key);
                     float2 z0 = npd_box_muller(rnd.x, rnd.y), z1 = npd_box_muller(rnd.z, rnd.w);
                     float4 yv;
-                    yv.x = xv.x + p.sigma * z0.x;
-                    yv.y = xv.y + p.sigma * z0.y;
-                    yv.z = xv.z + p.sigma * z1.x;
-                    yv.w = xv.w + p.sigma * z1.y;
+                    yv.x = fmaf(p.sigma, z0.x, xv.x);
+                    yv.y = fmaf(p.sigma, z0.y, xv.y);
+                    yv.z = fmaf(p.sigma, z1.x, xv.z);
+                    yv.w = fmaf(p.sigma, z1.y, xv.w);
                     *reinterpret_cast<float4 *>(p.y_out + r * N + e) = yv;
                 }
             }
@@ -157,10 +182,10 @@ __global__ void __launch_bounds__(256) awgn_kernel(const float *__restrict__ x, 
         if ((N & 3) == 0) {
             float4 xv = *reinterpret_cast<const float4 *>(x + r * N + e);
             float4 yv;
-            yv.x = xv.x + sigma * z0.x;
-            yv.y = xv.y + sigma * z0.y;
-            yv.z = xv.z + sigma * z1.x;
-            yv.w = xv.w + sigma * z1.y;
+            yv.x = fmaf(sigma, z0.x, xv.x);
+            yv.y = fmaf(sigma, z0.y, xv.y);
+            yv.z = fmaf(sigma, z1.x, xv.z);
+            yv.w = fmaf(sigma, z1.y, xv.w);
             *reinterpret_cast<float4 *>(y + r * N + e) = yv;
         } else {
             const float zz[4] = {z0.x, z0.y, z1.x, z1.y};

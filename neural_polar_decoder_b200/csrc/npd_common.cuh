@@ -102,11 +102,14 @@ __device__ __forceinline__ uint4 npd_philox4x32_10(uint4 c, uint2 k)
 // Box-Muller on two 32-bit words -> two N(0,1) samples.  u = (float(r) + 0.5) * 2^-32 in (0,1].
 __device__ __forceinline__ float2 npd_box_muller(uint32_t r0, uint32_t r1)
 {
-    float u0 = ((float)r0 + 0.5f) * 2.3283064365386963e-10f;
-    float u1 = ((float)r1 + 0.5f) * 2.3283064365386963e-10f;
-    // sqrt.approx (one MUFU, max error 1 ulp) instead of the IEEE square root's Newton sequence
-    float rad;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-2.0f * __logf(u0)));
+    // u = (r + 1/2) 2^-32 as one fused multiply-add (this file is compiled without FMA contraction)
+    float u0 = fmaf((float)r0, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    float u1 = fmaf((float)r1, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    // u0 lies in [2^-33, 1], never denormal: lg2.approx.ftz without __logf's denormal pre-scaling; sqrt.approx (one
+    // MUFU, max error 1 ulp) instead of the IEEE square root's Newton sequence.  -2 ln u = (-2 ln 2) lg2 u.
+    float l2, rad;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u0));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * l2));
     float sn, cs;
     __sincosf(6.283185307179586f * u1, &sn, &cs);
     return make_float2(rad * cs, rad * sn);
