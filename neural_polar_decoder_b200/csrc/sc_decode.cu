@@ -1115,11 +1115,21 @@ int launch_quad(const npd_code *code, ScParams p, cudaStream_t st)
     int max_warps = env_int("NPD_SC_WARPS", 24);
     if (warps_per_sm > max_warps) warps_per_sm = max_warps;
     if (warps_per_sm < 1) warps_per_sm = 1;
-    int wpb = 1;
-    while (wpb < 4 && warps_per_sm >= wpb * 2 && per_warp * wpb * 2 + 1024 <= budget) wpb *= 2;
-    int blocks_per_sm = (int)((size_t)(228 * 1024) / (per_warp * wpb + 1024));
-    if (blocks_per_sm * wpb > max_warps) blocks_per_sm = max_warps / wpb;
-    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    // warps per block: 4 unless smaller blocks pack at least 20 % more warps into the SM's 228 KB (every block also
+    // reserves 1 KB).  At N = 4096 a warp's state is 70 KB: blocks of two leave a third of the shared memory empty
+    // (2 warps per SM, 8.3e6 cw/s; single-warp blocks: 3 warps, 1.17e7).  At N = 1024 the 13th warp that single-warp
+    // blocks would add costs more than it brings (9.8e7 vs 1.44e8 cw/s: the y rows of 13 x 8 x 148 codewords no
+    // longer stay in L2 between the four passes).
+    int wpb = 1, blocks_per_sm = 1;
+    {
+        int best = 0;
+        for (int w = env_int("NPD_SC_WPB", 4); w >= 1; w >>= 1) {
+            if (per_warp * w + 1024 > budget) continue;
+            int b = (int)((size_t)(228 * 1024) / (per_warp * w + 1024));
+            if (b * w > max_warps) b = max_warps / w;
+            if (b >= 1 && 5 * b * w >= 6 * best) { best = b * w; wpb = w; blocks_per_sm = b; }
+        }
+    }
     const int64_t ngroups = (p.B + 7) / 8;
     int64_t grid = (int64_t)dp.sm_count * blocks_per_sm;
     const int64_t need = (ngroups + wpb - 1) / wpb;
