@@ -97,11 +97,16 @@ def bench_gru(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
+    def tail():
+        torch.index_select(decoded, 1, info_t, out=dec_info)
+        _lib.check(lib.npd_count_errors(_lib.ptr(msg), _lib.ptr(dec_info), B, K, _lib._vp(counts.data_ptr()), st))
+
+    for _ in range(args.warmup):  # the WHOLE step: the gather / count kernels' first launches load their modules
+        step()                    # (40 ms on a fresh box, which used to land in the timed region)
+        tail()
     if world > 1:
         dist.all_reduce(counts)  # warm-up of the collective too (its first call sets up NCCL channels)
-        counts.zero_()
+    counts.zero_()
     sync()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -113,8 +118,7 @@ def bench_gru(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
         ev[i][0].record()
         step()
         ev[i][1].record()
-        torch.index_select(decoded, 1, info_t, out=dec_info)
-        _lib.check(lib.npd_count_errors(_lib.ptr(msg), _lib.ptr(dec_info), B, K, _lib._vp(counts.data_ptr()), st))
+        tail()
     if world > 1:
         dist.all_reduce(counts)
     t_end.record()
@@ -274,11 +278,17 @@ def bench_conv(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    def tail():
+        # decisions on the info positions = sign(logits) (run_models.py:338-339), then the error counters
+        torch.sign(torch.index_select(logits, 1, info_t), out=dec_info)
+        _lib.check(lib.npd_count_errors(_lib.ptr(msg), _lib.ptr(dec_info), B, K, _lib._vp(counts.data_ptr()), st))
+
+    for _ in range(args.warmup):  # the whole step, so that no kernel's first launch falls into the timed region
         step()
+        tail()
     if world > 1:
         dist.all_reduce(counts)  # warm-up of the collective too (its first call sets up NCCL channels)
-        counts.zero_()
+    counts.zero_()
     sync()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -290,9 +300,7 @@ def bench_conv(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
         ev[i][0].record()
         step()
         ev[i][1].record()
-        # decisions on the info positions = sign(logits) (run_models.py:338-339), then the error counters
-        torch.sign(torch.index_select(logits, 1, info_t), out=dec_info)
-        _lib.check(lib.npd_count_errors(_lib.ptr(msg), _lib.ptr(dec_info), B, K, _lib._vp(counts.data_ptr()), st))
+        tail()
     if world > 1:
         dist.all_reduce(counts)
     t_end.record()
