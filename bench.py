@@ -28,6 +28,8 @@ WORKLOADS = {
                    desc="SC Polar(1024,512), polarization-weight frozen set, AWGN 2 dB"),
     "sc256": dict(kind="sc", N=256, K=128, snr=2.0, batch=524288,
                   desc="SC Polar(256,128), reference reliability table, AWGN 2 dB"),
+    "sc2048": dict(kind="sc", N=2048, K=1024, snr=2.0, batch=65536,
+                   desc="SC Polar(2048,1024), polarization-weight frozen set, AWGN 2 dB"),
     "sc4096": dict(kind="sc", N=4096, K=2048, snr=2.0, batch=32768,
                    desc="SC Polar(4096,2048), polarization-weight frozen set, AWGN 2 dB"),
     "sc64": dict(kind="sc", N=64, K=22, snr=0.0, batch=2097152,

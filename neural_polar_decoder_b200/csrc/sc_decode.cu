@@ -39,6 +39,7 @@ struct ScParams {
     uint32_t pac_taps, pac_state_mask;
     int scan_flagged;      // group kernel: 1 = only codewords whose decoded[cw][0] is the NaN sentinel
     int slog;              // lane kernel: highest stored level
+    float *scratch;        // quad kernel, N >= 2048: level n-2 of every resident warp ([warp][element][8 codewords])
     long long *trace;      // bench-only (NPD_SC_TRACE): cycles of warp 0 / block 0's second group: top, levels, block, merge, output, total
 };
 
@@ -739,16 +740,21 @@ __device__ __forceinline__ void quad_node(const float (&L)[S / 4], QuadCtx &c)
 // word index of element e of codeword c inside a stored level: [element][8], codeword XOR-swizzled
 __device__ __forceinline__ int quad_idx(int e, int c) { return e * 8 + (c ^ ((e >> 2) & 7)); }
 
-__host__ __device__ inline size_t quad_warp_smem_bytes(int n)
+// gl: the top gl stored levels (n-2: half of the stored tree, n-3: a quarter) live in an L2-resident global scratch
+// instead of shared memory
+__host__ __device__ inline size_t quad_warp_smem_bytes(int n, int gl = 0)
 {
     const int slog = n - 2;
-    return (size_t)4 * 8 * ((2u << slog) - 64u) + (size_t)4 * 2 * ((1u << n) >> 5) * 8;
+    return (size_t)4 * 8 * ((2u << (slog - gl)) - 64u) + (size_t)4 * 2 * ((1u << n) >> 5) * 8;
 }
+// floats of global scratch per warp: level L <= n-2 starts at quad_scratch_off(n, L)
+__host__ __device__ inline size_t quad_scratch_off(int n, int level) { return (size_t)8 * ((2u << (n - 2)) - (2u << level)); }
+__host__ __device__ inline size_t quad_scratch_floats(int n, int gl) { return gl ? quad_scratch_off(n, n - 2 - gl) : 0; }
 
 // Level n-2 of the 8 codewords of the group for quarter r of the code, from y: lane = element (coalesced loads
 // of y[j], y[j+h], y[j+2h], y[j+3h], h = N/4, 32 loads in flight per lane), level n-1 folded in.  G1 / G0: the
 // level n-1 / n-2 node on the path is a right child (g with the partial sums of its left sibling) or not (f).
-template <int NLOG, bool G1, bool G0, bool FULL>
+template <int NLOG, bool G1, bool G0, bool FULL, bool GTOP = false>
 __device__ __forceinline__ void quad_top_phase(const ScParams &p, float *dst, const uint32_t *PS, const float *ygrp,
                                                int nvalid, int r, int lane)
 {
@@ -786,7 +792,12 @@ __device__ __forceinline__ void quad_top_phase(const ScParams &p, float *dst, co
             } else {
                 o = npd_f_minsum(a0, a1);
             }
-            drow[cc ^ kx] = o;
+            if (GTOP) v[cc][0] = o;  // global scratch: no bank swizzle, the lane's 32-byte row goes out as two vectors
+            else drow[cc ^ kx] = o;
+        }
+        if (GTOP) {
+            __stcg(reinterpret_cast<float4 *>(drow), make_float4(v[0][0], v[1][0], v[2][0], v[3][0]));
+            __stcg(reinterpret_cast<float4 *>(drow) + 1, make_float4(v[4][0], v[5][0], v[6][0], v[7][0]));
         }
     };
     // explicit two-deep software pipeline: the 32 loads of the next slice are in flight while this one is reduced
@@ -827,23 +838,74 @@ __device__ __forceinline__ void quad_level(float *tree, const uint32_t *PSw, con
     }
 }
 
-template <int LV>
+// global scratch level LV+1 ([element][8 codewords], unswizzled) -> stored level LV, lane = element like the top phase:
+// a lane reads its two 32-byte rows as four 16-byte vectors (the (quarter, codeword) mapping of quad_level would issue
+// sixteen 4-byte loads for the same data) and stores transposed with the level's bank swizzle
+template <int LV, bool G, bool GOUT>
+__device__ __forceinline__ void quad_level_from_scratch(const float *gpar, float *tree, float *gch, const uint32_t *PSl, int lane)
+{
+    constexpr int H = 1 << LV;
+    float *ch = tree + 8 * ((1 << LV) - 64);
+    const int kx = (lane >> 2) & 7;
+#pragma unroll 4
+    for (int slice = 0; slice < H / 32; ++slice) {
+        const int j = slice * 32 + lane;
+        const float4 *pa = reinterpret_cast<const float4 *>(gpar + (size_t)j * 8);
+        const float4 *pb = reinterpret_cast<const float4 *>(gpar + (size_t)(j + H) * 8);
+        const float4 a0 = __ldcg(pa), a1 = __ldcg(pa + 1), b0 = __ldcg(pb), b1 = __ldcg(pb + 1);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float *drow = ch + j * 8;
+        float o[8];
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {
+            if (G) {
+                const uint32_t sg = ((PSl[slice * 8 + cc] >> lane) & 1u) << 31;
+                o[cc] = __uint_as_float(__float_as_uint(a[cc]) ^ sg) + b[cc];
+            } else {
+                o[cc] = npd_f_minsum(a[cc], b[cc]);
+            }
+            if (!GOUT) drow[cc ^ kx] = o[cc];
+        }
+        if (GOUT) {  // the child level is a scratch level too
+            __stcg(reinterpret_cast<float4 *>(gch + (size_t)j * 8), make_float4(o[0], o[1], o[2], o[3]));
+            __stcg(reinterpret_cast<float4 *>(gch + (size_t)j * 8) + 1, make_float4(o[4], o[5], o[6], o[7]));
+        }
+    }
+}
+
+// GL = how many of the levels LV+1, LV, ... are scratch levels (LV+1 is one when GL >= 1, LV itself when GL >= 2);
+// NL = log2 of the code length
+template <int LV, int GL = 0, int NL = 0>
 struct QuadLevelsDown {
-    static __device__ __forceinline__ void run(float *tree, const uint32_t *PS, const int (&off)[8], int sub, int cl, int top, int o)
+    static __device__ __forceinline__ void run(float *tree, const uint32_t *PS, const int (&off)[8], int sub, int cl, int top, int o,
+                                               float *scratch = nullptr)
     {
         if (LV <= top) {  // warp-uniform
-            if (LV == top) quad_level<LV, true>(tree, PS + ((o - (1 << LV)) >> 5) * 8 + cl, off, sub);
-            else quad_level<LV, false>(tree, nullptr, off, sub);
+            if (GL >= 1) {
+                const float *gpar = scratch + quad_scratch_off(NL, LV + 1);
+                float *gch = scratch + quad_scratch_off(NL, LV);
+                __syncwarp();
+                if (LV == top)
+                    quad_level_from_scratch<LV, true, (GL >= 2)>(gpar, tree, gch, PS + ((o - (1 << LV)) >> 5) * 8, 8 * sub + cl);
+                else
+                    quad_level_from_scratch<LV, false, (GL >= 2)>(gpar, tree, gch, nullptr, 8 * sub + cl);
+                __syncwarp();
+            } else if (LV == top) {
+                quad_level<LV, true>(tree, PS + ((o - (1 << LV)) >> 5) * 8 + cl, off, sub);
+            } else {
+                quad_level<LV, false>(tree, nullptr, off, sub);
+            }
         }
-        QuadLevelsDown<LV - 1>::run(tree, PS, off, sub, cl, top, o);
+        QuadLevelsDown<LV - 1, (GL > 0 ? GL - 1 : 0), NL>::run(tree, PS, off, sub, cl, top, o, scratch);
     }
 };
-template <>
-struct QuadLevelsDown<5> {
-    static __device__ __forceinline__ void run(float *, const uint32_t *, const int (&)[8], int, int, int, int) {}
+template <int NL>
+struct QuadLevelsDown<5, 0, NL> {
+    static __device__ __forceinline__ void run(float *, const uint32_t *, const int (&)[8], int, int, int, int, float * = nullptr) {}
 };
 
-template <int NLOG, bool TRACE = false>
+template <int NLOG, bool TRACE = false, int GL = 0>
 __global__ void __launch_bounds__(128) sc_quad_kernel(const ScParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -853,11 +915,15 @@ __global__ void __launch_bounds__(128) sc_quad_kernel(const ScParams p)
     const int wpb = blockDim.x >> 5;
     const int sub = lane >> 3, cl = lane & 7;
 
-    unsigned char *base = smem_raw + (size_t)warp * quad_warp_smem_bytes(NLOG);
-    float *tree = reinterpret_cast<float *>(base);  // level lv (6 <= lv <= SLOG) at 8 * (2^lv - 64)
-    uint32_t *PS = reinterpret_cast<uint32_t *>(tree + 8 * ((2 << SLOG) - 64));
+    constexpr bool GTOP = GL > 0;
+    unsigned char *base = smem_raw + (size_t)warp * quad_warp_smem_bytes(NLOG, GL);
+    float *tree = reinterpret_cast<float *>(base);  // level lv (6 <= lv <= SLOG - GL) at 8 * (2^lv - 64)
+    uint32_t *PS = reinterpret_cast<uint32_t *>(tree + 8 * ((2 << (SLOG - GL)) - 64));
     uint32_t *US = PS + NW * 8;
-    float *top_dst = tree + 8 * ((1 << SLOG) - 64);
+    // level SLOG (the current quarter of the code, half of the stored tree): shared memory, or -- GL > 0, large N --
+    // this warp's slice of a global scratch that stays in L2 (written once, read twice as whole 32-byte rows)
+    float *scratch = GTOP ? p.scratch + ((size_t)blockIdx.x * wpb + warp) * quad_scratch_floats(NLOG, GL) : nullptr;
+    float *top_dst = GTOP ? scratch : tree + 8 * ((1 << SLOG) - 64);
 
     int off[8];
 #pragma unroll
@@ -889,23 +955,23 @@ __global__ void __launch_bounds__(128) sc_quad_kernel(const ScParams p)
                 __syncwarp();
                 if (nvalid == 8) {
                     switch (r) {
-                    case 0: quad_top_phase<NLOG, false, false, true>(p, top_dst, PS, ygrp, 8, r, lane); break;
-                    case 1: quad_top_phase<NLOG, false, true, true>(p, top_dst, PS, ygrp, 8, r, lane); break;
-                    case 2: quad_top_phase<NLOG, true, false, true>(p, top_dst, PS, ygrp, 8, r, lane); break;
-                    default: quad_top_phase<NLOG, true, true, true>(p, top_dst, PS, ygrp, 8, r, lane); break;
+                    case 0: quad_top_phase<NLOG, false, false, true, GTOP>(p, top_dst, PS, ygrp, 8, r, lane); break;
+                    case 1: quad_top_phase<NLOG, false, true, true, GTOP>(p, top_dst, PS, ygrp, 8, r, lane); break;
+                    case 2: quad_top_phase<NLOG, true, false, true, GTOP>(p, top_dst, PS, ygrp, 8, r, lane); break;
+                    default: quad_top_phase<NLOG, true, true, true, GTOP>(p, top_dst, PS, ygrp, 8, r, lane); break;
                     }
                 } else {
                     switch (r) {
-                    case 0: quad_top_phase<NLOG, false, false, false>(p, top_dst, PS, ygrp, nvalid, r, lane); break;
-                    case 1: quad_top_phase<NLOG, false, true, false>(p, top_dst, PS, ygrp, nvalid, r, lane); break;
-                    case 2: quad_top_phase<NLOG, true, false, false>(p, top_dst, PS, ygrp, nvalid, r, lane); break;
-                    default: quad_top_phase<NLOG, true, true, false>(p, top_dst, PS, ygrp, nvalid, r, lane); break;
+                    case 0: quad_top_phase<NLOG, false, false, false, GTOP>(p, top_dst, PS, ygrp, nvalid, r, lane); break;
+                    case 1: quad_top_phase<NLOG, false, true, false, GTOP>(p, top_dst, PS, ygrp, nvalid, r, lane); break;
+                    case 2: quad_top_phase<NLOG, true, false, false, GTOP>(p, top_dst, PS, ygrp, nvalid, r, lane); break;
+                    default: quad_top_phase<NLOG, true, true, false, GTOP>(p, top_dst, PS, ygrp, nvalid, r, lane); break;
                     }
                 }
                 __syncwarp();
             }
             if (tr) { t_b = clock64(); t_top += t_b - t_a; t_a = t_b; }
-            QuadLevelsDown<SLOG - 1>::run(tree, PS, off, sub, cl, top, o);
+            QuadLevelsDown<SLOG - 1, GL, NLOG>::run(tree, PS, off, sub, cl, top, o, scratch);
             if (tr) { t_b = clock64(); t_lev += t_b - t_a; t_a = t_b; }
             // level 5 straight into registers: L[i] = element 4 i + sub (level 6 sits at offset 0)
             float L[8];
@@ -1105,7 +1171,13 @@ int launch_quad(const npd_code *code, ScParams p, cudaStream_t st)
     DeviceProps dp;
     if (npd_get_device_props(&dp)) return NPD_ECUDA;
     const int n = code->n;
-    const size_t per_warp = quad_warp_smem_bytes(n);
+    // N >= 2048: levels n-2 and n-3 (3/4 of the stored tree) go to a global scratch: 22 KB instead of 70 KB of shared
+    // memory per warp at N = 4096, 10 warps per SM instead of 3 (1.17e7 -> 1.62e7 cw/s; one scratch level: 1.57e7).
+    // At N = 1024 the same change measured slower (9.6e7 vs 1.44e8 cw/s at 12 warps: the scratch round trip costs
+    // more than the shared-memory one and 12 warps already fit), so it stays off there.
+    const int gl = n >= 11 ? max(0, min(2, env_int("NPD_SC_GTOP", 2))) : 0;  // scratch levels: 0, 1 or 2
+    const bool gtop = gl > 0;
+    const size_t per_warp = quad_warp_smem_bytes(n, gl);
     const size_t budget = (size_t)dp.smem_optin;
     if (per_warp + 1024 > budget) {
         npd_set_error("SC quad kernel: N=%d needs %zu B of shared memory per warp", code->N, per_warp);
@@ -1142,8 +1214,8 @@ int launch_quad(const npd_code *code, ScParams p, cudaStream_t st)
     case 8: kern = sc_quad_kernel<8>; break;
     case 9: kern = sc_quad_kernel<9>; break;
     case 10: kern = trace_path ? sc_quad_kernel<10, true> : sc_quad_kernel<10>; break;
-    case 11: kern = sc_quad_kernel<11>; break;
-    case 12: kern = sc_quad_kernel<12>; break;
+    case 11: kern = gl >= 2 ? sc_quad_kernel<11, false, 2> : gl == 1 ? sc_quad_kernel<11, false, 1> : sc_quad_kernel<11>; break;
+    case 12: kern = gl >= 2 ? sc_quad_kernel<12, false, 2> : gl == 1 ? sc_quad_kernel<12, false, 1> : sc_quad_kernel<12>; break;
     default: npd_set_error("SC quad kernel: n=%d outside 8..12", n); return NPD_EUNSUPPORTED;
     }
     NPD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpb)));
@@ -1151,8 +1223,11 @@ int launch_quad(const npd_code *code, ScParams p, cudaStream_t st)
         NPD_CHECK_CUDA(cudaMalloc(&p.trace, 6 * sizeof(long long)));
         NPD_CHECK_CUDA(cudaMemsetAsync(p.trace, 0, 6 * sizeof(long long), st));
     }
+    if (gtop)  // stream-ordered: concurrent decodes on other streams get their own scratch
+        NPD_CHECK_CUDA(cudaMallocAsync(&p.scratch, (size_t)grid * wpb * quad_scratch_floats(n, gl) * sizeof(float), st));
     kern<<<(unsigned)grid, 32 * wpb, per_warp * wpb, st>>>(p);
     NPD_CHECK_CUDA(cudaGetLastError());
+    if (gtop) NPD_CHECK_CUDA(cudaFreeAsync(p.scratch, st));
     if (trace_path) {
         long long h[6];
         NPD_CHECK_CUDA(cudaStreamSynchronize(st));

@@ -87,6 +87,27 @@ def test_sc_vs_oracle_seeded(N, K, B):
         assert torch.equal(dec2, dec)
 
 
+@pytest.mark.parametrize("N,K,B", [(1024, 512, 1500), (2048, 1024, 1203), (4096, 2048, 1001)])
+def test_sc_quad_kernel_many_groups(N, K, B):
+    """The throughput kernel (decisions only; level n-2 in the global scratch for N >= 2048) on enough codewords to
+    occupy several warps per SM, ragged last group: identical to the leaf-LLR path, itself checked against the oracle
+    above, and to the oracle on a sample."""
+    from neural_polar_decoder_b200 import construct
+    rs = np.random.RandomState(N)
+    info = np.sort(construct.polarization_weight_order(N)[:K])
+    code = _code(N, info)
+    msg = torch.from_numpy((1.0 - 2.0 * rs.randint(0, 2, size=(B, K))).astype(np.float32)).cuda()
+    x = code.encode_plotkin(msg)
+    y = x + 10 ** (-2.0 / 20) * torch.from_numpy(rs.randn(B, N).astype(np.float32)).cuda()
+    _, dec_llr = code.sc_decode_new(y, 2.0)
+    for _ in range(3):  # repeated launches re-use the stream-ordered scratch
+        _, dec_quad = code.sc_decode_new(y, 2.0, return_llr=False)
+        assert torch.equal(dec_quad, dec_llr)
+    _, _, do = oracle.sc_decode(y[-40:].cpu().numpy(), 2.0, _n(N), info)
+    assert np.array_equal(dec_quad[-40:].cpu().numpy(), do)
+    assert (dec_quad == msg).float().mean() > 0.9
+
+
 def test_sc_frozen_prior_not_forced():
     """|L| > infty on a frozen leaf must flip the decision: use a tiny infty."""
     from neural_polar_decoder_b200 import construct
