@@ -359,7 +359,8 @@ def bench_enc(args, w, rank, world, local_rank):
         "e2e": {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "note": "the generator has no host-side input; its output feeds the decoders on the device"},
         "roofline": {"kernel": "encode_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
-                     "frac": achieved / peaks["hbm"], "traffic": None, "peak_source": peaks["src"], "kernel_ms": kern_ms,
+                     "frac": achieved / peaks["hbm"], "traffic": ncu_traffic(args.workload, B)[0],
+                     "traffic_source": ncu_traffic(args.workload, B)[1], "peak_source": peaks["src"], "kernel_ms": kern_ms,
                      "alg_bytes_per_launch": alg_bytes},
     }
 
