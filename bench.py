@@ -34,6 +34,8 @@ WORKLOADS = {
                    desc="SC Polar(4096,2048), polarization-weight frozen set, AWGN 2 dB"),
     "sc64": dict(kind="sc", N=64, K=22, snr=0.0, batch=2097152,
                  desc="SC Polar(64,22), reference 'polar' profile, AWGN 0 dB"),
+    "pac32": dict(kind="sc", N=32, K=16, snr=2.0, batch=4194304, pac_g=53,
+                  desc="PAC(32,16) SC decoder (pac_sc_decode), RM profile, g = 53, AWGN 2 dB"),
     "enc1024": dict(kind="enc", N=1024, K=512, snr=2.0, batch=131072,
                     desc="message generation + Plotkin encoder + BPSK/AWGN channel, Polar(1024,512), 2 dB (Philox noise)"),
     "scl64": dict(kind="sc", N=64, K=22, snr=0.0, batch=262144, L=4,
@@ -77,6 +79,9 @@ def make_code(w):
     from neural_polar_decoder_b200 import PolarCode, construct
     N, K = w["N"], w["K"]
     n = int(np.log2(N))
+    if w.get("pac_g"):
+        from neural_polar_decoder_b200 import PAC
+        return PAC(None, N, K, w["pac_g"])
     if N <= 256:
         rs = construct.reference_rs256()
         return PolarCode(n, K, None, rs=rs[rs < N])
@@ -149,7 +154,10 @@ def cpu_rate_sc(w, seconds, threads, rng_seed=0):
     N, K = w["N"], w["K"]
     n = int(np.log2(N))
     from neural_polar_decoder_b200 import construct
-    if N <= 256:
+    g = w.get("pac_g")
+    if g:
+        info = np.sort(np.asarray(make_code(w).B))
+    elif N <= 256:
         rs = construct.reference_rs256()
         info = np.sort(rs[rs < N][:K])
     else:
@@ -158,12 +166,14 @@ def cpu_rate_sc(w, seconds, threads, rng_seed=0):
 
     def frames(B):
         msg = (1.0 - 2.0 * r.randint(0, 2, size=(B, K))).astype(np.float32)
-        x = oracle.polar_encode(msg, n, info)
+        x = oracle.pac_encode(msg, n, info, g) if g else oracle.polar_encode(msg, n, info)
         return (x + 10 ** (-w["snr"] / 20) * r.randn(B, N)).astype(np.float32)
 
     def run(y):
         t0 = time.perf_counter()
-        if w.get("L"):
+        if g:
+            oracle.run_threaded(lambda lo, hi: oracle.pac_sc_decode(y[lo:hi], w["snr"], n, info, g), y.shape[0], threads)
+        elif w.get("L"):
             oracle.run_threaded(lambda lo, hi: oracle.scl_decode(y[lo:hi], w["snr"], n, info, w["L"]), y.shape[0], threads)
         else:
             oracle.run_threaded(lambda lo, hi: oracle.sc_decode(y[lo:hi], w["snr"], n, info), y.shape[0], threads)
@@ -390,7 +400,9 @@ def bench_sc(args, w, rank, world, local_rank):
     L = int(w.get("L", 0))
 
     def decode_call():
-        if L:
+        if w.get("pac_g"):
+            _lib.check(lib.npd_pac_sc_decode(h.h, _lib.ptr(y), scale, None, None, _lib.ptr(dec), None, B, st))
+        elif L:
             _lib.check(lib.npd_scl_decode(h.h, _lib.ptr(y), scale, L, None, _lib.ptr(dec), B, st))
         else:
             _lib.check(lib.npd_sc_decode(h.h, _lib.ptr(y), scale, None, None, _lib.ptr(dec), B, st))
@@ -444,6 +456,8 @@ def bench_sc(args, w, rank, world, local_rank):
     msg_host = msg[:e2e_B:61].cpu()
     e2e_steps = max(3, min(args.steps, 10))
     def host_call():
+        if w.get("pac_g"):
+            return code.pac_sc_decode(y_host, snr)[:2]
         if L:
             return code.scl_decode(y_host, snr, L, False, return_llr=False)
         return code.sc_decode_new(y_host, snr, return_llr=False)
