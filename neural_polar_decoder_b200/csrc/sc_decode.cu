@@ -39,6 +39,7 @@ struct ScParams {
     uint32_t pac_taps, pac_state_mask;
     int scan_flagged;      // group kernel: 1 = only codewords whose decoded[cw][0] is the NaN sentinel
     int slog;              // lane kernel: highest stored level
+    int vec_out;           // quad kernel: 16-byte output stores (K % 4 == 0, aligned `decoded`)
     float *scratch;        // quad kernel, N >= 2048: level n-2 of every resident warp ([warp][element][8 codewords])
     long long *trace;      // bench-only (NPD_SC_TRACE): cycles of warp 0 / block 0's second group: top, levels, block, merge, output, total
 };
@@ -1015,6 +1016,42 @@ __global__ void __launch_bounds__(128) sc_quad_kernel(const ScParams p)
         fl |= __shfl_xor_sync(NPD_FULL, fl, 16);
         __syncwarp();
         float *dst0 = p.decoded + cw0 * p.K;
+        // (measured: +4.5 % at N = 256, where the output phase is a larger share; nothing at N = 1024, so the code is
+        // only compiled into the short-code kernels)
+        if (NLOG <= 9 && p.vec_out) {
+            // four consecutive k per lane: the info positions arrive as one 16-byte load, the 8 codewords' decision
+            // words of a position as two, and every codeword's four decisions leave as one 16-byte store
+            for (int k0 = 0; k0 < p.K; k0 += 128 * 4) {
+                int4 pos[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int k = k0 + 128 * i + 4 * lane;
+                    pos[i] = k < p.K ? __ldg(reinterpret_cast<const int4 *>(p.info + k)) : make_int4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int k = k0 + 128 * i + 4 * lane;
+                    if (k < p.K) {
+                        const int ps[4] = {pos[i].x, pos[i].y, pos[i].z, pos[i].w};
+                        uint32_t w[4][8];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 lo = *reinterpret_cast<const uint4 *>(US + (ps[j] >> 5) * 8);
+                            const uint4 hi = *reinterpret_cast<const uint4 *>(US + (ps[j] >> 5) * 8 + 4);
+                            const int sh = ps[j] & 31;
+                            w[j][0] = lo.x >> sh; w[j][1] = lo.y >> sh; w[j][2] = lo.z >> sh; w[j][3] = lo.w >> sh;
+                            w[j][4] = hi.x >> sh; w[j][5] = hi.y >> sh; w[j][6] = hi.z >> sh; w[j][7] = hi.w >> sh;
+                        }
+#pragma unroll
+                        for (int cc = 0; cc < 8; ++cc)
+                            if (cc < nvalid)
+                                *reinterpret_cast<float4 *>(dst0 + (size_t)cc * p.K + k) =
+                                    make_float4((w[0][cc] & 1u) ? -1.0f : 1.0f, (w[1][cc] & 1u) ? -1.0f : 1.0f,
+                                                (w[2][cc] & 1u) ? -1.0f : 1.0f, (w[3][cc] & 1u) ? -1.0f : 1.0f);
+                    }
+                }
+            }
+        } else
         for (int k0 = 0; k0 < p.K; k0 += 32 * 16) {
             // the info positions of 16 rounds are fetched together (they were 16 exposed L2 round trips per group)
             int pos[16];
@@ -1207,6 +1244,7 @@ int launch_quad(const npd_code *code, ScParams p, cudaStream_t st)
     const int64_t need = (ngroups + wpb - 1) / wpb;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
+    p.vec_out = (p.K & 3) == 0 && (reinterpret_cast<uintptr_t>(p.decoded) & 15) == 0 && env_int("NPD_SC_VECOUT", 1) != 0;
     void (*kern)(const ScParams) = nullptr;
     const char *trace_path = getenv("NPD_SC_TRACE");  // bench-only (synchronises!): phase cycles of one group, N = 1024
     if (trace_path && n != 10) trace_path = nullptr;
