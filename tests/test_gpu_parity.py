@@ -390,6 +390,35 @@ def test_gru_conditionings_vs_reference_fixture(golden, nm):
     assert not d.is_cuda and np.array_equal(d.numpy()[safe], dec.decode(net, False, y).cpu().numpy()[safe])
 
 
+def test_gru_head_mlp_envelope_and_workspace():
+    """Outside the MLP-head envelope the library says so (no silent fallback); a decode without the head's workspace
+    is refused; npd_gru_workspace_bytes is zero for the Linear head."""
+    from neural_polar_decoder_b200 import _lib, construct, synth
+    from neural_polar_decoder_b200.rnn_all import RNN_Model, RNN_decoder
+    N, K, H = 32, 16, 256
+    rs = construct.reference_rs256()
+    info = np.sort(rs[rs < N][:K])
+    lib = _lib.load()
+    sd = synth.with_mlp_head(synth.gru_state_dict(3, N, H, 2), 3, H, 40, 2)   # y_hidden_size 40: not a multiple of 16
+    net = RNN_Model('GRU', N + 2, H, 1, 2, N, 40, 0, out_linear_depth=2)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    with pytest.raises(_lib.NpdError, match="multiple of 16"):
+        net.npd_handle(N)
+    sd = synth.with_mlp_head(synth.gru_state_dict(3, N, H, 2), 3, H, 48, 2)
+    net = RNN_Model('GRU', N + 2, H, 1, 2, N, 48, 0, out_linear_depth=2)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    h = net.npd_handle(N)
+    assert lib.npd_gru_workspace_bytes(h.h, 100) >= 2 * 2 * 64 * 48 * 2
+    dec = RNN_decoder('y_input', N, info, onehot=True)
+    y = torch.randn(100, N, device="cuda")
+    out = torch.empty(100, N, device="cuda")
+    rc = lib.npd_gru_decode(h.h, dec._loss_code(info).h, _lib.ptr(y), None, None, None, _lib.ptr(out), 100, None, 0,
+                            _lib.stream_ptr())
+    assert rc != 0 and b"workspace" in lib.npd_last_error()
+    plain = RNN_Model('GRU', N + 2, H, 1, 2, N, 0, 0)
+    assert lib.npd_gru_workspace_bytes(plain.npd_handle(N).h, 100) == 0
+
+
 def test_gru_h0_ragged_batch_both_kernels():
     """npd_gru_decode_h0 at a batch that is not a multiple of the tile, H = 256 (CTA-pair kernel) and H = 128
     (single-CTA kernel), against the fp32 oracle under forced feedback."""
