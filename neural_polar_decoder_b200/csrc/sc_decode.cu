@@ -22,6 +22,7 @@
 //    (sign, is-zero), so û in {-1,0,+1} is carried exactly.  In scan mode it visits only the flagged
 //    codewords.  Ties need an exact fp32 cancellation; they do not occur on real-valued noise.
 #include "npd_common.cuh"
+#include <mutex>
 
 namespace {
 
@@ -1203,6 +1204,31 @@ int launch_lane(const npd_code *code, ScParams p, cudaStream_t st)
     return NPD_OK;
 }
 
+// Library-owned memory pool for the quad kernel's scratch: stream-ordered allocations that stay cached across
+// synchronisations (the device's default pool hands freed memory back at every sync, and the next launch then pays a
+// fresh 70 MB mapping -- measured as sporadic 2x slower launches)
+int scratch_pool(cudaMemPool_t *out)
+{
+    static std::mutex mu;
+    static cudaMemPool_t pools[64] = {};
+    int dev = 0;
+    NPD_CHECK_CUDA(cudaGetDevice(&dev));
+    NPD_REQUIRE(dev >= 0 && dev < 64, "SC quad kernel: device index %d not supported", dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if (!pools[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        NPD_CHECK_CUDA(cudaMemPoolCreate(&pools[dev], &props));
+        uint64_t keep = ~(uint64_t)0;
+        NPD_CHECK_CUDA(cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+    *out = pools[dev];
+    return NPD_OK;
+}
+
 int launch_quad(const npd_code *code, ScParams p, cudaStream_t st)
 {
     DeviceProps dp;
@@ -1221,7 +1247,9 @@ int launch_quad(const npd_code *code, ScParams p, cudaStream_t st)
         return NPD_EUNSUPPORTED;
     }
     int warps_per_sm = (int)((size_t)(228 * 1024) / (per_warp + 256));
-    int max_warps = env_int("NPD_SC_WARPS", 24);
+    // resident warps per SM: beyond these the y rows and scratch of the resident codewords thrash L2 (measured at
+    // N = 4096: 8 warps 1.97e7 cw/s, 10 warps 1.84e7; at N = 2048: 12 warps 5.5e7, 20 warps 5.0e7, 8 warps 4.9e7)
+    int max_warps = env_int("NPD_SC_WARPS", n >= 12 ? 8 : n == 11 ? 12 : 24);
     if (warps_per_sm > max_warps) warps_per_sm = max_warps;
     if (warps_per_sm < 1) warps_per_sm = 1;
     // warps per block: 4 unless smaller blocks pack at least 20 % more warps into the SM's 228 KB (every block also
@@ -1261,8 +1289,11 @@ int launch_quad(const npd_code *code, ScParams p, cudaStream_t st)
         NPD_CHECK_CUDA(cudaMalloc(&p.trace, 6 * sizeof(long long)));
         NPD_CHECK_CUDA(cudaMemsetAsync(p.trace, 0, 6 * sizeof(long long), st));
     }
-    if (gtop)  // stream-ordered: concurrent decodes on other streams get their own scratch
-        NPD_CHECK_CUDA(cudaMallocAsync(&p.scratch, (size_t)grid * wpb * quad_scratch_floats(n, gl) * sizeof(float), st));
+    if (gtop) {  // stream-ordered: concurrent decodes on other streams get their own scratch
+        cudaMemPool_t pool;
+        if (int rc = scratch_pool(&pool)) return rc;
+        NPD_CHECK_CUDA(cudaMallocFromPoolAsync(&p.scratch, (size_t)grid * wpb * quad_scratch_floats(n, gl) * sizeof(float), pool, st));
+    }
     kern<<<(unsigned)grid, 32 * wpb, per_warp * wpb, st>>>(p);
     NPD_CHECK_CUDA(cudaGetLastError());
     if (gtop) NPD_CHECK_CUDA(cudaFreeAsync(p.scratch, st));
