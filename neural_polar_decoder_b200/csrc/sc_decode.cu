@@ -1255,8 +1255,8 @@ int launch_quad(const npd_code *code, ScParams p, cudaStream_t st)
     // warps per block: 4 unless smaller blocks pack at least 20 % more warps into the SM's 228 KB (every block also
     // reserves 1 KB).  At N = 4096 a warp's state is 70 KB: blocks of two leave a third of the shared memory empty
     // (2 warps per SM, 8.3e6 cw/s; single-warp blocks: 3 warps, 1.17e7).  Small blocks are a last resort, though: at
-    // N = 1024 thirteen single-warp blocks ran at 9.8e7 cw/s against 1.44e8 for three four-warp blocks -- warp 0 of
-    // every block presumably lands on the same scheduler of the SM, so only whole four-warp blocks use all four.
+    // N = 1024 and the same 12 warps per SM, one- or two-warp blocks measured 14 % slower than four-warp blocks
+    // (0.89 vs 0.78 ms), and a 13th warp (thirteen single-warp blocks) ran at 9.8e7 cw/s against 1.44e8.
     int wpb = 1, blocks_per_sm = 1;
     {
         int best = 0;
