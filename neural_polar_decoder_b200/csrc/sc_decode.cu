@@ -1236,9 +1236,11 @@ int launch_quad(const npd_code *code, ScParams p, cudaStream_t st)
     const int n = code->n;
     // N >= 2048: levels n-2 and n-3 (3/4 of the stored tree) go to a global scratch: 22 KB instead of 70 KB of shared
     // memory per warp at N = 4096, 10 warps per SM instead of 3 (1.17e7 -> 1.62e7 cw/s; one scratch level: 1.57e7).
-    // At N = 1024 the same change measured slower (9.6e7 vs 1.44e8 cw/s at 12 warps: the scratch round trip costs
-    // more than the shared-memory one and 12 warps already fit), so it stays off there.
-    const int gl = n >= 11 ? max(0, min(2, env_int("NPD_SC_GTOP", 2))) : 0;  // scratch levels: 0, 1 or 2
+    // At N = 1024 the same change measures slower at every occupancy (best: one scratch level, 16 warps, 0.835 ms per
+    // 131072 codewords against 0.775 ms for 12 warps with the whole tree in shared memory), so it stays off there
+    // (NPD_SC_GTOP10 = 1 | 2 turns it on for experiments).
+    const int gl = n >= 11 ? max(0, min(2, env_int("NPD_SC_GTOP", 2)))  // scratch levels: 0, 1 or 2
+                           : n == 10 ? max(0, min(2, env_int("NPD_SC_GTOP10", 0))) : 0;
     const bool gtop = gl > 0;
     const size_t per_warp = quad_warp_smem_bytes(n, gl);
     const size_t budget = (size_t)dp.smem_optin;
@@ -1279,7 +1281,8 @@ int launch_quad(const npd_code *code, ScParams p, cudaStream_t st)
     switch (n) {
     case 8: kern = sc_quad_kernel<8>; break;
     case 9: kern = sc_quad_kernel<9>; break;
-    case 10: kern = trace_path ? sc_quad_kernel<10, true> : sc_quad_kernel<10>; break;
+    case 10: kern = gl >= 2 ? sc_quad_kernel<10, false, 2> : gl == 1 ? sc_quad_kernel<10, false, 1>
+                  : trace_path ? sc_quad_kernel<10, true> : sc_quad_kernel<10>; break;
     case 11: kern = gl >= 2 ? sc_quad_kernel<11, false, 2> : gl == 1 ? sc_quad_kernel<11, false, 1> : sc_quad_kernel<11>; break;
     case 12: kern = gl >= 2 ? sc_quad_kernel<12, false, 2> : gl == 1 ? sc_quad_kernel<12, false, 1> : sc_quad_kernel<12>; break;
     default: npd_set_error("SC quad kernel: n=%d outside 8..12", n); return NPD_EUNSUPPORTED;
