@@ -12,8 +12,12 @@
  *    pointer to a contiguous row-major float32 array unless its name starts with `h_` (host).
  *  - BPSK convention of the reference: bit 0 <-> +1.0f, bit 1 <-> -1.0f (polar.py:130-132).
  *  - Kernels are enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream)
- *    on the CURRENT device; the call returns without synchronising.  No per-call allocation: scratch
- *    is passed in by the caller.  Handles own small device-side tables / repacked weights.
+ *    on the CURRENT device; the call returns without synchronising.  Scratch is passed in by the
+ *    caller where an entry point has a `workspace` argument; the one exception is npd_sc_decode at
+ *    N >= 2048, whose level scratch is a stream-ordered allocation (cudaMallocFromPoolAsync /
+ *    cudaFreeAsync on `stream`) from a library-owned pool that keeps its memory across calls.
+ *    Handles own small device-side tables / repacked weights.  The library never reads the
+ *    environment (experiment switches exist only in -DNPD_DEBUG_KNOBS builds).
  *  - Return value: 0 on success, a negative NPD_E* code otherwise; npd_last_error() gives a
  *    thread-local message.  There is no CPU fallback anywhere: without a CUDA device every compute
  *    entry point returns NPD_ECUDA.
@@ -205,6 +209,9 @@ int npd_conv_decode(const npd_conv_t *conv, const float *y, float *bits, int64_t
  * same device are serialised. */
 int npd_sc_decode_host(const npd_code_t *code, const float *h_y, float llr_scale,
                        const float *h_use_gt, float *h_leaf_llr, float *h_decoded, int64_t B);
+/* Rows per pipeline chunk for every npd_*_host call of this process (0 = sized automatically from the row width;
+ * rounded up to the kernel's tile).  A tuning / test hook: results never depend on it. */
+int npd_host_set_chunk(int64_t rows);
 int npd_scl_decode_host(const npd_code_t *code, const float *h_y, float llr_scale, int list_size,
                         float *h_leaf_llr, float *h_decoded, int64_t B);
 int npd_pac_sc_decode_host(const npd_code_t *code, const float *h_y, float llr_scale,

@@ -42,6 +42,7 @@ SIGNATURES = {
     "npd_conv_workspace_bytes": (_sz, [_vp, _i64]),
     "npd_conv_forward": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
     "npd_sc_decode_host": (_int, [_vp, _vp, _f32, _vp, _vp, _vp, _i64]),
+    "npd_host_set_chunk": (_int, [_i64]),
     "npd_pac_sc_decode_host": (_int, [_vp, _vp, _f32, _vp, _vp, _vp, _vp, _i64]),
     "npd_gru_decode_host": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
     "npd_conv_forward_host": (_int, [_vp, _vp, _vp, _vp, _i64]),

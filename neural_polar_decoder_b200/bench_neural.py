@@ -170,7 +170,7 @@ def bench_gru(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
                 "d2h_bytes_per_step": e2e_B * N * 4, "batch_per_gpu": e2e_B, "steps": e2e_steps,
                 "api": "RNN_decoder.decode(net, False, pinned host y) -> host decisions (npd_gru_decode_host pipeline)"},
         "gpu_launches": 3 * args.steps,
-        "roofline": {"kernel": "gru_decode_kernel3 (CTA-pair, cta_group::2)" if os.environ.get("NPD_GRU_PAIR", "1") != "0" else "gru_decode_kernel",
+        "roofline": {"kernel": "gru_decode_kernel3 (CTA-pair, cta_group::2)",
                      "bound": "tensor", "achieved": achieved,
                      "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
                      "traffic": traffic, "traffic_source": traffic_src,

@@ -763,8 +763,8 @@ static int conv_forward_impl(const npd_conv_t *cv, const float *y, float *logits
         cp.in4 = in4 ? in4 + b0 * CC * CN : nullptr;
         cp.B = nb; cp.n_pass = (nb + CV_CW - 1) / CV_CW;
         memcpy(cp.layers, cv->layers, sizeof(cp.layers));
-        { const char *d = getenv("NPD_CONV_DBG"); cp.dbg = d ? atoi(d) : 0; }
-        const char *trace_path = (b0 == 0) ? getenv("NPD_CONV_TRACE") : nullptr;  // bench-only (synchronises!)
+        { const char *d = npd_knob("NPD_CONV_DBG"); cp.dbg = d ? atoi(d) : 0; }
+        const char *trace_path = (b0 == 0) ? npd_knob("NPD_CONV_TRACE") : nullptr;  // bench-only (synchronises!)
         if (trace_path) {
             NPD_CHECK_CUDA(cudaMalloc(&cp.trace, sizeof(long long) * CV_LAYERS * 8));
             NPD_CHECK_CUDA(cudaMemsetAsync(cp.trace, 0, sizeof(long long) * CV_LAYERS * 8, st));

@@ -1620,7 +1620,7 @@ NPD_API int npd_gru_decode_h0(const npd_gru_t *g, const npd_code_t *code, const 
         p.head_depth = g->head_depth; p.head_yh = g->head_yh; p.head_w1 = g->d_head_w1; p.head_wh = g->d_head_wh;
         p.head_b = g->d_head_b; p.head_wl = g->d_head_wl; p.head_act = (__half *)ws;
     }
-    { const char *d = getenv("NPD_GRU_PAIR"); if (d) use_pair = use_pair && atoi(d) != 0; }
+    { const char *d = npd_knob("NPD_GRU_PAIR"); if (d) use_pair = use_pair && atoi(d) != 0; }
     // the 2-SM tensor-copy variant (no relay) works but measures slower than relay + linear bulk copies (12.4 vs 11.4 ms
     // per 37888 codewords): opt-in with NPD_GRU_TMAP=1
     // NPD_GRU_QUAD=1: clusters of four (two MMA pairs that take turns fetching every half-tile and multicast it to the CTA
@@ -1628,14 +1628,14 @@ NPD_API int npd_gru_decode_h0(const npd_gru_t *g, const npd_code_t *code, const 
     // 37888 codewords -- a ring slot then frees only when BOTH pairs have consumed it, which couples their schedules --
     // so plain pairs stay the default.
     p.quad = 0;
-    { const char *d = getenv("NPD_GRU_QUAD"); if (d) p.quad = use_pair && atoi(d) != 0; }
+    { const char *d = npd_knob("NPD_GRU_QUAD"); if (d) p.quad = use_pair && atoi(d) != 0; }
     p.use_tmap = 0;
-    { const char *d = getenv("NPD_GRU_TMAP"); if (d) p.use_tmap = g->have_tmap2 && atoi(d) != 0; }
+    { const char *d = npd_knob("NPD_GRU_TMAP"); if (d) p.use_tmap = g->have_tmap2 && atoi(d) != 0; }
     if (p.use_tmap) p.quad = 0;
-    { const char *d = getenv("NPD_GRU_DBG"); p.dbg = d ? atoi(d) : 0; }
+    { const char *d = npd_knob("NPD_GRU_DBG"); p.dbg = d ? atoi(d) : 0; }
     int64_t grid = ((B + 2 * TILE_B - 1) / (2 * TILE_B)) * 2;  // CTA pairs (clusters of 2); an odd tile count pads with an idle-data CTA
     if (p.quad) grid = (grid + 3) / 4 * 4;
-    const char *trace_path = getenv("NPD_GRU_TRACE");  // bench-only: dump CTA 0's event clocks (synchronises!)
+    const char *trace_path = npd_knob("NPD_GRU_TRACE");  // bench-only: dump CTA 0's event clocks (synchronises!)
     if (trace_path) NPD_CHECK_CUDA(cudaMalloc(&p.trace, sizeof(long long) * g->N * TRACE_SLOTS));
     if (trace_path) NPD_CHECK_CUDA(cudaMemsetAsync(p.trace, 0, sizeof(long long) * g->N * TRACE_SLOTS, (cudaStream_t)stream));
     CUtensorMap tm = g->tmap2;

@@ -8,6 +8,7 @@
 // (PCIe is full duplex, so the copies in both directions overlap too).  Device staging memory is
 // owned by a per-device pipe object and only ever grows; the calls are synchronous (the outputs are
 // complete in host memory on return) and serialised per device by a mutex.
+#include <atomic>
 #include <stdlib.h>
 
 #include <mutex>
@@ -72,11 +73,9 @@ struct Carver {
     }
 };
 
-int64_t env_chunk()
-{
-    const char *e = getenv("NPD_HOST_CHUNK");
-    return e ? atoll(e) : 0;
-}
+std::atomic<int64_t> g_chunk_rows{0};  // npd_host_set_chunk: 0 = sized automatically
+
+int64_t env_chunk() { return g_chunk_rows.load(std::memory_order_relaxed); }
 
 // body(slot arena, lo, n, stream) enqueues H2D + kernels + D2H for rows [lo, lo+n) on `stream`.
 template <class Body>
@@ -127,6 +126,13 @@ int64_t pick_chunk(int64_t B, size_t row_bytes, int64_t granule, size_t target_b
 }
 
 }  // namespace
+
+NPD_API int npd_host_set_chunk(int64_t rows)
+{
+    NPD_REQUIRE(rows >= 0, "npd_host_set_chunk: rows < 0");
+    g_chunk_rows.store(rows, std::memory_order_relaxed);
+    return NPD_OK;
+}
 
 NPD_API int npd_sc_decode_host(const npd_code_t *code, const float *h_y, float llr_scale,
                                const float *h_use_gt, float *h_leaf_llr, float *h_decoded, int64_t B)

@@ -29,6 +29,17 @@ void npd_set_error(const char *fmt, ...);
         }                                                                                     \
     } while (0)
 
+// ---- experiment switches ---------------------------------------------------------------------------
+// Kernel-selection / trace / "skip part of the work" switches read from the environment exist only in builds made
+// with -DNPD_DEBUG_KNOBS (`make DEBUG_KNOBS=1`, used by tools/exp_*.sh and the trace tools).  The shipped libnpd.so
+// never reads the environment: what it launches and what it returns depend on the call's arguments only.
+#ifdef NPD_DEBUG_KNOBS
+#include <stdlib.h>
+static inline const char *npd_knob(const char *name) { return getenv(name); }
+#else
+static inline const char *npd_knob(const char *) { return nullptr; }
+#endif
+
 // ---- code object ------------------------------------------------------------------------------
 struct npd_code {
     int n, N, K;

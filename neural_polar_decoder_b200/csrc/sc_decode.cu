@@ -1086,7 +1086,7 @@ __global__ void __launch_bounds__(128) sc_quad_kernel(const ScParams p)
 
 int env_int(const char *name, int dflt)
 {
-    const char *v = getenv(name);
+    const char *v = npd_knob(name);
     return v ? atoi(v) : dflt;
 }
 
@@ -1276,7 +1276,7 @@ int launch_quad(const npd_code *code, ScParams p, cudaStream_t st)
     if (grid < 1) grid = 1;
     p.vec_out = (p.K & 3) == 0 && (reinterpret_cast<uintptr_t>(p.decoded) & 15) == 0 && env_int("NPD_SC_VECOUT", 1) != 0;
     void (*kern)(const ScParams) = nullptr;
-    const char *trace_path = getenv("NPD_SC_TRACE");  // bench-only (synchronises!): phase cycles of one group, N = 1024
+    const char *trace_path = npd_knob("NPD_SC_TRACE");  // bench-only (synchronises!): phase cycles of one group, N = 1024
     if (trace_path && n != 10) trace_path = nullptr;
     switch (n) {
     case 8: kern = sc_quad_kernel<8>; break;

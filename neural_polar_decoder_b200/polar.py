@@ -2,8 +2,8 @@
 and sc_decode_new, each forwarding to one libnpd.so entry point (hand-written sm_100a kernels).
 
 Signatures, attribute names and tensor contracts follow reference polar.py:66-148, 201-207, 465-484.
-Out of scope: the recursive exact-LSE `sc_decode`, soft/neural SC variants, CRC, SC-list,
-bitwise MAP and the analysis/plotting helpers.
+`scl_decode` (SC-list, polar.py:777-876) is covered too.  Out of scope: the recursive exact-LSE
+`sc_decode`, soft/neural SC variants, CRC, bitwise MAP and the analysis/plotting helpers.
 """
 import numpy as np
 import torch
@@ -72,6 +72,13 @@ class PolarCode:
         """reference polar.py:128-148.  message [B,K] of +-1 -> codeword [B,N] of +-1 (same device)."""
         src_dev = message.device
         msg = _lib.to_device_f32(message)
+        if custom_info_positions is not None:
+            # `u[:, custom_info_positions] = message` (polar.py:133-136): message column j goes to position custom[j]
+            # in the caller's order; the code handle keeps positions sorted, so permute the columns instead
+            custom = np.asarray(custom_info_positions)
+            order = np.argsort(custom, kind="stable")
+            if not np.array_equal(order, np.arange(len(order))):
+                msg = msg.index_select(1, torch.as_tensor(order, device=msg.device)).contiguous()
         with torch.cuda.device(msg.device):
             h = self._handle(custom_info_positions)
             assert msg.dim() == 2 and msg.shape[1] == h.K, (tuple(msg.shape), h.K)

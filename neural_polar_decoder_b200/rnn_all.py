@@ -310,13 +310,17 @@ def get_code(code_type, rate_profile, N, K, g=None, args=None):
     elif rate_profile == 'RM':
         rmweight = np.array([construct.count_set_bits(i) for i in range(N)])
         code = PolarCode(n, K, args, F=np.sort(np.argsort(rmweight)[:-K]))
-    elif rate_profile == 'sorted':
+    elif rate_profile == 'sorted':  # rnn_all.py:1089-1091: the target_K best positions in ascending index order
+        first = np.sort(rs[:target_K].copy())
+        rs[:target_K] = first
+        code = PolarCode(n, K, args, rs=rs)
+    elif rate_profile == 'sorted_last':  # rnn_all.py:1108-1110: ... in descending index order
         first = np.sort(rs[:target_K].copy())
         rs[:target_K] = first[::-1]
         code = PolarCode(n, K, args, rs=rs)
-    elif rate_profile == 'sorted_last':
-        first = np.sort(rs[:target_K].copy())
-        rs[:target_K] = first
+    elif rate_profile == 'random':  # rnn_all.py:1179-1180
+        first = rs[:target_K].copy()
+        rs[:target_K] = np.random.RandomState(seed=getattr(args, "random_seed", 42)).permutation(first)
         code = PolarCode(n, K, args, rs=rs)
     elif rate_profile == 'rev_polar':
         first = rs[:target_K].copy()
@@ -328,7 +332,13 @@ def get_code(code_type, rate_profile, N, K, g=None, args=None):
     code.frozen_inds = code.frozen_positions
     code.rate_profile = rate_profile
     code.encode = code.encode_plotkin
-    code.msg_indices = np.arange(K)
+    loss_only = getattr(args, "loss_only", None)
+    if loss_only is not None:  # rnn_all.py:1189-1192: score (and train on) the first `loss_only` positions of rs only
+        code.loss_inds = np.sort(rs[:loss_only].copy())
+        code.msg_indices = np.where(np.isin(code.info_inds, code.loss_inds))[0]
+    else:
+        code.loss_inds = None
+        code.msg_indices = np.arange(K)
     return code
 
 

@@ -30,7 +30,7 @@ def _gru(oracle, rng, N, K, H, B):
     d, lg = gru_decode(net, dec._loss_code(info), torch.from_numpy(y).cuda(), forced=torch.from_numpy(do).cuda(),
                        want_logits=True)
     err = np.abs(lg.cpu().numpy() - lo)
-    tol = 1e-2 * (np.abs(lo) + np.sqrt((lo ** 2).mean()))
+    tol = 1e-2 * np.abs(lo) + 2e-3  # north_star: 1e-2 relative; SURVEY 7: + 2e-3 absolute for near-zero logits
     assert (err <= tol).all(), "GRU logits differ from the oracle: max err %.3e" % err.max()
     print("smoke: GRU(2x%d) Polar(%d,%d) logits within tolerance on %d frames (max err %.2e)" % (H, N, K, B, err.max()))
 

@@ -58,22 +58,41 @@ def polar_RNN_full_test(net, polar, snr_range, Test_Data_Generator, run_ML=False
     counts = torch.zeros(nb, ns, 3, 2, dtype=torch.int64, device=device)
     sizes, frame0 = [], 0
     seed = rng.get_seed() if seed is None else seed
+    # --loss_only (rnn_all.py:850-891, 1189-1192): both decoders run genie-aided outside `loss_inds` and only the
+    # message columns `msg_indices` are scored
+    loss_inds = getattr(polar, "loss_inds", None)
+    sel = None
+    if loss_inds is not None:
+        sel = torch.as_tensor(np.asarray(polar.msg_indices), device=device)
+    n_scored = polar.K if sel is None else int(sel.numel())
+
+    def scored(t):
+        return t if sel is None else t.index_select(1, sel)
+
     with torch.cuda.device(device):
         for k, msg_bits in enumerate(Test_Data_Generator):
             msg = _lib.to_device_f32(msg_bits, device)
             sizes.append(msg.shape[0])
             x = polar.encode_plotkin(msg)
+            gt = None
+            if loss_inds is not None:  # rnn_all.py:844-845
+                gt = torch.ones(msg.shape[0], polar.N, device=device)
+                gt[:, info] = msg
+            msg_s = scored(msg)
             for si, snr in enumerate(snr_range):
                 y = polar.channel(x, snr, point=(1 << 31) | si, cw_offset=frame0, seed=seed)
-                _, dec_sc = polar.sc_decode_new(y, snr, return_llr=False)
-                _count_into(counts[k, si, 1], msg, dec_sc)  # .sign() is the identity on {-1,0,+1}
-                if run_SCL:  # rnn_all.py:866-872 (args.list_size in the reference)
+                _, dec_sc = polar.sc_decode_new(y, snr, gt, return_llr=False)
+                _count_into(counts[k, si, 1], msg_s, scored(dec_sc))  # .sign() is the identity on {-1,0,+1}
+                if run_SCL:  # rnn_all.py:857-870 (args.list_size in the reference)
                     _, dec_scl = polar.scl_decode(y, snr, list_size, False, return_llr=False)
-                    _count_into(counts[k, si, 2], msg, dec_scl)
-                dec = decoder.decode(net, False, y)
-                _count_into(counts[k, si, 0], msg, dec.index_select(1, info))
+                    _count_into(counts[k, si, 2], msg_s, scored(dec_scl))
+                if loss_inds is None:
+                    dec = decoder.decode(net, False, y)
+                else:
+                    dec = decoder.decode(net, False, y, gt, loss_inds=loss_inds)
+                _count_into(counts[k, si, 0], msg_s, scored(dec.index_select(1, info)))
             frame0 += msg.shape[0]
-    (ber_r, bler_r), (ber_s, bler_s), (ber_l, bler_l) = _rates(counts, sizes, polar.K, ns, 3)
+    (ber_r, bler_r), (ber_s, bler_s), (ber_l, bler_l) = _rates(counts, sizes, n_scored, ns, 3)
     zeros = [0. for _ in snr_range]
     return (ber_r, bler_r, ber_s, bler_s, ber_l, bler_l, list(zeros), list(zeros), list(zeros), list(zeros))
 

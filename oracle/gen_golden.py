@@ -342,6 +342,14 @@ def misc_cases():
                        (128, 64, "polar"), (256, 128, "polar"), (64, 22, "RM")]:
         code = ref_shim.get_code("Polar", prof, N, K)
         out["info_%s_%d_%d" % (prof, N, K)] = np.asarray(code.info_positions, dtype=np.int32)
+    # curriculum stages K < target_K for every rate profile (rnn_all.py:1075-1181) and --loss_only (1189-1192)
+    for prof in ("polar", "sorted", "sorted_last", "rev_polar", "random"):
+        for N, K, tK in [(64, 8, 22), (64, 14, 22), (32, 6, 16)]:
+            code = ref_shim.get_code("Polar", prof, N, K, target_K=tK, random_seed=42)
+            out["cur_%s_%d_%d_%d" % (prof, N, K, tK)] = np.asarray(code.info_positions, dtype=np.int32)
+    code = ref_shim.get_code("Polar", "rev_polar", 64, 22, target_K=22, loss_only=6)
+    out["lossonly_inds"] = np.asarray(code.loss_inds, dtype=np.int32)
+    out["lossonly_msg"] = np.asarray(code.msg_indices, dtype=np.int32)
     for N, K, g in [(32, 16, 53), (64, 32, 53), (128, 64, 133)]:
         pac = ref_shim.get_code("PAC", "RM", N, K, g=g)
         out["pacinfo_%d_%d" % (N, K)] = np.asarray(pac.B, dtype=np.int32)

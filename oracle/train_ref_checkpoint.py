@@ -85,8 +85,12 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--test_size", type=int, default=100000)
     ap.add_argument("--rate_profile", default="polar")
+    ap.add_argument("--threads", type=int, default=os.cpu_count() or 1)
+    ap.add_argument("--snr_start", type=float, default=-2.0)
+    ap.add_argument("--snr_end", type=float, default=4.0)
+    ap.add_argument("--snr_points", type=int, default=7)
     a = ap.parse_args()
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(a.threads)
 
     work = tempfile.mkdtemp(prefix="npd_ref_train_")
     os.chdir(work)  # the reference writes ./Supervised_RNN_Polar_Results/... relative to the cwd
@@ -102,7 +106,8 @@ def main():
                 "--tfr_min", "1", "--tfr_max", "1", "--dec_train_snr", "0", "--lr", "0.001",
                 "--print_freq", "1000000", "--model_save_per", "1000000", "--gpu", "-1", "--fresh",
                 "--id", "npd_stage%d" % K, "--save_path", save,
-                "--test_snr_start", "-2", "--test_snr_end", "4", "--snr_points", "7",
+                "--test_snr_start", str(a.snr_start), "--test_snr_end", str(a.snr_end),
+                "--snr_points", str(a.snr_points),
                 "--test_size", str(a.test_size if last else 1000),
                 "--test_batch_size", str(10000 if last else 1000)]
         if prev:

@@ -74,6 +74,25 @@ def test_info_sets_match_reference(golden):
     assert code.info_positions.tolist() == [27, 29, 30, 31, 39, 43, 45, 46, 47] + list(range(51, 64))
 
 
+def test_curriculum_info_sets_match_reference(golden):
+    """K < target_K (every run_crisp.sh stage but the last) for every rate profile, and --loss_only."""
+    import argparse
+    from neural_polar_decoder_b200.rnn_all import get_code
+    g = golden("misc")
+    seen = 0
+    for key in g.files:
+        if not key.startswith("cur_"):
+            continue
+        prof, N, K, tK = key[4:].rsplit("_", 3)
+        code = get_code("Polar", prof, int(N), int(K), args=argparse.Namespace(target_K=int(tK), random_seed=42))
+        assert np.array_equal(code.info_positions, g[key]), key
+        seen += 1
+    assert seen == 15
+    code = get_code("Polar", "rev_polar", 64, 22, args=argparse.Namespace(target_K=22, loss_only=6))
+    assert np.array_equal(code.loss_inds, g["lossonly_inds"])
+    assert np.array_equal(code.msg_indices, g["lossonly_msg"])
+
+
 def test_polarcode_constructor_variants():
     from neural_polar_decoder_b200 import PolarCode, construct
     c = PolarCode(3, 4)  # rs=None default: the K largest indices (polar.py:93-96)

@@ -61,11 +61,15 @@ def test_result_paths_match_reference_known_answers():
                        "npd_stage16")
 
 
-def _trained():
-    names = [f[:-5] for f in os.listdir(GOLD) if f.startswith("crisp_gru_") and f.endswith(".json")]
+def _trained_names():
+    return sorted(f[:-5] for f in os.listdir(GOLD) if f.startswith("crisp_gru_") and f.endswith(".json"))
+
+
+def _trained(name=None):
+    names = _trained_names()
     if not names:
         pytest.skip("no trained reference checkpoint fixture")
-    name = sorted(names)[0]
+    name = names[0] if name is None else name
     with open(os.path.join(GOLD, name + ".json")) as f:
         return os.path.join(GOLD, name + ".pt"), json.load(f)
 
@@ -82,11 +86,12 @@ def test_reference_checkpoint_loads_with_reference_keys():
 
 
 @pytest.mark.gpu
-def test_cli_test_mode_reproduces_reference_curve(capsys):
-    """`--test` through the drop-in on the reference-trained checkpoint: the GRU and SC BER/BLER curves must agree
-    with the curves the live reference printed for the same checkpoint within Monte-Carlo 95% confidence
-    intervals (independent noise on both sides)."""
-    path, meta = _trained()
+@pytest.mark.parametrize("name", _trained_names())
+def test_cli_test_mode_reproduces_reference_curve(capsys, name):
+    """`--test` through the drop-in on a reference-trained checkpoint: the GRU and SC BER/BLER curves must agree
+    with the curves the live reference printed for the same checkpoint within two-sample Monte-Carlo intervals at a
+    family-wise 95 % level (independent noise on both sides; tests/mcstats.py)."""
+    path, meta = _trained(name)
     argv = [a for a in meta["final_stage_argv"]]
     for flag in ("--load_path", "--save_path"):
         if flag in argv:
@@ -98,13 +103,42 @@ def test_cli_test_mode_reproduces_reference_curve(capsys):
     res = cli.run_test(args)
     printed = capsys.readouterr().out
     assert "BERs of RNN:" in printed and "BERs of SC decoding:" in printed and "Model loaded at step" in printed
-    n = meta["test_size"]
-    K = meta["K"]
+    _check_curves(args, res, meta, path)
+
+
+def _frame_vars(args, path, snr_range, frames=20000):
+    """Per-frame bit-error-fraction variances (GRU, SC) per SNR point from a fresh sample through the drop-in."""
+    from neural_polar_decoder_b200.rnn_all import RNN_decoder, get_code
+    import mcstats
+    code = get_code(args.code, args.rate_profile, args.N, args.K, args.g, args=args)
+    decoder = RNN_decoder(args.decoding_type, args.N, code.info_inds, args.onehot, args.reverse_order)
+    net, _, _ = cli.net_from_checkpoint(path)
+    g = torch.Generator().manual_seed(99)
+    msg = (1.0 - 2.0 * torch.randint(0, 2, (frames, args.K), generator=g).float()).cuda()
+    x = code.encode_plotkin(msg)
+    info = torch.as_tensor(np.asarray(code.info_positions), device="cuda")
+    out = []
+    for si, snr in enumerate(snr_range):
+        y = code.channel(x, snr, point=(1 << 30) | si, seed=1234)
+        _, dsc = code.sc_decode_new(y, snr, return_llr=False)
+        drn = decoder.decode(net, False, y).index_select(1, info)
+        out.append((mcstats.frame_fraction_var(msg, drn), mcstats.frame_fraction_var(msg, dsc)))
+    return out
+
+
+def _check_curves(args, res, meta, path):
+    import mcstats
+    n_ref = n_ours = meta["test_size"]
     assert np.allclose(res["snr_range"], meta["snr_range"])
-    for ours, ref, per in ((res["bers_RNN"], meta["bers_RNN"], n), (res["bers_SC"], meta["bers_SC"], n),
-                           (res["blers_RNN"], meta["blers_RNN"], n), (res["blers_SC"], meta["blers_SC"], n)):
-        for a, b in zip(ours, ref):
-            p = 0.5 * (a + b)
-            # block errors are the independent events; a bit-error rate has at most K-fold correlated terms
-            sigma = np.sqrt(2 * max(p * (1 - p), 1e-9) / per) * (np.sqrt(K) if ours is res["bers_RNN"] or ours is res["bers_SC"] else 1.0)
-            assert abs(a - b) <= 4 * sigma + 2e-5, (a, b, sigma)
+    ns = len(meta["snr_range"])
+    z = mcstats.z_familywise(4 * ns)  # family-wise 95 % over the 4 curves x ns points asserted here
+    fv = _frame_vars(args, path, meta["snr_range"])
+    print("curve test: %d comparisons, z = %.3f" % (4 * ns, z))
+    for i in range(ns):
+        for name, which in (("RNN", 0), ("SC", 1)):
+            a, b = res["blers_" + name][i], meta["blers_" + name][i]
+            hw = mcstats.bler_halfwidth(a, n_ours, b, n_ref, z)
+            assert abs(a - b) <= hw, ("bler", name, i, a, b, hw)
+            a, b = res["bers_" + name][i], meta["bers_" + name][i]
+            hw = mcstats.ber_halfwidth(fv[i][which], n_ours, n_ref, z)
+            assert abs(a - b) <= hw + 1e-6, ("ber", name, i, a, b, hw)

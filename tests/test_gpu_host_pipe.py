@@ -13,6 +13,19 @@ sys.path.insert(0, ROOT)
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _auto_chunk_after_test():
+    yield
+    from neural_polar_decoder_b200 import _lib
+    _lib.check(_lib.load().npd_host_set_chunk(0))
+
+
+def _set_chunk(_monkeypatch, rows):
+    """Force small pipeline chunks so that small batches still run several chunks through all three streams."""
+    from neural_polar_decoder_b200 import _lib
+    _lib.check(_lib.load().npd_host_set_chunk(int(rows)))
+
+
 def _frames(code, B, snr, seed):
     g = torch.Generator().manual_seed(seed)
     msg = 1.0 - 2.0 * torch.randint(0, 2, (B, code.K), generator=g).float()
@@ -31,7 +44,7 @@ def test_sc_host_equals_device(n, K, B, chunk, pinned, monkeypatch):
     _, y = _frames(code, B, 1.0, 5)
     y[0, :4] = 0.0  # exact ties take the flagged re-decode path inside a chunk
     if chunk:
-        monkeypatch.setenv("NPD_HOST_CHUNK", str(chunk))
+        _set_chunk(monkeypatch, chunk)
     yh = y.pin_memory() if pinned else y
     llr_d, dec_d = code.sc_decode_new(y.cuda(), 1.0)
     llr_h, dec_h = code.sc_decode_new(yh, 1.0)
@@ -55,7 +68,7 @@ def test_sc_host_empty():
 
 def test_pac_host_equals_device(monkeypatch):
     from neural_polar_decoder_b200.pac_code import PAC
-    monkeypatch.setenv("NPD_HOST_CHUNK", "256")
+    _set_chunk(monkeypatch, 256)
     code = PAC(None, 32, 16, 53)
     g = torch.Generator().manual_seed(3)
     msg = 1.0 - 2.0 * torch.randint(0, 2, (900, 16), generator=g).float()
@@ -68,7 +81,7 @@ def test_pac_host_equals_device(monkeypatch):
 
 def test_gru_host_equals_device(monkeypatch):
     from neural_polar_decoder_b200 import rnn_all, synth
-    monkeypatch.setenv("NPD_HOST_CHUNK", "128")
+    _set_chunk(monkeypatch, 128)
     N, K = 32, 16
     code = rnn_all.get_code('Polar', 'polar', N, K)
     sd = synth.gru_state_dict(4, N, 512, 2, head_gain=6.0)
@@ -86,7 +99,7 @@ def test_conv_host_equals_device(monkeypatch):
     import argparse
     from neural_polar_decoder_b200 import synth
     from neural_polar_decoder_b200.models import convNet
-    monkeypatch.setenv("NPD_HOST_CHUNK", "128")
+    _set_chunk(monkeypatch, 128)
     net = convNet(argparse.Namespace(embed_dim=128, max_len=64, N=64, dont_use_bias=False, dropout=0.1))
     net.load_state_dict({k: torch.from_numpy(v) for k, v in synth.conv_state_dict(2, 64, 128).items()})
     net.eval()

@@ -227,18 +227,19 @@ def test_mc_sweep_matches_stepwise():
 
 # ---------------------------------------------------------------------------------------------------
 # CRISP GRU sequential decoder (16-bit tensor-core operands, fp32 accumulate).  Tolerance on the logits
-# under forced (= reference) feedback: 1e-2 relative, |d| <= 1e-2 * (|ref| + rms(ref)) -- the rms term is
-# the floor for logits near zero (the fixtures' logits have rms 0.5-0.7).  The kernel rounds weights, y and
+# under forced (= reference) feedback: |d| <= 1e-2 * |ref| + 2e-3 (north_star's 1e-2 relative; the absolute
+# term is SURVEY 7's floor for logits near zero).  The kernel rounds weights, y and
 # the recurrent state to fp16 (same tensor-core rate as bf16, 8x finer mantissa): a CPU emulation with
 # bf16-rounded operands, oracle.gru_decode(round_bf16=True), shows max |d| = 1.15e-2 on gru64, i.e. bf16
 # would sit at the edge of this tolerance; fp16 is measured at ~1e-3.  Free-running decisions must be
 # identical wherever no earlier |logit| of that codeword is within the tolerance of zero.
 # ---------------------------------------------------------------------------------------------------
 GRU_RTOL = 1e-2
+GRU_ATOL = 2e-3
 
 
 def _gru_tol(ref):
-    return GRU_RTOL * (np.abs(ref) + np.sqrt((ref ** 2).mean()))
+    return GRU_RTOL * np.abs(ref) + GRU_ATOL
 
 
 def _gru_net(N, H, seed, gain):

@@ -43,7 +43,7 @@ dec = torch.empty(B, K).pin_memory()
 lib = _lib.load()
 hh = code._handle()
 for chunk in (0, 1024, 4096, 16384):
-    os.environ["NPD_HOST_CHUNK"] = str(chunk)
+    _lib.check(lib.npd_host_set_chunk(chunk))
     dt = t(lambda: _lib.check(lib.npd_sc_decode_host(hh.h, _lib.hptr(y), llr_scale(2.0), None, None, _lib.hptr(dec), B)))
     print("npd_sc_decode_host chunk %d: %.2f ms  %.2e cw/s  H2D %.1f GB/s" % (chunk, dt * 1e3, B / dt, B * N * 4 / dt / 1e9))
 dt = t(lambda: code.sc_decode_new(y, 2.0, return_llr=False))
