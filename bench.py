@@ -1,11 +1,16 @@
 #!/usr/bin/env python
 """bench.py -- decoded codewords/sec of the Monte-Carlo decode hot path on N B200s of one node.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sc1024|gru64|...] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload gru64|sc1024|mc1024|...] [--impl reference]
 
-One "step" = one pass of the hot path over one batch of synthetic AWGN frames that is already
-resident in HBM (value), or starts in pinned host memory and ends in host memory (e2e).
-Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition of every field.
+One "step" = one pass of the hot path over one batch of synthetic AWGN frames that is already resident in HBM
+(`value`), or starts in pinned host memory and ends in host memory (`e2e`).  Prints ONE JSON line (rank 0).
+The default line's top level is the headline's first half (CRISP-GRU Polar(64,22)); every other workload of
+BASELINE.json's configs rides along, with the same fields, under `roofline.other_workloads` (a key the driver's
+record keeps) and, for readers of the raw line, under `also`.  See DESIGN.md "Measurement" for every field.
+
+`--impl reference` never imports the product package: it times the reference's own CPU implementation through
+oracle/cpu_arm.py (the unmodified reference where /root/reference exists, the port elsewhere).
 """
 import argparse
 import json
@@ -21,9 +26,17 @@ import numpy as np  # noqa: E402
 
 METRIC = "decoded codewords/sec"
 UNIT = "codewords/s"
+GRU_CKPT = os.path.join(ROOT, "tests", "golden", "crisp_gru_N64_K22_H512.pt")
 
 WORKLOADS = {
-    # name: N, K, snr_db, per-GPU batch (y = B*N*4 bytes must exceed the 126 MB L2)
+    # name: N, K, snr_db, per-GPU batch (y = B*N*4 bytes must exceed the 126 MB L2 where the path is HBM-fed)
+    "gru64": dict(kind="gru", N=64, K=22, snr=0.0, batch=37888,
+                  desc="CRISP GRU(2x512, y_input, onehot) Polar(64,22), AWGN 0 dB"),
+    "gru64sweep": dict(kind="grusweep", N=64, K=22, snr=0.0, batch=10000, n_snr=5,
+                       desc="config 1 call pattern: polar_RNN_full_test, test_batch_size 10000 x 5 SNR points (-2..2 dB) "
+                            "per step, GRU + SC + counters through the drop-in loop"),
+    "gru32": dict(kind="gru", N=32, K=16, snr=0.0, batch=37888,
+                  desc="CRISP GRU(2x512, y_input, onehot) Polar(32,16), AWGN 0 dB, synthetic weights"),
     "sc1024": dict(kind="sc", N=1024, K=512, snr=2.0, batch=131072,
                    desc="SC Polar(1024,512), polarization-weight frozen set, AWGN 2 dB"),
     "sc256": dict(kind="sc", N=256, K=128, snr=2.0, batch=524288,
@@ -36,17 +49,41 @@ WORKLOADS = {
                  desc="SC Polar(64,22), reference 'polar' profile, AWGN 0 dB"),
     "pac32": dict(kind="sc", N=32, K=16, snr=2.0, batch=4194304, pac_g=53,
                   desc="PAC(32,16) SC decoder (pac_sc_decode), RM profile, g = 53, AWGN 2 dB"),
-    "enc1024": dict(kind="enc", N=1024, K=512, snr=2.0, batch=131072,
-                    desc="message generation + Plotkin encoder + BPSK/AWGN channel, Polar(1024,512), 2 dB (Philox noise)"),
     "scl64": dict(kind="sc", N=64, K=22, snr=0.0, batch=262144, L=4,
                   desc="SC-list (L=4) Polar(64,22), reference 'polar' profile, AWGN 0 dB"),
-    "gru64": dict(kind="gru", N=64, K=22, snr=0.0, batch=37888,
-                  desc="CRISP GRU(2x512, y_input, onehot) Polar(64,22), AWGN 0 dB, synthetic weights"),
-    "gru32": dict(kind="gru", N=32, K=16, snr=0.0, batch=37888,
-                  desc="CRISP GRU(2x512, y_input, onehot) Polar(32,16), AWGN 0 dB, synthetic weights"),
+    "enc1024": dict(kind="enc", N=1024, K=512, snr=2.0, batch=131072,
+                    desc="message generation + Plotkin encoder + BPSK/AWGN channel, Polar(1024,512), 2 dB (Philox noise)"),
+    # config 5: the fused generate -> encode -> noise -> decode -> count sweep (npd_mc_sc_sweep); batch = frames per step
+    "mc256": dict(kind="mc", N=256, K=128, snr=2.0, batch=16 << 20, chunk=1 << 19,
+                  desc="fused SC Monte-Carlo sweep Polar(256,128), 2 dB: generate + encode + AWGN + SC + count on the device"),
+    "mc1024": dict(kind="mc", N=1024, K=512, snr=2.0, batch=5 << 20, chunk=1 << 17,
+                   desc="fused SC Monte-Carlo sweep Polar(1024,512), 2 dB: generate + encode + AWGN + SC + count on the device"),
+    "mc4096": dict(kind="mc", N=4096, K=2048, snr=2.0, batch=1 << 20, chunk=1 << 15,
+                   desc="fused SC Monte-Carlo sweep Polar(4096,2048), 2 dB: generate + encode + AWGN + SC + count on the device"),
     "conv64": dict(kind="conv", N=64, K=22, snr=0.0, batch=131072,
                    desc="convNet(embed_dim 128) one-shot decoder Polar(64,22), AWGN 0 dB, synthetic weights"),
 }
+# what the default line carries besides its top level (gru64): name -> (steps cap, with a CPU baseline)
+DEFAULT_ALSO = [("sc1024", 20, True), ("conv64", 20, True), ("mc1024", 20, False), ("mc256", 6, False),
+                ("mc4096", 10, False), ("gru64sweep", 10, False), ("sc256", 10, False), ("sc4096", 10, False),
+                ("enc1024", 10, False), ("gru32", 10, False), ("pac32", 10, False)]
+
+
+def gru_weights_note(w):
+    if w["kind"] in ("gru", "grusweep") and w["N"] == 64 and os.path.exists(GRU_CKPT):
+        return "reference-trained checkpoint tests/golden/crisp_gru_N64_K22_H512.pt (oracle/train_ref_checkpoint.py)"
+    if w["kind"] in ("gru", "grusweep", "conv"):
+        return "synthetic (seeded random init)"
+    return None
+
+
+def workload_config(name, w):
+    """The `config` object -- identical in the product arm and the reference arm."""
+    c = {"workload": name, "desc": w["desc"], "N": w["N"], "K": w["K"], "snr_db": w["snr"], "batch_per_gpu": w["batch"]}
+    note = gru_weights_note(w)
+    if note:
+        c["weights"] = note
+    return c
 
 
 def measured_peaks():
@@ -144,79 +181,151 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------------
-# reference arm: the CPU restatement of the reference (oracle/) on the host cores
+# CPU legs (oracle/cpu_arm.py: the live reference where present, the port elsewhere).  No product import here.
 # ---------------------------------------------------------------------------------------------------
-def cpu_rate_sc(w, seconds, threads, rng_seed=0):
-    """Time oracle.sc_decode (the C restatement of polar.py:465-484) on a bounded sample.
-    -> (codewords/s, sample description)"""
+def _cpu_arm():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle
-    N, K = w["N"], w["K"]
-    n = int(np.log2(N))
-    from neural_polar_decoder_b200 import construct
-    g = w.get("pac_g")
-    if g:
-        info = np.sort(np.asarray(make_code(w).B))
-    elif N <= 256:
-        rs = construct.reference_rs256()
-        info = np.sort(rs[rs < N][:K])
-    else:
-        info = np.sort(construct.polarization_weight_order(N)[:K])
-    r = np.random.RandomState(rng_seed)
-
-    def frames(B):
-        msg = (1.0 - 2.0 * r.randint(0, 2, size=(B, K))).astype(np.float32)
-        x = oracle.pac_encode(msg, n, info, g) if g else oracle.polar_encode(msg, n, info)
-        return (x + 10 ** (-w["snr"] / 20) * r.randn(B, N)).astype(np.float32)
-
-    def run(y):
-        t0 = time.perf_counter()
-        if g:
-            oracle.run_threaded(lambda lo, hi: oracle.pac_sc_decode(y[lo:hi], w["snr"], n, info, g), y.shape[0], threads)
-        elif w.get("L"):
-            oracle.run_threaded(lambda lo, hi: oracle.scl_decode(y[lo:hi], w["snr"], n, info, w["L"]), y.shape[0], threads)
-        else:
-            oracle.run_threaded(lambda lo, hi: oracle.sc_decode(y[lo:hi], w["snr"], n, info), y.shape[0], threads)
-        return time.perf_counter() - t0
-
-    probe = max(threads, 8)
-    dt = run(frames(probe))
-    B = int(max(threads, min(1 << 20, probe / dt * seconds)))
-    dt = run(frames(B))
-    return B / dt, B, dt
+    import cpu_arm
+    return cpu_arm
 
 
-def reference_arm(args, w):
+def cpu_step_fn(w, threads):
+    """-> (step(B, seed) -> (rate, B, dt), kind, how, probe batch) for the workload's decoder on the host cores."""
+    ca = _cpu_arm()
+    kind_w = w["kind"]
+    if kind_w in ("gru", "grusweep"):
+        arm = ca.make_gru_arm(w["N"], w["K"], 512, 0)
+        return (lambda B, seed: ca.gru_rate(w["N"], w["K"], w["snr"], B, threads, seed, arm=arm)[:3]), arm[2], arm[3], 256
+    if kind_w == "conv":
+        arm = ca.make_conv_arm(w["N"], 128, 0)
+        return (lambda B, seed: ca.conv_rate(w["N"], w["snr"], B, threads, seed, arm=arm)[:3]), arm[1], arm[2], 256
+    arm = ca.make_sc_arm(w["N"], w["K"], w["snr"], threads, w.get("pac_g"), int(w.get("L", 0)))
+    probe = 32 if arm[2] == "reference" and w["N"] >= 1024 else max(threads, 64)
+    return (lambda B, seed: ca.sc_rate(w["N"], w["K"], w["snr"], B, threads, seed, w.get("pac_g"), int(w.get("L", 0)),
+                                       arm=arm)[:3]), arm[2], arm[3], probe
+
+
+def cpu_baseline(w, seconds=12.0):
+    """One bounded sample (about `seconds` of CPU work) of the workload's decoder on all host cores."""
+    threads = os.cpu_count() or 1
+    step, kind, how, probe = cpu_step_fn(w, threads)
+    rate, B, dt = step(probe, 0)
+    if dt < 0.5 * seconds:
+        B = int(max(probe, min(w["batch"], rate * seconds)))
+        rate, B, dt = step(B, 1)
+    return {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": "%d codewords of the same workload in %.1f s: %s" % (B, dt, how)}
+
+
+def reference_arm(args, name, w):
+    """`--impl reference`: K timed steps of the CPU implementation, each a bounded sample of the product arm's batch."""
     threads = os.cpu_count() or 1
     total_budget = 150.0
-    per_step = min(3.0, total_budget / max(1, args.steps + args.warmup))
-    rates, B = [], 0
-    if w["kind"] == "sc":
-        for i in range(args.warmup + args.steps):
-            rate, B, dt = cpu_rate_sc(w, per_step, threads, rng_seed=i)
-            if i >= args.warmup:
-                rates.append((B, dt))
-    else:
-        from neural_polar_decoder_b200 import bench_neural
-        for i in range(args.warmup + args.steps):
-            rate, B, dt = bench_neural.cpu_rate(w, per_step, threads, seed=i)
-            if i >= args.warmup:
-                rates.append((B, dt))
-    tot_cw = sum(b for b, _ in rates)
-    tot_t = sum(t for _, t in rates)
+    n_calls = max(1, args.steps + args.warmup)
+    step, kind, how, probe = cpu_step_fn(w, threads)
+    rate, _, dt0 = step(probe, 10 ** 6)
+    per_step = min(6.0, total_budget / n_calls)
+    B = int(max(probe, min(w["batch"], rate * per_step)))
+    if dt0 > per_step:  # one probe-sized call already exceeds the per-step budget (live torch-op SC at large N)
+        B = probe
+    runs = []
+    t_wall = time.perf_counter()
+    for i in range(n_calls):
+        r, b, dt = step(B, i)
+        if i >= args.warmup:
+            runs.append((b, dt))
+        if time.perf_counter() - t_wall > 2 * total_budget and len(runs) >= 1:
+            break  # keep the whole arm within a few minutes even on a slow host
+    tot_cw, tot_t = sum(b for b, _ in runs), sum(t for _, t in runs)
     value = tot_cw / tot_t
-    sample = "%d steps x ~%d codewords (%.1f s of CPU work)" % (len(rates), B, tot_t)
+    sample = "%d timed steps x %d codewords (of the %d-codeword batch) = %.1f s of CPU work on %d threads: %s" % (
+        len(runs), B, w["batch"], tot_t, threads, how)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, len(rates)),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, len(runs)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": w["desc"], "N": w["N"], "K": w["K"], "snr_db": w["snr"]},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "dtype": "f32", "data": "synthetic", "config": workload_config(name, w),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    return line
+
+
+# ---------------------------------------------------------------------------------------------------
+# in-bench parity: >= 1000 rows of a timed step's output against the oracle (the checker, never the product path)
+# ---------------------------------------------------------------------------------------------------
+def parity_check(w, sample):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    kind = w["kind"]
+    N, K = w["N"], w["K"]
+    n = int(np.log2(N))
+    rows = int(sample["y"].shape[0])
+    out = {"rows": rows}
+    if kind == "sc":
+        info = np.asarray(sample["info"], dtype=np.int32)
+        if w.get("pac_g"):
+            _, ref, _ = oracle.pac_sc_decode(sample["y"], w["snr"], n, info, w["pac_g"])
+            out["oracle"] = "oracle.pac_sc_decode (npd_oracle.c)"
+        elif w.get("L"):
+            _, ref = oracle.scl_decode(sample["y"], w["snr"], n, info, w["L"])
+            out["oracle"] = "oracle.scl_decode (npd_oracle.c)"
+        else:
+            ref = np.concatenate(oracle.run_threaded(lambda lo, hi: oracle.sc_decode(sample["y"][lo:hi], w["snr"], n, info)[2],
+                                                     rows, os.cpu_count() or 1))
+            out["oracle"] = "oracle.sc_decode (npd_oracle.c)"
+        out["mismatching_rows"] = int((ref != sample["decoded"]).any(axis=1).sum())
+        out["criterion"] = "bit-exact decisions"
+        out["ok"] = out["mismatching_rows"] == 0
+        return out
+    if kind == "gru":
+        import torch
+        from neural_polar_decoder_b200.rnn_all import gru_decode
+        info = np.asarray(sample["info"])
+        do, lo = oracle.gru_decode(sample["sd"], sample["y"], N, info)
+        tol = 1e-2 * np.abs(lo) + 2e-3
+        # (1) the timed step's free-running decisions: equal unless a near-zero logit came at or before the mismatch
+        risky_before = np.cumsum(np.abs(lo) <= tol, axis=1) > 0
+        mism = sample["decoded"] != do
+        out["decision_mismatches"] = int(mism.sum())
+        out["unexplained_mismatches"] = int((mism & ~risky_before).sum())
+        # (2) logits under forced (= oracle) feedback
+        _, lg = gru_decode(sample["net"], sample["loss_code"], torch.from_numpy(sample["y"]).cuda(),
+                           forced=torch.from_numpy(do).cuda(), want_logits=True)
+        err = np.abs(lg.cpu().numpy() - lo)
+        out["max_logit_err"] = float(err.max())
+        out["worst_err_over_tol"] = float((err / tol).max())
+        out["logit_rms"] = float(np.sqrt((lo ** 2).mean()))
+        out["oracle"] = "oracle.gru_decode (fp32 torch restatement of rnn_all.py:514-547)"
+        out["criterion"] = "|logit - ref| <= 1e-2 |ref| + 2e-3 under forced feedback; free-running decisions equal " \
+                           "except behind a logit within that tolerance of zero"
+        out["ok"] = out["unexplained_mismatches"] == 0 and out["worst_err_over_tol"] <= 1.0
+        return out
+    if kind == "conv":
+        ref = np.asarray(oracle.conv_forward(sample["sd"], sample["y"])).reshape(rows, N)
+        err = np.abs(sample["logits"] - ref)
+        tol = 1e-2 * np.abs(ref) + 2e-3
+        out["max_logit_err"] = float(err.max())
+        out["worst_err_over_tol"] = float((err / tol).max())
+        out["sign_flips_outside_tol"] = int(((np.sign(sample["logits"]) != np.sign(ref)) & (np.abs(ref) > tol)).sum())
+        out["oracle"] = "oracle.conv_forward (fp32 torch restatement of models.py:742-767)"
+        out["criterion"] = "|logit - ref| <= 1e-2 |ref| + 2e-3"
+        out["ok"] = out["worst_err_over_tol"] <= 1.0 and out["sign_flips_outside_tol"] == 0
+        return out
+    if kind == "mc":
+        # the sweep's counters for its first `rows` frames, reproduced by the oracle from the same Philox streams
+        info = np.asarray(sample["info"], dtype=np.int32)
+        ref = np.concatenate(oracle.run_threaded(lambda lo, hi: oracle.sc_decode(sample["y"][lo:hi], w["snr"], n, info)[2],
+                                                 rows, os.cpu_count() or 1))
+        bit, blk = oracle.count_errors(sample["msg"], ref)
+        out["oracle"] = "oracle.sc_decode + oracle.count_errors on the sweep's own first frames"
+        out["counts"] = sample["counts"]
+        out["oracle_counts"] = [bit, blk, rows]
+        out["criterion"] = "identical (bit errors, block errors, frames)"
+        out["ok"] = list(sample["counts"]) == [bit, blk, rows]
+        return out
+    return None
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -231,13 +340,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU codewords per step (0 = workload default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="default workload without the other workloads")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     also = []
     if args.workload == "default":
-        args.workload = default_workload()
-        if args.workload == "gru64" and args.impl == "b200":
-            also = ["sc1024", "conv64"]
+        args.workload = "gru64"
+        if not args.no_also:
+            also = list(DEFAULT_ALSO)
     w = dict(WORKLOADS[args.workload])
     if args.batch:
         w["batch"] = args.batch
@@ -248,7 +359,12 @@ def main():
 
     if args.impl == "reference":
         if rank == 0:
-            reference_arm(args, w)
+            line = reference_arm(args, args.workload, w)
+            if also:  # the headline's second half and config 4, one bounded sample each
+                line["cpu_baseline"]["other_workloads"] = {}
+                for name in ("sc1024", "conv64"):
+                    line["cpu_baseline"]["other_workloads"][name] = cpu_baseline(dict(WORKLOADS[name]), 10.0)
+            print(json.dumps(line))
         return 0
 
     import torch
@@ -265,54 +381,79 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    def run_workload(name, wl):
+    failed = []
+
+    def run_workload(name, wl, steps, with_cpu):
         a = argparse.Namespace(**vars(args))
-        a.workload = name
-        if wl["kind"] == "enc":
-            return bench_enc(a, wl, rank, world, local_rank)
-        if wl["kind"] == "sc":
+        a.workload, a.steps = name, steps
+        kind = wl["kind"]
+        if kind in ("gru", "grusweep") and wl["N"] == 64 and os.path.exists(GRU_CKPT):
+            wl["checkpoint"] = GRU_CKPT
+        if kind == "enc":
+            r = bench_enc(a, wl, rank, world, local_rank)
+        elif kind == "sc":
             r = bench_sc(a, wl, rank, world, local_rank)
+        elif kind == "mc":
+            r = bench_mc(a, wl, rank, world, local_rank)
         else:
             from neural_polar_decoder_b200 import bench_neural
             r = bench_neural.bench(a, wl, rank, world, local_rank, ClockSampler, measured_peaks)
-        if rank == 0 and not args.no_cpu_baseline and world == 1:
-            if wl["kind"] == "sc":
-                threads = os.cpu_count() or 1
-                rate, B, dt = cpu_rate_sc(wl, 12.0, threads)
-                r["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                                     "sample": "%d codewords of the same workload, %.1f s" % (B, dt)}
-            else:
-                from neural_polar_decoder_b200 import bench_neural
-                r["cpu_baseline"] = bench_neural.cpu_baseline(wl)
+        r["config"] = dict(workload_config(name, wl), **{k: v for k, v in r.get("config", {}).items()
+                                                         if k not in ("workload", "desc", "N", "K", "snr_db", "batch_per_gpu", "weights")})
+        sample = r.pop("_sample", None)
+        if rank == 0 and sample is not None and not args.no_parity:
+            r["parity_checked"] = parity_check(wl, sample)
+            if not r["parity_checked"]["ok"]:
+                failed.append(name)
+        if rank == 0 and with_cpu and not args.no_cpu_baseline and world == 1:
+            r["cpu_baseline"] = cpu_baseline(wl)
         return r
 
-    res = run_workload(args.workload, w)
+    res = run_workload(args.workload, w, args.steps, True)
     if also:
-        # the metric names two decoders (CRISP-GRU Polar(64,22) and SC Polar(1024,512)); the JSON line's top level
-        # is the first, the others ride along under "also" with the same fields (config 4's convNet too)
-        res["also"] = {}
-        for name in also:
-            r = run_workload(name, dict(WORKLOADS[name]))
-            res["also"][name] = {k: r[k] for k in ("value", "unit", "ms_per_step", "dtype", "config", "e2e", "gpu_launches",
-                                                    "roofline", "ber", "bler", "frames", "cpu_baseline") if k in r}
+        keep = ("value", "unit", "steps", "ms_per_step", "dtype", "config", "e2e", "gpu_launches", "roofline", "ber", "bler",
+                "frames", "cpu_baseline", "parity_checked", "scaling", "clocks")
+        others = {}
+        for name, cap, with_cpu in also:
+            r = run_workload(name, dict(WORKLOADS[name]), min(args.steps, cap), with_cpu)
+            others[name] = {k: r[k] for k in keep if k in r}
+        res["also"] = others
+        res["roofline"]["other_workloads"] = others
+        res["gpu_launches_all_workloads"] = res["gpu_launches"] + sum(o.get("gpu_launches", 0) for o in others.values())
     if rank == 0:
+        if failed:
+            res["parity_failed"] = failed
         print(json.dumps(res))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    return 0
+    return 1 if failed else 0
 
 
-def default_workload():
-    """The headline metric names CRISP-GRU Polar(64,22) and SC Polar(1024,512); the GRU line becomes
-    the default once its kernel is built into libnpd.so."""
-    try:
-        from neural_polar_decoder_b200 import bench_neural
-        if bench_neural.available():
-            return "gru64"
-    except Exception:
-        pass
-    return "sc1024"
+def _time_steps(torch, dist, world, dev, local_rank, warm, timed_body, steps, after_loop=None):
+    """Barrier + synchronize, CUDA events around exactly `steps` iterations, max over ranks -> (ms, clocks)."""
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    warm()
+    sync()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    t0.record()
+    for i in range(steps):
+        timed_body(i)
+    if after_loop is not None:
+        after_loop()
+    t1.record()
+    sync()
+    clocks = sampler.stop()
+    t = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()), clocks
 
 
 def bench_enc(args, w, rank, world, local_rank):
@@ -333,41 +474,27 @@ def bench_enc(args, w, rank, world, local_rank):
     def step(i):
         _lib.check(lib.npd_gen_encode_awgn(h.h, _lib.ptr(msg), None, _lib.ptr(y), B, sigma, 2026, i, rank * B, st))
 
-    for i in range(args.warmup):
-        step(i)
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0.record()
-    for i in range(args.steps):
-        step(i)
-    t1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    clocks = sampler.stop()
-    ms = t0.elapsed_time(t1)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms, clocks = _time_steps(torch, dist, world, dev, local_rank, lambda: [step(i) for i in range(args.warmup)], step, args.steps)
     kern_ms = ms / args.steps
     peaks = measured_peaks()
     alg_bytes = (4 * N + 4 * K) * B  # y and msg written once
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    # end to end: the generator has no host input; its product read back on the host = the messages + y of one step
+    e2e_B = min(B, 16384)
+    t0 = time.perf_counter()
+    for i in range(3):
+        _lib.check(lib.npd_gen_encode_awgn(h.h, _lib.ptr(msg), None, _lib.ptr(y), e2e_B, sigma, 2026, i, rank * B, st))
+        yh = y[:e2e_B].cpu()
+    e2e_dt = time.perf_counter() - t0
     return {
         "metric": "generated + encoded + noised codewords/sec", "value": world * B * args.steps / (ms * 1e-3), "unit": UNIT,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": kern_ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": w["desc"], "N": N, "K": K, "snr_db": snr, "batch_per_gpu": B,
-                   "l2_policy": "outputs larger than L2 (y = %d MB per GPU)" % (B * N * 4 >> 20)},
+        "config": {"l2_policy": "outputs larger than L2 (y = %d MB per GPU)" % (B * N * 4 >> 20)},
         "clocks": clocks, "gpu_launches": args.steps,
-        "e2e": {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                "note": "the generator has no host-side input; its output feeds the decoders on the device"},
+        "e2e": {"value": world * 3 * e2e_B / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": e2e_B * N * 4,
+                "batch_per_gpu": e2e_B, "steps": 3,
+                "api": "npd_gen_encode_awgn + y read back to (pageable) host memory; the generator has no host-side input"},
         "roofline": {"kernel": "encode_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm"], "traffic": ncu_traffic(args.workload, B)[0],
                      "traffic_source": ncu_traffic(args.workload, B)[1], "peak_source": peaks["src"], "kernel_ms": kern_ms,
@@ -407,54 +534,46 @@ def bench_sc(args, w, rank, world, local_rank):
         else:
             _lib.check(lib.npd_sc_decode(h.h, _lib.ptr(y), scale, None, None, _lib.ptr(dec), B, st))
 
-    def step():
-        decode_call()
+    def count_call():
         _lib.check(lib.npd_count_errors(_lib.ptr(msg), _lib.ptr(dec), B, K, _lib._vp(counts.data_ptr()), st))
 
-    def sync():
+    def warm():
+        for _ in range(args.warmup):
+            decode_call()
+            count_call()
         if world > 1:
-            dist.barrier()
+            dist.all_reduce(counts)  # warm-up of the collective too (its first call sets up NCCL channels)
         torch.cuda.synchronize()
+        counts.zero_()
 
-    for _ in range(args.warmup):
-        step()
-    if world > 1:
-        dist.all_reduce(counts)  # warm-up of the collective too (its first call sets up NCCL channels)
-    sync()
-    counts.zero_()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]
-    sync()
-    t_start = torch.cuda.Event(enable_timing=True)
-    t_end = torch.cuda.Event(enable_timing=True)
-    t_start.record()
-    for i in range(args.steps):
+
+    def body(i):
         ev[i][0].record()
         decode_call()
         ev[i][1].record()
-        _lib.check(lib.npd_count_errors(_lib.ptr(msg), _lib.ptr(dec), B, K, _lib._vp(counts.data_ptr()), st))
+        count_call()
         ev[i][2].record()
-    if world > 1:
-        dist.all_reduce(counts)  # the path's only collective: [bit errors, block errors, frames]
-    t_end.record()
-    sync()
-    clocks = sampler.stop()
-    elapsed_ms = t_start.elapsed_time(t_end)
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
+
+    def after():
+        if world > 1:
+            dist.all_reduce(counts)  # the path's only collective: [bit errors, block errors, frames]
+
+    elapsed_ms, clocks = _time_steps(torch, dist, world, dev, local_rank, warm, body, args.steps, after)
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in ev]))
     count_ms = float(np.mean([b.elapsed_time(c) for _, b, c in ev]))
     value = world * B * args.steps / (elapsed_ms * 1e-3)
+    rows = min(B, 1024)
+    sample = {"y": y[:rows].cpu().numpy(), "decoded": dec[:rows].cpu().numpy(),
+              "info": np.asarray(code.B if w.get("pac_g") else code.info_positions)}
 
     # ---- end to end through the drop-in with HOST buffers (H2D + kernel + D2H every step) ----
     e2e_B = min(B, 65536)
     y_host = y[:e2e_B].cpu().pin_memory()
     msg_host = msg[:e2e_B:61].cpu()
     e2e_steps = max(3, min(args.steps, 10))
+
     def host_call():
         if w.get("pac_g"):
             return code.pac_sc_decode(y_host, snr)[:2]
@@ -465,12 +584,14 @@ def bench_sc(args, w, rank, world, local_rank):
     d_host = None
     for _ in range(3):  # warm-up holds the previous result like the timed loop does (pinned-pool steady state)
         _, d_host = host_call()
-    sync()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     errs = 0
     for _ in range(e2e_steps):
         _, d_host = host_call()  # returns host tensors
-        errs += int((d_host[::61] != msg_host).sum())                  # the step's result is read on the host (every 61st frame checked here)
+        errs += int((d_host[::61] != msg_host).sum())  # the step's result is read on the host (every 61st frame checked here)
     torch.cuda.synchronize()
     e2e_dt = time.perf_counter() - t0
     e2e_t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
@@ -483,12 +604,12 @@ def bench_sc(args, w, rank, world, local_rank):
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     cnt = counts.tolist()
     traffic, traffic_src = ncu_traffic(args.workload, B)
-    res = {
+    lg = int(np.log2(N))
+    return {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": w["desc"], "N": N, "K": K, "snr_db": snr,
-                   "batch_per_gpu": B, "l2_policy": "inputs larger than L2 (y = %d MB per GPU)" % (B * N * 4 >> 20),
+        "config": {"l2_policy": "inputs larger than L2 (y = %d MB per GPU)" % (B * N * 4 >> 20),
                    "step": "npd_sc_decode (y in HBM -> decisions in HBM) + npd_count_errors; one NCCL all-reduce "
                            "of the 3 counters at the end of the timed region when n_gpus > 1"},
         "clocks": clocks,
@@ -497,23 +618,119 @@ def bench_sc(args, w, rank, world, local_rank):
                 "api": "PolarCode.sc_decode_new(pinned host y, snr) -> host decisions (npd_sc_decode_host: chunked H2D / "
                        "decode / D2H pipeline on three streams)", "sampled_bit_errors": errs},
         "gpu_launches": 2 * args.steps,
-        "roofline": {"kernel": "scl_kernel" if L else ("sc_quad_kernel" if N >= 256 else "sc_lane_kernel"), "bound": "hbm", "achieved": achieved, "peak": peaks["hbm"],
+        "roofline": {"kernel": "scl_kernel" if L else ("sc_quad_kernel" if N >= 256 else "sc_lane_kernel"), "bound": "hbm",
+                     "achieved": achieved, "peak": peaks["hbm"],
                      "unit": "GB/s", "frac": achieved / peaks["hbm"], "traffic": traffic,
                      "traffic_source": traffic_src, "peak_source": peaks["src"], "kernel_ms": kern_ms, "count_kernel_ms": count_ms,
                      "alg_bytes_per_launch": alg_bytes,
-                     "llr_updates_per_s": N * int(np.log2(N)) * B / (kern_ms * 1e-3),
+                     "llr_updates_per_s": N * lg * B / (kern_ms * 1e-3),
                      "smem_roofline": {"bound": "smem", "unit": "codewords/s",
                                        "achieved": B / (kern_ms * 1e-3),
-                                       "peak": 37.2e12 / (12.0 * N * int(np.log2(N))),
-                                       "frac": (B / (kern_ms * 1e-3)) / (37.2e12 / (12.0 * N * int(np.log2(N)))),
+                                       "peak": 37.2e12 / (12.0 * N * lg),
+                                       "frac": (B / (kern_ms * 1e-3)) / (37.2e12 / (12.0 * N * lg)),
                                        "note": "SURVEY.md 8(d) second bound: N log2 N LLR updates x 12 B of shared-memory traffic "
                                                "each at 37.2 TB/s chip-wide (148 SMs x 128 B/clk x 1.965 GHz)"},
                      "note": "the decoder is instruction-issue bound, not HBM bound: N log2 N serial-by-level LLR updates "
                              "per codeword against 4N+4K bytes (DESIGN.md 4.1)"},
         "ber": cnt[0] / float(world * B * args.steps * K), "bler": cnt[1] / float(world * B * args.steps),
-        "frames": world * B * args.steps,
+        "frames": world * B * args.steps, "_sample": sample,
     }
-    return res
+
+
+def bench_mc(args, w, rank, world, local_rank):
+    """BASELINE config 5: the fused Monte-Carlo SC sweep (generate -> encode -> AWGN -> SC decode -> count on the device,
+    polar.py:1258-1291's call pattern).  A step = one npd_mc_sc_sweep call over `batch` frames per GPU in chunks; rank r
+    owns the global frame range [r*steps*batch, (r+1)*steps*batch) and ONE all-reduce of the 3 counters ends the region."""
+    import torch
+    import torch.distributed as dist
+    from neural_polar_decoder_b200 import _lib, utils, sweep
+    lib = _lib.load()
+    N, K, F, snr, chunk = w["N"], w["K"], w["batch"], w["snr"], w["chunk"]
+    code = make_code(w)
+    h = code._handle()
+    dev = torch.device("cuda", local_rank)
+    sigma = float(np.float32(utils.snr_db2sigma(snr)))
+    scale = utils.llr_scale(snr)
+    seed = 2026
+    ws_bytes = lib.npd_mc_sc_workspace_bytes(h.h, chunk)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    counts = torch.zeros(3, dtype=torch.int64, device=dev)
+    st = _lib.stream_ptr()
+    base = rank * args.steps * F
+
+    def sweep_call(frames, offset):
+        _lib.check(lib.npd_mc_sc_sweep(h.h, frames, chunk, sigma, scale, seed, 0, offset, _lib._vp(ws.data_ptr()), ws_bytes,
+                                       _lib._vp(counts.data_ptr()), st))
+
+    # parity sample first: the sweep's counters over the first 1024 frames of this rank's range
+    rows = 1024
+    sweep_call(rows, base)
+    torch.cuda.synchronize()
+    first_counts = counts.tolist()
+    msg = torch.empty(rows, K, device=dev)
+    y = torch.empty(rows, N, device=dev)
+    _lib.check(lib.npd_gen_encode_awgn(h.h, _lib.ptr(msg), None, _lib.ptr(y), rows, sigma, seed, 0, base, st))
+    sample = {"y": y.cpu().numpy(), "msg": msg.cpu().numpy(), "counts": first_counts, "info": np.asarray(code.info_positions)}
+
+    def warm():
+        for _ in range(args.warmup):
+            sweep_call(min(F, 4 * chunk), base)
+        if world > 1:
+            dist.all_reduce(counts)
+        torch.cuda.synchronize()
+        counts.zero_()
+
+    def after():
+        if world > 1:
+            dist.all_reduce(counts)
+
+    elapsed_ms, clocks = _time_steps(torch, dist, world, dev, local_rank, warm,
+                                     lambda i: sweep_call(F, base + i * F), args.steps, after)
+    frames = world * F * args.steps
+    value = frames / (elapsed_ms * 1e-3)
+    cnt = counts.tolist()
+    assert cnt[2] == frames, (cnt, frames)
+
+    # end to end through the drop-in call a user makes: sweep.mc_sc_sweep(...) -> BER / BLER lists on the host
+    e2e_frames = min(F, 8 * chunk) * world
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ber, bler, fr, _ = sweep.mc_sc_sweep(code, [snr], e2e_frames, chunk=chunk, seed=seed + 1)
+    e2e_dt = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    peaks = measured_peaks()
+    n_chunks = -(-F // chunk)
+    alg_bytes = (4 * N + 4 * K) * F
+    achieved = alg_bytes * args.steps / (elapsed_ms * 1e-3) / 1e9 / 1.0
+    lg = int(np.log2(N))
+    per_gpu = F * args.steps / (elapsed_ms * 1e-3)
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"chunk": chunk, "frames_per_gpu": F * args.steps,
+                   "l2_policy": "two chunks in flight; a chunk's y (%d MB) makes one HBM round trip" % (chunk * N * 4 >> 20),
+                   "step": "npd_mc_sc_sweep over batch_per_gpu frames (Philox counters = global frame index); one NCCL "
+                           "all-reduce of the 3 counters at the end of the timed region when n_gpus > 1"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_frames / float(e2e_t.item()), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 24,
+                "batch_per_gpu": e2e_frames // world, "steps": 1,
+                "api": "sweep.mc_sc_sweep(code, [snr], frames) -> (ber, bler, frames) lists on the host; the frames are "
+                       "generated on the device, so the only transfer is the 24-byte counter read",
+                "ber": ber[0], "bler": bler[0]},
+        "gpu_launches": 3 * n_chunks * args.steps,
+        "roofline": {"kernel": "encode_kernel + sc_quad_kernel + count (fused sweep, per chunk)", "bound": "hbm",
+                     "achieved": achieved / world, "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / world / peaks["hbm"],
+                     "traffic": None, "peak_source": peaks["src"], "alg_bytes_per_launch": alg_bytes,
+                     "llr_updates_per_s": N * lg * per_gpu,
+                     "smem_roofline": {"bound": "smem", "unit": "codewords/s", "achieved": per_gpu,
+                                       "peak": 37.2e12 / (12.0 * N * lg), "frac": per_gpu / (37.2e12 / (12.0 * N * lg))},
+                     "note": "algorithmic bytes = the decoder's 4N+4K per frame; the sweep is issue-bound (generator Philox + "
+                             "SC level walk), DESIGN.md 4.4"},
+        "ber": cnt[0] / float(frames * K), "bler": cnt[1] / float(frames), "frames": frames, "_sample": sample,
+    }
 
 
 if __name__ == "__main__":

@@ -113,6 +113,11 @@ int npd_scl_decode(const npd_code_t *code, const float *y, float llr_scale, int 
  * npd_count_errors: numerators of errors_ber (utils.py:17-25) and errors_bler (utils.py:37-51):
  * counts[0] += #{round(a) != round(b)}, counts[1] += #rows with any mismatch, over a[B,K], b[B,K].
  * counts is a device uint64[2] that the call ACCUMULATES into (zero it first). */
+/* npd_count_errors_info: the same numerators for a decoder that returns full-length rows: msg[B,K] against
+ * decoded_full[:, info_positions] with decoded_full [B,N] -- `errors_ber(msg_bits, decoded_bits[:, polar.info_positions]
+ * .sign())` (rnn_all.py:875-879, run_models.py:338-346) without materialising the gathered tensor. */
+int npd_count_errors_info(const npd_code_t *code, const float *msg, const float *decoded_full, int64_t B,
+                          uint64_t *counts, void *stream);
 int npd_count_errors(const float *a, const float *b, int64_t B, int K, uint64_t *counts,
                      void *stream);
 
@@ -175,6 +180,19 @@ int npd_gru_decode(const npd_gru_t *gru, const npd_code_t *code, const float *y,
 int npd_gru_decode_h0(const npd_gru_t *gru, const npd_code_t *code, const float *y, const float *h0,
                       const float *forced, const float *genie, float *logits, float *decoded, int64_t B,
                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* npd_mc_gru_sweep: the inner loop of polar_RNN_full_test (rnn_all.py:843-879) for one SNR point and the GRU decoder
+ * without any host round trip: messages -> encode -> AWGN -> npd_gru_decode -> error counters, `chunk` codewords at a
+ * time (a multiple of 148 x 128 fills whole waves of CTA pairs).  Philox streams as npd_gen_encode_awgn (seed, point,
+ * global frame index cw_offset + row), so counts do not depend on the chunking or the GPU count.
+ *   code      : the polar/PAC code object (encoder + info positions to score)
+ *   loss_code : positions where the decoder decides (NULL = `code`: RNN_decoder.decode's default loss_inds)
+ *   counts    : device uint64[3], ACCUMULATED: bit errors, block errors, frames
+ *   workspace : >= npd_mc_gru_workspace_bytes(gru, code, chunk) bytes of device memory */
+size_t npd_mc_gru_workspace_bytes(const npd_gru_t *gru, const npd_code_t *code, int64_t chunk);
+int npd_mc_gru_sweep(const npd_gru_t *gru, const npd_code_t *code, const npd_code_t *loss_code, int64_t B,
+                     int64_t chunk, float sigma, uint64_t seed, uint32_t point, uint64_t cw_offset,
+                     void *workspace, size_t workspace_bytes, uint64_t *counts, void *stream);
 
 /* ---- convNet one-shot decoder ------------------------------------------------------------------
  * npd_conv_create / npd_conv_forward: convNet.forward (models.py:742-767; layers 701-740) with

@@ -1,6 +1,6 @@
-"""bench.py legs for the neural decoders (CRISP GRU): device-resident throughput, end-to-end through the
-drop-in API, tensor-pipe roofline, and the CPU baseline (torch eager nn.GRU stepping = what the reference's
-RNN_decoder.decode does, rnn_all.py:532-547)."""
+"""bench.py legs for the neural decoders (CRISP GRU, convNet): device-resident throughput, end-to-end through the
+drop-in API and the tensor-pipe roofline.  (The CPU legs live in oracle/cpu_arm.py: the reference arm must not
+import this package.)"""
 import json
 import os
 import time
@@ -15,27 +15,22 @@ METRIC = "decoded codewords/sec"
 UNIT = "codewords/s"
 
 
-def available():
-    try:
-        lib = _lib.load()
-    except Exception:
-        return False
-    # the stub returns NPD_EUNSUPPORTED without touching CUDA; a real build validates its arguments first
-    import ctypes
-    h = ctypes.c_void_p()
-    rc = lib.npd_gru_create(0, 0, None, None, None, None, None, None, None, None, None, None, ctypes.byref(h))
-    return rc == _lib.NPD_EINVAL
-
-
 def flops_per_codeword(N, H=512):
     """SURVEY.md App. D (hoisted form): N steps x (3 GEMV-equivalents H->3H + head) + the y projection."""
     return N * (2 * 3 * H * 3 * H + 2 * H) + 2 * N * 3 * H
 
 
 def _setup(w, seed=11):
+    """-> (net, info positions).  With w["checkpoint"]: the reference-trained CRISP GRU (reference checkpoint format,
+    rnn_all.py:1471-1479) loaded the way the CLI loads it; otherwise seeded synthetic weights of the same architecture."""
     N, K = w["N"], w["K"]
     rs = construct.reference_rs256()
     info = np.sort(rs[rs < N][:K])
+    if w.get("checkpoint"):
+        from .cli import net_from_checkpoint
+        net, cargs, _ = net_from_checkpoint(w["checkpoint"])
+        assert (cargs.N, cargs.K, cargs.rnn_feature_size) == (N, K, 512), "checkpoint shape does not match the workload"
+        return net, info
     sd = synth.gru_state_dict(seed, N, 512, 2, head_gain=8.0)
     net = RNN_Model('GRU', N + 2, 512, 1, 2, N, 0, 0)
     net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
@@ -62,6 +57,8 @@ def _traffic(workload, batch):
 def bench(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
     if w["kind"] == "conv":
         return bench_conv(args, w, rank, world, local_rank, ClockSampler, measured_peaks)
+    if w["kind"] == "grusweep":
+        return bench_grusweep(args, w, rank, world, local_rank, ClockSampler, measured_peaks)
     return bench_gru(args, w, rank, world, local_rank, ClockSampler, measured_peaks)
 
 
@@ -159,12 +156,10 @@ def bench_gru(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": w["desc"], "N": N, "K": K, "snr_db": snr, "batch_per_gpu": B,
-                   "l2_policy": "weights (4.8 MB fp16) are L2-resident by design; y = %.1f MB per GPU is read once per "
+        "config": {"l2_policy": "weights (4.8 MB fp16) are L2-resident by design; y = %.1f MB per GPU is read once per "
                                 "launch" % (B * N * 4 / 2 ** 20),
                    "step": "npd_gru_decode (all N autoregressive steps, one launch) + info-bit gather + "
-                           "npd_count_errors; one NCCL all-reduce of the counters when n_gpus > 1",
-                   "weights": "synthetic U(-1/sqrt(H), 1/sqrt(H)) (neural_polar_decoder_b200.synth, seed 11)"},
+                           "npd_count_errors; one NCCL all-reduce of the counters when n_gpus > 1"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_B * N * 4,
                 "d2h_bytes_per_step": e2e_B * N * 4, "batch_per_gpu": e2e_B, "steps": e2e_steps,
@@ -178,52 +173,74 @@ def bench_gru(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
                      "alg_flops_per_launch": fl, "flops_per_codeword": flops_per_codeword(N)},
         "ber": cnt[0] / float(world * B * args.steps * K), "bler": cnt[1] / float(world * B * args.steps),
         "frames": world * B * args.steps,
+        "_sample": {"y": y[:1024].cpu().numpy(), "decoded": decoded[:1024].cpu().numpy(), "info": info, "net": net,
+                    "loss_code": loss_code, "sd": {k: v.detach().cpu().numpy() for k, v in net.state_dict().items()}},
     }
 
 
-def cpu_rate(w, seconds, threads, seed=0):
-    if w["kind"] == "conv":
-        return cpu_rate_conv(w, seconds, threads, seed)
-    return cpu_rate_gru(w, seconds, threads, seed)
-
-
-def cpu_rate_gru(w, seconds, threads, seed=0):
-    """CPU leg: the reference's own per-step structure -- torch eager nn.GRU(seq_len 1) + nn.Linear + sign
-    feedback for N steps (rnn_all.py:532-547), fp32, all host threads."""
-    torch.set_num_threads(threads)
-    N, K = w["N"], w["K"]
+def bench_grusweep(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
+    """Config 1's own call pattern (rnn_all.py:1771-1773, 1897): polar_RNN_full_test on batches of test_batch_size =
+    10000 messages (host tensors, as the reference's DataLoader yields them) x n_snr SNR points.  A step = one batch:
+    encode, n_snr x (channel + SC decode + count), ONE stacked GRU decode launch of n_snr x 10000 codewords + counts.
+    value = GRU-decoded codewords/s (n_snr x batch per step)."""
+    import torch.distributed as dist
+    from . import sweep
+    from .polar import PolarCode
+    N, K, B, ns = w["N"], w["K"], w["batch"], w["n_snr"]
+    dev = torch.device("cuda", local_rank)
     net, info = _setup(w)
-    net = net.cpu().eval()
-    info_set = set(int(i) for i in info)
-    rng = np.random.RandomState(seed)
+    rs = construct.reference_rs256()
+    code = PolarCode(int(np.log2(N)), K, None, rs=rs[rs < N])
+    dec = RNN_decoder('y_input', N, info, onehot=True)
+    snrs = [-2.0 + 4.0 * i / (ns - 1) for i in range(ns)]
+    g = torch.Generator().manual_seed(7 + rank)
+    batches = [(2 * (torch.rand(B, K, generator=g) < 0.5).float() - 1).pin_memory() for _ in range(args.steps)]
 
-    def run(B):
-        y = torch.from_numpy((rng.choice([-1.0, 1.0], size=(B, N)) + 0.9 * rng.randn(B, N)).astype(np.float32))
-        t0 = time.perf_counter()
-        with torch.no_grad():
-            decoded = torch.ones(B, N)
-            hidden = torch.zeros(2, B, net.feature_size)
-            for ii in range(N):
-                prev = torch.ones(B) if ii == 0 else decoded[:, ii - 1].sign()
-                onehot = torch.eye(2)[(0.5 + 0.5 * prev).long()]
-                out, hidden = net(torch.cat([y.unsqueeze(1), onehot.view(B, 1, 2)], 2), hidden)
-                if ii in info_set:
-                    decoded[:, ii] = out.squeeze().sign()
-        return time.perf_counter() - t0
+    def run(bs, seed):
+        return sweep.polar_RNN_full_test(net, code, snrs, bs, False, False, False, decoder=dec, device=dev, seed=seed)
 
-    dt = run(256)
-    B = int(max(256, min(65536, 256 / dt * seconds)))
-    dt = run(B)
-    return B / dt, B, dt
-
-
-def cpu_baseline(w):
-    threads = os.cpu_count() or 1
-    rate, B, dt = cpu_rate(w, 12.0, threads)
-    how = ("torch eager Conv1d/GELU/Linear/LayerNorm stack as in models.py:742-767" if w["kind"] == "conv" else
-           "torch eager nn.GRU stepping as in rnn_all.py:532-547")
-    return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "%d codewords, %s, %.1f s" % (B, how, dt)}
+    for i in range(args.warmup):
+        run(batches[:1], 100 + i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    res = run(batches, 2026)  # `steps` batches; the counters are read back once at the end of the call
+    t1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    t = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    frames = world * ns * B * args.steps
+    peaks = measured_peaks()
+    achieved = flops_per_codeword(N) * ns * B * args.steps / (elapsed_ms * 1e-3) / 1e12
+    waves = -(-(ns * B) // (148 * 128))
+    return {
+        "metric": METRIC, "value": frames / (elapsed_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"snr_points": snrs,
+                   "step": "sweep.polar_RNN_full_test on one 10000-message host batch: encode + %d x (channel, SC decode, "
+                           "count) + one stacked GRU decode of %d codewords (%d waves of 74 CTA pairs, %.2f needed) + counts"
+                           % (ns, ns * B, waves, ns * B / (148.0 * 128))},
+        "clocks": clocks,
+        "e2e": {"value": frames / (elapsed_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * K * 4, "d2h_bytes_per_step": 0,
+                "batch_per_gpu": ns * B, "steps": args.steps,
+                "api": "polar_RNN_full_test(net, code, snr_range, batches of pinned host messages) -> BER/BLER lists; the "
+                       "noise is drawn on the device, the counters (%d B) are read back once per call" % (args.steps * ns * 48)},
+        "gpu_launches": (1 + 3 * ns + 1 + ns) * args.steps,
+        "roofline": {"kernel": "gru_decode_kernel3 inside the sweep step", "bound": "tensor", "achieved": achieved,
+                     "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
+                     "traffic": None, "peak_source": peaks["src"], "note": "whole sweep step, not the kernel alone"},
+        "ber": res[0], "bler": res[1], "ber_sc": res[2], "bler_sc": res[3], "frames": frames,
+    }
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -340,14 +357,12 @@ def bench_conv(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": w["desc"], "N": N, "K": K, "snr_db": snr, "batch_per_gpu": B,
-                   "l2_policy": "every step streams %.1f GB of fp16 activations through HBM between the two kernels "
+        "config": {"l2_policy": "every step streams %.1f GB of fp16 activations through HBM between the two kernels "
                                 "(workspace %.2f GB > L2), which evicts y and the weights' L2 lines each step"
                                 % (2 * B * 16384 / 1e9, wsn / 1e9),
                    "step": "npd_conv_forward (conv_stack_kernel + conv_fc_kernel per %d-codeword chunk) + sign/gather of "
                            "the info positions + npd_count_errors; one NCCL all-reduce of the counters when n_gpus > 1"
-                           % (wsn // (128 * 8192 * 2) * 128),
-                   "weights": "synthetic PyTorch-default-init (neural_polar_decoder_b200.synth, seed 21)"},
+                           % (wsn // (128 * 8192 * 2) * 128)},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_B * N * 4,
                 "d2h_bytes_per_step": e2e_B * N * 4, "batch_per_gpu": e2e_B, "steps": e2e_steps,
@@ -360,30 +375,6 @@ def bench_conv(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
                      "alg_flops_per_launch": fl, "flops_per_codeword": CONV_FLOPS_PER_CODEWORD},
         "ber": cnt[0] / float(world * B * args.steps * K), "bler": cnt[1] / float(world * B * args.steps),
         "frames": world * B * args.steps,
+        "_sample": {"y": y[:1024].cpu().numpy(), "logits": logits[:1024].cpu().numpy(),
+                    "sd": {k: v.detach().cpu().numpy() for k, v in net.state_dict().items()}},
     }
-
-
-def cpu_rate_conv(w, seconds, threads, seed=0):
-    """CPU leg: the reference's forward (models.py:742-767) with torch eager modules, fp32, all host threads."""
-    torch.set_num_threads(threads)
-    N = w["N"]
-    net = _setup_conv(w).cpu()
-    rng = np.random.RandomState(seed)
-
-    def run(B):
-        y = torch.from_numpy((rng.choice([-1.0, 1.0], size=(B, N)) + 0.9 * rng.randn(B, N)).astype(np.float32))
-        t0 = time.perf_counter()
-        with torch.no_grad():
-            x2 = net.layers1(y.unsqueeze(1))
-            x3 = net.layers2(x2) + x2
-            x4 = net.layers3(x3) + x3
-            x5 = net.layers4(x4) + x4
-            x6 = net.layers5(x5)
-            out = net.layer_norm(net.dropout(net.layersFin(torch.flatten(x6, start_dim=1))))
-            out.sign()
-        return time.perf_counter() - t0
-
-    dt = run(256)
-    B = int(max(256, min(1 << 17, 256 / dt * seconds)))
-    dt = run(B)
-    return B / dt, B, dt

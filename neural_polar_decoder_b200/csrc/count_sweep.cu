@@ -45,6 +45,48 @@ __global__ void __launch_bounds__(256) count_kernel(const float *__restrict__ a,
     }
 }
 
+// same counters for decisions that sit inside full-length rows: a[B,K] against b[r, cols[k]], b rows of length ldb
+// (the GRU / convNet decoders return [B,N]; callers of the reference index [:, info_positions], rnn_all.py:875)
+__global__ void __launch_bounds__(256) count_gather_kernel(const float *__restrict__ a, const float *__restrict__ b,
+                                                           const int32_t *__restrict__ cols, int64_t B, int K, int ldb,
+                                                           unsigned long long *counts, unsigned long long add_frames)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    unsigned long long bits = 0, blocks = 0;
+    for (int64_t r = warp; r < B; r += nwarps) {
+        uint32_t mism = 0;
+        for (int k = lane; k < K; k += 32)
+            mism += rintf(a[r * K + k]) != rintf(b[r * ldb + cols[k]]);
+        const uint32_t any = __ballot_sync(NPD_FULL, mism != 0);
+        bits += mism;
+        if (lane == 0 && any) blocks += 1;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) bits += __shfl_xor_sync(NPD_FULL, bits, s);
+    if (lane == 0) {
+        if (bits) atomicAdd(counts + 0, bits);
+        if (blocks) atomicAdd(counts + 1, blocks);
+        if (warp == 0 && add_frames) atomicAdd(counts + 2, add_frames);
+    }
+}
+
+int launch_count_gather(const float *a, const float *b, const int32_t *cols, int64_t B, int K, int ldb, uint64_t *counts,
+                        uint64_t add_frames, cudaStream_t st)
+{
+    DeviceProps dp;
+    if (npd_get_device_props(&dp)) return NPD_ECUDA;
+    int64_t grid = (B + 7) / 8;
+    const int64_t cap = (int64_t)dp.sm_count * 8;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    count_gather_kernel<<<(unsigned)grid, 256, 0, st>>>(a, b, cols, B, K, ldb, (unsigned long long *)counts,
+                                                        (unsigned long long)add_frames);
+    NPD_CHECK_CUDA(cudaGetLastError());
+    return NPD_OK;
+}
+
 int launch_count(const float *a, const float *b, int64_t B, int K, uint64_t *counts,
                  uint64_t add_frames, cudaStream_t st)
 {
@@ -69,6 +111,15 @@ NPD_API int npd_count_errors(const float *a, const float *b, int64_t B, int K, u
     NPD_REQUIRE(B >= 0 && K >= 1, "npd_count_errors: bad shape");
     if (B == 0) return NPD_OK;
     return launch_count(a, b, B, K, counts, 0, (cudaStream_t)stream);
+}
+
+NPD_API int npd_count_errors_info(const npd_code_t *code, const float *msg, const float *decoded_full, int64_t B,
+                                  uint64_t *counts, void *stream)
+{
+    NPD_REQUIRE(code && msg && decoded_full && counts, "npd_count_errors_info: null argument");
+    NPD_REQUIRE(B >= 0 && code->K >= 1, "npd_count_errors_info: bad shape");
+    if (B == 0) return NPD_OK;
+    return launch_count_gather(msg, decoded_full, code->d_info, B, code->K, code->N, counts, 0, (cudaStream_t)stream);
 }
 
 namespace {
@@ -144,6 +195,46 @@ NPD_API int npd_mc_sc_sweep(const npd_code_t *code, int64_t B, int64_t chunk, fl
         rc = launch_count(msg, dec, b, code->K, counts, (uint64_t)b, main_st);
         if (rc) return rc;
         NPD_CHECK_CUDA(cudaEventRecord(sp.consumed[slot], main_st));
+    }
+    return NPD_OK;
+}
+
+// ---- fused Monte-Carlo sweep for the CRISP GRU decoder ------------------------------------------------------------
+// generate -> encode -> AWGN -> npd_gru_decode -> count, chunk by chunk on the caller's stream, no host round trip.
+// The decode (0.3 us per codeword) is ~100x the generator and the counter, so the chunks simply run back to back.
+NPD_API size_t npd_mc_gru_workspace_bytes(const npd_gru_t *gru, const npd_code_t *code, int64_t chunk)
+{
+    if (!gru || !code || chunk <= 0) return 0;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    return al((size_t)chunk * code->K * 4) + 2 * al((size_t)chunk * code->N * 4) + al(npd_gru_workspace_bytes(gru, chunk));
+}
+
+NPD_API int npd_mc_gru_sweep(const npd_gru_t *gru, const npd_code_t *code, const npd_code_t *loss_code, int64_t B,
+                             int64_t chunk, float sigma, uint64_t seed, uint32_t point, uint64_t cw_offset,
+                             void *workspace, size_t workspace_bytes, uint64_t *counts, void *stream)
+{
+    NPD_REQUIRE(gru && code && workspace && counts, "npd_mc_gru_sweep: null argument");
+    NPD_REQUIRE(B >= 0 && chunk > 0, "npd_mc_gru_sweep: bad sizes");
+    NPD_REQUIRE(workspace_bytes >= npd_mc_gru_workspace_bytes(gru, code, chunk),
+                "npd_mc_gru_sweep: workspace too small (%zu < %zu)", workspace_bytes,
+                npd_mc_gru_workspace_bytes(gru, code, chunk));
+    if (!loss_code) loss_code = code;  // decisions on the info positions (RNN_decoder.decode's default loss_inds)
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    char *ws = (char *)workspace;
+    float *msg = (float *)ws;
+    float *y = (float *)(ws + al((size_t)chunk * code->K * 4));
+    float *dec = (float *)((char *)y + al((size_t)chunk * code->N * 4));
+    void *gws = (char *)dec + al((size_t)chunk * code->N * 4);
+    const size_t gws_bytes = npd_gru_workspace_bytes(gru, chunk);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int64_t done = 0; done < B; done += chunk) {
+        const int64_t b = (B - done < chunk) ? (B - done) : chunk;
+        int rc = npd_gen_encode_awgn(code, msg, nullptr, y, b, sigma, seed, point, cw_offset + done, stream);
+        if (rc) return rc;
+        rc = npd_gru_decode(gru, loss_code, y, nullptr, nullptr, nullptr, dec, b, gws_bytes ? gws : nullptr, gws_bytes, stream);
+        if (rc) return rc;
+        rc = launch_count_gather(msg, dec, code->d_info, b, code->K, code->N, counts, (uint64_t)b, st);
+        if (rc) return rc;
     }
     return NPD_OK;
 }

@@ -30,6 +30,26 @@ def _count_into(buf_row, a, b):
                                             _lib._vp(buf_row.data_ptr()), _lib.stream_ptr()))
 
 
+def _count_info_into(buf_row, handle, msg, full):
+    """msg [B,K] against full[:, info positions of `handle`] (full [B,N]) without materialising the gather."""
+    msg = msg.contiguous()
+    full = full.contiguous()
+    _lib.check(_lib.load().npd_count_errors_info(handle.h, _lib.ptr(msg), _lib.ptr(full), msg.shape[0],
+                                                 _lib._vp(buf_row.data_ptr()), _lib.stream_ptr()))
+
+
+# The sequential decoders run one CTA pair per 128 codewords for the whole decode, so a launch costs whole waves of
+# 74 pairs (148 SMs): the reference's test_batch_size of 10000 is 1.07 waves -- two waves of time.  The sweep loops
+# therefore stack the SNR points of a batch (same codewords, independent noise) into ONE decode launch; the Philox
+# noise of a frame depends on (seed, SNR point, global frame index) only, so the results equal per-point launches.
+_STACK_ROWS = 1 << 20
+
+
+def _snr_groups(n_snr, batch):
+    per = max(1, min(n_snr, _STACK_ROWS // max(int(batch), 1)))
+    return [list(range(i, min(i + per, n_snr))) for i in range(0, n_snr, per)]
+
+
 def _rates(counts, sizes, K, n_snr, n_dec):
     """counts [batches, n_snr, n_dec, 2] -> per decoder (ber list, bler list) as averages of per-batch rates."""
     c = counts.cpu().numpy().astype(np.float64)
@@ -79,18 +99,28 @@ def polar_RNN_full_test(net, polar, snr_range, Test_Data_Generator, run_ML=False
                 gt = torch.ones(msg.shape[0], polar.N, device=device)
                 gt[:, info] = msg
             msg_s = scored(msg)
-            for si, snr in enumerate(snr_range):
-                y = polar.channel(x, snr, point=(1 << 31) | si, cw_offset=frame0, seed=seed)
-                _, dec_sc = polar.sc_decode_new(y, snr, gt, return_llr=False)
-                _count_into(counts[k, si, 1], msg_s, scored(dec_sc))  # .sign() is the identity on {-1,0,+1}
-                if run_SCL:  # rnn_all.py:857-870 (args.list_size in the reference)
-                    _, dec_scl = polar.scl_decode(y, snr, list_size, False, return_llr=False)
-                    _count_into(counts[k, si, 2], msg_s, scored(dec_scl))
-                if loss_inds is None:
-                    dec = decoder.decode(net, False, y)
+            b = msg.shape[0]
+            for group in _snr_groups(ns, b):
+                ys = torch.empty(len(group) * b, polar.N, device=device)
+                for j, si in enumerate(group):
+                    snr = snr_range[si]
+                    y = polar.channel(x, snr, point=(1 << 31) | si, cw_offset=frame0, seed=seed)
+                    ys[j * b:(j + 1) * b] = y
+                    _, dec_sc = polar.sc_decode_new(y, snr, gt, return_llr=False)
+                    _count_into(counts[k, si, 1], msg_s, scored(dec_sc))  # .sign() is the identity on {-1,0,+1}
+                    if run_SCL:  # rnn_all.py:857-870 (args.list_size in the reference)
+                        _, dec_scl = polar.scl_decode(y, snr, list_size, False, return_llr=False)
+                        _count_into(counts[k, si, 2], msg_s, scored(dec_scl))
+                if loss_inds is None:  # one launch for all SNR points of the group
+                    dec = decoder.decode(net, False, ys)
                 else:
-                    dec = decoder.decode(net, False, y, gt, loss_inds=loss_inds)
-                _count_into(counts[k, si, 0], msg_s, scored(dec.index_select(1, info)))
+                    dec = decoder.decode(net, False, ys, gt.repeat(len(group), 1), loss_inds=loss_inds)
+                for j, si in enumerate(group):
+                    d = dec[j * b:(j + 1) * b]
+                    if sel is None:
+                        _count_info_into(counts[k, si, 0], polar._handle(), msg, d)
+                    else:
+                        _count_into(counts[k, si, 0], msg_s, scored(d.index_select(1, info)))
             frame0 += msg.shape[0]
     (ber_r, bler_r), (ber_s, bler_s), (ber_l, bler_l) = _rates(counts, sizes, n_scored, ns, 3)
     zeros = [0. for _ in snr_range]
@@ -114,13 +144,19 @@ def test_full_data(net, code, snr_range, Test_Data_Generator, run_fano=False, ru
             msg = _lib.to_device_f32(msg_bits, device)
             sizes.append(msg.shape[0])
             x = code.pac_encode(msg)
-            for si, snr in enumerate(snr_range):
-                y = code.channel(x, snr, point=(1 << 31) | si, cw_offset=frame0, seed=seed)
-                dec = decoder.decode(net, False, y)
-                _count_into(counts[k, si, 0], msg, dec.index_select(1, info))
-                if run_dumer:
-                    _, v_hat, _ = code.pac_sc_decode(y, snr)
-                    _count_into(counts[k, si, 1], msg, v_hat)
+            b = msg.shape[0]
+            for group in _snr_groups(ns, b):
+                ys = torch.empty(len(group) * b, code.N, device=device)
+                for j, si in enumerate(group):
+                    snr = snr_range[si]
+                    y = code.channel(x, snr, point=(1 << 31) | si, cw_offset=frame0, seed=seed)
+                    ys[j * b:(j + 1) * b] = y
+                    if run_dumer:
+                        _, v_hat, _ = code.pac_sc_decode(y, snr)
+                        _count_into(counts[k, si, 1], msg, v_hat)
+                dec = decoder.decode(net, False, ys)  # one launch for all SNR points of the group
+                for j, si in enumerate(group):
+                    _count_info_into(counts[k, si, 0], code._handle(), msg, dec[j * b:(j + 1) * b])
             frame0 += msg.shape[0]
     (ber_r, bler_r), (ber_d, bler_d) = _rates(counts, sizes, code.K, ns, 2)
     zeros = [0. for _ in snr_range]
@@ -215,7 +251,43 @@ def mc_sc_sweep(polar, snr_range, total_frames, chunk=1 << 17, seed=0, rank=None
     return finalize(counts, polar.K) + (counts,)
 
 
-def mc_decoder_sweep(polar, decode_fn, snr_range, total_frames, chunk=1 << 15, seed=0, rank=None, world=None,
+WAVE = 148 * 128  # codewords in one wave of the sequential decoders (a CTA pair per 128 codewords on 148 SMs)
+
+
+def round_to_waves(chunk):
+    """Chunk sizes for the sequential decoders: a whole number of waves (a 3.46-wave chunk costs 4 waves of time)."""
+    return max(WAVE, (int(chunk) + WAVE // 2) // WAVE * WAVE)
+
+
+def mc_gru_sweep(polar, net, decoder, snr_range, total_frames, chunk=2 * WAVE, seed=0, rank=None, world=None, group=None):
+    """GRU BER/BLER of `total_frames` frames per SNR point with generate -> decode -> count fused behind ONE library
+    call per SNR point (npd_mc_gru_sweep).  Same sharding and counters as mc_sc_sweep."""
+    import torch.distributed as dist
+    _lib.require_cuda()
+    if rank is None:
+        rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    lo, hi = shard_range(total_frames, rank, world)
+    lib = _lib.load()
+    h = polar._handle()
+    gh = net.npd_handle(polar.N)
+    loss = decoder._loss_code(decoder.info_inds)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    snr_range = list(snr_range)
+    counts = torch.zeros(len(snr_range), 3, dtype=torch.int64, device=dev)
+    chunk = int(max(1, min(round_to_waves(chunk), max(hi - lo, 1))))
+    ws_bytes = lib.npd_mc_gru_workspace_bytes(gh.h, h.h, chunk)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    for si, snr in enumerate(snr_range):
+        if hi > lo:
+            _lib.check(lib.npd_mc_gru_sweep(gh.h, h.h, loss.h, hi - lo, chunk, float(np.float32(utils.snr_db2sigma(snr))),
+                                            int(seed), si, lo, _lib._vp(ws.data_ptr()), ws_bytes,
+                                            _lib._vp(counts[si].data_ptr()), _lib.stream_ptr()))
+    reduce_counts(counts, group)
+    return finalize(counts, polar.K) + (counts,)
+
+
+def mc_decoder_sweep(polar, decode_fn, snr_range, total_frames, chunk=2 * WAVE, seed=0, rank=None, world=None,
                      group=None):
     """Same for any decoder: decode_fn(y[B,N]) -> decisions [B,N] (e.g. lambda y: decoder.decode(net, False, y))."""
     import torch.distributed as dist
@@ -238,8 +310,7 @@ def mc_decoder_sweep(polar, decode_fn, snr_range, total_frames, chunk=1 << 15, s
             _lib.check(lib.npd_gen_encode_awgn(h.h, _lib.ptr(msg), None, _lib.ptr(y), b,
                                                float(np.float32(utils.snr_db2sigma(snr))), int(seed), si, f0,
                                                _lib.stream_ptr()))
-            dec = decode_fn(y).index_select(1, info)
-            _count_into(counts[si], msg, dec)
+            _count_info_into(counts[si], h, msg, decode_fn(y))
             counts[si, 2] += b
     reduce_counts(counts, group)
     return finalize(counts, polar.K) + (counts,)

@@ -140,3 +140,74 @@ def test_mc_sweep_cli(capsys):
     assert mc_sweep.main(["--N", "256", "--K", "128", "--snr", "1.5", "2.5", "--frames", "200000", "--list_size", "4"]) == 0
     scl = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     assert scl["decoder"] == "SCL-4" and all(l < s for l, s in zip(scl["bler"], sc["bler"]))
+
+
+def test_count_errors_info_equals_gathered_count():
+    from neural_polar_decoder_b200 import _lib
+    from neural_polar_decoder_b200.sweep import _count_info_into, _count_into
+    code = _polar64()
+    rs = np.random.RandomState(3)
+    msg = torch.from_numpy((1.0 - 2.0 * rs.randint(0, 2, size=(777, 22))).astype(np.float32)).cuda()
+    full = torch.from_numpy(rs.choice([-1.0, 0.0, 1.0], size=(777, 64), p=[0.45, 0.1, 0.45]).astype(np.float32)).cuda()
+    info = torch.as_tensor(code.info_positions).cuda()
+    full[:, info] = torch.where(torch.from_numpy(rs.rand(777, 22) < 0.9).cuda(), msg, full[:, info])
+    a = torch.zeros(2, dtype=torch.int64, device="cuda")
+    b = torch.zeros(2, dtype=torch.int64, device="cuda")
+    _count_info_into(a, code._handle(), msg, full)
+    _count_into(b, msg, full.index_select(1, info))
+    bit, blk = oracle.count_errors(msg.cpu().numpy(), full[:, info].cpu().numpy())
+    assert a.tolist() == b.tolist() == [bit, blk] and 0 < blk < 777
+
+
+def test_mc_gru_sweep_equals_generic_driver():
+    """npd_mc_gru_sweep (generate -> decode -> count behind one call) == the generic Python driver, any chunking."""
+    from neural_polar_decoder_b200 import synth
+    from neural_polar_decoder_b200.rnn_all import RNN_Model, RNN_decoder
+    from neural_polar_decoder_b200.sweep import mc_decoder_sweep, mc_gru_sweep
+    code = _polar64()
+    sd = synth.gru_state_dict(11, 64, 512, 2, head_gain=8.0)
+    net = RNN_Model('GRU', 66, 512, 1, 2, 64, 0, 0)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    dec = RNN_decoder('y_input', 64, code.info_positions, onehot=True)
+    want = mc_decoder_sweep(code, lambda y: dec.decode(net, False, y), [0.0, 2.0], 5000, chunk=1999, seed=4, rank=0, world=1)[3]
+    got = mc_gru_sweep(code, net, dec, [0.0, 2.0], 5000, seed=4, rank=0, world=1)[3]
+    assert torch.equal(got, want) and got[:, 2].tolist() == [5000, 5000]
+    parts = [mc_gru_sweep(code, net, dec, [0.0, 2.0], 5000, seed=4, rank=r, world=3)[3] for r in range(3)]
+    assert torch.equal(parts[0] + parts[1] + parts[2], want)
+
+
+def test_loss_only_sweep_scores_genie_aided_subset(golden):
+    """--loss_only (rnn_all.py:850-891, 1189-1192): SC and the GRU run genie-aided outside loss_inds and only the
+    message columns msg_indices are scored.  SC list rebuilt with the oracle (use_gt) on the same noise."""
+    import argparse
+    from neural_polar_decoder_b200 import synth
+    from neural_polar_decoder_b200.rnn_all import RNN_Model, RNN_decoder, get_code
+    from neural_polar_decoder_b200.sweep import polar_RNN_full_test
+    code = get_code("Polar", "rev_polar", 64, 22, args=argparse.Namespace(target_K=22, loss_only=6))
+    g = golden("misc")
+    assert np.array_equal(code.loss_inds, g["lossonly_inds"]) and len(code.msg_indices) == 6
+    sd = synth.gru_state_dict(11, 64, 512, 2, head_gain=8.0)
+    net = RNN_Model('GRU', 66, 512, 1, 2, 64, 0, 0)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    dec = RNN_decoder('y_input', 64, code.info_positions, onehot=True)
+    rs = np.random.RandomState(2)
+    batches = [torch.from_numpy((1.0 - 2.0 * rs.randint(0, 2, size=(400, 22))).astype(np.float32)) for _ in range(2)]
+    snrs = [-2.0, 0.0]
+    res = polar_RNN_full_test(net, code, snrs, batches, decoder=dec, seed=9)
+    want, want_rnn, f0 = [0.0, 0.0], [0.0, 0.0], 0
+    sel = code.msg_indices
+    for msg in batches:
+        x = code.encode_plotkin(msg.cuda())
+        gt = np.ones((400, 64), np.float32)
+        gt[:, code.info_positions] = msg.numpy()
+        for si, snr in enumerate(snrs):
+            y = code.channel(x, snr, point=(1 << 31) | si, cw_offset=f0, seed=9)
+            _, _, d = oracle.sc_decode(y.cpu().numpy(), snr, 6, code.info_positions, use_gt=gt)
+            want[si] += (d[:, sel] != msg.numpy()[:, sel]).mean() / 2
+            dr = dec.decode(net, False, y, torch.from_numpy(gt).cuda(), loss_inds=code.loss_inds).cpu().numpy()
+            want_rnn[si] += (dr[:, code.info_positions][:, sel] != msg.numpy()[:, sel]).mean() / 2
+        f0 += 400
+    assert res[2] == pytest.approx(want, abs=1e-12)
+    assert res[0] == pytest.approx(want_rnn, abs=1e-12)
+    # genie-aided outside loss_inds: every scored SC decision equals the genie value where loss_inds is empty -> sanity
+    assert all(0.0 <= v < 0.5 for v in res[2])
