@@ -183,7 +183,7 @@ int npd_gru_decode_h0(const npd_gru_t *gru, const npd_code_t *code, const float 
 
 /* npd_mc_gru_sweep: the inner loop of polar_RNN_full_test (rnn_all.py:843-879) for one SNR point and the GRU decoder
  * without any host round trip: messages -> encode -> AWGN -> npd_gru_decode -> error counters, `chunk` codewords at a
- * time (a multiple of 148 x 128 fills whole waves of CTA pairs).  Philox streams as npd_gen_encode_awgn (seed, point,
+ * time (a multiple of 148 x 64 fills whole waves of CTA pairs).  Philox streams as npd_gen_encode_awgn (seed, point,
  * global frame index cw_offset + row), so counts do not depend on the chunking or the GPU count.
  *   code      : the polar/PAC code object (encoder + info positions to score)
  *   loss_code : positions where the decoder decides (NULL = `code`: RNN_decoder.decode's default loss_inds)
@@ -193,6 +193,36 @@ size_t npd_mc_gru_workspace_bytes(const npd_gru_t *gru, const npd_code_t *code, 
 int npd_mc_gru_sweep(const npd_gru_t *gru, const npd_code_t *code, const npd_code_t *loss_code, int64_t B,
                      int64_t chunk, float sigma, uint64_t seed, uint32_t point, uint64_t cw_offset,
                      void *workspace, size_t workspace_bytes, uint64_t *counts, void *stream);
+
+/* ---- CRISP GRU training step --------------------------------------------------------
+ * One iteration of the reference's training loop for rnn_type GRU / 'y_input' / onehot / 2 layers / Linear(H,1) head
+ * (rnn_all.py:1399-1437): decoder.decode(net, True, y, gt, tfr) teacher-forced (425-449) or student-forced (463-489),
+ * MSELoss on the loss positions (1413), backward, clip_grad_norm_(clip) (1432), torch.optim.AdamW step (1346, 1435;
+ * betas 0.9 / 0.999, eps 1e-8, weight_decay 0.01).  fp32 throughout.  The trainer owns parameters, gradients, Adam
+ * moments and the saved activations for up to max_batch codewords.
+ *   h_params : host fp32 blob in state_dict order: rnn.weight_ih_l0 [3H,N+2], rnn.weight_hh_l0 [3H,H], rnn.bias_ih_l0,
+ *              rnn.bias_hh_l0 [3H], rnn.weight_ih_l1 [3H,H], rnn.weight_hh_l1 [3H,H], rnn.bias_ih_l1, rnn.bias_hh_l1,
+ *              linear.weight [H], linear.bias [1]  (npd_gru_trainer_param_count(N, H) floats)
+ *   tf32     : 0 = fp32 GEMMs (parity mode), 1 = TF32 tensor-core GEMMs */
+typedef struct npd_gru_trainer npd_gru_trainer_t;
+size_t npd_gru_trainer_param_count(int N, int H);
+int npd_gru_trainer_create(int N, int H, int64_t max_batch, const float *h_params, int tf32,
+                           npd_gru_trainer_t **out);
+int npd_gru_trainer_destroy(npd_gru_trainer_t *trainer);
+/* what: 0 = parameters, 1 = gradients of the last step (after clipping), 2 = exp_avg, 3 = exp_avg_sq (synchronises) */
+int npd_gru_trainer_get(const npd_gru_trainer_t *trainer, int what, float *h_out);
+int npd_gru_trainer_set_params(npd_gru_trainer_t *trainer, const float *h_params, int reset_optimizer);
+/* npd_gru_train_step:
+ *   loss_code      : positions that enter the loss and, when student-forced, feed back sign(logit) (the info set)
+ *   y, gt [B,N]    : channel output; genie tensor (+1 on frozen positions, the message on info positions, 1401-1402)
+ *   teacher_forced : 1 = feedback gt[:, i-1] (tfr draw succeeded), 0 = the decoder's own detached decisions
+ *   lr, clip       : this step's learning rate (the caller runs the scheduler) and clip_grad_norm_ max norm (<= 0: off)
+ *   apply_update   : 0 = gradients only (readable through npd_gru_trainer_get(.., 1, ..))
+ *   h_loss_and_norm: NULL or host float[2] <- MSE loss, total gradient norm before clipping (synchronises `stream`)
+ *   logits [B,N]   : NULL or device output of every step's logit (decoded_vhat of the teacher-forced pass) */
+int npd_gru_train_step(npd_gru_trainer_t *trainer, const npd_code_t *loss_code, const float *y, const float *gt,
+                       int teacher_forced, int64_t B, float lr, float clip, int apply_update,
+                       float *h_loss_and_norm, float *logits, void *stream);
 
 /* ---- convNet one-shot decoder ------------------------------------------------------------------
  * npd_conv_create / npd_conv_forward: convNet.forward (models.py:742-767; layers 701-740) with

@@ -40,6 +40,12 @@ SIGNATURES = {
     "npd_gru_workspace_bytes": (_sz, [_vp, _i64]),
     "npd_gru_decode": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
     "npd_gru_decode_h0": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
+    "npd_gru_trainer_param_count": (_sz, [_int, _int]),
+    "npd_gru_trainer_create": (_int, [_int, _int, _i64, _vp, _int, _c.POINTER(_vp)]),
+    "npd_gru_trainer_destroy": (_int, [_vp]),
+    "npd_gru_trainer_get": (_int, [_vp, _int, _vp]),
+    "npd_gru_trainer_set_params": (_int, [_vp, _vp, _int]),
+    "npd_gru_train_step": (_int, [_vp, _vp, _vp, _vp, _int, _i64, _f32, _f32, _int, _vp, _vp, _vp]),
     "npd_conv_create": (_int, [_int, _int, _vp, _sz, _c.POINTER(_vp)]),
     "npd_conv_destroy": (_int, [_vp]),
     "npd_conv_workspace_bytes": (_sz, [_vp, _i64]),

@@ -221,7 +221,7 @@ def bench_grusweep(args, w, rank, world, local_rank, ClockSampler, measured_peak
     frames = world * ns * B * args.steps
     peaks = measured_peaks()
     achieved = flops_per_codeword(N) * ns * B * args.steps / (elapsed_ms * 1e-3) / 1e12
-    waves = -(-(ns * B) // (148 * 128))
+    waves = -(-(ns * B) // (148 * 64))
     return {
         "metric": METRIC, "value": frames / (elapsed_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -229,7 +229,7 @@ def bench_grusweep(args, w, rank, world, local_rank, ClockSampler, measured_peak
         "config": {"snr_points": snrs,
                    "step": "sweep.polar_RNN_full_test on one 10000-message host batch: encode + %d x (channel, SC decode, "
                            "count) + one stacked GRU decode of %d codewords (%d waves of 74 CTA pairs, %.2f needed) + counts"
-                           % (ns, ns * B, waves, ns * B / (148.0 * 128))},
+                           % (ns, ns * B, waves, ns * B / (148.0 * 64))},
         "clocks": clocks,
         "e2e": {"value": frames / (elapsed_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * K * 4, "d2h_bytes_per_step": 0,
                 "batch_per_gpu": ns * B, "steps": args.steps,

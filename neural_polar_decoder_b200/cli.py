@@ -10,7 +10,10 @@ What is mirrored
     reference training run left it; `--test_load_path` / `--model_iters` select a file as in 1749-1754;
   * checkpoint format {'net': state_dict, 'step': int, 'args': Namespace} (rnn_all.py:1471-1479);
   * the printed lines "Test SNRs :", "BERs of RNN:", "BERs of SC decoding:", "BERs of ML:", "Time taken".
-Not mirrored: training (raises unless --test), plotting, Fano / ML / RNN-list decoders (their lists print as zeros).
+  * without --test: the training loop (rnn_all.py:1386-1479) on the GPU for the run_crisp.sh configuration
+    (train.py / csrc/gru_train.cu), writing the reference's checkpoints to the reference's paths.
+Not mirrored: plotting, validation prints inside the training loop, Fano / ML / RNN-list decoders (their lists print as
+zeros).
 """
 import argparse
 import math
@@ -246,10 +249,11 @@ def main(argv=None):
     if args.only_args:
         print("Loaded args. Exiting")
         return 0
-    if not args.test:
-        raise SystemExit("neural_polar_decoder_b200 accelerates the evaluation path only: pass --test "
-                         "(training stays with the reference's rnn_all.py; its checkpoints load here unchanged)")
     if args.gpu >= 0:
         torch.cuda.set_device(args.gpu)
+    if not args.test:
+        # the reference trains and then falls through into its TESTING block (rnn_all.py:1386-1479, 1745-1905)
+        from .train import run_train
+        run_train(args)
     run_test(args)
     return 0

@@ -3,8 +3,9 @@ container with the reference's state_dict keys), RNN_decoder.decode ('y_input' a
 get_code.  The N-step autoregressive decode is ONE libnpd.so launch (csrc/gru_decode.cu).
 
 Reference: rnn_all.py:258-260 (get_onehot), 294-398 (RNN_Model), 400-561 (RNN_decoder),
-1015-1196 (get_code).  Out of scope: training branches (gradients), MLP heads
-(out_linear_depth > 1), LSTM / bidirectional / LayerNorm variants, the GRU list decoder."""
+1015-1196 (get_code).  MLP heads (out_linear_depth > 1), 'y_h0', use_ynn, scalar feedback and reverse order are
+covered by the same kernel; the training iteration (gradients) lives in train.py / csrc/gru_train.cu.  Out of scope
+(SURVEY.md 2): LSTM / bidirectional / LayerNorm variants, the GRU list decoder."""
 import ctypes
 import random
 
@@ -57,7 +58,7 @@ class RNN_Model(nn.Module):
             self.y_linears.append(nn.Linear(y_hidden_size, self.y_output_size - (y_size if skip else 0), bias=True))
         if out_linear_depth == 1:
             self.linear = nn.Linear(D * feature_size, output_size)
-        else:  # rnn_all.py:335-343; loads reference checkpoints, but the fused kernel has no MLP head (_supported)
+        else:  # rnn_all.py:335-343 (MLP head: npd_gru_set_head_mlp)
             layers = [nn.Linear(D * feature_size, y_hidden_size)]
             for _ in range(1, out_linear_depth - 1):
                 layers += [nn.SELU(), nn.Linear(y_hidden_size, y_hidden_size)]
@@ -235,7 +236,7 @@ class RNN_decoder:
         train=True is served for EVALUATION only (no autograd graph; the reference's test_model(tf=True) calls it
         under torch.no_grad(), rnn_all.py:982-984): teacher forcing (425-461) returns the raw outputs of all N
         steps with gt fed back; student forcing (462-512) returns raw outputs on the steps `ii in info_inds`, 1
-        elsewhere.  Training itself (gradients) is out of scope of the B200 path.
+        elsewhere.  The training iteration with gradients is train.GRUTrainer.step (csrc/gru_train.cu).
         One deviation, on a measure-zero input: a scalar (non-one-hot) feedback of exactly 0 (sign of a zero logit or
         of a zero genie value) enters the reference as 0 * w and this path as -w, the one-hot convention (258-260)."""
         if self.decoding_type not in ('y_input', 'y_h0'):
@@ -273,9 +274,9 @@ class RNN_decoder:
                 assert yd.shape[1] == N, "use_ynn: the y-MLP must emit N values (y_output_size = N, rnn_all.py:1320)"
             if train:
                 if torch.is_grad_enabled() and any(p.requires_grad for p in net.parameters()):
-                    raise NotImplementedError("training (rnn_all.py:422-512 with gradients) is out of scope of the "
-                                              "B200 path; call under torch.no_grad() for teacher-/student-forced "
-                                              "evaluation")
+                    raise NotImplementedError("decode(train=True) returns no autograd graph on the B200 path: the whole training "
+                                              "iteration (forward, backward, clip, AdamW) is train.GRUTrainer.step; call "
+                                              "under torch.no_grad() for teacher-/student-forced evaluation")
                 if random.random() < teacher_forcing_ratio:  # rnn_all.py:425
                     assert gt is not None and gt.shape[1] == N
                     _, logits = run(handle, self._loss_code(self.info_inds), yd, forced=like_y(gt), want_logits=True, **kw)

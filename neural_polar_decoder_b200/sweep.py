@@ -251,7 +251,7 @@ def mc_sc_sweep(polar, snr_range, total_frames, chunk=1 << 17, seed=0, rank=None
     return finalize(counts, polar.K) + (counts,)
 
 
-WAVE = 148 * 128  # codewords in one wave of the sequential decoders (a CTA pair per 128 codewords on 148 SMs)
+WAVE = 148 * 64  # codewords in one wave of the sequential decoders (64 per CTA, 148 SMs = 74 CTA pairs)
 
 
 def round_to_waves(chunk):

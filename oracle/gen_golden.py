@@ -194,6 +194,53 @@ def gru_cases():
     np.savez_compressed(os.path.join(OUT, "gru.npz"), **out)
 
 
+TRAIN_KEYS = ("rnn.weight_ih_l0", "rnn.weight_hh_l0", "rnn.bias_ih_l0", "rnn.bias_hh_l0", "rnn.weight_ih_l1",
+              "rnn.weight_hh_l1", "rnn.bias_ih_l1", "rnn.bias_hh_l1", "linear.weight", "linear.bias")
+
+
+def _blob(named):
+    return np.concatenate([named[k].detach().cpu().numpy().reshape(-1) for k in TRAIN_KEYS]).astype(np.float32)
+
+
+def gru_train_cases():
+    """Three iterations of the reference's OWN training-loop body (rnn_all.py:1399-1437) on a seeded RNN_Model:
+    decoder.decode(net, True, y, gt, tfr) -> MSELoss on the info positions -> backward -> clip_grad_norm_(0.25) ->
+    AdamW.step().  tfr = 1 draws teacher forcing, tfr = 0 student forcing (`random.random() < tfr`, 425)."""
+    ra = ref_shim.load("rnn_all")
+    N, K, H, B = 16, 8, 64, 96
+    ra.args = ref_shim.make_args(N=N, K=K)
+    code = ref_shim.get_code("Polar", "polar", N, K)
+    torch.manual_seed(5)
+    net = ra.RNN_Model("GRU", N + 2, H, 1, 2, N, 0, 0)
+    dec = ra.RNN_decoder("y_input", N, code.info_inds, onehot=True)
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-3)
+    loss_fn = torch.nn.MSELoss()
+    rs = np.random.RandomState(41)
+    out = {"cfg": np.array([N, K, H, B], dtype=np.int64), "info": np.asarray(code.info_inds, dtype=np.int32),
+           "lr": np.float64(1e-3), "clip": np.float64(0.25), "p0": _blob(dict(net.named_parameters()))}
+    for step, tfr in enumerate([1.0, 0.0, 1.0]):
+        msg = torch.from_numpy(bpsk_msgs(rs, B, K))
+        gt = torch.ones(B, N)
+        gt[:, code.info_inds] = msg
+        y = torch.from_numpy(noisy(rs, code.encode(msg).numpy(), 0.0))
+        decoded = dec.decode(net, True, y, gt, tfr)
+        loss = loss_fn(decoded[:, code.info_inds], msg)
+        loss.backward()
+        norm = torch.nn.utils.clip_grad_norm_(net.parameters(), 0.25)
+        out["s%d_y" % step] = y.numpy()
+        out["s%d_gt" % step] = gt.numpy()
+        out["s%d_teacher" % step] = np.int64(tfr >= 1.0)
+        out["s%d_loss" % step] = np.float64(loss.item())
+        out["s%d_norm" % step] = np.float64(float(norm))
+        out["s%d_grad" % step] = _blob({k: p.grad for k, p in net.named_parameters()})
+        out["s%d_decoded" % step] = decoded.detach().numpy()
+        opt.step()
+        opt.zero_grad()
+        out["s%d_p" % step] = _blob(dict(net.named_parameters()))
+        print("gru_train step", step, "loss", loss.item(), "norm", float(norm), flush=True)
+    np.savez_compressed(os.path.join(OUT, "gru_train.npz"), **out)
+
+
 def scl_cases():
     """SC-list decoder (polar.py:793-876, use_CRC=False) on real-valued noise at several list sizes."""
     rs = np.random.RandomState(2718)
@@ -376,6 +423,8 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     todo = a.only.split(",") if a.only else ["misc", "pac", "gru", "gru_modes", "gru_cond", "scl", "conv", "polar"]
+    if "gru_train" in todo:
+        gru_train_cases()
     if "gru_cond" in todo:
         gru_cond_cases()
     if "gru_modes" in todo:

@@ -301,6 +301,89 @@ def gru_decode(sd, y, N, info, forced=None, H=None, round_bf16=False, genie=None
     return decoded.numpy(), logits.numpy()
 
 
+TRAIN_KEYS = ("rnn.weight_ih_l0", "rnn.weight_hh_l0", "rnn.bias_ih_l0", "rnn.bias_hh_l0", "rnn.weight_ih_l1",
+              "rnn.weight_hh_l1", "rnn.bias_ih_l1", "rnn.bias_hh_l1", "linear.weight", "linear.bias")
+
+
+def train_shapes(N, H):
+    I = N + 2
+    return [(3 * H, I), (3 * H, H), (3 * H,), (3 * H,), (3 * H, H), (3 * H, H), (3 * H,), (3 * H,), (1, H), (1,)]
+
+
+def gru_train_step(blob, y, gt, N, H, info, teacher, lr=1e-3, clip=0.25, state=None):
+    """fp32 torch-autograd restatement of one iteration of the reference's training loop (rnn_all.py:1399-1437) for
+    GRU / 'y_input' / onehot / 2 layers / Linear(H,1): teacher-forced (425-449) or student-forced (463-489) pass,
+    MSELoss on the info positions (1413), backward, clip_grad_norm_ (1432), torch.optim.AdamW step (1346, 1435).
+    The GRU cell is written out gate by gate (no nn.GRU) so that the restatement is independent of torch's fused RNN.
+
+    blob : parameters as one fp32 vector in TRAIN_KEYS order;  state: None or (exp_avg, exp_avg_sq, step)
+    -> (new blob, clipped grad blob, loss, total grad norm, logits [B,N], new state)"""
+    import torch
+    y = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32))
+    gt = torch.from_numpy(np.ascontiguousarray(gt, dtype=np.float32))
+    B = y.shape[0]
+    params, o = [], 0
+    for shp in train_shapes(N, H):
+        n = int(np.prod(shp))
+        params.append(torch.from_numpy(np.array(blob[o:o + n], dtype=np.float32).reshape(shp)).requires_grad_(True))
+        o += n
+    Wih0, Whh0, bih0, bhh0, Wih1, Whh1, bih1, bhh1, Wo, bo = params
+    info_set = set(int(i) for i in info)
+    eye = torch.eye(2)
+
+    def cell(x, h, Wi, Wh, bi, bh):
+        gi, gh = x @ Wi.t() + bi, h @ Wh.t() + bh
+        r = torch.sigmoid(gi[:, :H] + gh[:, :H])
+        z = torch.sigmoid(gi[:, H:2 * H] + gh[:, H:2 * H])
+        n = torch.tanh(gi[:, 2 * H:] + r * gh[:, 2 * H:])
+        return (1 - z) * n + z * h
+
+    h0 = torch.zeros(B, H)
+    h1 = torch.zeros(B, H)
+    decoded = torch.ones(B, N)
+    outs = []
+    for ii in range(N):
+        if ii == 0:
+            prev = torch.ones(B)
+        elif teacher:
+            prev = gt[:, ii - 1]
+        else:
+            prev = decoded[:, ii - 1].sign().detach()
+        x = torch.cat([y, eye[(0.5 + 0.5 * prev).long()]], 1)
+        h0 = cell(x, h0, Wih0, Whh0, bih0, bhh0)
+        h1 = cell(h0, h1, Wih1, Whh1, bih1, bhh1)
+        out = (h1 @ Wo.t() + bo).view(-1)
+        outs.append(out)
+        if teacher or ii in info_set:
+            decoded = torch.cat([decoded[:, :ii], out.view(-1, 1), decoded[:, ii + 1:]], 1)
+    logits = torch.stack(outs, 1)
+    idx = torch.as_tensor(sorted(info_set))
+    loss = torch.nn.functional.mse_loss(logits[:, idx], gt[:, idx])
+    loss.backward()
+    norm = torch.nn.utils.clip_grad_norm_(params, clip) if clip and clip > 0 else torch.zeros(())
+    opt = torch.optim.AdamW(params, lr=lr)
+    if state is not None:
+        for p_, m_, v_ in zip(params, _split(state[0], N, H), _split(state[1], N, H)):
+            opt.state[p_] = {"step": torch.tensor(float(state[2])), "exp_avg": torch.from_numpy(m_.copy()),
+                             "exp_avg_sq": torch.from_numpy(v_.copy())}
+    grad = np.concatenate([p_.grad.numpy().reshape(-1) for p_ in params]).astype(np.float32)
+    opt.step()
+    new = np.concatenate([p_.detach().numpy().reshape(-1) for p_ in params]).astype(np.float32)
+    st = (np.concatenate([opt.state[p_]["exp_avg"].numpy().reshape(-1) for p_ in params]),
+          np.concatenate([opt.state[p_]["exp_avg_sq"].numpy().reshape(-1) for p_ in params]),
+          int(opt.state[params[0]]["step"]))
+    return new, grad, float(loss.item()), float(norm), logits.detach().numpy(), st
+
+
+def _split(blob, N, H):
+    out, o = [], 0
+    for shp in train_shapes(N, H):
+        n = int(np.prod(shp))
+        out.append(np.asarray(blob[o:o + n], dtype=np.float32).reshape(shp))
+        o += n
+    return out
+
+
 _CONV_SPEC = [  # (sequential name, index, dilation)   models.py:701-730, padding = 3*dilation
     ("layers1", 0, 1), ("layers1", 2, 2),
     ("layers2", 0, 4), ("layers2", 2, 1),

@@ -1,0 +1,111 @@
+"""GPU: the CRISP GRU training step (csrc/gru_train.cu) against three iterations of the LIVE reference's
+training-loop body (tests/golden/gru_train.npz: loss, clipped gradients, AdamW-updated parameters; teacher-, student-,
+teacher-forced) and against the oracle's autograd restatement at the flagship shape.  fp32 tolerances."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _net(N, H, blob):
+    from neural_polar_decoder_b200.rnn_all import RNN_Model
+    from neural_polar_decoder_b200.train import PARAM_KEYS
+    net = RNN_Model('GRU', N + 2, H, 1, 2, N, 0, 0)
+    sd, o = net.state_dict(), 0
+    for k in PARAM_KEYS:
+        n = sd[k].numel()
+        sd[k].copy_(torch.from_numpy(np.asarray(blob[o:o + n]).reshape(tuple(sd[k].shape))))
+        o += n
+    return net
+
+
+def _relerr(a, b):
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def test_train_steps_match_live_reference_fixture(golden):
+    from neural_polar_decoder_b200.rnn_all import RNN_decoder
+    from neural_polar_decoder_b200.train import GRUTrainer
+    g = golden("gru_train")
+    N, K, H, B = [int(v) for v in g["cfg"]]
+    net = _net(N, H, g["p0"])
+    dec = RNN_decoder('y_input', N, g["info"], onehot=True)
+    tr = GRUTrainer(net, N, B)
+    code = dec._loss_code(g["info"])
+    for s in range(3):
+        teacher = bool(g["s%d_teacher" % s])
+        loss, norm, logits = tr.step(code, torch.from_numpy(g["s%d_y" % s]).cuda(), torch.from_numpy(g["s%d_gt" % s]).cuda(),
+                                     teacher, float(g["lr"]), float(g["clip"]), want_logits=True)
+        assert loss == pytest.approx(float(g["s%d_loss" % s]), rel=2e-5), s
+        assert norm == pytest.approx(float(g["s%d_norm" % s]), rel=2e-4), s
+        if teacher:  # decoded_vhat of the teacher-forced pass = every step's logit
+            np.testing.assert_allclose(logits.cpu().numpy(), g["s%d_decoded" % s], atol=5e-6)
+        grad, ref = tr.get("grads"), g["s%d_grad" % s]
+        assert _relerr(grad, ref) <= 2e-4, (s, _relerr(grad, ref))
+        p, ref_p = tr.get("params"), g["s%d_p" % s]
+        # Adam's first steps move every weight by ~lr whatever the gradient's size: compare the DELTA, not just p
+        prev = g["p0"] if s == 0 else g["s%d_p" % (s - 1)]
+        assert np.abs((p - prev) - (ref_p - prev)).max() <= 2e-2 * float(g["lr"]), s
+        assert np.abs(p - ref_p).max() <= 3e-5 * float(g["lr"]) + 2e-7 or np.mean(np.abs(p - ref_p) > 1e-6) < 1e-3
+    # the nn.Module receives the trained weights and the decode kernel then runs on them
+    tr.sync_to_net()
+    from neural_polar_decoder_b200.train import _blob
+    assert np.array_equal(_blob(net), tr.get("params"))
+
+
+@pytest.mark.parametrize("teacher", [True, False])
+def test_train_step_flagship_shape_vs_oracle(teacher):
+    """Polar(64,22), H = 512 (run_crisp.sh): gradients of one iteration against the oracle's autograd restatement."""
+    from neural_polar_decoder_b200 import synth
+    from neural_polar_decoder_b200.rnn_all import RNN_Model, RNN_decoder, get_code
+    from neural_polar_decoder_b200.train import GRUTrainer, _blob
+    N, K, H, B = 64, 22, 512, 48
+    code = get_code("Polar", "rev_polar", N, K, args=argparse.Namespace(target_K=22))
+    sd = synth.gru_state_dict(5, N, H, 2, head_gain=2.0)
+    net = RNN_Model('GRU', N + 2, H, 1, 2, N, 0, 0)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    dec = RNN_decoder('y_input', N, code.info_inds, onehot=True)
+    rs = np.random.RandomState(3)
+    msg = (1.0 - 2.0 * rs.randint(0, 2, size=(B, K))).astype(np.float32)
+    gt = np.ones((B, N), np.float32)
+    gt[:, code.info_inds] = msg
+    y = (code.encode(torch.from_numpy(msg).cuda()).cpu().numpy() + rs.randn(B, N)).astype(np.float32)
+    blob = _blob(net)
+    new, grad, loss, norm, logits, _ = oracle.gru_train_step(blob, y, gt, N, H, code.info_inds, teacher, 1e-3, 0.25)
+    tr = GRUTrainer(net, N, B)
+    l2, n2, lg = tr.step(dec._loss_code(code.info_inds), torch.from_numpy(y).cuda(), torch.from_numpy(gt).cuda(), teacher,
+                         1e-3, 0.25, want_logits=True)
+    assert l2 == pytest.approx(loss, rel=5e-5) and n2 == pytest.approx(norm, rel=5e-4)
+    if teacher:
+        np.testing.assert_allclose(lg.cpu().numpy(), logits, atol=2e-5)
+    assert _relerr(tr.get("grads"), grad) <= 5e-4
+    assert np.abs(tr.get("params") - new).max() <= 2e-5
+
+
+def test_training_loop_learns_and_writes_reference_checkpoint(tmp_path, monkeypatch):
+    """`python -m neural_polar_decoder_b200.rnn_all <run_crisp.sh-style flags>` without --test: a short K = 4 stage trains
+    on the GPU (loss falls), leaves {'net','step','args'} where the reference would, and the TESTING block then loads it."""
+    from neural_polar_decoder_b200 import cli
+    monkeypatch.chdir(tmp_path)
+    torch.manual_seed(0)
+    import random
+    random.seed(0)
+    argv = ("--code Polar --rate_profile rev_polar --target_K 8 --N 16 --K 4 --decoding_type y_input --rnn_feature_size 128 "
+            "--num_steps 150 --batch_size 512 --rnn_depth 2 --tfr_min 1 --tfr_max 1 --dec_train_snr 0 --lr 0.003 "
+            "--scheduler step --lr_decay 100 --lr_decay_gamma 0.5 --onehot --id t1 --print_freq 50 --test_size 4000 "
+            "--test_batch_size 2000 --test_snr_start 0 --test_snr_end 4 --snr_points 3 --fresh").split()
+    args = cli.get_args(argv)
+    from neural_polar_decoder_b200.train import run_train
+    losses = run_train(args, out=lambda *a: None)
+    assert losses[-1][1] < 0.6 * losses[0][1], losses
+    results, final = cli.result_paths(args)
+    ck = cli.load_checkpoint(results + "/Models/model_final.pt")
+    assert set(ck) == {"net", "step", "args"} and ck["step"] == 150
+    assert cli.load_checkpoint(final)["step"] == 150
+    res = cli.run_test(args, out=lambda *a: None)
+    assert res["bers_RNN"][-1] < 0.2 and res["step"] == 150

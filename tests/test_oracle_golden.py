@@ -184,3 +184,24 @@ def test_scl_oracle_against_reference_fixtures(golden):
         if L == 1:  # a list of one is the SC decoder (without the frozen prior in the recursion)
             _, _, sc = oracle.sc_decode(g[nm + "_y"], float(g[nm + "_snr"]), n, g[nm + "_info"])
             assert np.array_equal(dec, sc)
+
+
+def test_gru_train_step_against_reference_fixture(golden):
+    """oracle.gru_train_step (gate-by-gate autograd restatement) against three iterations of the live reference's
+    training-loop body: loss, clipped gradients, updated parameters (teacher-, student-, teacher-forced)."""
+    g = golden("gru_train")
+    N, K, H, B = [int(v) for v in g["cfg"]]
+    blob, state = g["p0"], None
+    for s in range(3):
+        new, grad, loss, norm, logits, state = oracle.gru_train_step(
+            blob, g["s%d_y" % s], g["s%d_gt" % s], N, H, g["info"], bool(g["s%d_teacher" % s]), float(g["lr"]),
+            float(g["clip"]), state)
+        assert loss == pytest.approx(float(g["s%d_loss" % s]), rel=1e-5)
+        assert norm == pytest.approx(float(g["s%d_norm" % s]), rel=1e-4)
+        ref_grad = g["s%d_grad" % s]
+        assert np.abs(grad - ref_grad).max() <= 1e-5 * np.abs(ref_grad).max() + 1e-9
+        assert np.abs(new - g["s%d_p" % s]).max() <= 2e-6
+        if bool(g["s%d_teacher" % s]):
+            np.testing.assert_allclose(logits, g["s%d_decoded" % s], atol=2e-6)
+        blob = new
+    assert state[2] == 3
