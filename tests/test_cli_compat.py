@@ -142,3 +142,89 @@ def _check_curves(args, res, meta, path):
             a, b = res["bers_" + name][i], meta["bers_" + name][i]
             hw = mcstats.ber_halfwidth(fv[i][which], n_ours, n_ref, z)
             assert abs(a - b) <= hw + 1e-6, ("ber", name, i, a, b, hw)
+
+
+# ---- run_models.py (convNet, config 4) ------------------------------------------------------------------------------
+RUN_ALT_LAST = ("--model conv --N 64 --max_len 64 --K 22 --dec_train_snr -1 --embed_dim 128 --num_steps 1000 --lr 1e-3 "
+                "--batch_size 8192 --mult 1 --num_restarts 1 --print_freq 200 --code polar --previous_K 21 --previous_N 64 "
+                "--load_previous --model_iters 1000 --rate_profile polar --curriculum c2n --id c2n --previous_id c2n "
+                "--validation_snr 1 --target_K 22 --run 1").split()
+
+
+def test_run_models_args_and_paths():
+    from neural_polar_decoder_b200 import run_models
+    a = run_models.get_args(RUN_ALT_LAST)
+    assert (a.model, a.N, a.K, a.embed_dim, a.curriculum, a.g, a.are_we_doing_ML) == ("conv", 64, 22, 128, "c2n", 91, False)
+    results, final, previous = run_models.result_paths(a)
+    # the scheme of run_models.py:575-611 (the ".pt" path is a DIRECTORY in the reference)
+    assert results == "./Supervised_Xformer_decoder_Polar_Results/Polar_22_64/Scheme_polar/conv/8_depth_6/c2n/1"
+    assert final == "./Supervised_Xformer_decoder_Polar_Results/final_nets/Scheme_polar/N64_K22_conv_8_depth_6.pt/c2n/1"
+    assert previous == "./Supervised_Xformer_decoder_Polar_Results/Polar_21_64/Scheme_polar/conv/8_depth_6/c2n/1"
+    polar, target, info, tinfo = run_models.build_code(a)
+    assert info.tolist() == tinfo.tolist() == [27, 29, 30, 31, 39, 43, 45, 46, 47] + list(range(51, 64))
+    b = run_models.get_args("--model conv --N 64 --K 5 --target_K 22 --code polar --rate_profile polar --curriculum l2r".split())
+    assert run_models.build_code(b)[2].tolist() == tinfo[:5].tolist()
+    with pytest.raises(NotImplementedError):
+        run_models.build_model(run_models.get_args(["--model", "gpt", "--code", "polar"]))
+    with pytest.raises(SystemExit):
+        run_models.main(["--model", "conv", "--code", "polar", "--N", "64", "--K", "22"])
+
+
+def _conv_trained():
+    pt, js = os.path.join(GOLD, "conv_N64_K22_E128.pt"), os.path.join(GOLD, "conv_N64_K22_E128.json")
+    if not os.path.exists(pt):
+        pytest.skip("no trained reference convNet checkpoint fixture")
+    with open(js) as f:
+        return pt, json.load(f)
+
+
+def test_reference_conv_checkpoint_loads_with_reference_keys():
+    from neural_polar_decoder_b200 import run_models
+    pt, meta = _conv_trained()
+    ck = cli.load_checkpoint(pt)
+    assert set(ck) == {"xformer", "step", "args"}
+    net, cargs, step = run_models.net_from_checkpoint(pt)  # strict load_state_dict
+    assert (cargs.model, cargs.N, cargs.embed_dim) == ("conv", 64, 128) and not net.training
+
+
+@pytest.mark.gpu
+def test_run_models_test_mode_synthetic_checkpoint(tmp_path, monkeypatch, capsys):
+    """`--model conv --test` end to end on a checkpoint written in the reference's format at the reference's path."""
+    import argparse
+    from neural_polar_decoder_b200 import run_models, synth
+    monkeypatch.chdir(tmp_path)
+    argv = [a for a in RUN_ALT_LAST if a not in ("--load_previous",)] + ["--test", "--test_size", "4000", "--test_batch_size",
+                                                                         "2000", "--snr_points", "3", "--test_snr_end", "2"]
+    args = run_models.get_args(argv)
+    args.model_iters = None
+    _, final, _ = run_models.result_paths(args)
+    os.makedirs(final + "/Models")
+    sd = {k: torch.from_numpy(v) for k, v in synth.conv_state_dict(3, 64, 128).items()}
+    torch.save({"xformer": sd, "step": 7, "args": argparse.Namespace(**vars(args))}, final + "/Models/model_final.pt")
+    res = run_models.run_test(args)
+    out = capsys.readouterr().out
+    assert "Model loaded at step 7" in out and "BERs of Xformer:" in out and "BLERs of Xformer:" in out
+    assert len(res["bers_Xformer"]) == 3 and res["bers_SC"][0] > res["bers_SC"][-1] > 0
+    assert all(l <= s + 1e-9 for l, s in zip(res["blers_SCL"], res["blers_SC"]))
+
+
+@pytest.mark.gpu
+def test_run_models_reproduces_reference_conv_curve(capsys):
+    """The reference-trained convNet checkpoint through `--model conv --test`: convNet / SC / SC-list(4) curves within
+    two-sample Monte-Carlo intervals (family-wise 95 %) of what the live reference's testXformer printed."""
+    import mcstats
+    from neural_polar_decoder_b200 import run_models
+    pt, meta = _conv_trained()
+    argv = [a for a in meta["test_argv"]] + ["--test_load_path", pt]
+    i = argv.index("--test_size")
+    argv[i + 1] = "100000"
+    args = run_models.get_args(argv)
+    torch.manual_seed(2)
+    res = run_models.run_test(args)
+    n_ref, n_ours, ns = meta["test_size"], 100000, len(meta["snr_range"])
+    z = mcstats.z_familywise(3 * ns)
+    for i in range(ns):
+        for name in ("Xformer", "SC", "SCL"):
+            a, b = res["blers_" + name][i], meta["blers_" + name][i]
+            hw = mcstats.bler_halfwidth(a, n_ours, b, n_ref, z)
+            assert abs(a - b) <= hw, (name, i, a, b, hw)
