@@ -127,8 +127,15 @@ namespace {
 size_t mc_slot_bytes(const npd_code_t *code, int64_t chunk)
 {
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    return al((size_t)chunk * code->K * 4) * 2 + al((size_t)chunk * code->N * 4);
+    // plain layout: msg + decisions + y; fused-count layout (N >= 256): packed u words + flags + re-decode scratch + y
+    const size_t plain = al((size_t)chunk * code->K * 4) * 2 + al((size_t)chunk * code->N * 4);
+    const size_t fused = al((size_t)chunk * (code->N >> 5) * 4) + al((size_t)chunk) + al((size_t)chunk * code->K * 4) +
+                         al((size_t)chunk * code->N * 4);
+    return plain > fused ? plain : fused;
 }
+
+// the decoder counts its own errors (sc_quad_kernel's fused mode): no float messages / decisions, no count launch
+bool mc_fused_count(const npd_code_t *code) { return code->pac_g == 0 && code->n >= 8 && code->K >= 1; }
 
 // second stream + events of the sweep's two-deep pipeline, one set per device (created on first use)
 struct SweepPipe {
@@ -182,18 +189,32 @@ NPD_API int npd_mc_sc_sweep(const npd_code_t *code, int64_t B, int64_t chunk, fl
         const int slot = (int)(n_chunks & 1);
         const int64_t b = (B - done < chunk) ? (B - done) : chunk;
         char *ws = (char *)workspace + slot * slot_bytes;
-        float *msg = (float *)ws;
-        float *dec = (float *)(ws + al((size_t)chunk * code->K * 4));
-        float *y = (float *)(ws + 2 * al((size_t)chunk * code->K * 4));
         if (n_chunks >= 2) NPD_CHECK_CUDA(cudaStreamWaitEvent(sp.gen, sp.consumed[slot], 0));  // slot's previous chunk counted
-        int rc = npd_gen_encode_awgn(code, msg, nullptr, y, b, sigma, seed, point, cw_offset + done, sp.gen);
-        if (rc) return rc;
-        NPD_CHECK_CUDA(cudaEventRecord(sp.generated[slot], sp.gen));
-        NPD_CHECK_CUDA(cudaStreamWaitEvent(main_st, sp.generated[slot], 0));
-        rc = npd_sc_decode(code, y, llr_scale, nullptr, nullptr, dec, b, main_st);
-        if (rc) return rc;
-        rc = launch_count(msg, dec, b, code->K, counts, (uint64_t)b, main_st);
-        if (rc) return rc;
+        int rc;
+        if (mc_fused_count(code)) {
+            uint32_t *ubits = (uint32_t *)ws;
+            unsigned char *flags = (unsigned char *)(ws + al((size_t)chunk * (code->N >> 5) * 4));
+            float *dec = (float *)((char *)flags + al((size_t)chunk));
+            float *y = (float *)((char *)dec + al((size_t)chunk * code->K * 4));
+            rc = npd_gen_encode_awgn_bits(code, ubits, y, b, sigma, seed, point, cw_offset + done, sp.gen);
+            if (rc) return rc;
+            NPD_CHECK_CUDA(cudaEventRecord(sp.generated[slot], sp.gen));
+            NPD_CHECK_CUDA(cudaStreamWaitEvent(main_st, sp.generated[slot], 0));
+            rc = npd_sc_decode_count(code, y, llr_scale, ubits, dec, flags, b, counts, main_st);
+            if (rc) return rc;
+        } else {
+            float *msg = (float *)ws;
+            float *dec = (float *)(ws + al((size_t)chunk * code->K * 4));
+            float *y = (float *)(ws + 2 * al((size_t)chunk * code->K * 4));
+            rc = npd_gen_encode_awgn(code, msg, nullptr, y, b, sigma, seed, point, cw_offset + done, sp.gen);
+            if (rc) return rc;
+            NPD_CHECK_CUDA(cudaEventRecord(sp.generated[slot], sp.gen));
+            NPD_CHECK_CUDA(cudaStreamWaitEvent(main_st, sp.generated[slot], 0));
+            rc = npd_sc_decode(code, y, llr_scale, nullptr, nullptr, dec, b, main_st);
+            if (rc) return rc;
+            rc = launch_count(msg, dec, b, code->K, counts, (uint64_t)b, main_st);
+            if (rc) return rc;
+        }
         NPD_CHECK_CUDA(cudaEventRecord(sp.consumed[slot], main_st));
     }
     return NPD_OK;

@@ -18,6 +18,7 @@ struct EncParams {
     float *msg_out;       // [B,K] or null
     float *x_out;         // [B,N] or null
     float *y_out;         // [B,N] or null
+    uint32_t *ubits_out;  // [B, N/32] or null: the rate-profiled word V (message bits at the info positions), packed
     const int32_t *info;
     int64_t B;
     int n, K;
@@ -99,6 +100,8 @@ __global__ void __launch_bounds__(128) encode_kernel(const EncParams p)
             if (bit) atomicOr(&V[pos >> 5], 1u << (pos & 31));
         }
         __syncwarp();
+        if (p.ubits_out)
+            for (int i = lane; i < NW; i += 32) p.ubits_out[r * NW + i] = V[i];
         if (p.pac_M) {
             // rate-1 convolutional pre-coder: u_i = v_i xor (xor over taps j of v_{i-j})
             for (int i0 = 0; i0 < N; i0 += 32) {
@@ -235,6 +238,17 @@ NPD_API int npd_gen_encode_awgn(const npd_code_t *code, float *msg, float *x, fl
     p.K = code->K; p.pac_taps = code->pac_taps; p.pac_M = code->pac_g ? code->pac_M : 0;
     p.sigma = sigma; p.seed = seed; p.point = point; p.cw_offset = cw_offset;
     return launch_encode(code, p, (cudaStream_t)stream);
+}
+
+// internal (count_sweep.cu): the fused sweep's generator -- y and the packed transmitted u words, no float messages
+int npd_gen_encode_awgn_bits(const npd_code *code, uint32_t *ubits, float *y, int64_t B, float sigma, uint64_t seed,
+                             uint32_t point, uint64_t cw_offset, cudaStream_t st)
+{
+    EncParams p{};
+    p.ubits_out = ubits; p.y_out = y; p.info = code->d_info; p.B = B; p.n = code->n;
+    p.K = code->K; p.pac_taps = code->pac_taps; p.pac_M = code->pac_g ? code->pac_M : 0;
+    p.sigma = sigma; p.seed = seed; p.point = point; p.cw_offset = cw_offset;
+    return launch_encode(code, p, st);
 }
 
 NPD_API int npd_awgn(const float *x, float *y, int64_t B, int N, float sigma, uint64_t seed,

@@ -63,6 +63,12 @@ struct DeviceProps {
 };
 int npd_get_device_props(DeviceProps *p);
 
+// fused-sweep internals (encode_channel.cu / sc_decode.cu, used by count_sweep.cu)
+int npd_gen_encode_awgn_bits(const npd_code *code, uint32_t *ubits, float *y, int64_t B, float sigma, uint64_t seed,
+                             uint32_t point, uint64_t cw_offset, cudaStream_t st);
+int npd_sc_decode_count(const npd_code *code, const float *y, float llr_scale, const uint32_t *ubits, float *decoded_scratch,
+                        unsigned char *flags, int64_t B, uint64_t *counts, cudaStream_t st);
+
 // code length and channel count of forward()'s `in4` output of a convNet handle (conv_net.cu)
 void npd_conv_dims(const npd_conv *cv, int *N, int *in4_channels);
 

@@ -42,6 +42,12 @@ struct ScParams {
     int slog;              // lane kernel: highest stored level
     int vec_out;           // quad kernel: 16-byte output stores (K % 4 == 0, aligned `decoded`)
     float *scratch;        // quad kernel, N >= 2048: level n-2 of every resident warp ([warp][element][8 codewords])
+    // fused error counting (the Monte-Carlo sweep): instead of writing decisions, the quad kernel compares its u-domain
+    // decision words with the generator's packed u words on the info positions and accumulates the counters
+    const uint32_t *ubits;       // [B, N/32] transmitted u (message bits at the info positions, 0 elsewhere) or null
+    const uint32_t *info_words;  // [N/32] bit i = position i carries information
+    unsigned long long *counts;  // [2] bit errors, block errors (accumulated) -- non-null selects the fused mode
+    unsigned char *flags;        // [B] fused mode: 1 = codeword needs the exact re-decode (replaces the NaN sentinel)
     long long *trace;      // bench-only (NPD_SC_TRACE): cycles of warp 0 / block 0's second group: top, levels, block, merge, output, total
 };
 
@@ -283,8 +289,12 @@ __global__ void __launch_bounds__(64) sc_group_kernel(const ScParams p)
             const int64_t cw = ch * 32 + lane;
             bool flag = false;
             if (cw < p.B) {
-                const float v = p.decoded[cw * p.K];
-                flag = (v != v);
+                if (p.flags) {
+                    flag = p.flags[cw] != 0;
+                } else {
+                    const float v = p.decoded[cw * p.K];
+                    flag = (v != v);
+                }
             }
             uint32_t mask = __ballot_sync(NPD_FULL, flag);
             while (mask) {
@@ -936,6 +946,7 @@ __global__ void __launch_bounds__(128) sc_quad_kernel(const ScParams p)
     c.infty = p.infty;
     c.thr0 = 0.99f * p.infty;
 
+    unsigned long long cnt_bits = 0, cnt_blocks = 0;  // fused counting: this lane's codewords (lanes with sub == 0)
     const int64_t ngroups = (p.B + 7) / 8;
     for (int64_t grp = (int64_t)blockIdx.x * wpb + warp; grp < ngroups; grp += (int64_t)gridDim.x * wpb) {
         const int64_t cw0 = grp * 8;
@@ -1016,6 +1027,26 @@ __global__ void __launch_bounds__(128) sc_quad_kernel(const ScParams p)
         fl |= __shfl_xor_sync(NPD_FULL, fl, 8);
         fl |= __shfl_xor_sync(NPD_FULL, fl, 16);
         __syncwarp();
+        if (p.counts) {
+            // fused counting: lane (sub, cl) xors the words q = sub, sub + 4, ... of codeword cl's decisions with the
+            // transmitted u words, masked to the info positions; flagged codewords are left to the exact path
+            uint32_t e = 0u;
+            if (ok) {
+                const uint32_t *ub = p.ubits + cw * NW;
+                for (int q = sub; q < NW; q += 4) e += __popc((US[q * 8 + cl] ^ __ldg(ub + q)) & __ldg(p.info_words + q));
+            }
+            e += __shfl_xor_sync(NPD_FULL, e, 8);
+            e += __shfl_xor_sync(NPD_FULL, e, 16);
+            if (sub == 0 && ok) {
+                p.flags[cw] = fl ? 1 : 0;
+                if (!fl) {
+                    cnt_bits += e;
+                    cnt_blocks += e != 0u;
+                }
+            }
+            __syncwarp();
+            continue;
+        }
         float *dst0 = p.decoded + cw0 * p.K;
         // (measured: +4.5 % at N = 256, where the output phase is a larger share; nothing at N = 1024, so the code is
         // only compiled into the short-code kernels)
@@ -1080,6 +1111,17 @@ __global__ void __launch_bounds__(128) sc_quad_kernel(const ScParams p)
             const long long t_end = clock64();
             p.trace[0] = t_top; p.trace[1] = t_lev; p.trace[2] = t_blk; p.trace[3] = t_mrg;
             p.trace[4] = t_end - t_loop_end; p.trace[5] = t_end - t_start;
+        }
+    }
+    if (p.counts) {
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            cnt_bits += __shfl_xor_sync(NPD_FULL, cnt_bits, o);
+            cnt_blocks += __shfl_xor_sync(NPD_FULL, cnt_blocks, o);
+        }
+        if (lane == 0) {
+            if (cnt_bits) atomicAdd(p.counts + 0, cnt_bits);
+            if (cnt_blocks) atomicAdd(p.counts + 1, cnt_blocks);
         }
     }
 }
@@ -1345,7 +1387,66 @@ int dispatch(const npd_code *code, ScParams p, cudaStream_t st)
     return dispatch_group<PAC>(code, p, st);
 }
 
+// fused mode, after the exact re-decode: count the flagged codewords from their float decisions (a tie decision 0
+// differs from +-1, utils.py:23) and add the chunk's frame count
+__global__ void __launch_bounds__(256) count_flagged_kernel(const unsigned char *__restrict__ flags, const float *__restrict__ decoded,
+                                                            const uint32_t *__restrict__ ubits, const int32_t *__restrict__ info,
+                                                            int64_t B, int K, int NW, unsigned long long *counts,
+                                                            unsigned long long add_frames)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t ch = warp; ch * 32 < B; ch += nwarps) {
+        const int64_t cw = ch * 32 + lane;
+        uint32_t mask = __ballot_sync(NPD_FULL, cw < B && flags[cw] != 0);
+        while (mask) {
+            const int64_t c = ch * 32 + (__ffs(mask) - 1);
+            mask &= mask - 1;
+            uint32_t e = 0u;
+            for (int k = lane; k < K; k += 32) {
+                const int pos = __ldg(info + k);
+                const float want = ((ubits[c * NW + (pos >> 5)] >> (pos & 31)) & 1u) ? -1.0f : 1.0f;
+                e += rintf(decoded[c * K + k]) != want;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(NPD_FULL, e, o);
+            if (lane == 0 && e) {
+                atomicAdd(counts + 0, (unsigned long long)e);
+                atomicAdd(counts + 1, 1ull);
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && add_frames) atomicAdd(counts + 2, add_frames);
+}
+
 }  // namespace
+
+// internal (count_sweep.cu): SC-decode B codewords of a plain polar code with N >= 256 and accumulate
+// counts[0..2] += (bit errors, block errors, B) against the transmitted u words -- no decisions are written except the
+// exact re-decodes of flagged codewords into `decoded_scratch` [B,K]
+int npd_sc_decode_count(const npd_code *code, const float *y, float llr_scale, const uint32_t *ubits, float *decoded_scratch,
+                        unsigned char *flags, int64_t B, uint64_t *counts, cudaStream_t st)
+{
+    NPD_REQUIRE(code && y && ubits && decoded_scratch && flags && counts, "npd_sc_decode_count: null argument");
+    NPD_REQUIRE(code->pac_g == 0 && code->n >= 8 && code->K >= 1, "npd_sc_decode_count: plain polar codes with N >= 256 only");
+    if (B == 0) return NPD_OK;
+    ScParams p{};
+    p.y = y; p.decoded = decoded_scratch; p.info = code->d_info; p.frozen_words = code->d_frozen_words;
+    p.B = B; p.n = code->n; p.K = code->K; p.scale = llr_scale; p.infty = code->infty;
+    p.ubits = ubits; p.info_words = code->d_info_words; p.counts = (unsigned long long *)counts; p.flags = flags;
+    if (int rc = launch_quad(code, p, st)) return rc;
+    p.scan_flagged = 1;
+    if (int rc = dispatch_group<false>(code, p, st)) return rc;
+    DeviceProps dp;
+    if (npd_get_device_props(&dp)) return NPD_ECUDA;
+    int64_t grid = (B + 255) / 256;
+    if (grid > dp.sm_count * 4) grid = dp.sm_count * 4;
+    count_flagged_kernel<<<(unsigned)grid, 256, 0, st>>>(flags, decoded_scratch, ubits, code->d_info, B, code->K, code->N >> 5,
+                                                          (unsigned long long *)counts, (unsigned long long)B);
+    NPD_CHECK_CUDA(cudaGetLastError());
+    return NPD_OK;
+}
 
 NPD_API int npd_sc_decode(const npd_code_t *code, const float *y, float llr_scale,
                           const float *use_gt, float *leaf_llr, float *decoded, int64_t B,

@@ -225,6 +225,36 @@ def test_mc_sweep_matches_stepwise():
     assert 0 < blk < B
 
 
+@pytest.mark.parametrize("N,K,infty,B", [(256, 128, 1000.0, 3000), (1024, 512, 1000.0, 2500), (512, 200, 6.0, 2000),
+                                         (256, 128, 2.0, 1500)])
+def test_mc_sweep_fused_count_matches_oracle(N, K, infty, B):
+    """N >= 256: the sweep's decoder counts its own errors (u-domain decision words against the generator's packed u
+    words).  A small frozen prior makes the rate-0 bound fail on many codewords, which exercises the flagged ->
+    exact re-decode -> count_flagged path; counts must equal the oracle's on the very same frames either way."""
+    from neural_polar_decoder_b200 import _lib, construct, utils
+    info = np.sort(construct.polarization_weight_order(N)[:K])
+    code = _code(N, info, infty=infty)
+    h = code._handle()
+    lib = _lib.load()
+    snr, seed, chunk = 1.5, 21, 1024
+    sigma = float(np.float32(utils.snr_db2sigma(snr)))
+    ws_bytes = lib.npd_mc_sc_workspace_bytes(h.h, chunk)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    counts = torch.zeros(3, dtype=torch.int64, device="cuda")
+    _lib.check(lib.npd_mc_sc_sweep(h.h, B, chunk, sigma, utils.llr_scale(snr), seed, 2, 100, _lib._vp(ws.data_ptr()),
+                                   ws_bytes, _lib._vp(counts.data_ptr()), _lib.stream_ptr()))
+    msg = torch.empty(B, K, device="cuda")
+    y = torch.empty(B, N, device="cuda")
+    _lib.check(lib.npd_gen_encode_awgn(h.h, _lib.ptr(msg), None, _lib.ptr(y), B, sigma, seed, 2, 100, _lib.stream_ptr()))
+    _, _, do = oracle.sc_decode(y.cpu().numpy(), snr, _n(N), info, infty=infty)
+    bit, blk = oracle.count_errors(msg.cpu().numpy(), do)
+    assert counts.tolist() == [bit, blk, B]
+    assert 0 < blk < B
+    # and the plain decode entry point agrees with the oracle on the same frames (flagged codewords included)
+    _, dec = code.sc_decode_new(y, snr, return_llr=False)
+    assert np.array_equal(dec.cpu().numpy(), do)
+
+
 # ---------------------------------------------------------------------------------------------------
 # CRISP GRU sequential decoder (16-bit tensor-core operands, fp32 accumulate).  Tolerance on the logits
 # under forced (= reference) feedback: |d| <= 1e-2 * |ref| + 2e-3 (north_star's 1e-2 relative; the absolute
