@@ -115,9 +115,10 @@ int npd_scl_decode(const npd_code_t *code, const float *y, float llr_scale, int 
  * counts is a device uint64[2] that the call ACCUMULATES into (zero it first). */
 /* npd_count_errors_info: the same numerators for a decoder that returns full-length rows: msg[B,K] against
  * decoded_full[:, info_positions] with decoded_full [B,N] -- `errors_ber(msg_bits, decoded_bits[:, polar.info_positions]
- * .sign())` (rnn_all.py:875-879, run_models.py:338-346) without materialising the gathered tensor. */
+ * .sign())` (rnn_all.py:875-879, run_models.py:338-346) without materialising the gathered tensor.  take_sign != 0
+ * applies the `.sign()` to decoded_full first (logits in, e.g. convNet's), 0 compares the values as errors_ber does. */
 int npd_count_errors_info(const npd_code_t *code, const float *msg, const float *decoded_full, int64_t B,
-                          uint64_t *counts, void *stream);
+                          int take_sign, uint64_t *counts, void *stream);
 int npd_count_errors(const float *a, const float *b, int64_t B, int K, uint64_t *counts,
                      void *stream);
 

@@ -29,7 +29,7 @@ SIGNATURES = {
     "npd_scl_decode_host": (_int, [_vp, _vp, _f32, _int, _vp, _vp, _i64]),
     "npd_pac_sc_decode": (_int, [_vp, _vp, _f32, _vp, _vp, _vp, _vp, _i64, _vp]),
     "npd_count_errors": (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
-    "npd_count_errors_info": (_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "npd_count_errors_info": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp]),
     "npd_mc_gru_workspace_bytes": (_sz, [_vp, _vp, _i64]),
     "npd_mc_gru_sweep": (_int, [_vp, _vp, _vp, _i64, _i64, _f32, _u64, _u32, _u64, _vp, _sz, _vp, _vp]),
     "npd_mc_sc_workspace_bytes": (_sz, [_vp, _i64]),

@@ -94,9 +94,8 @@ def bench_gru(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def tail():
-        torch.index_select(decoded, 1, info_t, out=dec_info)
-        _lib.check(lib.npd_count_errors(_lib.ptr(msg), _lib.ptr(dec_info), B, K, _lib._vp(counts.data_ptr()), st))
+    def tail():  # errors_ber / errors_bler of decoded[:, info_positions] against the messages, one kernel
+        _lib.check(lib.npd_count_errors_info(h.h, _lib.ptr(msg), _lib.ptr(decoded), B, 0, _lib._vp(counts.data_ptr()), st))
 
     for _ in range(args.warmup):  # the WHOLE step: the gather / count kernels' first launches load their modules
         step()                    # (40 ms on a fresh box, which used to land in the timed region)
@@ -158,13 +157,13 @@ def bench_gru(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
         "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "config": {"l2_policy": "weights (4.8 MB fp16) are L2-resident by design; y = %.1f MB per GPU is read once per "
                                 "launch" % (B * N * 4 / 2 ** 20),
-                   "step": "npd_gru_decode (all N autoregressive steps, one launch) + info-bit gather + "
-                           "npd_count_errors; one NCCL all-reduce of the counters when n_gpus > 1"},
+                   "step": "npd_gru_decode (all N autoregressive steps, one launch) + npd_count_errors_info; one NCCL "
+                           "all-reduce of the counters when n_gpus > 1"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_B * N * 4,
                 "d2h_bytes_per_step": e2e_B * N * 4, "batch_per_gpu": e2e_B, "steps": e2e_steps,
                 "api": "RNN_decoder.decode(net, False, pinned host y) -> host decisions (npd_gru_decode_host pipeline)"},
-        "gpu_launches": 3 * args.steps,
+        "gpu_launches": 2 * args.steps,
         "roofline": {"kernel": "gru_decode_kernel3 (CTA-pair, cta_group::2)",
                      "bound": "tensor", "achieved": achieved,
                      "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
@@ -296,9 +295,8 @@ def bench_conv(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
         torch.cuda.synchronize()
 
     def tail():
-        # decisions on the info positions = sign(logits) (run_models.py:338-339), then the error counters
-        torch.sign(torch.index_select(logits, 1, info_t), out=dec_info)
-        _lib.check(lib.npd_count_errors(_lib.ptr(msg), _lib.ptr(dec_info), B, K, _lib._vp(counts.data_ptr()), st))
+        # decisions on the info positions = sign(logits) (run_models.py:338-339) and the error counters, one kernel
+        _lib.check(lib.npd_count_errors_info(h.h, _lib.ptr(msg), _lib.ptr(logits), B, 1, _lib._vp(counts.data_ptr()), st))
 
     for _ in range(args.warmup):  # the whole step, so that no kernel's first launch falls into the timed region
         step()
@@ -360,14 +358,14 @@ def bench_conv(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
         "config": {"l2_policy": "every step streams %.1f GB of fp16 activations through HBM between the two kernels "
                                 "(workspace %.2f GB > L2), which evicts y and the weights' L2 lines each step"
                                 % (2 * B * 16384 / 1e9, wsn / 1e9),
-                   "step": "npd_conv_forward (conv_stack_kernel + conv_fc_kernel per %d-codeword chunk) + sign/gather of "
-                           "the info positions + npd_count_errors; one NCCL all-reduce of the counters when n_gpus > 1"
+                   "step": "npd_conv_forward (conv_stack_kernel + conv_fc_kernel per %d-codeword chunk) + "
+                           "npd_count_errors_info (sign + gather + count); one NCCL all-reduce of the counters when n_gpus > 1"
                            % (wsn // (128 * 8192 * 2) * 128)},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_B * N * 4,
                 "d2h_bytes_per_step": e2e_B * N * 4, "batch_per_gpu": e2e_B, "steps": e2e_steps,
                 "api": "convNet.decode(pinned host y, info_positions, None, device) -> host bits (npd_conv_forward_host pipeline)"},
-        "gpu_launches": (2 * chunks + 4) * args.steps,
+        "gpu_launches": (2 * chunks + 1) * args.steps,
         "roofline": {"kernel": "conv_stack_kernel + conv_fc_kernel (one npd_conv_forward call)", "bound": "tensor",
                      "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["bf16_sustained"], "traffic": traffic, "traffic_source": traffic_src,

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) count_kernel(const float *__restrict__ a,
 // (the GRU / convNet decoders return [B,N]; callers of the reference index [:, info_positions], rnn_all.py:875)
 __global__ void __launch_bounds__(256) count_gather_kernel(const float *__restrict__ a, const float *__restrict__ b,
                                                            const int32_t *__restrict__ cols, int64_t B, int K, int ldb,
-                                                           unsigned long long *counts, unsigned long long add_frames)
+                                                           int take_sign, unsigned long long *counts, unsigned long long add_frames)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -57,8 +57,11 @@ __global__ void __launch_bounds__(256) count_gather_kernel(const float *__restri
     unsigned long long bits = 0, blocks = 0;
     for (int64_t r = warp; r < B; r += nwarps) {
         uint32_t mism = 0;
-        for (int k = lane; k < K; k += 32)
-            mism += rintf(a[r * K + k]) != rintf(b[r * ldb + cols[k]]);
+        for (int k = lane; k < K; k += 32) {
+            float v = b[r * ldb + cols[k]];
+            if (take_sign) v = v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f);  // `.sign()` of logits (run_models.py:338-339)
+            mism += rintf(a[r * K + k]) != rintf(v);
+        }
         const uint32_t any = __ballot_sync(NPD_FULL, mism != 0);
         bits += mism;
         if (lane == 0 && any) blocks += 1;
@@ -72,8 +75,8 @@ __global__ void __launch_bounds__(256) count_gather_kernel(const float *__restri
     }
 }
 
-int launch_count_gather(const float *a, const float *b, const int32_t *cols, int64_t B, int K, int ldb, uint64_t *counts,
-                        uint64_t add_frames, cudaStream_t st)
+int launch_count_gather(const float *a, const float *b, const int32_t *cols, int64_t B, int K, int ldb, int take_sign,
+                        uint64_t *counts, uint64_t add_frames, cudaStream_t st)
 {
     DeviceProps dp;
     if (npd_get_device_props(&dp)) return NPD_ECUDA;
@@ -81,7 +84,7 @@ int launch_count_gather(const float *a, const float *b, const int32_t *cols, int
     const int64_t cap = (int64_t)dp.sm_count * 8;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-    count_gather_kernel<<<(unsigned)grid, 256, 0, st>>>(a, b, cols, B, K, ldb, (unsigned long long *)counts,
+    count_gather_kernel<<<(unsigned)grid, 256, 0, st>>>(a, b, cols, B, K, ldb, take_sign, (unsigned long long *)counts,
                                                         (unsigned long long)add_frames);
     NPD_CHECK_CUDA(cudaGetLastError());
     return NPD_OK;
@@ -114,12 +117,12 @@ NPD_API int npd_count_errors(const float *a, const float *b, int64_t B, int K, u
 }
 
 NPD_API int npd_count_errors_info(const npd_code_t *code, const float *msg, const float *decoded_full, int64_t B,
-                                  uint64_t *counts, void *stream)
+                                  int take_sign, uint64_t *counts, void *stream)
 {
     NPD_REQUIRE(code && msg && decoded_full && counts, "npd_count_errors_info: null argument");
     NPD_REQUIRE(B >= 0 && code->K >= 1, "npd_count_errors_info: bad shape");
     if (B == 0) return NPD_OK;
-    return launch_count_gather(msg, decoded_full, code->d_info, B, code->K, code->N, counts, 0, (cudaStream_t)stream);
+    return launch_count_gather(msg, decoded_full, code->d_info, B, code->K, code->N, take_sign, counts, 0, (cudaStream_t)stream);
 }
 
 namespace {
@@ -254,7 +257,7 @@ NPD_API int npd_mc_gru_sweep(const npd_gru_t *gru, const npd_code_t *code, const
         if (rc) return rc;
         rc = npd_gru_decode(gru, loss_code, y, nullptr, nullptr, nullptr, dec, b, gws_bytes ? gws : nullptr, gws_bytes, stream);
         if (rc) return rc;
-        rc = launch_count_gather(msg, dec, code->d_info, b, code->K, code->N, counts, (uint64_t)b, st);
+        rc = launch_count_gather(msg, dec, code->d_info, b, code->K, code->N, 0, counts, (uint64_t)b, st);
         if (rc) return rc;
     }
     return NPD_OK;

@@ -30,11 +30,11 @@ def _count_into(buf_row, a, b):
                                             _lib._vp(buf_row.data_ptr()), _lib.stream_ptr()))
 
 
-def _count_info_into(buf_row, handle, msg, full):
+def _count_info_into(buf_row, handle, msg, full, take_sign=False):
     """msg [B,K] against full[:, info positions of `handle`] (full [B,N]) without materialising the gather."""
     msg = msg.contiguous()
     full = full.contiguous()
-    _lib.check(_lib.load().npd_count_errors_info(handle.h, _lib.ptr(msg), _lib.ptr(full), msg.shape[0],
+    _lib.check(_lib.load().npd_count_errors_info(handle.h, _lib.ptr(msg), _lib.ptr(full), msg.shape[0], int(take_sign),
                                                  _lib._vp(buf_row.data_ptr()), _lib.stream_ptr()))
 
 

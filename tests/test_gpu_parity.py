@@ -577,3 +577,29 @@ def test_sc_code_without_information_bits():
     assert dec.shape == (100, 0) and np.array_equal(llr.cpu().numpy(), lo)
     llr_h, dec_h = code.sc_decode_new(torch.from_numpy(y), 1.0)
     assert dec_h.shape == (100, 0) and np.array_equal(llr_h.numpy(), lo)
+
+
+def test_fp16_operand_range_guards():
+    """Weights are rounded to fp16 tensor-core operands: creating a decoder from weights outside fp16's finite range must
+    fail loudly (NPD_EUNSUPPORTED) instead of decoding with inf operands."""
+    import argparse
+    from neural_polar_decoder_b200 import _lib, synth
+    from neural_polar_decoder_b200.models import convNet
+    from neural_polar_decoder_b200.rnn_all import RNN_Model
+    sd = synth.gru_state_dict(3, 32, 256, 2)
+    sd["rnn.weight_hh_l1"] = sd["rnn.weight_hh_l1"].copy()
+    sd["rnn.weight_hh_l1"][7, 9] = 7.0e4
+    net = RNN_Model('GRU', 34, 256, 1, 2, 32, 0, 0)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    with pytest.raises(_lib.NpdError) as e:
+        net.npd_handle(32)
+    assert e.value.code == _lib.NPD_EUNSUPPORTED and "fp16" in str(e.value)
+    csd = synth.conv_state_dict(4, 64, 128)
+    key = sorted(k for k in csd if k.endswith("weight") and csd[k].ndim == 3)[0]
+    csd[key] = csd[key].copy()
+    csd[key].flat[5] = float("nan")
+    cnet = convNet(argparse.Namespace(embed_dim=128, max_len=64, N=64, dont_use_bias=False, dropout=0.0))
+    cnet.load_state_dict({k: torch.from_numpy(v) for k, v in csd.items()})
+    with pytest.raises(_lib.NpdError) as e:
+        cnet.npd_handle()
+    assert e.value.code == _lib.NPD_EUNSUPPORTED
