@@ -60,13 +60,19 @@ WORKLOADS = {
                    desc="fused SC Monte-Carlo sweep Polar(1024,512), 2 dB: generate + encode + AWGN + SC + count on the device"),
     "mc4096": dict(kind="mc", N=4096, K=2048, snr=2.0, batch=1 << 20, chunk=1 << 15,
                    desc="fused SC Monte-Carlo sweep Polar(4096,2048), 2 dB: generate + encode + AWGN + SC + count on the device"),
+    "train64": dict(kind="train", N=64, K=22, snr=0.0, batch=4096, tf32=0,
+                    desc="CRISP GRU(2x512) training iteration Polar(64,22), run_crisp.sh batch 4096, teacher-forced: forward + "
+                         "BPTT + clip + AdamW on the device (fp32 GEMMs)"),
+    "train64tf32": dict(kind="train", N=64, K=22, snr=0.0, batch=4096, tf32=1,
+                        desc="the same training iteration with TF32 tensor-core GEMMs"),
     "conv64": dict(kind="conv", N=64, K=22, snr=0.0, batch=131072,
                    desc="convNet(embed_dim 128) one-shot decoder Polar(64,22), AWGN 0 dB, synthetic weights"),
 }
 # what the default line carries besides its top level (gru64): name -> (steps cap, with a CPU baseline)
 DEFAULT_ALSO = [("sc1024", 20, True), ("conv64", 20, True), ("mc1024", 20, False), ("mc256", 6, False),
                 ("mc4096", 10, False), ("gru64sweep", 10, False), ("sc256", 10, False), ("sc4096", 10, False),
-                ("enc1024", 10, False), ("gru32", 10, False), ("pac32", 10, False)]
+                ("enc1024", 10, False), ("gru32", 10, False), ("pac32", 10, False), ("train64", 5, False),
+                ("train64tf32", 5, False)]
 
 
 def gru_weights_note(w):
@@ -196,6 +202,9 @@ def cpu_step_fn(w, threads):
     if kind_w in ("gru", "grusweep"):
         arm = ca.make_gru_arm(w["N"], w["K"], 512, 0)
         return (lambda B, seed: ca.gru_rate(w["N"], w["K"], w["snr"], B, threads, seed, arm=arm)[:3]), arm[2], arm[3], 256
+    if kind_w == "train":
+        arm = ca.make_train_arm(w["N"], w["K"], 512, 0)
+        return (lambda B, seed: ca.train_rate(w["N"], w["K"], w["snr"], B, threads, seed, arm=arm)[:3]), arm[2], arm[3], 128
     if kind_w == "conv":
         arm = ca.make_conv_arm(w["N"], 128, 0)
         return (lambda B, seed: ca.conv_rate(w["N"], w["snr"], B, threads, seed, arm=arm)[:3]), arm[1], arm[2], 256
@@ -395,6 +404,8 @@ def main():
             r = bench_sc(a, wl, rank, world, local_rank)
         elif kind == "mc":
             r = bench_mc(a, wl, rank, world, local_rank)
+        elif kind == "train":
+            r = bench_train(a, wl, rank, world, local_rank)
         else:
             from neural_polar_decoder_b200 import bench_neural
             r = bench_neural.bench(a, wl, rank, world, local_rank, ClockSampler, measured_peaks)
@@ -735,6 +746,82 @@ def bench_mc(args, w, rank, world, local_rank):
                      "note": "algorithmic bytes = the decoder's 4N+4K per frame; the sweep is issue-bound (generator Philox + "
                              "SC level walk), DESIGN.md 4.4"},
         "ber": cnt[0] / float(frames * K), "bler": cnt[1] / float(frames), "frames": frames, "_sample": sample,
+    }
+
+
+def bench_train(args, w, rank, world, local_rank):
+    """one iteration of the reference's training loop (rnn_all.py:1399-1437) per step, teacher-forced, on a
+    fresh batch generated on the device.  The reference has no distributed training: under torchrun every rank trains an
+    independent replica ("replicas only"), value = trained codewords/s over all replicas."""
+    import torch
+    import torch.distributed as dist
+    from neural_polar_decoder_b200 import _lib, construct, synth, utils
+    from neural_polar_decoder_b200.polar import PolarCode
+    from neural_polar_decoder_b200.rnn_all import RNN_Model, RNN_decoder
+    from neural_polar_decoder_b200.train import GRUTrainer
+    lib = _lib.load()
+    N, K, B, snr = w["N"], w["K"], w["batch"], w["snr"]
+    dev = torch.device("cuda", local_rank)
+    rs = construct.reference_rs256()
+    code = PolarCode(int(np.log2(N)), K, None, rs=rs[rs < N])
+    info = code.info_positions
+    sd = synth.gru_state_dict(11, N, 512, 2, head_gain=2.0)
+    net = RNN_Model('GRU', N + 2, 512, 1, 2, N, 0, 0)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    dec = RNN_decoder('y_input', N, info, onehot=True)
+    loss_code = dec._loss_code(info)
+    tr = GRUTrainer(net, N, B, tf32=bool(w["tf32"]))
+    h = code._handle()
+    sigma = float(np.float32(utils.snr_db2sigma(snr)))
+    msg = torch.empty(B, K, device=dev)
+    y = torch.empty(B, N, device=dev)
+    gt = torch.ones(B, N, device=dev)
+    info_t = torch.as_tensor(np.asarray(info), device=dev)
+    st = _lib.stream_ptr()
+    losses = []
+
+    def step(i, want=False):
+        _lib.check(lib.npd_gen_encode_awgn(h.h, _lib.ptr(msg), None, _lib.ptr(y), B, sigma, 2026, i, rank * B, st))
+        gt[:, info_t] = msg
+        loss, _, _ = tr.step(loss_code, y, gt, True, 1e-3, 0.25, want_loss=want)
+        if want:
+            losses.append(loss)
+
+    ms, clocks = _time_steps(torch, dist, world, dev, local_rank, lambda: [step(i, i == 0) for i in range(args.warmup)],
+                             lambda i: step(args.warmup + i), args.steps)
+    step(args.warmup + args.steps, True)
+    # end to end: pinned host y / gt in, loss out, every step
+    y_h, gt_h = y.cpu().pin_memory(), gt.cpu().pin_memory()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(3):
+        loss, _, _ = tr.step(loss_code, y_h, gt_h, True, 1e-3, 0.25, want_loss=True)
+    e2e_dt = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    peaks = measured_peaks()
+    step_ms = ms / args.steps
+    flops = 3.0 * (N * (2 * 3 * 512 * 3 * 512 + 2 * 512) + 2 * N * 3 * 512) * B  # forward + two backward GEMM families
+    achieved = flops / (step_ms * 1e-3) / 1e12
+    return {
+        "metric": "trained codewords/sec", "value": world * B * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "tf32" if w["tf32"] else "f32", "data": "synthetic",
+        "config": {"step": "npd_gen_encode_awgn + gt scatter + npd_gru_train_step (64 forward steps with saved gates, 64 backward "
+                           "steps, clip_grad_norm_ 0.25, AdamW lr 1e-3); independent replicas when n_gpus > 1",
+                   "loss_first_last": [losses[0], losses[-1]] if losses else None},
+        "clocks": clocks,
+        "e2e": {"value": world * 3 * B / float(e2e_t.item()), "unit": UNIT, "h2d_bytes_per_step": 2 * B * N * 4,
+                "d2h_bytes_per_step": 8, "batch_per_gpu": B, "steps": 3,
+                "api": "train.GRUTrainer.step(loss_code, pinned host y, pinned host gt, ...) -> host loss"},
+        "gpu_launches": (2 + 64 * 6 + 64 * 9 + 12) * args.steps,
+        "roofline": {"kernel": "cuBLAS SGEMM (library GEMMs) + cell_fwd / cell_bwd / head / adamw kernels", "bound": "tensor",
+                     "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["bf16_sustained"], "traffic": None, "peak_source": peaks["src"],
+                     "alg_flops_per_launch": flops,
+                     "note": "3 x the decode's 302 MFLOP per codeword; fp32 (parity) GEMMs run on the CUDA cores, so the 16-bit "
+                             "tensor peak is the contract's denominator, not this arithmetic's ceiling"},
     }
 
 

@@ -157,6 +157,63 @@ def gru_rate(N, K, snr, B, threads, seed=0, H=512, arm=None):
     return B / dt, B, dt, kind, how
 
 
+# ---- CRISP GRU training iteration (rnn_all.py:1399-1437) -------------------------------------------------------------
+def make_train_arm(N, K, H=512, seed=0):
+    """-> (step_fn(y, gt) running one forward / backward / clip / AdamW iteration, info, kind, how)."""
+    import torch
+    info = info_set(N, K)
+    idx = torch.as_tensor(info.astype(np.int64))
+    if have_reference():
+        ra = ref_shim.load("rnn_all")
+        ra.args = ref_shim.make_args(N=N, K=K)
+        torch.manual_seed(seed)
+        net = ra.RNN_Model("GRU", N + 2, H, 1, 2, N, 0, 0)
+        dec = ra.RNN_decoder("y_input", N, info, onehot=True)
+        fwd = lambda y, gt: dec.decode(net, True, y, gt, 1.0)  # noqa: E731
+        kind, how = "reference", "unmodified rnn_all.RNN_decoder.decode(net, True, y, gt, 1.0) + MSELoss + backward + clip + AdamW"
+    else:
+        port = _PortGRU(N, H, None, seed)
+        net = port.net.train()
+        eye = torch.eye(2)
+
+        def fwd(y, gt):
+            B = y.shape[0]
+            hidden = torch.zeros(2, B, H)
+            outs = []
+            for ii in range(N):
+                prev = torch.ones(B) if ii == 0 else gt[:, ii - 1]
+                out, hidden = net(torch.cat([y.unsqueeze(1), eye[(0.5 + 0.5 * prev).long()].view(B, 1, 2)], 2), hidden)
+                outs.append(out.view(-1))
+            return torch.stack(outs, 1)
+        kind, how = "port", "torch autograd over nn.GRU(seq_len 1) steps as rnn_all.py:425-449 + MSELoss + backward + clip + AdamW"
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-3)
+    loss_fn = torch.nn.MSELoss()
+
+    def step(y, gt):
+        y, gt = torch.from_numpy(y), torch.from_numpy(gt)
+        loss = loss_fn(fwd(y, gt)[:, idx], gt[:, idx])
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 0.25)
+        opt.step()
+        opt.zero_grad()
+        return float(loss.item())
+    return step, info, kind, how
+
+
+def train_rate(N, K, snr, B, threads, seed=0, H=512, arm=None):
+    import torch
+    torch.set_num_threads(threads)
+    fn, info, kind, how = arm if arm is not None else make_train_arm(N, K, H, seed)
+    rs = np.random.RandomState(seed)
+    msg, y = _frames(rs, B, N, K, info, snr, int(np.log2(N)))
+    gt = np.ones((B, N), np.float32)
+    gt[:, info] = msg
+    t0 = time.perf_counter()
+    fn(y, gt)
+    dt = time.perf_counter() - t0
+    return B / dt, B, dt, kind, how
+
+
 # ---- SC family ---------------------------------------------------------------------------------------------------
 def make_sc_arm(N, K, snr, threads, pac_g=None, L=0):
     """-> (decode_fn(y), info, kind, how)."""
