@@ -47,7 +47,11 @@ struct ScParams {
     const uint32_t *ubits;       // [B, N/32] transmitted u (message bits at the info positions, 0 elsewhere) or null
     const uint32_t *info_words;  // [N/32] bit i = position i carries information
     unsigned long long *counts;  // [2] bit errors, block errors (accumulated) -- non-null selects the fused mode
-    unsigned char *flags;        // [B] fused mode: 1 = codeword needs the exact re-decode (replaces the NaN sentinel)
+    unsigned char *flags;        // [B] fused / packed mode: 1 = codeword needs the exact re-decode (replaces the NaN sentinel)
+    // packed mode (sub-block decodes of the split large-N path): decision words (u domain) and the block's encoded
+    // partial sums (x domain) go out as bit words at [cw * out_words + word_off + q]; no float outputs
+    uint32_t *us_out, *xs_out;
+    int out_words, word_off;
     long long *trace;      // bench-only (NPD_SC_TRACE): cycles of warp 0 / block 0's second group: top, levels, block, merge, output, total
 };
 
@@ -1027,6 +1031,18 @@ __global__ void __launch_bounds__(128) sc_quad_kernel(const ScParams p)
         fl |= __shfl_xor_sync(NPD_FULL, fl, 8);
         fl |= __shfl_xor_sync(NPD_FULL, fl, 16);
         __syncwarp();
+        if (p.us_out) {
+            if (ok) {
+                uint32_t *uo = p.us_out + cw * p.out_words + p.word_off, *xo = p.xs_out + cw * p.out_words + p.word_off;
+                for (int q = sub; q < NW; q += 4) {
+                    uo[q] = US[q * 8 + cl];
+                    xo[q] = PS[q * 8 + cl];  // after the last merge: the Plotkin encoding of the block's decisions
+                }
+                if (sub == 0 && fl) p.flags[cw] = 1;
+            }
+            __syncwarp();
+            continue;
+        }
         if (p.counts) {
             // fused counting: lane (sub, cl) xors the words q = sub, sub + 4, ... of codeword cl's decisions with the
             // transmitted u words, masked to the info positions; flagged codewords are left to the exact path
@@ -1271,11 +1287,10 @@ int scratch_pool(cudaMemPool_t *out)
     return NPD_OK;
 }
 
-int launch_quad(const npd_code *code, ScParams p, cudaStream_t st)
+int launch_quad_n(const npd_code *code, const int n, ScParams p, cudaStream_t st)
 {
     DeviceProps dp;
     if (npd_get_device_props(&dp)) return NPD_ECUDA;
-    const int n = code->n;
     // N >= 2048: levels n-2 and n-3 (3/4 of the stored tree) go to a global scratch: 22 KB instead of 70 KB of shared
     // memory per warp at N = 4096, 10 warps per SM instead of 3 (1.17e7 -> 1.62e7 cw/s; one scratch level: 1.57e7).
     // At N = 1024 the same change measures slower at every occupancy (best: one scratch level, 16 warps, 0.835 ms per
@@ -1356,6 +1371,147 @@ int launch_quad(const npd_code *code, ScParams p, cudaStream_t st)
         }
     }
     return NPD_OK;
+}
+
+// =================================================================================================
+// split path (N = 4096; works for 2048 too): the top log2(N/1024) levels as streaming kernels, then 1024-leaf sub-block decodes
+// =================================================================================================
+// A codeword of N = Q * 1024 leaves is Q sub-blocks that the successive-cancellation schedule visits in order; the input
+// LLRs of sub-block r (level 10 of the tree) depend on y and on the ENCODED decisions of sub-blocks < r only.  So:
+//   for r in 0..Q-1:  split_top_kernel   level-10 LLRs of sub-block r for every codeword of the chunk (one thread per
+//                                        element: Q coalesced y loads, the f / g of the top one or two levels)
+//                     sc_quad_kernel<10> decodes the sub-blocks (its y = that LLR buffer, scale 1, its frozen words =
+//                                        the sub-block's; packed mode: decision words + encoded partial sums as bits)
+//   then one output kernel (float decisions on the info positions + NaN sentinel of flagged codewords, or the fused
+//   error count).  Arithmetic and its order are those of the monolithic kernel's top phase (quad_top_phase), so results
+//   stay bit-identical.  Why: at N = 4096 the monolithic kernel keeps only 8-10 warps per SM resident (22 KB of state
+//   per warp + a global scratch) and re-reads 16 KB of y per codeword four times through a latency-bound warp; here the
+//   top levels are bandwidth-bound streaming passes at full occupancy and the sub-block decode runs at the N = 1024
+//   kernel's 12 warps per SM with its whole tree in shared memory.
+template <int T>  // T = log2(Q): 1 or 2 levels above the sub-blocks
+__global__ void __launch_bounds__(256) split_top_kernel(const float *__restrict__ y, const uint32_t *__restrict__ xs,
+                                                        float *__restrict__ llr, int64_t C, int r, float scale, int words)
+{
+    constexpr int Q = 1 << T, S = 1024;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C * S) return;
+    const int64_t cw = i >> 10;
+    const int j = (int)(i & (S - 1));
+    const float *row = y + cw * (int64_t)(Q * S);
+    const uint32_t *xw = xs + cw * words;  // encoded decisions of this codeword's finished sub-blocks, 32 words each
+    auto bit = [&](int blk) -> uint32_t { return ((xw[blk * 32 + (j >> 5)] >> (j & 31)) & 1u) << 31; };
+    float o;
+    if (T == 1) {
+        const float v0 = scale * row[j], v1 = scale * row[j + S];  // polar.py:468-469
+        o = (r == 0) ? npd_f_minsum(v0, v1) : __uint_as_float(__float_as_uint(v0) ^ bit(0)) + v1;
+    } else {
+        const float v0 = scale * row[j], v1 = scale * row[j + S], v2 = scale * row[j + 2 * S], v3 = scale * row[j + 3 * S];
+        float a0, a1;  // level n-1 elements j and j + 1024
+        if (r >= 2) {  // right half: g with the encoding of the left half's decisions = (x0 ^ x1, x1)
+            const uint32_t b0 = bit(0), b1 = bit(1);
+            a0 = __uint_as_float(__float_as_uint(v0) ^ (b0 ^ b1)) + v2;
+            a1 = __uint_as_float(__float_as_uint(v1) ^ b1) + v3;
+        } else {
+            a0 = npd_f_minsum(v0, v2);
+            a1 = npd_f_minsum(v1, v3);
+        }
+        o = (r & 1) ? __uint_as_float(__float_as_uint(a0) ^ bit(r - 1)) + a1 : npd_f_minsum(a0, a1);
+    }
+    llr[i] = o;
+}
+
+// decision words -> float decisions on the info positions (one warp per codeword, lane = k) + the NaN sentinel
+__global__ void __launch_bounds__(256) split_out_kernel(const uint32_t *__restrict__ us, const unsigned char *__restrict__ flags,
+                                                        const int32_t *__restrict__ info, float *__restrict__ decoded,
+                                                        int64_t C, int K, int words)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t cw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (cw >= C) return;
+    const uint32_t *w = us + cw * words;
+    for (int k = lane; k < K; k += 32) {
+        const int pos = __ldg(info + k);
+        decoded[cw * K + k] = ((w[pos >> 5] >> (pos & 31)) & 1u) ? -1.0f : 1.0f;
+    }
+    __syncwarp();
+    if (lane == 0 && flags[cw]) decoded[cw * K] = __int_as_float(0x7fc00000);  // exact re-decode (dispatch_group, scan mode)
+}
+
+// fused counting over the decision words (one warp per codeword); flagged codewords are left to the exact path
+__global__ void __launch_bounds__(256) split_count_kernel(const uint32_t *__restrict__ us, const uint32_t *__restrict__ ubits,
+                                                          const uint32_t *__restrict__ info_words,
+                                                          const unsigned char *__restrict__ flags_in, unsigned char *__restrict__ flags_out,
+                                                          int64_t C, int words, unsigned long long *counts)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t cw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (cw >= C) return;
+    const bool fl = flags_in[cw] != 0;
+    uint32_t e = 0u;
+    for (int q = lane; q < words; q += 32) e += __popc((us[cw * words + q] ^ ubits[cw * words + q]) & __ldg(info_words + q));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(NPD_FULL, e, o);
+    if (lane == 0) {
+        flags_out[cw] = fl ? 1 : 0;
+        if (!fl && e) {
+            atomicAdd(counts + 0, (unsigned long long)e);
+            atomicAdd(counts + 1, 1ull);
+        }
+    }
+}
+
+int launch_quad_split(const npd_code *code, ScParams p, cudaStream_t st)
+{
+    const int n = code->n, T = n - 10, Q = 1 << T, words = code->N >> 5;
+    DeviceProps dp;
+    if (npd_get_device_props(&dp)) return NPD_ECUDA;
+    cudaMemPool_t pool;
+    if (int rc = scratch_pool(&pool)) return rc;
+    // one chunk per 131072 codewords (0.5 GB of level-10 LLRs): the sub-block decode runs in rounds of sm_count x 12 warps x
+    // 8 codewords, so large chunks keep the last, partly filled round's share small
+    const int64_t chunk = p.B < 131072 ? p.B : 131072;
+    float *llr = nullptr;
+    uint32_t *us = nullptr, *xs = nullptr;
+    unsigned char *flags = nullptr;
+    NPD_CHECK_CUDA(cudaMallocFromPoolAsync((void **)&llr, (size_t)chunk * 1024 * sizeof(float), pool, st));
+    NPD_CHECK_CUDA(cudaMallocFromPoolAsync((void **)&us, (size_t)chunk * words * 4, pool, st));
+    NPD_CHECK_CUDA(cudaMallocFromPoolAsync((void **)&xs, (size_t)chunk * words * 4, pool, st));
+    NPD_CHECK_CUDA(cudaMallocFromPoolAsync((void **)&flags, (size_t)chunk, pool, st));
+    for (int64_t c0 = 0; c0 < p.B; c0 += chunk) {
+        const int64_t C = p.B - c0 < chunk ? p.B - c0 : chunk;
+        NPD_CHECK_CUDA(cudaMemsetAsync(flags, 0, (size_t)C, st));
+        for (int r = 0; r < Q; ++r) {
+            const unsigned grid = (unsigned)((C * 1024 + 255) / 256);
+            if (T == 1) split_top_kernel<1><<<grid, 256, 0, st>>>(p.y + c0 * code->N, xs, llr, C, r, p.scale, words);
+            else split_top_kernel<2><<<grid, 256, 0, st>>>(p.y + c0 * code->N, xs, llr, C, r, p.scale, words);
+            NPD_CHECK_CUDA(cudaGetLastError());
+            ScParams s{};
+            s.y = llr; s.scale = 1.0f; s.infty = p.infty; s.B = C; s.n = 10; s.K = 0;
+            s.frozen_words = p.frozen_words + r * 32;
+            s.us_out = us; s.xs_out = xs; s.out_words = words; s.word_off = r * 32; s.flags = flags;
+            if (int rc = launch_quad_n(code, 10, s, st)) return rc;
+        }
+        const unsigned wgrid = (unsigned)((C * 32 + 255) / 256);
+        if (p.counts)
+            split_count_kernel<<<wgrid, 256, 0, st>>>(us, p.ubits + c0 * words, p.info_words, flags, p.flags + c0, C, words, p.counts);
+        else
+            split_out_kernel<<<wgrid, 256, 0, st>>>(us, flags, p.info, p.decoded + c0 * p.K, C, p.K, words);
+        NPD_CHECK_CUDA(cudaGetLastError());
+    }
+    NPD_CHECK_CUDA(cudaFreeAsync(llr, st));
+    NPD_CHECK_CUDA(cudaFreeAsync(us, st));
+    NPD_CHECK_CUDA(cudaFreeAsync(xs, st));
+    NPD_CHECK_CUDA(cudaFreeAsync(flags, st));
+    return NPD_OK;
+}
+
+int launch_quad(const npd_code *code, ScParams p, cudaStream_t st)
+{
+    // N = 4096: split path, 1.37 ms per 32768 codewords against 1.55 ms for the monolithic kernel with its global scratch
+    // (NPD_SC_SPLIT=0 in a debug-knob build).  At N = 2048 the monolithic kernel still wins (1.19 vs 1.24 ms per 65536):
+    // its two top-phase passes over y are cheap next to the split path's extra launches and round quantisation.
+    if (code->n >= env_int("NPD_SC_SPLIT_MIN_N", 12) && env_int("NPD_SC_SPLIT", 1) != 0) return launch_quad_split(code, p, st);
+    return launch_quad_n(code, code->n, p, st);
 }
 
 template <bool PAC, bool EXTRAS>

@@ -87,11 +87,11 @@ def test_sc_vs_oracle_seeded(N, K, B):
         assert torch.equal(dec2, dec)
 
 
-@pytest.mark.parametrize("N,K,B", [(1024, 512, 1500), (2048, 1024, 1203), (4096, 2048, 1001)])
+@pytest.mark.parametrize("N,K,B", [(1024, 512, 1500), (2048, 1024, 1203), (4096, 2048, 1001), (4096, 2048, 9001)])
 def test_sc_quad_kernel_many_groups(N, K, B):
-    """The throughput kernel (decisions only; level n-2 in the global scratch for N >= 2048) on enough codewords to
-    occupy several warps per SM, ragged last group: identical to the leaf-LLR path, itself checked against the oracle
-    above, and to the oracle on a sample."""
+    """The throughput path (decisions only; N >= 2048: top levels as streaming kernels + 1024-leaf sub-block decodes,
+    N = 4096: split path) on enough codewords to occupy several warps per SM, ragged last group: identical to
+    the leaf-LLR path, itself checked against the oracle above, and to the oracle on a sample."""
     from neural_polar_decoder_b200 import construct
     rs = np.random.RandomState(N)
     info = np.sort(construct.polarization_weight_order(N)[:K])
@@ -226,7 +226,8 @@ def test_mc_sweep_matches_stepwise():
 
 
 @pytest.mark.parametrize("N,K,infty,B", [(256, 128, 1000.0, 3000), (1024, 512, 1000.0, 2500), (512, 200, 6.0, 2000),
-                                         (256, 128, 2.0, 1500)])
+                                         (256, 128, 2.0, 1500), (2048, 1024, 1000.0, 300), (2048, 700, 5.0, 200),
+                                         (4096, 2048, 8.0, 100)])
 def test_mc_sweep_fused_count_matches_oracle(N, K, infty, B):
     """N >= 256: the sweep's decoder counts its own errors (u-domain decision words against the generator's packed u
     words).  A small frozen prior makes the rate-0 bound fail on many codewords, which exercises the flagged ->
