@@ -337,6 +337,27 @@ def parity_check(w, sample):
     return None
 
 
+def curve_check(wl, r, world):
+    """BER / BLER of the timed steps against the curve the LIVE reference printed for the same checkpoint at this SNR
+    (tests/golden/<checkpoint>.json): two-sample z-score of the block-error rates.  Every step decodes the same resident
+    frames, so the sample is batch x n_gpus frames."""
+    import math
+    meta_path = wl["checkpoint"][:-3] + ".json"
+    try:
+        with open(meta_path) as f:
+            meta = json.load(f)
+        i = [abs(s - wl["snr"]) < 1e-9 for s in meta["snr_range"]].index(True)
+    except Exception as e:  # no recorded point at this SNR
+        return {"ok": None, "note": "no reference point: %s" % e}
+    n1, n2 = wl["batch"] * world, meta["test_size"]
+    p1, p2 = r["bler"], meta["blers_RNN"][i]
+    p = (p1 * n1 + p2 * n2) / float(n1 + n2)
+    z = (p1 - p2) / math.sqrt(max(p * (1 - p), 1e-12) * (1.0 / n1 + 1.0 / n2))
+    return {"snr_db": wl["snr"], "ber": r["ber"], "bler": p1, "reference_ber": meta["bers_RNN"][i], "reference_bler": p2,
+            "frames": n1, "reference_frames": n2, "z_bler": z, "ok": abs(z) < 3.29,
+            "criterion": "|z| < 3.29 (two-sided 99.9 % two-sample interval on the block-error rate)"}
+
+
 # ---------------------------------------------------------------------------------------------------
 # product arm
 # ---------------------------------------------------------------------------------------------------
@@ -411,6 +432,8 @@ def main():
             r = bench_neural.bench(a, wl, rank, world, local_rank, ClockSampler, measured_peaks)
         r["config"] = dict(workload_config(name, wl), **{k: v for k, v in r.get("config", {}).items()
                                                          if k not in ("workload", "desc", "N", "K", "snr_db", "batch_per_gpu", "weights")})
+        if kind == "gru" and wl.get("checkpoint") and rank == 0:
+            r["curve_check"] = curve_check(wl, r, world)
         sample = r.pop("_sample", None)
         if rank == 0 and sample is not None and not args.no_parity:
             r["parity_checked"] = parity_check(wl, sample)
@@ -423,7 +446,7 @@ def main():
     res = run_workload(args.workload, w, args.steps, True)
     if also:
         keep = ("value", "unit", "steps", "ms_per_step", "dtype", "config", "e2e", "gpu_launches", "roofline", "ber", "bler",
-                "frames", "cpu_baseline", "parity_checked", "scaling", "clocks")
+                "frames", "cpu_baseline", "parity_checked", "curve_check", "scaling", "clocks", "metric")
         others = {}
         for name, cap, with_cpu in also:
             r = run_workload(name, dict(WORKLOADS[name]), min(args.steps, cap), with_cpu)

@@ -194,6 +194,35 @@ def gru_cases():
     np.savez_compressed(os.path.join(OUT, "gru.npz"), **out)
 
 
+def gru_trained_cases():
+    """Logits of the reference-TRAINED CRISP GRU (tests/golden/crisp_gru_N64_K22_H512.pt, oracle/train_ref_checkpoint.py)
+    from the live reference on noisy codewords at -2 / 0 / 2 dB: where |logit| ~ 1, which synthetic weights never reach."""
+    ra = ref_shim.load("rnn_all")
+    path = os.path.join(OUT, "crisp_gru_N64_K22_H512.pt")
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    a = ck["args"]
+    N, K, H = a.N, a.K, a.rnn_feature_size
+    ra.args = ref_shim.make_args(N=N, K=K, target_K=a.target_K)
+    code = ref_shim.get_code("Polar", a.rate_profile, N, K, target_K=a.target_K)
+    net = ra.RNN_Model("GRU", N + 2, H, 1, 2, N, 0, 0)
+    net.load_state_dict(ck["net"])
+    dec = ra.RNN_decoder("y_input", N, code.info_inds, onehot=True)
+    rs = np.random.RandomState(64)
+    out = {"cfg": np.array([N, K, H], dtype=np.int64), "info": np.asarray(code.info_inds, dtype=np.int32)}
+    ys, ds, ls, snrs = [], [], [], []
+    for snr in (-2.0, 0.0, 2.0):
+        msg = bpsk_msgs(rs, 96, K)
+        y = noisy(rs, code.encode_plotkin(torch.from_numpy(msg)).numpy(), snr)
+        d_ref = dec.decode(net, False, torch.from_numpy(y))
+        d2, lg = _ref_gru_logits(ra, net, dec, torch.from_numpy(y), N, code.info_inds)
+        assert torch.equal(d_ref, d2)
+        ys.append(y); ds.append(d_ref.numpy()); ls.append(lg.numpy()); snrs += [snr] * 96
+        print("gru_trained snr", snr, "|logit| mean on info", float(lg[:, code.info_inds].abs().mean()),
+              "BER", float((d_ref[:, code.info_inds].numpy() != msg).mean()), flush=True)
+    out.update(y=np.concatenate(ys), decoded=np.concatenate(ds), logits=np.concatenate(ls), snr=np.array(snrs))
+    np.savez_compressed(os.path.join(OUT, "gru_trained.npz"), **out)
+
+
 TRAIN_KEYS = ("rnn.weight_ih_l0", "rnn.weight_hh_l0", "rnn.bias_ih_l0", "rnn.bias_hh_l0", "rnn.weight_ih_l1",
               "rnn.weight_hh_l1", "rnn.bias_ih_l1", "rnn.bias_hh_l1", "linear.weight", "linear.bias")
 
@@ -425,6 +454,8 @@ if __name__ == "__main__":
     todo = a.only.split(",") if a.only else ["misc", "pac", "gru", "gru_modes", "gru_cond", "scl", "conv", "polar"]
     if "gru_train" in todo:
         gru_train_cases()
+    if "gru_trained" in todo:
+        gru_trained_cases()
     if "gru_cond" in todo:
         gru_cond_cases()
     if "gru_modes" in todo:

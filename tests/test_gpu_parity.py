@@ -308,6 +308,35 @@ def test_gru_logits_vs_reference_fixture(golden, name):
     assert (dfree == ref_dec).mean() > 0.99
 
 
+def test_gru_trained_checkpoint_logits_vs_reference(golden):
+    """The reference-TRAINED Polar(64,22), H = 512 checkpoint (config 1): forced-feedback logits against the live
+    reference's within 1e-2 |ref| + 2e-3 where |logit| ~ 1, free-running decisions equal except behind a near-zero logit."""
+    import os
+    from neural_polar_decoder_b200 import cli
+    from neural_polar_decoder_b200.rnn_all import RNN_decoder, gru_decode
+    from conftest import GOLDEN
+    path = os.path.join(GOLDEN, "crisp_gru_N64_K22_H512.pt")
+    if not os.path.exists(path):
+        pytest.skip("no trained Polar(64,22) checkpoint fixture")
+    g = golden("gru_trained")
+    N, K, H = [int(v) for v in g["cfg"]]
+    net, cargs, _ = cli.net_from_checkpoint(path)
+    dec = RNN_decoder('y_input', N, g["info"], onehot=True)
+    y = torch.from_numpy(g["y"]).cuda()
+    ref_logits, ref_dec = g["logits"], g["decoded"]
+    assert np.abs(ref_logits[:, g["info"]]).mean() > 0.3, "a trained net regresses to +-1 targets"
+    _, lg = gru_decode(net, dec._loss_code(dec.info_inds), y, forced=torch.from_numpy(ref_dec).cuda(), want_logits=True)
+    err = np.abs(lg.cpu().numpy() - ref_logits)
+    tol = _gru_tol(ref_logits)
+    print("trained: logit err max %.3e, worst err/tol %.2f, |logit| mean %.2f" % (err.max(), (err / tol).max(),
+                                                                                  np.abs(ref_logits).mean()))
+    assert (err <= tol).all(), err.max()
+    dfree = dec.decode(net, False, y).cpu().numpy()
+    risky_before = np.cumsum(np.abs(ref_logits) <= tol, axis=1) > 0
+    assert not ((dfree != ref_dec) & ~risky_before).any()
+    assert (dfree == ref_dec).mean() > 0.995
+
+
 def test_gru_vs_oracle_ragged_batch():
     """B not a multiple of the 64-codeword tile, several CTAs; oracle = fp32 torch restatement."""
     from neural_polar_decoder_b200 import construct
