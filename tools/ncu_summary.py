@@ -37,3 +37,24 @@ def num(k):
 
 
 print("dram traffic per launch (read+write) bytes: %d" % (num("dram__bytes_read.sum") + num("dram__bytes_write.sum")))
+
+# more than one captured launch (e.g. the N = 4096 split path = 4 x top kernel + 4 x sub-block decode + output kernel):
+# per-launch duration / DRAM bytes and the totals
+if len(rows) > 3:
+    def val(row, key):
+        i = hdr.index(key)
+        u, v = units[i], row[i]
+        f = float(v.replace(",", "") or 0)
+        return f * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "Tbyte": 1e12, "ms": 1e3, "us": 1.0, "ns": 1e-3,
+                    "s": 1e6}.get(u, 1)
+    tot_t = tot_b = 0.0
+    print("all %d captured launches:" % (len(rows) - 2))
+    for r in rows[2:]:
+        if len(r) != len(hdr):
+            continue
+        t = val(r, "gpu__time_duration.sum")
+        b = val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")
+        tot_t += t
+        tot_b += b
+        print("  %-70s %10.1f us %14d B" % (r[hdr.index("Kernel Name")][:70], t, b))
+    print("total: %.1f us, dram traffic (read+write) %d B" % (tot_t, tot_b))
