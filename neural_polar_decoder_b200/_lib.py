@@ -38,6 +38,7 @@ SIGNATURES = {
     "npd_gru_destroy": (_int, [_vp]),
     "npd_gru_set_head_mlp": (_int, [_vp, _int, _int, _vp]),
     "npd_gru_workspace_bytes": (_sz, [_vp, _i64]),
+    "npd_gru_set_option": (_int, [_vp, _int, _int]),
     "npd_gru_decode": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
     "npd_gru_decode_h0": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
     "npd_gru_trainer_param_count": (_sz, [_int, _int]),

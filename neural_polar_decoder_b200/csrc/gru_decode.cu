@@ -69,6 +69,7 @@ struct GruParams {
     const float *head_b;         // [head_depth - 1][Yh]
     const float *head_wl;        // [Yh]; its bias is b_out
     __half *head_act;            // workspace: [CTA][2][64][Yh] activations (L2-resident ping-pong)
+    __half *h_lo;                // pair kernel: rounding residual of the fp16 state, [pair][2 layers][H/32][16 chunks][32 units][8]
     const uint32_t *info_words;  // bit i = position i is an info (loss) position
     float *logits;               // [B,N] or null
     float *decoded;              // [B,N]
@@ -216,14 +217,35 @@ __device__ __forceinline__ float rcp_approx(float x)
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-// one MUFU.TANH per activation (max relative error 2^-11, the rounding the fp16 recurrent state gets anyway);
-// sigmoid(x) = 0.5 + 0.5 tanh(x / 2) takes the pre-halved argument
-__device__ __forceinline__ float tanh_f(float x)
+// Precision of the recurrent path (measured on the reference-TRAINED Polar(64,22) checkpoint, where |logit| ~ 1 and the
+// update gate z sits near 1 for long-memory units).  h' = (1 - z) n + z h accumulates over N steps whatever
+// perturbs z, n or the stored h by ~2^-12: with tanh.approx (max relative error 2^-11) for the gates, r / z parked as fp16
+// between their accumulators and the n accumulator, and the state kept only as the fp16 MMA operand, the forced-feedback
+// logit error reached 7e-3 (1.5-2.4 x the north-star tolerance 1e-2 |ref| + 2e-3).  Therefore:
+//   NPD_GRU_ZC    the update gate is computed as zc = 1 - z = sigmoid(-x) through ex2.approx + rcp.approx (two MUFU, relative
+//                 error ~1e-7) and parked as fp16: its RELATIVE rounding keeps long-memory units (z -> 1) exact where a parked
+//                 fp16 z (or tanh.approx's 2^-11) perturbs h by 2.4e-4 |h - n| every step; h' = h - zc (h - n)
+//   NPD_GRU_LO    the rounding residual of the fp16 state (hnew - fp16(hnew), itself fp16) lives in an L2-resident global
+//                 buffer owned by the thread that wrote it; the update reads hi + lo, the tensor cores read hi
+//   NPD_GRU_ACT   bits 1 / 2: r / n through ex2 + rcp as well (measured: no gain in logit error, +3 % time; off)
+#ifndef NPD_GRU_ACT
+#define NPD_GRU_ACT 0
+#endif
+#ifndef NPD_GRU_ZC
+#define NPD_GRU_ZC 1
+#endif
+#ifndef NPD_GRU_LO
+#define NPD_GRU_LO 1
+#endif
+__device__ __forceinline__ float tanh_mufu(float x)
 {
     float r;
     asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+// tanh(x) = 1 - 2 / (1 + e^(2x)); e = inf gives 1, e = 0 gives -1; absolute error ~1e-7
+__device__ __forceinline__ float tanh_exact(float x) { return fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(x * 2.885390082f)), 1.0f); }
+__device__ __forceinline__ float tanh_f(float x) { return (NPD_GRU_ACT & 4) ? tanh_exact(x) : tanh_mufu(x); }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b)
 {
     const __half2 h = __floats2half2_rn(a, b);
@@ -233,7 +255,15 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t w)
 {
     return __half22float2(*reinterpret_cast<const __half2 *>(&w));
 }
-__device__ __forceinline__ float sigmoid_half_arg(float half_x) { return fmaf(tanh_f(half_x), 0.5f, 0.5f); }
+// sigmoid(x) = 0.5 + 0.5 tanh(x / 2) takes the pre-halved argument; EXACT: 1 / (1 + e^(-x)) = rcp(1 + ex2(-2 half_x log2 e))
+template <bool EXACT>
+__device__ __forceinline__ float sigmoid_half_arg_t(float half_x)
+{
+    return EXACT ? rcp_approx(1.0f + ex2_approx(half_x * -2.885390082f)) : fmaf(tanh_mufu(half_x), 0.5f, 0.5f);
+}
+__device__ __forceinline__ float sigmoid_half_arg(float half_x) { return sigmoid_half_arg_t<false>(half_x); }
+// 1 - sigmoid(x) = 1 / (1 + e^x) from the pre-halved argument, relative error ~1e-7
+__device__ __forceinline__ float sigmoid_compl_half_arg(float half_x) { return rcp_approx(1.0f + ex2_approx(half_x * 2.885390082f)); }
 
 // byte offset of element (row c, k) inside a K-major SWIZZLE_128B operand buffer of 64-row chunks
 __device__ __forceinline__ uint32_t b_off(int c, int k)
@@ -1147,7 +1177,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
                         wo = __ldg(p.w_out + u);
                     }
                     const uint32_t t0 = tmem_base + lane_addr + col0;
-                    uint32_t rp[CW3 / 2], zp[CW3 / 2];  // r and z of the 32 columns as fp16 pairs
+                    uint32_t rp[CW3 / 2], zp[CW3 / 2];  // r and z (NPD_GRU_ZC: 1 - z) of the 32 columns as fp16 pairs
                     // ---- R, then Z: drained as soon as they complete ----
 #pragma unroll
                     for (int a = 0; a < 2; ++a) {
@@ -1170,14 +1200,43 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
 #pragma unroll
                             for (int i = 0; i < 8; i += 2) {
                                 const bool p0 = (layer == 0) && ((bits >> (cc + i)) & 1u), p1 = (layer == 0) && ((bits >> (cc + i + 1)) & 1u);
-                                const float s0 = sigmoid_half_arg(fmaf(v[i], 0.5f, a == 0 ? (p0 ? hr1 : hr0) : (p0 ? hz1 : hz0)));
-                                const float s1 = sigmoid_half_arg(fmaf(v[i + 1], 0.5f, a == 0 ? (p1 ? hr1 : hr0) : (p1 ? hz1 : hz0)));
+                                const float x0 = fmaf(v[i], 0.5f, a == 0 ? (p0 ? hr1 : hr0) : (p0 ? hz1 : hz0));
+                                const float x1 = fmaf(v[i + 1], 0.5f, a == 0 ? (p1 ? hr1 : hr0) : (p1 ? hz1 : hz0));
+                                float s0, s1;
+                                if (a == 0) {
+                                    s0 = sigmoid_half_arg_t<(NPD_GRU_ACT & 2) != 0>(x0);
+                                    s1 = sigmoid_half_arg_t<(NPD_GRU_ACT & 2) != 0>(x1);
+                                } else if (NPD_GRU_ZC) {
+                                    s0 = sigmoid_compl_half_arg(x0);
+                                    s1 = sigmoid_compl_half_arg(x1);
+                                } else {
+                                    s0 = sigmoid_half_arg(x0);
+                                    s1 = sigmoid_half_arg(x1);
+                                }
                                 (a == 0 ? rp : zp)[(cc + i) >> 1] = pack_h2(s0, s1);
                             }
                         }
                     }
                     // ---- the job's last accumulators: NH (layer 0; NI is the hoisted projection), NH + NI (layer 1) ----
                     if (warp == 0) trace_ev(p, step, 19 + 0 * (layer * 4 + j));
+#if NPD_GRU_LO
+                    // residual of this thread's 32 state values, 16 bytes (8 codewords) per chunk, laid out
+                    // [pair][layer][unit / 32][chunk of 8 codewords][unit % 32][8] so that a warp's access is 512 contiguous bytes
+                    // (the kernel streams ~8 TB/s of weights from L2: half-used 32-byte sectors here cost 4.5 ms per launch)
+                    uint4 *lo_base = reinterpret_cast<uint4 *>(p.h_lo) +
+                                     ((((size_t)(blockIdx.x >> 1) * 2 + layer) * (H / 32) + (u >> 5)) * (PAIR_CW / 8) + (col0 >> 3)) * 32 + (u & 31);
+#ifndef NPD_GRU_LO_AHEAD
+#define NPD_GRU_LO_AHEAD 1  // chunks fetched ahead of their use (1..4): measured flat, the cost is L2 bandwidth, not latency
+#endif
+                    uint4 lo_q[NPD_GRU_LO_AHEAD];
+#pragma unroll
+                    for (int c = 0; c < NPD_GRU_LO_AHEAD; ++c) lo_q[c] = make_uint4(0u, 0u, 0u, 0u);
+                    const bool use_lo = p.h_lo != nullptr;  // npd_gru_set_option(NPD_GRU_OPT_RESIDUAL_STATE): uniform
+                    if (use_lo && step > 0) {
+#pragma unroll
+                        for (int c = 0; c < NPD_GRU_LO_AHEAD; ++c) lo_q[c] = __ldcg(lo_base + 32 * c);
+                    }
+#endif
                     wait_acc(3);
                     if (layer == 1) wait_acc(2);
                     if (warp == 0) trace_ev(p, step, 20 + 2 * (layer * 4 + j));
@@ -1187,6 +1246,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
                         unsigned short hold[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) hold[i] = ld_cluster_u16(h_owner + b_off(row0 + cc + i, u));
+#if NPD_GRU_LO
+                        uint4 *lo_ptr = lo_base + 32 * (cc / 8);
+                        const uint4 lo4 = lo_q[(cc / 8) % NPD_GRU_LO_AHEAD];  // fetched NPD_GRU_LO_AHEAD chunks ahead
+                        if (use_lo && cc / 8 + NPD_GRU_LO_AHEAD < CW3 / 8 && step > 0) lo_q[(cc / 8) % NPD_GRU_LO_AHEAD] = __ldcg(lo_ptr + 32 * NPD_GRU_LO_AHEAD);
+#endif
                         tmem_ld8(t0 + 3 * PAIR_CW + cc, aNH);
                         if (layer == 1) tmem_ld8(t0 + 2 * PAIR_CW + cc, aNI);
                         tmem_ld_wait();
@@ -1204,6 +1268,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
                             }
                         }
                         float hsum[8];
+#if NPD_GRU_LO
+                        const uint32_t lo_in[4] = {lo4.x, lo4.y, lo4.z, lo4.w};
+                        uint32_t lo_out[4] = {0u, 0u, 0u, 0u};
+#endif
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const bool plus = (layer == 0) && ((bits >> (cc + i)) & 1u);
@@ -1211,9 +1279,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
                             const float r = (i & 1) ? r2.y : r2.x, z = (i & 1) ? z2.y : z2.x;
                             const float nn = tanh_f(fmaf(r, aNH[i] + b_hn, aNI[i] + (plus ? bn1 : bn0)));
                             const float ho = __half2float(__ushort_as_half(hold[i]));
-                            const float hnew = fmaf(z, ho - nn, nn);  // (1 - z) n + z h
+                            float hnew = NPD_GRU_ZC ? fmaf(-z, ho - nn, ho)   // h - (1 - z) (h - n), `z` holds 1 - z
+                                                    : fmaf(z, ho - nn, nn);   // (1 - z) n + z h
+#if NPD_GRU_LO
+                            // the residual of the old state enters last (its load has the whole gate math to land): + z lo
+                            hnew = fmaf(__half2float(__ushort_as_half((unsigned short)(lo_in[i >> 1] >> (16 * (i & 1))))),
+                                        NPD_GRU_ZC ? 1.0f - z : z, hnew);
+#endif
                             hsum[i] = wo * hnew;
                             const unsigned short hb = __half_as_ushort(__float2half_rn(hnew));
+#if NPD_GRU_LO
+                            lo_out[i >> 1] |= (uint32_t)__half_as_ushort(__float2half_rn(hnew - __half2float(__ushort_as_half(hb)))) << (16 * (i & 1));
+#endif
                             if (j == JOBS2 - 1) {
                                 // the last accumulator of the layer's last job is full: every MMA reading the old state retired
                                 st_cluster_u16(h_owner + b_off(row0 + cc + i, u), hb);
@@ -1222,6 +1299,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
                                 if ((i & 1) == 0) staged[si] = hb; else staged[si] |= (uint32_t)hb << 16;
                             }
                         }
+#if NPD_GRU_LO
+                        if (use_lo) __stcg(lo_ptr, make_uint4(lo_out[0], lo_out[1], lo_out[2], lo_out[3]));
+#endif
                         if (layer == 1 && need_head) {
                             // head: reduce the 8 columns over the warp's 32 units; lane l < 8 ends with column cc + l
 #pragma unroll
@@ -1353,6 +1433,7 @@ struct npd_gru {
     float *d_consts0, *d_consts1, *d_w_out;
     size_t smem_bytes;
     int head_depth, head_yh;   // MLP head (npd_gru_set_head_mlp); depth 0 = the Linear(H,1) head of npd_gru_create
+    int residual_state;        // npd_gru_set_option(NPD_GRU_OPT_RESIDUAL_STATE): 1 (default) = fp16 state + fp16 residual
     __half *d_head_w1, *d_head_wh;
     float *d_head_b, *d_head_wl;
 };
@@ -1471,6 +1552,7 @@ NPD_API int npd_gru_create(int N, int H, const float *w_ih0, const float *w_hh0,
     npd_gru *g = (npd_gru *)calloc(1, sizeof(npd_gru));
     if (!g) return NPD_ENOMEM;
     g->N = N; g->H = H; g->tiles_per_step = n_tiles; g->b_out = b_out[0];
+    g->residual_state = 1;
     g->smem_bytes = Smem::total(H);
     g->tiles_per_step2 = n_tiles2;
     g->smem_bytes3 = Smem3::total(H);
@@ -1583,9 +1665,25 @@ NPD_API int npd_gru_set_head_mlp(npd_gru_t *g, int depth, int Yh, const float *h
     return NPD_OK;
 }
 
+// bytes of the pair kernel's residual-state buffer: [pair][2 layers][H][128 codewords] fp16
+static size_t gru_lo_bytes(const npd_gru *g, int64_t B)
+{
+    if (!NPD_GRU_LO || !g->residual_state || !g->d_wpack2 || g->head_depth > 1) return 0;
+    return (size_t)((B + 2 * TILE_B - 1) / (2 * TILE_B) + 1) * 2 * g->H * (2 * TILE_B) * sizeof(__half);
+}
+
+NPD_API int npd_gru_set_option(npd_gru_t *g, int option, int value)
+{
+    NPD_REQUIRE(g, "npd_gru_set_option: null handle");
+    NPD_REQUIRE(option == NPD_GRU_OPT_RESIDUAL_STATE, "npd_gru_set_option: unknown option %d", option);
+    g->residual_state = value != 0;
+    return NPD_OK;
+}
+
 NPD_API size_t npd_gru_workspace_bytes(const npd_gru_t *g, int64_t B)
 {
-    if (!g || g->head_depth <= 1 || B <= 0) return 0;
+    if (!g || B <= 0) return 0;
+    if (g->head_depth <= 1) return gru_lo_bytes(g, B);  // optional: without it the library's own pool is used
     return (size_t)((B + TILE_B - 1) / TILE_B + 1) * 2 * TILE_B * g->head_yh * sizeof(__half);  // +1: the padding CTA of a cluster
 }
 
@@ -1621,6 +1719,20 @@ NPD_API int npd_gru_decode_h0(const npd_gru_t *g, const npd_code_t *code, const 
         p.head_b = g->d_head_b; p.head_wl = g->d_head_wl; p.head_act = (__half *)ws;
     }
     { const char *d = npd_knob("NPD_GRU_PAIR"); if (d) use_pair = use_pair && atoi(d) != 0; }
+    // residual of the fp16 recurrent state (pair kernel): the caller's workspace when it is large enough, else a
+    // stream-ordered allocation from the library's pool (memory stays cached across calls)
+    const size_t lo_need = use_pair ? gru_lo_bytes(g, B) : 0;
+    void *lo_owned = nullptr;
+    if (lo_need) {
+        if (ws && ws_bytes >= lo_need) {
+            p.h_lo = (__half *)ws;
+        } else {
+            cudaMemPool_t pool;
+            if (int rc = npd_scratch_pool(&pool)) return rc;
+            NPD_CHECK_CUDA(cudaMallocFromPoolAsync(&lo_owned, lo_need, pool, (cudaStream_t)stream));
+            p.h_lo = (__half *)lo_owned;
+        }
+    }
     // the 2-SM tensor-copy variant (no relay) works but measures slower than relay + linear bulk copies (12.4 vs 11.4 ms
     // per 37888 codewords): opt-in with NPD_GRU_TMAP=1
     // NPD_GRU_QUAD=1: clusters of four (two MMA pairs that take turns fetching every half-tile and multicast it to the CTA
@@ -1654,6 +1766,7 @@ NPD_API int npd_gru_decode_h0(const npd_gru_t *g, const npd_code_t *code, const 
     cfg.numAttrs = 1;
     NPD_CHECK_CUDA(cudaLaunchKernelExC(&cfg, use_pair ? gru_kernel3_for(g->H) : gru_kernel_for(g->H), args));
     NPD_CHECK_CUDA(cudaGetLastError());
+    if (lo_owned) NPD_CHECK_CUDA(cudaFreeAsync(lo_owned, (cudaStream_t)stream));
     if (trace_path) {
         std::vector<long long> h((size_t)g->N * TRACE_SLOTS);
         NPD_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));

@@ -63,6 +63,9 @@ struct DeviceProps {
 };
 int npd_get_device_props(DeviceProps *p);
 
+// library-owned stream-ordered memory pool that keeps its memory across synchronisations (sc_decode.cu)
+int npd_scratch_pool(cudaMemPool_t *out);
+
 // fused-sweep internals (encode_channel.cu / sc_decode.cu, used by count_sweep.cu)
 int npd_gen_encode_awgn_bits(const npd_code *code, uint32_t *ubits, float *y, int64_t B, float sigma, uint64_t seed,
                              uint32_t point, uint64_t cw_offset, cudaStream_t st);

@@ -1287,6 +1287,10 @@ int scratch_pool(cudaMemPool_t *out)
     return NPD_OK;
 }
 
+}  // namespace
+int npd_scratch_pool(cudaMemPool_t *out) { return scratch_pool(out); }  // shared with gru_decode.cu (residual state)
+namespace {
+
 int launch_quad_n(const npd_code *code, const int n, ScParams p, cudaStream_t st)
 {
     DeviceProps dp;

@@ -106,13 +106,25 @@ class RNN_Model(nn.Module):
         if not self._supported():
             raise NotImplementedError("fused decode supports GRU, 2 layers, unidirectional, no LayerNorm, 1 output")
         sd = self.state_dict()
-        key = (N, onehot, y_in, torch.cuda.current_device()) + tuple((k, v._version, v.data_ptr()) for k, v in sd.items())
+        key = (N, onehot, y_in, _GRU_PRECISION, torch.cuda.current_device()) + tuple((k, v._version, v.data_ptr()) for k, v in sd.items())
         if self._npd is not None and self._npd[0] == key:
             return self._npd[1]
         handle = GruHandle(N, self.feature_size, sd, onehot=onehot, y_in=y_in, head_depth=self.out_linear_depth,
                            y_hidden=self.y_hidden_size)
         self._npd = (key, handle)
         return handle
+
+
+_GRU_PRECISION = "exact"
+
+
+def set_gru_precision(mode):
+    """'exact' (default): the CTA-pair kernel keeps the fp16 rounding residual of the recurrent state (include/npd.h,
+    NPD_GRU_OPT_RESIDUAL_STATE) -- logits of trained checkpoints within 1e-2 |ref| + 2e-3 of the reference;
+    'fast': fp16-only state, ~14 % faster, logit error up to ~3 x larger.  Applies to handles created afterwards."""
+    global _GRU_PRECISION
+    assert mode in ("exact", "fast")
+    _GRU_PRECISION = mode
 
 
 class GruHandle:
@@ -155,6 +167,7 @@ class GruHandle:
         self._keep = None
         if mlp is not None:
             _lib.check(lib.npd_gru_set_head_mlp(h, int(head_depth), int(y_hidden), ctypes.c_void_p(mlp.data_ptr())))
+        _lib.check(lib.npd_gru_set_option(h, 1, int(_GRU_PRECISION == "exact")))  # NPD_GRU_OPT_RESIDUAL_STATE
 
     def __del__(self):
         try:

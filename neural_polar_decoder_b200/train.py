@@ -77,7 +77,7 @@ class GRUTrainer:
                 sd[k].copy_(torch.from_numpy(blob[o:o + n].reshape(tuple(sd[k].shape))))
                 o += n
         if hasattr(net, "_npd"):
-            net._npd = {}  # repacked decode weights are stale now
+            net._npd = None  # repacked decode weights are stale now
         return net
 
     def step(self, loss_code, y, gt, teacher_forced, lr, clip=0.25, apply_update=True, want_logits=False, want_loss=True):

@@ -337,6 +337,34 @@ def test_gru_trained_checkpoint_logits_vs_reference(golden):
     assert (dfree == ref_dec).mean() > 0.995
 
 
+def test_gru_fast_precision_mode_is_looser_but_bounded(golden):
+    """rnn_all.set_gru_precision('fast') drops the residual state: same decisions away from near-zero logits, logit error
+    within 4 x the tolerance on the trained checkpoint (measured ~1.3 x), and 'exact' is restored afterwards."""
+    import os
+    from neural_polar_decoder_b200 import cli, rnn_all
+    from neural_polar_decoder_b200.rnn_all import RNN_decoder, gru_decode
+    from conftest import GOLDEN
+    path = os.path.join(GOLDEN, "crisp_gru_N64_K22_H512.pt")
+    if not os.path.exists(path):
+        pytest.skip("no trained Polar(64,22) checkpoint fixture")
+    g = golden("gru_trained")
+    net, _, _ = cli.net_from_checkpoint(path)
+    dec = RNN_decoder('y_input', 64, g["info"], onehot=True)
+    y, forced = torch.from_numpy(g["y"]).cuda(), torch.from_numpy(g["decoded"]).cuda()
+    tol = _gru_tol(g["logits"])
+    errs = {}
+    try:
+        for mode in ("fast", "exact"):
+            rnn_all.set_gru_precision(mode)
+            _, lg = gru_decode(net, dec._loss_code(dec.info_inds), y, forced=forced, want_logits=True)
+            errs[mode] = np.abs(lg.cpu().numpy() - g["logits"])
+    finally:
+        rnn_all.set_gru_precision("exact")
+    print("fast worst err/tol %.2f, exact %.2f" % ((errs["fast"] / tol).max(), (errs["exact"] / tol).max()))
+    assert (errs["exact"] <= tol).all() and (errs["fast"] <= 4 * tol).all()
+    assert errs["exact"].mean() < errs["fast"].mean()
+
+
 def test_gru_vs_oracle_ragged_batch():
     """B not a multiple of the 64-codeword tile, several CTAs; oracle = fp32 torch restatement."""
     from neural_polar_decoder_b200 import construct
