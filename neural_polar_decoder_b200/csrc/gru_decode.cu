@@ -661,10 +661,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel(const GruPar
                         for (int i = 0; i < 8; ++i) {
                             const bool plus = (layer == 0) && ((bits >> (cc + i)) & 1u);
                             const float r = sigmoid_half_arg(fmaf(aR[i], 0.5f, plus ? hr1 : hr0));
-                            const float z = sigmoid_half_arg(fmaf(aZ[i], 0.5f, plus ? hz1 : hz0));
                             const float nn = tanh_f(fmaf(r, aNH[i] + b_hn, aNI[i] + (plus ? bn1 : bn0)));
                             const float hold = __half2float(*reinterpret_cast<const __half *>(s_h + b_off(col0 + cc + i, u)));
+#if NPD_GRU_ZC
+                            // update gate as zc = 1 - z through ex2 + rcp (see NPD_GRU_ZC above): h' = h - zc (h - n)
+                            const float zc = sigmoid_compl_half_arg(fmaf(aZ[i], 0.5f, plus ? hz1 : hz0));
+                            const float hnew = fmaf(-zc, hold - nn, hold);
+#else
+                            const float z = sigmoid_half_arg(fmaf(aZ[i], 0.5f, plus ? hz1 : hz0));
                             const float hnew = fmaf(z, hold - nn, nn);  // (1 - z) n + z h
+#endif
                             if (layer == 1) head[cc + i] = fmaf(wo, hnew, head[cc + i]);
                             const unsigned short hb = __half_as_ushort(__float2half_rn(hnew));
                             if (j == JOBS - 1) {
