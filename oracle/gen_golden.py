@@ -410,6 +410,30 @@ def conv_cases():
     np.savez_compressed(os.path.join(OUT, "conv.npz"), **out)
 
 
+def conv_trained_cases():
+    """Logits of the reference-TRAINED convNet (tests/golden/conv_N64_K22_E128.pt, oracle/train_ref_conv_checkpoint.py)
+    from the live reference's forward on noisy codewords at -2 / 0 / 2 dB."""
+    md = ref_shim.load("models")
+    ck = torch.load(os.path.join(OUT, "conv_N64_K22_E128.pt"), map_location="cpu", weights_only=False)
+    a = ck["args"]
+    net = md.convNet(a)
+    net.load_state_dict(ck["xformer"])
+    net.eval()
+    code = ref_shim.get_code("Polar", "polar", a.N, a.K)
+    rs = np.random.RandomState(65)
+    ys, ls, bs = [], [], []
+    for snr in (-2.0, 0.0, 2.0):
+        msg = bpsk_msgs(rs, 96, a.K)
+        y = noisy(rs, code.encode_plotkin(torch.from_numpy(msg)).numpy(), snr)
+        with torch.no_grad():
+            _, bits, _, logits, _ = net(torch.from_numpy(y), None, None, "cpu")
+        ys.append(y); ls.append(logits.squeeze(-1).numpy()); bs.append(bits.squeeze(-1).numpy())
+        print("conv_trained snr", snr, "|logit| mean", float(logits.abs().mean()),
+              "BER", float((bits.squeeze(-1)[:, code.info_positions].numpy() != msg).mean()), flush=True)
+    np.savez_compressed(os.path.join(OUT, "conv_trained.npz"), y=np.concatenate(ys), logits=np.concatenate(ls),
+                        bits=np.concatenate(bs), info=np.asarray(code.info_positions, dtype=np.int32))
+
+
 def misc_cases():
     """Info sets and the reference's error counters on small hand-made inputs."""
     ra = ref_shim.load("rnn_all")
@@ -456,6 +480,8 @@ if __name__ == "__main__":
         gru_train_cases()
     if "gru_trained" in todo:
         gru_trained_cases()
+    if "conv_trained" in todo:
+        conv_trained_cases()
     if "gru_cond" in todo:
         gru_cond_cases()
     if "gru_modes" in todo:

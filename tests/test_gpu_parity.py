@@ -575,6 +575,28 @@ def test_conv_logits_vs_reference_fixture(golden):
     assert torch.equal(bits2, bits)
 
 
+def test_conv_trained_checkpoint_logits_vs_reference(golden):
+    """The reference-TRAINED convNet (c2n curriculum K = 1..22 run by the live run_models.py): logits through the
+    `'xformer'` checkpoint loader within 1e-2 |ref| + 2e-3 of the live reference's, decisions equal away from zero."""
+    import os
+    from neural_polar_decoder_b200 import run_models
+    from conftest import GOLDEN
+    path = os.path.join(GOLDEN, "conv_N64_K22_E128.pt")
+    if not os.path.exists(path):
+        pytest.skip("no trained convNet checkpoint fixture")
+    g = golden("conv_trained")
+    net, cargs, step = run_models.net_from_checkpoint(path)
+    y, ref = torch.from_numpy(g["y"]).cuda(), g["logits"]
+    lg = net.logits(y).cpu().numpy()
+    err, tol = np.abs(lg - ref), _conv_tol(ref)
+    print("conv trained: logit err max %.3e mean %.3e, worst err/tol %.3f, |logit| mean %.2f" % (
+        err.max(), err.mean(), (err / tol).max(), np.abs(ref).mean()))
+    assert (err <= tol).all(), err.max()
+    bits, _ = net.decode(y, g["info"], None, "cuda")
+    safe = np.abs(ref) > tol
+    assert np.array_equal(bits.squeeze(-1).cpu().numpy()[safe], g["bits"][safe])
+
+
 @pytest.mark.parametrize("B", [1, 5, 6, 7, 127, 129, 1000])
 def test_conv_vs_oracle_ragged_batches(B):
     """Batch sizes around the 6-codeword CTA pass and the 128-codeword GEMM tile; oracle = fp32 torch
