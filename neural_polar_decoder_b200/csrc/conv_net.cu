@@ -20,9 +20,9 @@
 // 3-stage bulk-copy pipeline), then GELU -> fp16 operand in shared memory -> W2 (N = 64) -> GELU -> W3
 // (N = 64) as two more MMA passes, and LayerNorm(64, eps 1e-6) in registers (one thread = one codeword).
 //
-// Precision: fp16 operands (weights, activations), fp32 accumulation and bias; the conv-stack GELU runs on fp16
-// pairs (its result is the next fp16 operand), the Linear-head GELUs and LayerNorm in fp32.  GELU is the tanh
-// form (tc_common.cuh); parity target is the reference's logits within 1e-2 relative + 2e-3 absolute.
+// Precision: fp16 operands (weights, activations), fp32 accumulation, bias, GELU and LayerNorm.  GELU is an
+// erf-accurate fitted form evaluated in fp32 (tc_common.cuh: the tanh form alone costs 3e-3 on the logits of the
+// reference-trained checkpoint); parity target is the reference's logits within 1e-2 relative + 2e-3 absolute.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -119,10 +119,17 @@ __device__ __forceinline__ void epi_block(uint32_t taddr, int c, const float *bi
         const float4 b0 = *reinterpret_cast<const float4 *>(bias + cc);
         const float4 b1 = *reinterpret_cast<const float4 *>(bias + cc + 4);
         uint4 pk;
+#ifdef NPD_CONV_GELU_TANH_H2  // round 1: tanh form on fp16 pairs (3e-3 logit error on the trained checkpoint)
         pk.x = gelu_h2(pack_half2(v[8 * j + 0] + b0.x, v[8 * j + 1] + b0.y));
         pk.y = gelu_h2(pack_half2(v[8 * j + 2] + b0.z, v[8 * j + 3] + b0.w));
         pk.z = gelu_h2(pack_half2(v[8 * j + 4] + b1.x, v[8 * j + 5] + b1.y));
         pk.w = gelu_h2(pack_half2(v[8 * j + 6] + b1.z, v[8 * j + 7] + b1.w));
+#else  // erf-accurate GELU in fp32 (tc_common.cuh), rounded once to the next layer's fp16 operand
+        pk.x = pack_half2(gelu_f(v[8 * j + 0] + b0.x), gelu_f(v[8 * j + 1] + b0.y));
+        pk.y = pack_half2(gelu_f(v[8 * j + 2] + b0.z), gelu_f(v[8 * j + 3] + b0.w));
+        pk.z = pack_half2(gelu_f(v[8 * j + 4] + b1.x), gelu_f(v[8 * j + 5] + b1.y));
+        pk.w = pack_half2(gelu_f(v[8 * j + 6] + b1.z), gelu_f(v[8 * j + 7] + b1.w));
+#endif
         uint4 *dst = reinterpret_cast<uint4 *>(orow + ((((cc & 63) >> 3) ^ sw) << 4));
         if (RES) {  // input_{k+1} = layers_k(input_k) + input_k (models.py:748-755)
             const uint4 xr = *dst;

@@ -116,17 +116,24 @@ __device__ __forceinline__ float rcp_approx(float x)
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-// GELU, tanh form written as x * sigmoid(2 sqrt(2/pi) (x + 0.044715 x^3)): 2 MUFU + 5 FP32 ops, relative
-// error of the sigmoid ~2^-22.  |gelu_tanh - gelu_erf| <= 3e-4 everywhere (SURVEY.md 7 measured 1.1e-5 on the
-// logits), inside the 1e-2 logit tolerance and below the fp16 rounding of the activations it feeds.
+// GELU.  The reference's nn.GELU() is the exact erf form (models.py:703).  The usual tanh form
+// 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))) is off by up to 4.7e-4, which on the reference-TRAINED convNet
+// accumulates through the ten conv layers to 3e-3 on the logits -- by itself the whole tolerance (round 1 measured 1e-5 on
+// random-init weights).  Here: x * sigmoid(2 x (c1 + c3 x^2 + c5 x^4)) with the odd quintic fitted to the erf form
+// (minimax over [-8, 8]: |gelu_fit - gelu_erf| <= 2.6e-5), the sigmoid through ex2.approx + rcp.approx (relative
+// error ~2^-22): 2 MUFU + 7 FP32 operations.  The polynomial argument is clamped to [-8, 8] (its quintic term turns it over
+// beyond |x| ~ 10); outside, sigmoid is 0 or 1 to fp32 precision and the result is 0 or x like the erf form.
 __device__ __forceinline__ float gelu_f(float x)
 {
-    const float k0 = -2.3022081986f;   // -2 sqrt(2/pi) log2(e)
-    const float k1 = -0.1029432396f;   // k0 * 0.044715
-    const float w = x * fmaf(x * x, k1, k0);
+    const float c1 = -2.0f * 1.4426950409f * 7.97507884e-01f;   // -2 log2(e) c_k
+    const float c3 = -2.0f * 1.4426950409f * 3.70056460e-02f;
+    const float c5 = -2.0f * 1.4426950409f * -3.51516783e-04f;
+    const float xc = fminf(fmaxf(x, -8.0f), 8.0f);
+    const float x2 = xc * xc;
+    const float w = xc * fmaf(x2, fmaf(x2, c5, c3), c1);
     return x * rcp_approx(1.0f + ex2_approx(w));
 }
-// Same GELU on two fp16 lanes: 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))) with one MUFU.TANH for the pair
+// (round 1, kept for reference measurements) tanh-form GELU on two fp16 lanes: 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))) with one MUFU.TANH for the pair
 // (6 half2 instructions per two elements).  Inputs are the fp32 accumulator + bias rounded to fp16; the result
 // is the fp16 operand of the next layer, so every intermediate carries the precision of its consumer.
 __device__ __forceinline__ uint32_t gelu_h2(uint32_t xb)

@@ -504,8 +504,19 @@ def test_gru_head_mlp_envelope_and_workspace():
     rc = lib.npd_gru_decode(h.h, dec._loss_code(info).h, _lib.ptr(y), None, None, None, _lib.ptr(out), 100, None, 0,
                             _lib.stream_ptr())
     assert rc != 0 and b"workspace" in lib.npd_last_error()
+    # Linear(H,1) head: the workspace is the optional residual-state buffer of the CTA-pair kernel (the library's own
+    # pool serves a caller that passes none); the 'fast' precision mode needs none
+    from neural_polar_decoder_b200 import rnn_all
     plain = RNN_Model('GRU', N + 2, H, 1, 2, N, 0, 0)
-    assert lib.npd_gru_workspace_bytes(plain.npd_handle(N).h, 100) == 0
+    assert lib.npd_gru_workspace_bytes(plain.npd_handle(N).h, 100) == 2 * 2 * H * 128 * 2
+    rc = lib.npd_gru_decode(plain.npd_handle(N).h, dec._loss_code(info).h, _lib.ptr(y), None, None, None, _lib.ptr(out), 100,
+                            None, 0, _lib.stream_ptr())
+    assert rc == 0
+    try:
+        rnn_all.set_gru_precision("fast")
+        assert lib.npd_gru_workspace_bytes(plain.npd_handle(N).h, 100) == 0
+    finally:
+        rnn_all.set_gru_precision("exact")
 
 
 def test_gru_h0_ragged_batch_both_kernels():
