@@ -197,8 +197,15 @@ __global__ void __launch_bounds__(256) awgn_kernel(const float *__restrict__ x, 
     }
 }
 
+// the kernels move rows as 16-byte vectors whenever the row length allows it: base pointers must then be 16-byte aligned
+// (torch allocations are 256-byte aligned; a view with an odd storage offset is not)
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 int launch_encode(const npd_code *code, const EncParams &p, cudaStream_t st)
 {
+    NPD_REQUIRE(((p.K & 3) != 0 || aligned16(p.msg_out)) && (code->N < 4 || (aligned16(p.x_out) && aligned16(p.y_out))),
+                "npd encoder: output pointers must be 16-byte aligned (msg %p x %p y %p)", (void *)p.msg_out, (void *)p.x_out,
+                (void *)p.y_out);
     DeviceProps dp;
     if (npd_get_device_props(&dp)) return NPD_ECUDA;
     const int NW = (code->N + 31) / 32;
@@ -256,6 +263,7 @@ NPD_API int npd_awgn(const float *x, float *y, int64_t B, int N, float sigma, ui
 {
     NPD_REQUIRE(x && y, "npd_awgn: null argument");
     NPD_REQUIRE(B >= 0 && N >= 1, "npd_awgn: bad shape");
+    NPD_REQUIRE((N & 3) != 0 || (aligned16(x) && aligned16(y)), "npd_awgn: x and y must be 16-byte aligned when N %% 4 == 0");
     if (B == 0) return NPD_OK;
     DeviceProps dp;
     if (npd_get_device_props(&dp)) return NPD_ECUDA;

@@ -694,3 +694,38 @@ def test_fp16_operand_range_guards():
     with pytest.raises(_lib.NpdError) as e:
         cnet.npd_handle()
     assert e.value.code == _lib.NPD_EUNSUPPORTED
+
+
+def test_encoder_rejects_misaligned_outputs_and_edge_batches():
+    """16-byte vector stores need aligned bases: a view with an odd storage offset is refused (NPD_EINVAL) instead of
+    faulting; empty batches are no-ops in every new round-2 entry point."""
+    from neural_polar_decoder_b200 import _lib, construct, synth, utils
+    from neural_polar_decoder_b200.rnn_all import RNN_Model, RNN_decoder
+    from neural_polar_decoder_b200.sweep import _count_info_into, mc_gru_sweep, mc_sc_sweep
+    lib = _lib.load()
+    N, K = 64, 22
+    rs = construct.reference_rs256()
+    info = np.sort(rs[rs < N][:K])
+    code = _code(N, info)
+    h = code._handle()
+    buf = torch.empty(8 * N + 1, device="cuda")
+    rc = lib.npd_gen_encode_awgn(h.h, None, None, _lib._vp(buf.data_ptr() + 4), 8, 1.0, 0, 0, 0, _lib.stream_ptr())
+    assert rc == _lib.NPD_EINVAL and b"aligned" in lib.npd_last_error()
+    x = torch.ones(8, N, device="cuda")
+    rc = lib.npd_awgn(_lib.ptr(x), _lib._vp(buf.data_ptr() + 4), 8, N, 1.0, 0, 0, 0, _lib.stream_ptr())
+    assert rc == _lib.NPD_EINVAL
+    # empty batches
+    counts = torch.zeros(2, dtype=torch.int64, device="cuda")
+    _count_info_into(counts, h, torch.zeros(0, K, device="cuda"), torch.zeros(0, N, device="cuda"))
+    assert counts.tolist() == [0, 0]
+    assert mc_sc_sweep(code, [1.0], 0, rank=0, world=1)[2] == [0]
+    sd = synth.gru_state_dict(11, N, 256, 2)
+    net = RNN_Model('GRU', N + 2, 256, 1, 2, N, 0, 0)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    dec = RNN_decoder('y_input', N, info, onehot=True)
+    assert mc_gru_sweep(code, net, dec, [1.0], 0, rank=0, world=1)[2] == [0]
+    # one frame, and a frame count that is not a multiple of anything
+    got = mc_gru_sweep(code, net, dec, [1.0], 1, seed=3, rank=0, world=1)[3]
+    assert int(got[0, 2]) == 1
+    assert mc_sc_sweep(_code(256, np.sort(construct.polarization_weight_order(256)[:128])), [2.0], 1001, chunk=333, rank=0,
+                       world=1)[2] == [1001]
