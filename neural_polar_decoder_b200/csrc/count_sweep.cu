@@ -110,18 +110,18 @@ int launch_count(const float *a, const float *b, int64_t B, int K, uint64_t *cou
 NPD_API int npd_count_errors(const float *a, const float *b, int64_t B, int K, uint64_t *counts,
                              void *stream)
 {
-    NPD_REQUIRE(a && b && counts, "npd_count_errors: null argument");
     NPD_REQUIRE(B >= 0 && K >= 1, "npd_count_errors: bad shape");
-    if (B == 0) return NPD_OK;
+    if (B == 0) return NPD_OK;  // an empty tensor has no storage: nothing to count, nothing to dereference
+    NPD_REQUIRE(a && b && counts, "npd_count_errors: null argument");
     return launch_count(a, b, B, K, counts, 0, (cudaStream_t)stream);
 }
 
 NPD_API int npd_count_errors_info(const npd_code_t *code, const float *msg, const float *decoded_full, int64_t B,
                                   int take_sign, uint64_t *counts, void *stream)
 {
-    NPD_REQUIRE(code && msg && decoded_full && counts, "npd_count_errors_info: null argument");
-    NPD_REQUIRE(B >= 0 && code->K >= 1, "npd_count_errors_info: bad shape");
+    NPD_REQUIRE(code && B >= 0 && code->K >= 1, "npd_count_errors_info: bad shape");
     if (B == 0) return NPD_OK;
+    NPD_REQUIRE(msg && decoded_full && counts, "npd_count_errors_info: null argument");
     return launch_count_gather(msg, decoded_full, code->d_info, B, code->K, code->N, take_sign, counts, 0, (cudaStream_t)stream);
 }
 

@@ -69,7 +69,7 @@ struct GruParams {
     const float *head_b;         // [head_depth - 1][Yh]
     const float *head_wl;        // [Yh]; its bias is b_out
     __half *head_act;            // workspace: [CTA][2][64][Yh] activations (L2-resident ping-pong)
-    __half *h_lo;                // pair kernel: rounding residual of the fp16 state, [pair][2 layers][H/32][16 chunks][32 units][8]
+    signed char *h_lo;           // pair kernel: rounding residual of the fp16 state in units of 2^-19, [pair][2 layers][H/32][16 chunks][32 units][8]
     const uint32_t *info_words;  // bit i = position i is an info (loss) position
     float *logits;               // [B,N] or null
     float *decoded;              // [B,N]
@@ -225,8 +225,9 @@ __device__ __forceinline__ float rcp_approx(float x)
 //   NPD_GRU_ZC    the update gate is computed as zc = 1 - z = sigmoid(-x) through ex2.approx + rcp.approx (two MUFU, relative
 //                 error ~1e-7) and parked as fp16: its RELATIVE rounding keeps long-memory units (z -> 1) exact where a parked
 //                 fp16 z (or tanh.approx's 2^-11) perturbs h by 2.4e-4 |h - n| every step; h' = h - zc (h - n)
-//   NPD_GRU_LO    the rounding residual of the fp16 state (hnew - fp16(hnew), itself fp16) lives in an L2-resident global
-//                 buffer owned by the thread that wrote it; the update reads hi + lo, the tensor cores read hi
+//   NPD_GRU_LO    the rounding residual of the fp16 state (hnew - fp16(hnew); |h| < 1, so |residual| <= 2^-12: one signed byte in
+//                 units of 2^-19) lives in an L2-resident global buffer owned by the thread that wrote it; the update reads
+//                 hi + lo, the tensor cores read hi
 //   NPD_GRU_ACT   bits 1 / 2: r / n through ex2 + rcp as well (measured: no gain in logit error, +3 % time; off)
 #ifndef NPD_GRU_ACT
 #define NPD_GRU_ACT 0
@@ -1226,17 +1227,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
                     // ---- the job's last accumulators: NH (layer 0; NI is the hoisted projection), NH + NI (layer 1) ----
                     if (warp == 0) trace_ev(p, step, 19 + 0 * (layer * 4 + j));
 #if NPD_GRU_LO
-                    // residual of this thread's 32 state values, 16 bytes (8 codewords) per chunk, laid out
-                    // [pair][layer][unit / 32][chunk of 8 codewords][unit % 32][8] so that a warp's access is 512 contiguous bytes
+                    // residual of this thread's 32 state values, 8 bytes (8 codewords) per chunk, laid out
+                    // [pair][layer][unit / 32][chunk of 8 codewords][unit % 32][8] so that a warp's access is 256 contiguous bytes
                     // (the kernel streams ~8 TB/s of weights from L2: half-used 32-byte sectors here cost 4.5 ms per launch)
-                    uint4 *lo_base = reinterpret_cast<uint4 *>(p.h_lo) +
+                    uint2 *lo_base = reinterpret_cast<uint2 *>(p.h_lo) +
                                      ((((size_t)(blockIdx.x >> 1) * 2 + layer) * (H / 32) + (u >> 5)) * (PAIR_CW / 8) + (col0 >> 3)) * 32 + (u & 31);
 #ifndef NPD_GRU_LO_AHEAD
 #define NPD_GRU_LO_AHEAD 1  // chunks fetched ahead of their use (1..4): measured flat, the cost is L2 bandwidth, not latency
 #endif
-                    uint4 lo_q[NPD_GRU_LO_AHEAD];
+                    uint2 lo_q[NPD_GRU_LO_AHEAD];
 #pragma unroll
-                    for (int c = 0; c < NPD_GRU_LO_AHEAD; ++c) lo_q[c] = make_uint4(0u, 0u, 0u, 0u);
+                    for (int c = 0; c < NPD_GRU_LO_AHEAD; ++c) lo_q[c] = make_uint2(0u, 0u);
                     const bool use_lo = p.h_lo != nullptr;  // npd_gru_set_option(NPD_GRU_OPT_RESIDUAL_STATE): uniform
                     if (use_lo && step > 0) {
 #pragma unroll
@@ -1253,8 +1254,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
 #pragma unroll
                         for (int i = 0; i < 8; ++i) hold[i] = ld_cluster_u16(h_owner + b_off(row0 + cc + i, u));
 #if NPD_GRU_LO
-                        uint4 *lo_ptr = lo_base + 32 * (cc / 8);
-                        const uint4 lo4 = lo_q[(cc / 8) % NPD_GRU_LO_AHEAD];  // fetched NPD_GRU_LO_AHEAD chunks ahead
+                        uint2 *lo_ptr = lo_base + 32 * (cc / 8);
+                        const uint2 lo4 = lo_q[(cc / 8) % NPD_GRU_LO_AHEAD];  // fetched NPD_GRU_LO_AHEAD chunks ahead
                         if (use_lo && cc / 8 + NPD_GRU_LO_AHEAD < CW3 / 8 && step > 0) lo_q[(cc / 8) % NPD_GRU_LO_AHEAD] = __ldcg(lo_ptr + 32 * NPD_GRU_LO_AHEAD);
 #endif
                         tmem_ld8(t0 + 3 * PAIR_CW + cc, aNH);
@@ -1275,8 +1276,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
                         }
                         float hsum[8];
 #if NPD_GRU_LO
-                        const uint32_t lo_in[4] = {lo4.x, lo4.y, lo4.z, lo4.w};
-                        uint32_t lo_out[4] = {0u, 0u, 0u, 0u};
+                        const uint32_t lo_in[2] = {lo4.x, lo4.y};
+                        uint32_t lo_out[2] = {0u, 0u};
 #endif
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -1289,13 +1290,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
                                                     : fmaf(z, ho - nn, nn);   // (1 - z) n + z h
 #if NPD_GRU_LO
                             // the residual of the old state enters last (its load has the whole gate math to land): + z lo
-                            hnew = fmaf(__half2float(__ushort_as_half((unsigned short)(lo_in[i >> 1] >> (16 * (i & 1))))),
-                                        NPD_GRU_ZC ? 1.0f - z : z, hnew);
+                            {
+                                int q8;  // signed byte i of the chunk, sign-extended
+                                asm("bfe.s32 %0, %1, %2, 8;" : "=r"(q8) : "r"(lo_in[i >> 2]), "r"(8 * (i & 3)));
+                                hnew = fmaf((float)q8 * 1.9073486328125e-06f, NPD_GRU_ZC ? 1.0f - z : z, hnew);  // 2^-19
+                            }
 #endif
                             hsum[i] = wo * hnew;
                             const unsigned short hb = __half_as_ushort(__float2half_rn(hnew));
 #if NPD_GRU_LO
-                            lo_out[i >> 1] |= (uint32_t)__half_as_ushort(__float2half_rn(hnew - __half2float(__ushort_as_half(hb)))) << (16 * (i & 1));
+                            {
+                                int q8;  // residual in units of 2^-19, saturated to a signed byte (|residual| <= 2^-12 while |h| < 1)
+                                asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(q8) : "f"((hnew - __half2float(__ushort_as_half(hb))) * 524288.0f));
+                                asm("bfi.b32 %0, %1, %0, %2, 8;" : "+r"(lo_out[i >> 2]) : "r"(q8), "r"(8 * (i & 3)));
+                            }
 #endif
                             if (j == JOBS2 - 1) {
                                 // the last accumulator of the layer's last job is full: every MMA reading the old state retired
@@ -1306,7 +1314,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruPa
                             }
                         }
 #if NPD_GRU_LO
-                        if (use_lo) __stcg(lo_ptr, make_uint4(lo_out[0], lo_out[1], lo_out[2], lo_out[3]));
+                        if (use_lo) __stcg(lo_ptr, make_uint2(lo_out[0], lo_out[1]));
 #endif
                         if (layer == 1 && need_head) {
                             // head: reduce the 8 columns over the warp's 32 units; lane l < 8 ends with column cc + l
@@ -1671,11 +1679,11 @@ NPD_API int npd_gru_set_head_mlp(npd_gru_t *g, int depth, int Yh, const float *h
     return NPD_OK;
 }
 
-// bytes of the pair kernel's residual-state buffer: [pair][2 layers][H][128 codewords] fp16
+// bytes of the pair kernel's residual-state buffer: [pair][2 layers][H][128 codewords] signed bytes
 static size_t gru_lo_bytes(const npd_gru *g, int64_t B)
 {
     if (!NPD_GRU_LO || !g->residual_state || !g->d_wpack2 || g->head_depth > 1) return 0;
-    return (size_t)((B + 2 * TILE_B - 1) / (2 * TILE_B) + 1) * 2 * g->H * (2 * TILE_B) * sizeof(__half);
+    return (size_t)((B + 2 * TILE_B - 1) / (2 * TILE_B) + 1) * 2 * g->H * (2 * TILE_B);
 }
 
 NPD_API int npd_gru_set_option(npd_gru_t *g, int option, int value)
@@ -1731,12 +1739,12 @@ NPD_API int npd_gru_decode_h0(const npd_gru_t *g, const npd_code_t *code, const 
     void *lo_owned = nullptr;
     if (lo_need) {
         if (ws && ws_bytes >= lo_need) {
-            p.h_lo = (__half *)ws;
+            p.h_lo = (signed char *)ws;
         } else {
             cudaMemPool_t pool;
             if (int rc = npd_scratch_pool(&pool)) return rc;
             NPD_CHECK_CUDA(cudaMallocFromPoolAsync(&lo_owned, lo_need, pool, (cudaStream_t)stream));
-            p.h_lo = (__half *)lo_owned;
+            p.h_lo = (signed char *)lo_owned;
         }
     }
     // the 2-SM tensor-copy variant (no relay) works but measures slower than relay + linear bulk copies (12.4 vs 11.4 ms

@@ -508,7 +508,7 @@ def test_gru_head_mlp_envelope_and_workspace():
     # pool serves a caller that passes none); the 'fast' precision mode needs none
     from neural_polar_decoder_b200 import rnn_all
     plain = RNN_Model('GRU', N + 2, H, 1, 2, N, 0, 0)
-    assert lib.npd_gru_workspace_bytes(plain.npd_handle(N).h, 100) == 2 * 2 * H * 128 * 2
+    assert lib.npd_gru_workspace_bytes(plain.npd_handle(N).h, 100) == 2 * 2 * H * 128
     rc = lib.npd_gru_decode(plain.npd_handle(N).h, dec._loss_code(info).h, _lib.ptr(y), None, None, None, _lib.ptr(out), 100,
                             None, 0, _lib.stream_ptr())
     assert rc == 0
