@@ -156,10 +156,10 @@ int npd_gru_destroy(npd_gru_t *gru);
 int npd_gru_set_head_mlp(npd_gru_t *gru, int depth, int y_hidden_size, const float *h_params);
 
 /* Options of a GRU decoder handle.  NPD_GRU_OPT_RESIDUAL_STATE (default 1): the CTA-pair kernel (H = 256 / 512) keeps,
- * next to the fp16 recurrent state the tensor cores read, the fp16 rounding residual of that state in an L2-resident
+ * next to the fp16 recurrent state the tensor cores read, the rounding residual of that state (one signed byte) in an L2-resident
  * buffer (npd_gru_workspace_bytes, or the library's pool) and updates h' = h - (1 - z)(h - n) from hi + lo.  On the
  * reference-trained Polar(64,22) checkpoint the forced-feedback logit error drops from 9e-3 (2.6 x the tolerance
- * 1e-2 |ref| + 2e-3) to 3e-3 (at the fp16-operand floor) for +14 % decode time; 0 = the faster fp16-only state. */
+ * 1e-2 |ref| + 2e-3) to 3e-3 (at the fp16-operand floor) for +10 % decode time; 0 = the faster fp16-only state. */
 #define NPD_GRU_OPT_RESIDUAL_STATE 1
 int npd_gru_set_option(npd_gru_t *gru, int option, int value);
 
