@@ -56,6 +56,8 @@ def main():
            "bers_SC": res["bers_SC"], "blers_SC": res["blers_SC"],
            "cpu_reference_checkpoint_bers_RNN": json.load(open(os.path.join(ROOT, "tests/golden/crisp_gru_N64_K22_H512.json")))["bers_RNN"]}
     json.dump(out, open(a.out, "w"), indent=1)
+    import shutil
+    shutil.copyfile(prev, a.out[:-5] + ".pt")  # the final reference-format checkpoint {'net', 'step', 'args'}
     print(json.dumps({k: out[k] for k in ("train_seconds", "bers_RNN", "bers_SC")}))
 
 
