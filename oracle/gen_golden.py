@@ -194,11 +194,14 @@ def gru_cases():
     np.savez_compressed(os.path.join(OUT, "gru.npz"), **out)
 
 
-def gru_trained_cases():
-    """Logits of the reference-TRAINED CRISP GRU (tests/golden/crisp_gru_N64_K22_H512.pt, oracle/train_ref_checkpoint.py)
-    from the live reference on noisy codewords at -2 / 0 / 2 dB: where |logit| ~ 1, which synthetic weights never reach."""
+def gru_trained_cases(ckpt="crisp_gru_N64_K22_H512", out_name="gru_trained"):
+    """Logits of a TRAINED CRISP GRU from the live reference on noisy codewords at -2 / 0 / 2 dB: where |logit| ~ 1, which
+    synthetic weights never reach.  Checkpoints: crisp_gru_N64_K22_H512.pt (trained by the reference on CPU,
+    oracle/train_ref_checkpoint.py) and crisp_gru_N64_K22_H512_gputrained.pt (same curriculum, 5700 iterations at batch 4096
+    through this repo's GPU training loop, tools/gpu_curriculum.py: BER within 1.4x of SC) -- both in the reference's
+    checkpoint format, both evaluated here by the reference's own RNN_Model / RNN_decoder."""
     ra = ref_shim.load("rnn_all")
-    path = os.path.join(OUT, "crisp_gru_N64_K22_H512.pt")
+    path = os.path.join(OUT, ckpt + ".pt")
     ck = torch.load(path, map_location="cpu", weights_only=False)
     a = ck["args"]
     N, K, H = a.N, a.K, a.rnn_feature_size
@@ -220,7 +223,7 @@ def gru_trained_cases():
         print("gru_trained snr", snr, "|logit| mean on info", float(lg[:, code.info_inds].abs().mean()),
               "BER", float((d_ref[:, code.info_inds].numpy() != msg).mean()), flush=True)
     out.update(y=np.concatenate(ys), decoded=np.concatenate(ds), logits=np.concatenate(ls), snr=np.array(snrs))
-    np.savez_compressed(os.path.join(OUT, "gru_trained.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, out_name + ".npz"), **out)
 
 
 TRAIN_KEYS = ("rnn.weight_ih_l0", "rnn.weight_hh_l0", "rnn.bias_ih_l0", "rnn.bias_hh_l0", "rnn.weight_ih_l1",
@@ -480,6 +483,8 @@ if __name__ == "__main__":
         gru_train_cases()
     if "gru_trained" in todo:
         gru_trained_cases()
+    if "gru_trained_gpu" in todo:
+        gru_trained_cases("crisp_gru_N64_K22_H512_gputrained", "gru_trained_gpu")
     if "conv_trained" in todo:
         conv_trained_cases()
     if "gru_cond" in todo:

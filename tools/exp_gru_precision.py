@@ -7,11 +7,15 @@ CHILD = r'''
 import sys, os, time, numpy as np, torch
 sys.path.insert(0, %r)
 from neural_polar_decoder_b200 import _lib
-_lib.LIB_PATH = os.path.join(%r, "neural_polar_decoder_b200", "libnpd_%%s.so" %% sys.argv[1])
+_lib.LIB_PATH = os.path.join(%r, "neural_polar_decoder_b200", "libnpd%%s.so" %% ("" if sys.argv[1] == "default" else "_" + sys.argv[1]))
+CK = os.environ.get("CK", "crisp_gru_N64_K22_H512"); FX = os.environ.get("FX", "gru_trained")
 from neural_polar_decoder_b200 import cli
 from neural_polar_decoder_b200.rnn_all import RNN_decoder, gru_decode
-g = np.load(os.path.join(%r, "tests/golden/gru_trained.npz"))
-net, cargs, _ = cli.net_from_checkpoint(os.path.join(%r, "tests/golden/crisp_gru_N64_K22_H512.pt"))
+g = np.load(os.path.join(%r, "tests/golden/" + FX + ".npz"))
+net, cargs, _ = cli.net_from_checkpoint(os.path.join(%r, "tests/golden/" + CK + ".pt"))
+if os.environ.get("FAST"):
+    from neural_polar_decoder_b200 import rnn_all
+    rnn_all.set_gru_precision("fast")
 N = 64
 dec = RNN_decoder('y_input', N, g["info"], onehot=True)
 code = dec._loss_code(dec.info_inds)
@@ -28,7 +32,8 @@ sd = {k: v.detach().cpu().numpy() for k, v in net.state_dict().items()}
 do, lo = oracle.gru_decode(sd, yn, N, info)
 _, lg2 = gru_decode(net, code, torch.from_numpy(yn).cuda(), forced=torch.from_numpy(do).cuda(), want_logits=True)
 e2 = np.abs(lg2.cpu().numpy() - lo); t2 = 1e-2 * np.abs(lo) + 2e-3
-print("%%s: 1024 frames vs oracle: max %%.2e worst err/tol %%.2f frac>tol %%.1e" %% (sys.argv[1], e2.max(), (e2 / t2).max(), (e2 > t2).mean()))
+print("%%s: 1024 frames vs oracle: max %%.2e worst err/tol %%.2f frac>tol %%.1e  |logit| rms %%.2f" %% (sys.argv[1], e2.max(), (e2 / t2).max(), (e2 > t2).mean(), np.sqrt((lo ** 2).mean())))
+w = np.unravel_index((e2 / t2).argmax(), e2.shape); print("   worst entry: ref %%.4f err %%.2e step %%d" %% (lo[w], e2[w], w[1]))
 B = 37888
 yb = y.repeat((B + y.shape[0] - 1) // y.shape[0], 1)[:B].contiguous()
 for _ in range(3): gru_decode(net, code, yb)
