@@ -252,6 +252,11 @@ def _setup_conv(w, seed=21):
     import argparse
     from .models import convNet
     N = w["N"]
+    if w.get("checkpoint"):  # the reference-trained convNet ({'xformer', 'step', 'args'}, run_models.py:980-983)
+        from .run_models import net_from_checkpoint
+        net, cargs, _ = net_from_checkpoint(w["checkpoint"])
+        assert (cargs.N, cargs.embed_dim) == (N, 128), "checkpoint shape does not match the workload"
+        return net
     sd = synth.conv_state_dict(seed, N, 128)
     net = convNet(argparse.Namespace(embed_dim=128, max_len=N, N=N, dont_use_bias=False, dropout=0.1))
     net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})

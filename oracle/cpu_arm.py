@@ -264,6 +264,9 @@ def make_conv_arm(N=64, E=128, seed=0):
         rm = ref_shim.load("models")
         torch.manual_seed(seed)
         net = rm.convNet(argparse.Namespace(embed_dim=E, max_len=N, N=N, dont_use_bias=False, dropout=0.1))
+        ck = os.path.join(GOLD, "conv_N%d_K22_E%d.pt" % (N, E))
+        if os.path.exists(ck):  # the reference-trained checkpoint, like the product arm
+            net.load_state_dict(torch.load(ck, map_location="cpu", weights_only=False)["xformer"])
         net.eval()
         info = info_set(N, 22)
 
