@@ -68,6 +68,8 @@ WORKLOADS = {
                          "BPTT + clip + AdamW on the device (fp32 GEMMs)"),
     "train64tf32": dict(kind="train", N=64, K=22, snr=0.0, batch=4096, tf32=1,
                         desc="the same training iteration with TF32 tensor-core GEMMs"),
+    "train64bf16": dict(kind="train", N=64, K=22, snr=0.0, batch=4096, tf32=2,
+                        desc="the same training iteration with bf16 tensor-core GEMMs (fp32 data, accumulation and optimizer)"),
     "conv64": dict(kind="conv", N=64, K=22, snr=0.0, batch=131072,
                    desc="convNet(embed_dim 128) one-shot decoder Polar(64,22), AWGN 0 dB"),
 }
@@ -75,7 +77,7 @@ WORKLOADS = {
 DEFAULT_ALSO = [("sc1024", 20, True), ("conv64", 20, True), ("gru64fast", 20, False), ("mc1024", 20, False), ("mc256", 6, False),
                 ("mc4096", 10, False), ("gru64sweep", 10, False), ("sc256", 10, False), ("sc4096", 10, False),
                 ("enc1024", 10, False), ("gru32", 10, False), ("pac32", 10, False), ("train64", 5, False),
-                ("train64tf32", 5, False)]
+                ("train64tf32", 5, False), ("train64bf16", 5, False)]
 
 
 def gru_weights_note(w):
@@ -816,7 +818,7 @@ def bench_train(args, w, rank, world, local_rank):
     net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
     dec = RNN_decoder('y_input', N, info, onehot=True)
     loss_code = dec._loss_code(info)
-    tr = GRUTrainer(net, N, B, tf32=bool(w["tf32"]))
+    tr = GRUTrainer(net, N, B, tf32=int(w["tf32"]))
     h = code._handle()
     sigma = float(np.float32(utils.snr_db2sigma(snr)))
     msg = torch.empty(B, K, device=dev)
@@ -853,7 +855,7 @@ def bench_train(args, w, rank, world, local_rank):
     return {
         "metric": "trained codewords/sec", "value": world * B * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "tf32" if w["tf32"] else "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": ("f32", "tf32", "bf16", "f16")[int(w["tf32"])], "data": "synthetic",
         "config": {"step": "npd_gen_encode_awgn + gt scatter + npd_gru_train_step (64 forward steps with saved gates, 64 backward "
                            "steps, clip_grad_norm_ 0.25, AdamW lr 1e-3); independent replicas when n_gpus > 1",
                    "loss_first_last": [losses[0], losses[-1]] if losses else None},

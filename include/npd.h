@@ -212,7 +212,8 @@ int npd_mc_gru_sweep(const npd_gru_t *gru, const npd_code_t *code, const npd_cod
  *   h_params : host fp32 blob in state_dict order: rnn.weight_ih_l0 [3H,N+2], rnn.weight_hh_l0 [3H,H], rnn.bias_ih_l0,
  *              rnn.bias_hh_l0 [3H], rnn.weight_ih_l1 [3H,H], rnn.weight_hh_l1 [3H,H], rnn.bias_ih_l1, rnn.bias_hh_l1,
  *              linear.weight [H], linear.bias [1]  (npd_gru_trainer_param_count(N, H) floats)
- *   tf32     : 0 = fp32 GEMMs (parity mode), 1 = TF32 tensor-core GEMMs */
+ *   tf32     : GEMM arithmetic on the fp32 data: 0 = fp32 (parity mode), 1 = TF32, 2 = bf16, 3 = fp16 tensor cores (fp32
+ *              accumulation; master weights, saved activations, gate math and the optimizer stay fp32) */
 typedef struct npd_gru_trainer npd_gru_trainer_t;
 size_t npd_gru_trainer_param_count(int N, int H);
 int npd_gru_trainer_create(int N, int H, int64_t max_batch, const float *h_params, int tf32,

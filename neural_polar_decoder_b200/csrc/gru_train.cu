@@ -15,7 +15,8 @@
 //             (d h_prev = dgh W_hh, d input = dgi W_ih), weight gradients accumulated as dg^T h GEMMs (beta = 1);
 //             bias / one-hot-column gradients fall out of per-row accumulators reduced once at the end;
 //   update    one fused kernel: global grad-norm clip coefficient + AdamW.
-// The GEMMs are plain library GEMMs (cuBLAS SGEMM, optionally TF32 tensor-op math); everything else is this file.
+// The GEMMs are plain library GEMMs (cublasGemmEx on fp32 data; inner products in fp32, or on TF32 / bf16 / fp16 tensor
+// cores with fp32 accumulation); everything else is this file.
 #include <cublas_v2.h>
 #include <math.h>
 #include <string.h>
@@ -33,6 +34,18 @@
         }                                                                             \
     } while (0)
 
+// fp32 in / fp32 out GEMM whose inner products run as: 0 = fp32 FMA (pedantic; the parity mode), 1 = TF32 tensor cores,
+// 2 = bf16 tensor cores, 3 = fp16 tensor cores (cuBLAS down-converts the fp32 operands internally; accumulation stays fp32)
+static cublasStatus_t gemm32(cublasHandle_t h, int mode, cublasOperation_t ta, cublasOperation_t tb, int m, int n, int k,
+                             const float *alpha, const float *A, int lda, const float *B, int ldb, const float *beta, float *C,
+                             int ldc)
+{
+    const cublasComputeType_t ct = mode == 1 ? CUBLAS_COMPUTE_32F_FAST_TF32 : mode == 2 ? CUBLAS_COMPUTE_32F_FAST_16BF
+                                 : mode == 3 ? CUBLAS_COMPUTE_32F_FAST_16F : CUBLAS_COMPUTE_32F_PEDANTIC;
+    return cublasGemmEx(h, ta, tb, m, n, k, alpha, A, CUDA_R_32F, lda, B, CUDA_R_32F, ldb, beta, C, CUDA_R_32F, ldc, ct,
+                        CUBLAS_GEMM_DEFAULT);
+}
+
 struct npd_gru_trainer {
     int N, H, I;        // code length (= steps), hidden size, layer-0 input width N + 2
     int64_t max_batch;
@@ -45,6 +58,7 @@ struct npd_gru_trainer {
     int64_t step;       // optimizer step count (bias correction)
     float beta1, beta2, eps, weight_decay;
     cublasHandle_t blas;
+    int gemm_mode;      // see gemm32
     // activations (sized for max_batch)
     float *saved;       // [2 layers][N steps][5: r, z, n, ghn, h][B*H]
     float *gy;          // [B,3H]  y-part of the layer-0 input projection
@@ -301,7 +315,8 @@ NPD_API int npd_gru_trainer_create(int N, int H, int64_t max_batch, const float 
     NPD_CHECK_CUDA(cudaMemset(t->zeros, 0, BH * sizeof(float)));
     NPD_CHECK_CUDA(cudaMemcpy(t->p, h_params, o * sizeof(float), cudaMemcpyHostToDevice));
     NPD_CHECK_CUBLAS(cublasCreate(&t->blas));
-    NPD_CHECK_CUBLAS(cublasSetMathMode(t->blas, tf32 ? CUBLAS_TF32_TENSOR_OP_MATH : CUBLAS_PEDANTIC_MATH));
+    t->gemm_mode = tf32 < 0 ? 0 : tf32 > 3 ? 3 : tf32;
+    NPD_CHECK_CUBLAS(cublasSetMathMode(t->blas, t->gemm_mode ? CUBLAS_DEFAULT_MATH : CUBLAS_PEDANTIC_MATH));
     NPD_CHECK_CUBLAS(cublasSetPointerMode(t->blas, CUBLAS_POINTER_MODE_HOST));
     *out = t;
     return NPD_OK;
@@ -364,19 +379,19 @@ NPD_API int npd_gru_train_step(npd_gru_trainer_t *t, const npd_code_t *loss_code
     NPD_CHECK_CUDA(cudaMemsetAsync(t->acc, 0, 5 * (size_t)BG * sizeof(float), st));
     // ---- forward ----
     // gy[B,3H] = y[B,N] . W_ih0[:, :N]^T   (row-major views as column-major: C^T = W . y^T)
-    NPD_CHECK_CUBLAS(cublasSgemm(t->blas, CUBLAS_OP_T, CUBLAS_OP_N, G, (int)B, N, &one, P + t->o_wih0, I, y, N, &zero, t->gy, G));
+    NPD_CHECK_CUBLAS(gemm32(t->blas, t->gemm_mode, CUBLAS_OP_T, CUBLAS_OP_N, G, (int)B, N, &one, P + t->o_wih0, I, y, N, &zero, t->gy, G));
     // feedback entering step 0 is +1 (rnn_all.py:444)
     fill_kernel<<<blocks_for(B), 256, 0, st>>>(t->fb, 1.0f, B);
     for (int s = 0; s < N; ++s) {
         // layer 0
-        NPD_CHECK_CUBLAS(cublasSgemm(t->blas, CUBLAS_OP_T, CUBLAS_OP_N, G, (int)B, H, &one, P + t->o_whh0, H, h_of(0, s - 1), H,
+        NPD_CHECK_CUBLAS(gemm32(t->blas, t->gemm_mode, CUBLAS_OP_T, CUBLAS_OP_N, G, (int)B, H, &one, P + t->o_whh0, H, h_of(0, s - 1), H,
                                      &zero, t->gh, G));
         cell_fwd_kernel<true><<<blocks_for(BH), 256, 0, st>>>(t->gy, t->gh, P + t->o_bih0, P + t->o_bhh0, P + t->o_wih0, I, N,
                                                               t->fb + (size_t)s * B, h_of(0, s - 1), sv(0, s), B, H);
         // layer 1
-        NPD_CHECK_CUBLAS(cublasSgemm(t->blas, CUBLAS_OP_T, CUBLAS_OP_N, G, (int)B, H, &one, P + t->o_wih1, H, h_of(0, s), H, &zero,
+        NPD_CHECK_CUBLAS(gemm32(t->blas, t->gemm_mode, CUBLAS_OP_T, CUBLAS_OP_N, G, (int)B, H, &one, P + t->o_wih1, H, h_of(0, s), H, &zero,
                                      t->gi, G));
-        NPD_CHECK_CUBLAS(cublasSgemm(t->blas, CUBLAS_OP_T, CUBLAS_OP_N, G, (int)B, H, &one, P + t->o_whh1, H, h_of(1, s - 1), H,
+        NPD_CHECK_CUBLAS(gemm32(t->blas, t->gemm_mode, CUBLAS_OP_T, CUBLAS_OP_N, G, (int)B, H, &one, P + t->o_whh1, H, h_of(1, s - 1), H,
                                      &zero, t->gh, G));
         cell_fwd_kernel<false><<<blocks_for(BH), 256, 0, st>>>(t->gi, t->gh, P + t->o_bih1, P + t->o_bhh1, nullptr, I, N, nullptr,
                                                                h_of(1, s - 1), sv(1, s), B, H);
@@ -399,21 +414,21 @@ NPD_API int npd_gru_train_step(npd_gru_trainer_t *t, const npd_code_t *loss_code
                                          Gd + t->o_wout, 1));
         // dW_hh1 += dgh^T h1_{s-1} ; dW_ih1 += dgi^T h0_s
         if (s > 0)
-            NPD_CHECK_CUBLAS(cublasSgemm(t->blas, CUBLAS_OP_N, CUBLAS_OP_T, H, G, (int)B, &one, h_of(1, s - 1), H, t->dgh, G, &one,
+            NPD_CHECK_CUBLAS(gemm32(t->blas, t->gemm_mode, CUBLAS_OP_N, CUBLAS_OP_T, H, G, (int)B, &one, h_of(1, s - 1), H, t->dgh, G, &one,
                                          Gd + t->o_whh1, H));
-        NPD_CHECK_CUBLAS(cublasSgemm(t->blas, CUBLAS_OP_N, CUBLAS_OP_T, H, G, (int)B, &one, h_of(0, s), H, t->dgi, G, &one,
+        NPD_CHECK_CUBLAS(gemm32(t->blas, t->gemm_mode, CUBLAS_OP_N, CUBLAS_OP_T, H, G, (int)B, &one, h_of(0, s), H, t->dgi, G, &one,
                                      Gd + t->o_wih1, H));
         // dh1 (for step s-1) = dh * z (already written) + dgh W_hh1 ; dx1 = dgi W_ih1
         if (s > 0)
-            NPD_CHECK_CUBLAS(cublasSgemm(t->blas, CUBLAS_OP_N, CUBLAS_OP_N, H, (int)B, G, &one, P + t->o_whh1, H, t->dgh, G, &one, t->dh1, H));
-        NPD_CHECK_CUBLAS(cublasSgemm(t->blas, CUBLAS_OP_N, CUBLAS_OP_N, H, (int)B, G, &one, P + t->o_wih1, H, t->dgi, G, &zero, t->dx1, H));
+            NPD_CHECK_CUBLAS(gemm32(t->blas, t->gemm_mode, CUBLAS_OP_N, CUBLAS_OP_N, H, (int)B, G, &one, P + t->o_whh1, H, t->dgh, G, &one, t->dh1, H));
+        NPD_CHECK_CUBLAS(gemm32(t->blas, t->gemm_mode, CUBLAS_OP_N, CUBLAS_OP_N, H, (int)B, G, &one, P + t->o_wih1, H, t->dgi, G, &zero, t->dx1, H));
         // layer 0: dh = dh0 + dx1
         cell_bwd_kernel<true><<<blocks_for(BH), 256, 0, st>>>(sv(0, s), h_of(0, s - 1), t->dh0, t->dx1, nullptr, nullptr,
                                                               t->fb + (size_t)s * B, t->dgi, t->dgh, acc0p, acc0n, acc0h, B, H);
         if (s > 0) {
-            NPD_CHECK_CUBLAS(cublasSgemm(t->blas, CUBLAS_OP_N, CUBLAS_OP_T, H, G, (int)B, &one, h_of(0, s - 1), H, t->dgh, G, &one,
+            NPD_CHECK_CUBLAS(gemm32(t->blas, t->gemm_mode, CUBLAS_OP_N, CUBLAS_OP_T, H, G, (int)B, &one, h_of(0, s - 1), H, t->dgh, G, &one,
                                          Gd + t->o_whh0, H));
-            NPD_CHECK_CUBLAS(cublasSgemm(t->blas, CUBLAS_OP_N, CUBLAS_OP_N, H, (int)B, G, &one, P + t->o_whh0, H, t->dgh, G, &one, t->dh0, H));
+            NPD_CHECK_CUBLAS(gemm32(t->blas, t->gemm_mode, CUBLAS_OP_N, CUBLAS_OP_N, H, (int)B, G, &one, P + t->o_whh0, H, t->dgh, G, &one, t->dh0, H));
         }
     }
     // bias gradients and the two one-hot columns of W_ih0 from the per-row accumulators
@@ -426,7 +441,7 @@ NPD_API int npd_gru_train_step(npd_gru_trainer_t *t, const npd_code_t *loss_code
     colsum_kernel<<<cg, 256, 0, st>>>(acc1h, nullptr, Gd + t->o_bhh1, 1, B, G, 0);
     // d W_ih0[:, :N] = (sum_s dgi0_s)^T y  -- y is the same in every step
     add_kernel<<<blocks_for(BG), 256, 0, st>>>(acc0p, acc0n, BG);
-    NPD_CHECK_CUBLAS(cublasSgemm(t->blas, CUBLAS_OP_N, CUBLAS_OP_T, N, G, (int)B, &one, y, N, acc0p, G, &zero, Gd + t->o_wih0, I));
+    NPD_CHECK_CUBLAS(gemm32(t->blas, t->gemm_mode, CUBLAS_OP_N, CUBLAS_OP_T, N, G, (int)B, &one, y, N, acc0p, G, &zero, Gd + t->o_wih0, I));
     // the GEMM above wrote rows of width N with leading dimension I: columns N, N+1 were untouched (set by the colsums)
     sum_kernel<<<64, 256, 0, st>>>(t->dout, (int64_t)N * B, Gd + t->o_bout, 0);
     NPD_CHECK_CUDA(cudaGetLastError());

@@ -33,7 +33,8 @@ def _blob(net):
 class GRUTrainer:
     """Device-side training state (parameters, gradients, Adam moments, saved activations) of one RNN_Model."""
 
-    def __init__(self, net, N, max_batch, tf32=False):
+    def __init__(self, net, N, max_batch, tf32=0):
+        """tf32: GEMM arithmetic, 0 = fp32 (parity), 1 = TF32, 2 = bf16, 3 = fp16 tensor cores (include/npd.h)."""
         _lib.require_cuda()
         self.net, self.N, self.H, self.max_batch = net, int(N), int(net.feature_size), int(max_batch)
         if net.input_size != self.N + 2:
@@ -43,7 +44,7 @@ class GRUTrainer:
         self.n_params = int(self.lib.npd_gru_trainer_param_count(self.N, self.H))
         assert blob.size == self.n_params, (blob.size, self.n_params)
         h = ctypes.c_void_p()
-        _lib.check(self.lib.npd_gru_trainer_create(self.N, self.H, self.max_batch, blob.ctypes.data, int(bool(tf32)),
+        _lib.check(self.lib.npd_gru_trainer_create(self.N, self.H, self.max_batch, blob.ctypes.data, int(tf32),
                                                    ctypes.byref(h)))
         self.h = h
 

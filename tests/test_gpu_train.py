@@ -120,3 +120,30 @@ def test_training_loop_learns_and_writes_reference_checkpoint(tmp_path, monkeypa
     assert cli.load_checkpoint(final)["step"] == 150
     res = cli.run_test(args, out=lambda *a: None)
     assert res["bers_RNN"][-1] < 0.2 and res["step"] == 150
+
+
+@pytest.mark.parametrize("mode,rel", [(1, 2e-2), (2, 1e-1), (3, 3e-2)])
+def test_train_step_tensor_core_gemm_modes(mode, rel):
+    """tf32 / bf16 / fp16 tensor-core GEMMs (fp32 data, accumulation and optimizer): gradients within the mode's operand
+    precision of the fp32 parity mode's, same loss to 3 digits."""
+    from neural_polar_decoder_b200 import synth
+    from neural_polar_decoder_b200.rnn_all import RNN_Model, RNN_decoder, get_code
+    from neural_polar_decoder_b200.train import GRUTrainer
+    N, K, H, B = 32, 16, 256, 256
+    code = get_code("Polar", "polar", N, K)
+    sd = synth.gru_state_dict(5, N, H, 2, head_gain=2.0)
+    rs = np.random.RandomState(3)
+    msg = (1.0 - 2.0 * rs.randint(0, 2, size=(B, K))).astype(np.float32)
+    gt = np.ones((B, N), np.float32)
+    gt[:, code.info_inds] = msg
+    y = torch.from_numpy((code.encode(torch.from_numpy(msg).cuda()).cpu().numpy() + rs.randn(B, N)).astype(np.float32)).cuda()
+    res = {}
+    for m in (0, mode):
+        net = RNN_Model('GRU', N + 2, H, 1, 2, N, 0, 0)
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        dec = RNN_decoder('y_input', N, code.info_inds, onehot=True)
+        tr = GRUTrainer(net, N, B, tf32=m)
+        loss, norm, _ = tr.step(dec._loss_code(code.info_inds), y, torch.from_numpy(gt).cuda(), True, 1e-3, 0.25, apply_update=False)
+        res[m] = (loss, norm, tr.get("grads"))
+    assert res[mode][0] == pytest.approx(res[0][0], rel=2e-3)
+    assert _relerr(res[mode][2], res[0][2]) <= rel, _relerr(res[mode][2], res[0][2])
