@@ -77,7 +77,7 @@ WORKLOADS = {
 DEFAULT_ALSO = [("sc1024", 20, True), ("conv64", 20, True), ("gru64fast", 20, False), ("mc1024", 20, False), ("mc256", 6, False),
                 ("mc4096", 10, False), ("gru64sweep", 10, False), ("sc256", 10, False), ("sc4096", 10, False),
                 ("enc1024", 10, False), ("gru32", 10, False), ("pac32", 10, False), ("train64", 5, False),
-                ("train64tf32", 5, False), ("train64bf16", 5, False)]
+                ("train64tf32", 5, False)]
 
 
 def gru_weights_note(w):
