@@ -34,7 +34,8 @@ def _frames(code, B, snr, seed):
     return msg, y
 
 
-@pytest.mark.parametrize("n,K,B,chunk", [(6, 22, 1000, 256), (10, 512, 3000, 512), (8, 128, 777, 0), (5, 16, 1, 0)])
+@pytest.mark.parametrize("n,K,B,chunk", [(6, 22, 1000, 256), (10, 512, 3000, 512), (8, 128, 777, 0), (5, 16, 1, 0),
+                                         (12, 2048, 700, 256)])
 @pytest.mark.parametrize("pinned", [False, True])
 def test_sc_host_equals_device(n, K, B, chunk, pinned, monkeypatch):
     from neural_polar_decoder_b200 import PolarCode, construct
