@@ -915,7 +915,10 @@ __device__ __forceinline__ void tmap_g2s_pair(uint32_t dst, const CUtensorMap *t
 }
 
 template <int KH>
-__global__ void __launch_bounds__(NUM_THREADS, 1) gru_decode_kernel3(const GruParams p, const __grid_constant__ CUtensorMap tmap)
+#ifndef NPD_GRU_K3_BOUNDS
+#define NPD_GRU_K3_BOUNDS __launch_bounds__(NUM_THREADS, 1)
+#endif
+__global__ void NPD_GRU_K3_BOUNDS gru_decode_kernel3(const GruParams p, const __grid_constant__ CUtensorMap tmap)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int H = KH * 64, JOBS2 = H / 256;
