@@ -230,6 +230,7 @@ def mc_sc_sweep(polar, snr_range, total_frames, chunk=1 << 17, seed=0, rank=None
     """SC BER/BLER of `total_frames` frames per SNR point, fused on the device (npd_mc_sc_sweep)."""
     import torch.distributed as dist
     _lib.require_cuda()
+    collective = rank is None  # explicit (rank, world) = a caller-simulated shard: no all-reduce, the caller sums
     if rank is None:
         rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
         world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -247,7 +248,8 @@ def mc_sc_sweep(polar, snr_range, total_frames, chunk=1 << 17, seed=0, rank=None
             _lib.check(lib.npd_mc_sc_sweep(h.h, hi - lo, chunk, float(np.float32(utils.snr_db2sigma(snr))),
                                            utils.llr_scale(snr), int(seed), si, lo, _lib._vp(ws.data_ptr()), ws_bytes,
                                            _lib._vp(counts[si].data_ptr()), _lib.stream_ptr()))
-    reduce_counts(counts, group)
+    if collective:
+        reduce_counts(counts, group)
     return finalize(counts, polar.K) + (counts,)
 
 
@@ -264,6 +266,7 @@ def mc_gru_sweep(polar, net, decoder, snr_range, total_frames, chunk=2 * WAVE, s
     call per SNR point (npd_mc_gru_sweep).  Same sharding and counters as mc_sc_sweep."""
     import torch.distributed as dist
     _lib.require_cuda()
+    collective = rank is None  # explicit (rank, world) = a caller-simulated shard: no all-reduce, the caller sums
     if rank is None:
         rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
         world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -283,7 +286,8 @@ def mc_gru_sweep(polar, net, decoder, snr_range, total_frames, chunk=2 * WAVE, s
             _lib.check(lib.npd_mc_gru_sweep(gh.h, h.h, loss.h, hi - lo, chunk, float(np.float32(utils.snr_db2sigma(snr))),
                                             int(seed), si, lo, _lib._vp(ws.data_ptr()), ws_bytes,
                                             _lib._vp(counts[si].data_ptr()), _lib.stream_ptr()))
-    reduce_counts(counts, group)
+    if collective:
+        reduce_counts(counts, group)
     return finalize(counts, polar.K) + (counts,)
 
 
@@ -292,6 +296,7 @@ def mc_decoder_sweep(polar, decode_fn, snr_range, total_frames, chunk=2 * WAVE, 
     """Same for any decoder: decode_fn(y[B,N]) -> decisions [B,N] (e.g. lambda y: decoder.decode(net, False, y))."""
     import torch.distributed as dist
     _lib.require_cuda()
+    collective = rank is None  # explicit (rank, world) = a caller-simulated shard: no all-reduce, the caller sums
     if rank is None:
         rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
         world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -312,5 +317,6 @@ def mc_decoder_sweep(polar, decode_fn, snr_range, total_frames, chunk=2 * WAVE, 
                                                _lib.stream_ptr()))
             _count_info_into(counts[si], h, msg, decode_fn(y))
             counts[si, 2] += b
-    reduce_counts(counts, group)
+    if collective:
+        reduce_counts(counts, group)
     return finalize(counts, polar.K) + (counts,)
