@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import _lib, construct, synth, utils
-from .rnn_all import RNN_Model, RNN_decoder, gru_decode
+from .rnn_all import RNN_Model, RNN_decoder
 
 METRIC = "decoded codewords/sec"
 UNIT = "codewords/s"
@@ -81,10 +81,8 @@ def bench_gru(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
     gh = net.npd_handle(N)
     loss_code = dec._loss_code(info)
     decoded = torch.empty(B, N, device=dev)
-    info_t = torch.as_tensor(info, device=dev)
     counts = torch.zeros(3, dtype=torch.int64, device=dev)
     st = _lib.stream_ptr()
-    dec_info = torch.empty(B, K, device=dev)
 
     def step():
         _lib.check(lib.npd_gru_decode(gh.h, loss_code.h, _lib.ptr(y), None, None, None, _lib.ptr(decoded), B, None, 0, st))
@@ -285,8 +283,6 @@ def bench_conv(args, w, rank, world, local_rank, ClockSampler, measured_peaks):
     ws = ch.workspace(B, dev)
     wsp, wsn = ctypes.c_void_p(ws.data_ptr()), ws.numel()
     logits = torch.empty(B, N, device=dev)
-    info_t = torch.as_tensor(info, device=dev)
-    dec_info = torch.empty(B, K, device=dev)
     counts = torch.zeros(3, dtype=torch.int64, device=dev)
     st = _lib.stream_ptr()
     chunks = -(-B // (wsn // (128 * 8192 * 2) * 128))

@@ -15,7 +15,7 @@ import time
 import numpy as np
 import torch
 
-from . import _lib, utils
+from . import _lib
 
 PARAM_KEYS = ("rnn.weight_ih_l0", "rnn.weight_hh_l0", "rnn.bias_ih_l0", "rnn.bias_hh_l0", "rnn.weight_ih_l1",
               "rnn.weight_hh_l1", "rnn.bias_ih_l1", "rnn.bias_hh_l1", "linear.weight", "linear.bias")
