@@ -856,14 +856,15 @@ def bench_train(args, w, rank, world, local_rank):
         "metric": "trained codewords/sec", "value": world * B * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": ("f32", "tf32", "bf16", "f16")[int(w["tf32"])], "data": "synthetic",
-        "config": {"step": "npd_gen_encode_awgn + gt scatter + npd_gru_train_step (64 forward steps with saved gates, 64 backward "
-                           "steps, clip_grad_norm_ 0.25, AdamW lr 1e-3); independent replicas when n_gpus > 1",
+        "config": {"step": "npd_gen_encode_awgn + gt scatter + npd_gru_train_step (64 forward steps per layer with saved gates, 64 "
+                           "backward steps per layer, all-steps GEMMs for the inter-layer and weight-gradient products, "
+                           "clip_grad_norm_ 0.25, AdamW lr 1e-3); independent replicas when n_gpus > 1",
                    "loss_first_last": [losses[0], losses[-1]] if losses else None},
         "clocks": clocks,
         "e2e": {"value": world * 3 * B / float(e2e_t.item()), "unit": UNIT, "h2d_bytes_per_step": 2 * B * N * 4,
                 "d2h_bytes_per_step": 8, "batch_per_gpu": B, "steps": 3,
                 "api": "train.GRUTrainer.step(loss_code, pinned host y, pinned host gt, ...) -> host loss"},
-        "gpu_launches": (2 + 64 * 6 + 64 * 9 + 12) * args.steps,
+        "gpu_launches": (2 + (4 * 64 + 4) + (4 * 64 + 14) + 2) * args.steps,  # cuBLAS split-K reductions not counted
         "roofline": {"kernel": "cuBLAS SGEMM (library GEMMs) + cell_fwd / cell_bwd / head / adamw kernels", "bound": "tensor",
                      "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["bf16_sustained"], "traffic": None, "peak_source": peaks["src"],

@@ -7,18 +7,28 @@
 //     loss.backward(); clip_grad_norm_(net.parameters(), clip)  (1431-1432)
 //     optimizer.step()   [torch.optim.AdamW, default betas / eps / weight_decay]  (1346, 1435)
 // All arithmetic is fp32 (the reference trains in fp32; parity = gradients and updated weights against the live
-// reference at fp32 round-off).  Structure:
-//   forward   N steps; per step 3 GEMMs [B,H] x [H,3H] (W_hh0, W_ih1, W_hh1; the y-part of W_ih0 is hoisted out of
-//             the loop as in the decode kernel) + fused gate kernels that SAVE r, z, n, (W_hn h + b_hn)
-//             and h for the backward pass + the head (dot product, loss, d loss / d logit, next feedback bit);
-//   backward  N steps in reverse; per step and layer one fused gate-gradient kernel and two GEMMs
-//             (d h_prev = dgh W_hh, d input = dgi W_ih), weight gradients accumulated as dg^T h GEMMs (beta = 1);
-//             bias / one-hot-column gradients fall out of per-row accumulators reduced once at the end;
+// reference at fp32 round-off in GEMM mode 0).  Structure (round 2, second version: layer-wise instead of step-wise
+// wherever the data dependencies allow it):
+//   forward   the y-part of W_ih0 hoisted out of the loop (one GEMM).  Teacher-forced: the feedback of
+//             every step is known up front, so layer 0 runs its N steps (one recurrent GEMM [B,H] x [H,3H] + one fused
+//             gate kernel per step), W_ih1 . h0 of ALL steps is ONE GEMM [N B,H] x [H,3H], layer 1 runs its N steps,
+//             and the head (dot product, loss, d loss / d logit) is one launch over N B rows.  Student-forced: the
+//             feedback of step t+1 is the sign of step t's logit, so the two layers and the head advance step by step.
+//             The gate kernels SAVE r, z, n, (W_hn h + b_hn) and h, time-major per quantity ([layer][quantity][step][B H]),
+//             so that "h of all steps" is one contiguous GEMM operand.
+//   backward  layer 1 for t = N-1..0 (fused gate-gradient kernel -> dgi1[t], dgh1[t]; dh1 += dgh1[t] W_hh1), then for
+//             ALL steps at once d x1 = dgi1 W_ih1, dW_ih1 = dgi1^T h0, dW_hh1 = dgh1[1:]^T h1[:-1]; layer 0 the same
+//             way.  The detached feedback carries no gradient, so this order is valid for both forcing modes.  Weight
+//             gradients are therefore 4 GEMMs with K = N B instead of 4 N accumulating GEMMs with K = B (those were 55 %
+//             of the first version's time: 6 output tiles on 148 SMs).  Bias and one-hot-column gradients: every thread
+//             of the gate-gradient kernel owns one unit of 8 consecutive rows and keeps their column sums in registers;
+//             the [B/8, 7, H] partials are reduced once at the end (deterministic).
 //   update    one fused kernel: global grad-norm clip coefficient + AdamW.
 // The GEMMs are plain library GEMMs (cublasGemmEx on fp32 data; inner products in fp32, or on TF32 / bf16 / fp16 tensor
 // cores with fp32 accumulation); everything else is this file.
 #include <cublas_v2.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -59,37 +69,44 @@ struct npd_gru_trainer {
     float beta1, beta2, eps, weight_decay;
     cublasHandle_t blas;
     int gemm_mode;      // see gemm32
-    // activations (sized for max_batch)
-    float *saved;       // [2 layers][N steps][5: r, z, n, ghn, h][B*H]
-    float *gy;          // [B,3H]  y-part of the layer-0 input projection
-    float *gi, *gh;     // [B,3H]  GEMM outputs of the current step
-    float *dgi, *dgh;   // [B,3H]
-    float *acc;         // [5][B,3H]: layer-0 dgi split by feedback sign (2), layer-0 dgh, layer-1 dgi, layer-1 dgh
-    float *dh0, *dh1, *dx1, *zeros;  // [B,H]
+    // activations (sized for max_batch; addressed with the CALL's batch B, so every [step][B ..] block is contiguous)
+    float *saved;       // [2 layers][5: r, z, n, ghn, h][N steps][B*H]
+    float *gy;          // [B,3H]  y-part of the layer-0 input projection; after the backward pass: sum over steps of dgi0
+    float *gh;          // [B,3H]  recurrent GEMM output of the current step
+    float *dgi, *dgh;   // [N steps][B,3H]  gate gradients of the layer being processed; dgi doubles as W_ih1 . h0 of all
+                        //                  steps in the forward pass
+    float *dx1;         // [N steps][B,H]   gradient entering layer 0 from layer 1
+    float *part;        // [2 layers][ceil(B/8)][7][H] column sums of the gate gradients, see cell_bwd_kernel
+    float *dh, *zeros;  // [B,H]
     float *fb;          // [N][B] feedback entering step t (+-1)
     float *out, *dout;  // [N][B] logits, d loss / d logit
     float *scal;        // [4]: loss sum, grad norm^2, spare
+    unsigned char *is_loss;    // [N] device copy of the loss set's indicator
+    unsigned char *h_is_loss;  // [N] what is_loss holds (uploaded only when the loss set changes)
+    int is_loss_valid;
 };
 
 namespace {
+
+constexpr int kRowsPerThread = 8;  // cell_bwd_kernel: rows whose column sums one thread keeps in registers
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // ---- forward gate kernel: one thread per (row b, unit j) -------------------------------------------------------
 // LAYER0: gi = gy[b, g*H+j] + b_ih[g*H+j] + W_ih0[g*H+j, N + idx(fb[b])]   (one-hot feedback = column select)
 // else  : gi = gi_buf[b, g*H+j] + b_ih[g*H+j]
+// sv points at quantity 0 of this (layer, step); the five saved quantities are qs floats apart
 template <bool LAYER0>
 __global__ void __launch_bounds__(256) cell_fwd_kernel(const float *__restrict__ gi_src, const float *__restrict__ gh,
                                                        const float *__restrict__ b_ih, const float *__restrict__ b_hh,
                                                        const float *__restrict__ w_ih0, int I, int N,
                                                        const float *__restrict__ fb, const float *__restrict__ h_prev,
-                                                       float *__restrict__ sv, int64_t B, int H)
+                                                       float *__restrict__ sv, size_t qs, int64_t B, int H)
 {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B * H) return;
     const int64_t b = idx / H;
     const int j = (int)(idx - b * H);
-    const int64_t BH = B * H;
     float gir = gi_src[b * 3 * H + j] + b_ih[j];
     float giz = gi_src[b * 3 * H + H + j] + b_ih[H + j];
     float gin = gi_src[b * 3 * H + 2 * H + j] + b_ih[2 * H + j];
@@ -107,105 +124,120 @@ __global__ void __launch_bounds__(256) cell_fwd_kernel(const float *__restrict__
     const float n = tanhf(gin + r * ghn);
     const float hp = h_prev[idx];
     sv[idx] = r;
-    sv[BH + idx] = z;
-    sv[2 * BH + idx] = n;
-    sv[3 * BH + idx] = ghn;
-    sv[4 * BH + idx] = (1.0f - z) * n + z * hp;
+    sv[qs + idx] = z;
+    sv[2 * qs + idx] = n;
+    sv[3 * qs + idx] = ghn;
+    sv[4 * qs + idx] = (1.0f - z) * n + z * hp;
 }
 
-// ---- head: logit = h1 . w_out + b_out (one warp per row), loss terms, next step's feedback ------------------------
+// feedback of all steps under teacher forcing: +1 into step 0 (rnn_all.py:444), gt[:, t-1] into step t (447)
+__global__ void __launch_bounds__(256) teacher_fb_kernel(const float *__restrict__ gt, float *__restrict__ fb, int64_t B, int N)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * N) return;
+    const int64_t s = idx / B, b = idx - s * B;
+    fb[idx] = s == 0 ? 1.0f : gt[b * N + (s - 1)];
+}
+
+// ---- head: logit = h1 . w_out + b_out (one warp per row of [steps t0 .. t0 + nsteps) x B), loss terms, and under
+// student forcing the next step's feedback ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) head_fwd_kernel(const float *__restrict__ h1, const float *__restrict__ w_out,
                                                        const float *__restrict__ b_out, const float *__restrict__ gt,
-                                                       int N, int t, int is_loss, int teacher, float inv_count,
-                                                       float *__restrict__ out_t, float *__restrict__ dout_t,
-                                                       float *__restrict__ fb_next, float *__restrict__ logits_out,
-                                                       float *loss_sum, int64_t B, int H)
+                                                       int N, int t0, int nsteps, const unsigned char *__restrict__ is_loss_t,
+                                                       int write_fb, float inv_count, float *__restrict__ out,
+                                                       float *__restrict__ dout, float *__restrict__ fb,
+                                                       float *__restrict__ logits_out, float *loss_sum, int64_t B, int H)
 {
     const int lane = threadIdx.x & 31;
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (row >= B) return;
+    if (row >= B * nsteps) return;
     float s = 0.0f;
     for (int j = lane; j < H; j += 32) s += h1[row * H + j] * w_out[j];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(NPD_FULL, s, o);
     if (lane == 0) {
+        const int t = t0 + (int)(row / B);
+        const int64_t b = row % B;
+        const int is_loss = is_loss_t[t];
         const float o = s + b_out[0];
-        out_t[row] = o;
-        if (logits_out) logits_out[row * N + t] = o;
-        const float target = gt[row * N + t];
+        out[(int64_t)t * B + b] = o;
+        if (logits_out) logits_out[b * N + t] = o;
         float d = 0.0f;
         if (is_loss) {
-            const float e = o - target;
+            const float e = o - gt[b * N + t];
             d = 2.0f * e * inv_count;           // d mean((o - target)^2) / d o
             atomicAdd(loss_sum, e * e);
         }
-        dout_t[row] = d;
-        if (fb_next) {
-            // teacher forcing feeds gt[:, t] (rnn_all.py:447); student forcing feeds sign(decoded[:, t]) where decoded is
-            // the logit on loss (= info) positions and stays +1 elsewhere (463-489); sign(0) = 0 one-hots like -1
-            float f = teacher ? target : (is_loss ? (o > 0.0f ? 1.0f : (o < 0.0f ? -1.0f : 0.0f)) : 1.0f);
-            fb_next[row] = f;
-        }
+        dout[(int64_t)t * B + b] = d;
+        if (write_fb && t + 1 < N)
+            // student forcing feeds sign(decoded[:, t]) where decoded is the logit on loss (= info) positions and stays
+            // +1 elsewhere (rnn_all.py:463-489); sign(0) = 0 one-hots like -1
+            fb[(int64_t)(t + 1) * B + b] = is_loss ? (o > 0.0f ? 1.0f : (o < 0.0f ? -1.0f : 0.0f)) : 1.0f;
     }
 }
 
 // ---- backward gate kernel ------------------------------------------------------------------------------------------
 // dh = dh_next[b,j] + extra, where extra = dout[b] * w_out[j] (layer 1) or dx1[b,j] (layer 0).
-// Writes dgi / dgh [B,3H], overwrites dh_next with the direct path dh * z (the GEMM dgh W_hh is then accumulated on top
-// with beta = 1) and adds dgi / dgh into the per-row accumulators (bias and one-hot-column gradients).
+// Writes this step's dgi / dgh [B,3H] and overwrites dh_next with the direct path dh * z (the GEMM dgh W_hh is then
+// accumulated on top with beta = 1).  One thread owns unit j of kRowsPerThread consecutive rows and adds their gate
+// gradients into part[chunk][7][H] (stream-ordered launches, one owner per entry: no atomics): 0-2 = dgi (r, z, n) of rows
+// whose feedback is +1 (all rows in layer 1), 3-5 = the same for feedback -1 / 0, 6 = dgh's n part.
 template <bool LAYER0>
-__global__ void __launch_bounds__(256) cell_bwd_kernel(const float *__restrict__ sv, const float *__restrict__ h_prev,
+__global__ void __launch_bounds__(256) cell_bwd_kernel(const float *__restrict__ sv, size_t qs, const float *__restrict__ h_prev,
                                                        float *__restrict__ dh_next, const float *__restrict__ extra,
                                                        const float *__restrict__ dout, const float *__restrict__ w_out,
                                                        const float *__restrict__ fb, float *__restrict__ dgi,
-                                                       float *__restrict__ dgh, float *__restrict__ acc_gi_pos,
-                                                       float *__restrict__ acc_gi_neg, float *__restrict__ acc_gh,
-                                                       int64_t B, int H)
+                                                       float *__restrict__ dgh, float *__restrict__ part, int64_t B, int H)
 {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= B * H) return;
-    const int64_t b = idx / H;
-    const int j = (int)(idx - b * H);
-    const int64_t BH = B * H;
-    const float r = sv[idx], z = sv[BH + idx], n = sv[2 * BH + idx], ghn = sv[3 * BH + idx];
-    const float hp = h_prev[idx];
-    float dh = dh_next[idx];
-    dh += LAYER0 ? extra[idx] : dout[b] * w_out[j];
-    const float dn = dh * (1.0f - z);
-    const float dz = dh * (hp - n);
-    const float dn_pre = dn * (1.0f - n * n);
-    const float dr_pre = dn_pre * ghn * r * (1.0f - r);
-    const float dz_pre = dz * z * (1.0f - z);
-    dh_next[idx] = dh * z;
-    const int64_t o = b * 3 * H + j;
-    dgi[o] = dr_pre;
-    dgi[o + H] = dz_pre;
-    dgi[o + 2 * H] = dn_pre;
-    dgh[o] = dr_pre;
-    dgh[o + H] = dz_pre;
-    dgh[o + 2 * H] = dn_pre * r;
-    float *ag = acc_gi_pos;
-    if (LAYER0 && !(fb[b] > 0.0f)) ag = acc_gi_neg;
-    ag[o] += dr_pre;
-    ag[o + H] += dz_pre;
-    ag[o + 2 * H] += dn_pre;
-    acc_gh[o] += dr_pre;
-    acc_gh[o + H] += dz_pre;
-    acc_gh[o + 2 * H] += dn_pre * r;
+    const int j = blockIdx.y * blockDim.x + threadIdx.x;
+    if (j >= H) return;
+    const int64_t b0 = (int64_t)blockIdx.x * kRowsPerThread;
+    float a[7] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    const float wo = LAYER0 ? 0.0f : w_out[j];
+#pragma unroll
+    for (int i = 0; i < kRowsPerThread; ++i) {
+        const int64_t b = b0 + i;
+        if (b >= B) break;
+        const int64_t idx = b * H + j;
+        const float r = sv[idx], z = sv[qs + idx], n = sv[2 * qs + idx], ghn = sv[3 * qs + idx];
+        const float hp = h_prev[idx];
+        float dh = dh_next[idx];
+        dh += LAYER0 ? extra[idx] : dout[b] * wo;
+        const float dn = dh * (1.0f - z);
+        const float dz = dh * (hp - n);
+        const float dn_pre = dn * (1.0f - n * n);
+        const float dr_pre = dn_pre * ghn * r * (1.0f - r);
+        const float dz_pre = dz * z * (1.0f - z);
+        dh_next[idx] = dh * z;
+        const int64_t o = b * 3 * H + j;
+        dgi[o] = dr_pre;
+        dgi[o + H] = dz_pre;
+        dgi[o + 2 * H] = dn_pre;
+        dgh[o] = dr_pre;
+        dgh[o + H] = dz_pre;
+        dgh[o + 2 * H] = dn_pre * r;
+        if (LAYER0 && !(fb[b] > 0.0f)) { a[3] += dr_pre; a[4] += dz_pre; a[5] += dn_pre; }
+        else { a[0] += dr_pre; a[1] += dz_pre; a[2] += dn_pre; }
+        a[6] += dn_pre * r;
+    }
+    float *pp = part + (size_t)blockIdx.x * 7 * H + j;
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+        if (LAYER0 || k < 3 || k == 6) pp[(size_t)k * H] += a[k];
 }
 
-// dst[c * dst_stride] (+)= sum_b src[b, c] (+ src2[b, c]); one block per 32 columns, 8 warps striding over rows
-__global__ void __launch_bounds__(256) colsum_kernel(const float *__restrict__ src, const float *__restrict__ src2,
-                                                     float *__restrict__ dst, int64_t dst_stride, int64_t B, int C, int accumulate)
+// dst[c * dst_stride] = sum_b src[b * ld + c] (+ src2[b * ld + c]); one block per 32 columns, 8 warps striding over rows
+__global__ void __launch_bounds__(256) colsum_kernel(const float *__restrict__ src, const float *__restrict__ src2, int64_t ld,
+                                                     float *__restrict__ dst, int64_t dst_stride, int64_t B, int64_t C)
 {
     __shared__ float part[8][33];
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int64_t c = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
     const int w = threadIdx.x >> 5;
     float s = 0.0f;
     if (c < C)
         for (int64_t b = w; b < B; b += 8) {
-            s += src[b * C + c];
-            if (src2) s += src2[b * C + c];
+            s += src[b * ld + c];
+            if (src2) s += src2[b * ld + c];
         }
     part[w][threadIdx.x & 31] = s;
     __syncthreads();
@@ -213,20 +245,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float *__restrict__ s
         float t = 0.0f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x & 31];
-        if (accumulate) dst[(int64_t)c * dst_stride] += t; else dst[(int64_t)c * dst_stride] = t;
+        dst[c * dst_stride] = t;
     }
-}
-
-__global__ void __launch_bounds__(256) fill_kernel(float *__restrict__ a, float v, int64_t n)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) a[i] = v;
-}
-
-__global__ void __launch_bounds__(256) add_kernel(float *__restrict__ a, const float *__restrict__ b, int64_t n)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) a[i] += b[i];
 }
 
 __global__ void __launch_bounds__(256) sum_kernel(const float *__restrict__ x, int64_t n, float *out, int square)
@@ -278,6 +298,10 @@ NPD_API int npd_gru_trainer_create(int N, int H, int64_t max_batch, const float 
     NPD_REQUIRE(out && h_params, "npd_gru_trainer_create: null argument");
     NPD_REQUIRE(N >= 2 && N <= 4096 && H >= 8 && H <= 4096 && max_batch >= 1, "npd_gru_trainer_create: bad shape N=%d H=%d B=%lld",
                 N, H, (long long)max_batch);
+    // the all-steps GEMMs take N * B as a 32-bit dimension; the step-sum of dgi0 indexes B * 3H columns
+    NPD_REQUIRE((int64_t)N * max_batch <= 0x7fffffffLL && max_batch * 3 * (int64_t)H <= 0x7fffffffLL,
+                "npd_gru_trainer_create: N * max_batch = %lld (or max_batch * 3H) exceeds the GEMM index range",
+                (long long)N * (long long)max_batch);
     DeviceProps dp;
     if (npd_get_device_props(&dp)) return NPD_ECUDA;
     auto *t = new npd_gru_trainer();
@@ -297,20 +321,28 @@ NPD_API int npd_gru_trainer_create(int N, int H, int64_t max_batch, const float 
     t->o_bout = o; o += 1;
     t->n_params = o;
     t->beta1 = 0.9f; t->beta2 = 0.999f; t->eps = 1e-8f; t->weight_decay = 0.01f;  // torch.optim.AdamW defaults
-    const size_t B = (size_t)max_batch, BH = B * Hs, BG = B * G;
+    const size_t B = (size_t)max_batch, BH = B * Hs, BG = B * G, Ns = (size_t)N;
+    const size_t chunks = (B + kRowsPerThread - 1) / kRowsPerThread;
     auto alloc = [&](float **p, size_t n) { return cudaMalloc((void **)p, n * sizeof(float)); };
 #define TR_ALLOC(ptr, n) do { cudaError_t e__ = alloc(&(ptr), (n)); if (e__ != cudaSuccess) { \
         npd_set_error("npd_gru_trainer_create: cudaMalloc of %zu floats failed: %s", (size_t)(n), cudaGetErrorString(e__)); \
         npd_gru_trainer_destroy(t); return NPD_ENOMEM; } } while (0)
     TR_ALLOC(t->p, 4 * o);
     t->g = t->p + o; t->m = t->g + o; t->v = t->m + o;
-    TR_ALLOC(t->saved, 2 * (size_t)N * 5 * BH);
-    TR_ALLOC(t->gy, BG); TR_ALLOC(t->gi, BG); TR_ALLOC(t->gh, BG); TR_ALLOC(t->dgi, BG); TR_ALLOC(t->dgh, BG);
-    TR_ALLOC(t->acc, 5 * BG);
-    TR_ALLOC(t->dh0, BH); TR_ALLOC(t->dh1, BH); TR_ALLOC(t->dx1, BH); TR_ALLOC(t->zeros, BH);
-    TR_ALLOC(t->fb, (size_t)N * B); TR_ALLOC(t->out, (size_t)N * B); TR_ALLOC(t->dout, (size_t)N * B);
+    TR_ALLOC(t->saved, 2 * Ns * 5 * BH);
+    TR_ALLOC(t->gy, BG); TR_ALLOC(t->gh, BG);
+    TR_ALLOC(t->dgi, Ns * BG); TR_ALLOC(t->dgh, Ns * BG); TR_ALLOC(t->dx1, Ns * BH);
+    TR_ALLOC(t->part, 2 * chunks * 7 * Hs);
+    TR_ALLOC(t->dh, BH); TR_ALLOC(t->zeros, BH);
+    TR_ALLOC(t->fb, Ns * B); TR_ALLOC(t->out, Ns * B); TR_ALLOC(t->dout, Ns * B);
     TR_ALLOC(t->scal, 4);
 #undef TR_ALLOC
+    t->h_is_loss = (unsigned char *)malloc(Ns);
+    if (!t->h_is_loss || cudaMalloc((void **)&t->is_loss, Ns) != cudaSuccess) {
+        npd_set_error("npd_gru_trainer_create: cudaMalloc of %zu bytes failed", Ns);
+        npd_gru_trainer_destroy(t);
+        return NPD_ENOMEM;
+    }
     NPD_CHECK_CUDA(cudaMemset(t->p, 0, 4 * o * sizeof(float)));
     NPD_CHECK_CUDA(cudaMemset(t->zeros, 0, BH * sizeof(float)));
     NPD_CHECK_CUDA(cudaMemcpy(t->p, h_params, o * sizeof(float), cudaMemcpyHostToDevice));
@@ -326,9 +358,11 @@ NPD_API int npd_gru_trainer_destroy(npd_gru_trainer_t *t)
 {
     if (!t) return NPD_OK;
     if (t->blas) cublasDestroy(t->blas);
-    float *ptrs[] = {t->p, t->saved, t->gy, t->gi, t->gh, t->dgi, t->dgh, t->acc, t->dh0, t->dh1, t->dx1, t->zeros, t->fb,
-                     t->out, t->dout, t->scal};
+    float *ptrs[] = {t->p, t->saved, t->gy, t->gh, t->dgi, t->dgh, t->dx1, t->part, t->dh, t->zeros, t->fb, t->out, t->dout,
+                     t->scal};
     for (float *p : ptrs) if (p) cudaFree(p);
+    if (t->is_loss) cudaFree(t->is_loss);
+    free(t->h_is_loss);
     delete t;
     return NPD_OK;
 }
@@ -364,85 +398,113 @@ NPD_API int npd_gru_train_step(npd_gru_trainer_t *t, const npd_code_t *loss_code
     NPD_REQUIRE(loss_code->K >= 1, "npd_gru_train_step: empty loss set");
     cudaStream_t st = (cudaStream_t)stream;
     NPD_CHECK_CUBLAS(cublasSetStream(t->blas, st));
-    const int N = t->N, H = t->H, I = t->I, G = 3 * H;
+    const int N = t->N, H = t->H, I = t->I, G = 3 * H, mode = t->gemm_mode;
     const int64_t BH = B * H, BG = B * (int64_t)G;
+    const int NB = (int)((int64_t)N * B);  // rows of the all-steps operands (checked at create)
     const float one = 1.0f, zero = 0.0f;
-    std::vector<char> is_loss(N, 0);
+    std::vector<unsigned char> is_loss(N, 0);
     for (int k = 0; k < loss_code->K; ++k) is_loss[loss_code->h_info[k]] = 1;
+    if (!t->is_loss_valid || memcmp(t->h_is_loss, is_loss.data(), (size_t)N) != 0) {  // once per curriculum stage
+        memcpy(t->h_is_loss, is_loss.data(), (size_t)N);
+        NPD_CHECK_CUDA(cudaMemcpyAsync(t->is_loss, t->h_is_loss, (size_t)N, cudaMemcpyHostToDevice, st));
+        t->is_loss_valid = 1;
+    }
     const float inv_count = 1.0f / ((float)B * (float)loss_code->K);  // nn.MSELoss(): mean over B x K
     float *P = t->p, *Gd = t->g;
-    auto sv = [&](int layer, int step) { return t->saved + ((size_t)layer * N + step) * 5 * (size_t)BH; };
-    auto h_of = [&](int layer, int step) -> const float * { return step < 0 ? t->zeros : sv(layer, step) + 4 * (size_t)BH; };
+    const size_t qs = (size_t)N * (size_t)BH;  // floats between two saved quantities of a layer
+    auto sv = [&](int layer, int step) { return t->saved + (size_t)layer * 5 * qs + (size_t)step * (size_t)BH; };
+    auto h_all = [&](int layer) { return t->saved + (size_t)layer * 5 * qs + 4 * qs; };  // [N B, H]
+    auto h_of = [&](int layer, int step) -> const float * { return step < 0 ? t->zeros : h_all(layer) + (size_t)step * (size_t)BH; };
+    const int64_t chunks = (B + kRowsPerThread - 1) / kRowsPerThread;
+    float *part0 = t->part, *part1 = t->part + (size_t)chunks * 7 * H;
 
     NPD_CHECK_CUDA(cudaMemsetAsync(t->scal, 0, 4 * sizeof(float), st));
     NPD_CHECK_CUDA(cudaMemsetAsync(Gd, 0, t->n_params * sizeof(float), st));
-    NPD_CHECK_CUDA(cudaMemsetAsync(t->acc, 0, 5 * (size_t)BG * sizeof(float), st));
+    NPD_CHECK_CUDA(cudaMemsetAsync(t->part, 0, 2 * (size_t)chunks * 7 * H * sizeof(float), st));
     // ---- forward ----
-    // gy[B,3H] = y[B,N] . W_ih0[:, :N]^T   (row-major views as column-major: C^T = W . y^T)
-    NPD_CHECK_CUBLAS(gemm32(t->blas, t->gemm_mode, CUBLAS_OP_T, CUBLAS_OP_N, G, (int)B, N, &one, P + t->o_wih0, I, y, N, &zero, t->gy, G));
-    // feedback entering step 0 is +1 (rnn_all.py:444)
-    fill_kernel<<<blocks_for(B), 256, 0, st>>>(t->fb, 1.0f, B);
-    for (int s = 0; s < N; ++s) {
-        // layer 0
-        NPD_CHECK_CUBLAS(gemm32(t->blas, t->gemm_mode, CUBLAS_OP_T, CUBLAS_OP_N, G, (int)B, H, &one, P + t->o_whh0, H, h_of(0, s - 1), H,
-                                     &zero, t->gh, G));
+    // row-major [rows, cols] arrays are cuBLAS column-major [cols, rows]: out[rows, G] = in[rows, K] . W[G, K]^T is
+    // gemm(T, N, G, rows, K, W, in)
+    auto layer0_step = [&](int s) -> cublasStatus_t {
+        cublasStatus_t e = gemm32(t->blas, mode, CUBLAS_OP_T, CUBLAS_OP_N, G, (int)B, H, &one, P + t->o_whh0, H, h_of(0, s - 1), H, &zero, t->gh, G);
         cell_fwd_kernel<true><<<blocks_for(BH), 256, 0, st>>>(t->gy, t->gh, P + t->o_bih0, P + t->o_bhh0, P + t->o_wih0, I, N,
-                                                              t->fb + (size_t)s * B, h_of(0, s - 1), sv(0, s), B, H);
-        // layer 1
-        NPD_CHECK_CUBLAS(gemm32(t->blas, t->gemm_mode, CUBLAS_OP_T, CUBLAS_OP_N, G, (int)B, H, &one, P + t->o_wih1, H, h_of(0, s), H, &zero,
-                                     t->gi, G));
-        NPD_CHECK_CUBLAS(gemm32(t->blas, t->gemm_mode, CUBLAS_OP_T, CUBLAS_OP_N, G, (int)B, H, &one, P + t->o_whh1, H, h_of(1, s - 1), H,
-                                     &zero, t->gh, G));
-        cell_fwd_kernel<false><<<blocks_for(BH), 256, 0, st>>>(t->gi, t->gh, P + t->o_bih1, P + t->o_bhh1, nullptr, I, N, nullptr,
-                                                               h_of(1, s - 1), sv(1, s), B, H);
-        head_fwd_kernel<<<blocks_for(B * 32), 256, 0, st>>>(h_of(1, s), P + t->o_wout, P + t->o_bout, gt, N, s, is_loss[s],
-                                                            teacher_forced, inv_count, t->out + (size_t)s * B,
-                                                            t->dout + (size_t)s * B, s + 1 < N ? t->fb + (size_t)(s + 1) * B : nullptr,
-                                                            logits_out, t->scal, B, H);
+                                                              t->fb + (size_t)s * B, h_of(0, s - 1), sv(0, s), qs, B, H);
+        return e;
+    };
+    auto layer1_step = [&](int s) -> cublasStatus_t {
+        cublasStatus_t e = gemm32(t->blas, mode, CUBLAS_OP_T, CUBLAS_OP_N, G, (int)B, H, &one, P + t->o_whh1, H, h_of(1, s - 1), H, &zero, t->gh, G);
+        cell_fwd_kernel<false><<<blocks_for(BH), 256, 0, st>>>(t->dgi + (size_t)s * BG, t->gh, P + t->o_bih1, P + t->o_bhh1, nullptr, I, N,
+                                                               nullptr, h_of(1, s - 1), sv(1, s), qs, B, H);
+        return e;
+    };
+    auto head = [&](int t0, int nsteps, int write_fb) {
+        head_fwd_kernel<<<blocks_for((int64_t)nsteps * B * 32), 256, 0, st>>>(h_of(1, t0), P + t->o_wout, P + t->o_bout, gt, N, t0, nsteps,
+                                                                             t->is_loss, write_fb, inv_count, t->out, t->dout, t->fb,
+                                                                             logits_out, t->scal, B, H);
+    };
+    // gy[B,3H] = y[B,N] . W_ih0[:, :N]^T
+    NPD_CHECK_CUBLAS(gemm32(t->blas, mode, CUBLAS_OP_T, CUBLAS_OP_N, G, (int)B, N, &one, P + t->o_wih0, I, y, N, &zero, t->gy, G));
+    teacher_fb_kernel<<<blocks_for((int64_t)N * B), 256, 0, st>>>(gt, t->fb, B, N);  // student forcing overwrites steps >= 1
+    if (teacher_forced) {
+        for (int s = 0; s < N; ++s) NPD_CHECK_CUBLAS(layer0_step(s));
+        // W_ih1 . h0 of all steps into the (still unused) dgi buffer
+        NPD_CHECK_CUBLAS(gemm32(t->blas, mode, CUBLAS_OP_T, CUBLAS_OP_N, G, NB, H, &one, P + t->o_wih1, H, h_all(0), H, &zero, t->dgi, G));
+        for (int s = 0; s < N; ++s) NPD_CHECK_CUBLAS(layer1_step(s));
+        head(0, N, 0);
+    } else {
+        for (int s = 0; s < N; ++s) {
+            NPD_CHECK_CUBLAS(layer0_step(s));
+            NPD_CHECK_CUBLAS(gemm32(t->blas, mode, CUBLAS_OP_T, CUBLAS_OP_N, G, (int)B, H, &one, P + t->o_wih1, H, h_of(0, s), H, &zero,
+                                    t->dgi + (size_t)s * BG, G));
+            NPD_CHECK_CUBLAS(layer1_step(s));
+            head(s, 1, 1);
+        }
     }
     NPD_CHECK_CUDA(cudaGetLastError());
     // ---- backward ----
-    float *acc0p = t->acc, *acc0n = t->acc + BG, *acc0h = t->acc + 2 * BG, *acc1i = t->acc + 3 * BG, *acc1h = t->acc + 4 * BG;
-    NPD_CHECK_CUDA(cudaMemsetAsync(t->dh0, 0, (size_t)BH * sizeof(float), st));
-    NPD_CHECK_CUDA(cudaMemsetAsync(t->dh1, 0, (size_t)BH * sizeof(float), st));
+    // in[rows, G] . W[G, K] -> out[rows, K] is gemm(N, N, K, rows, G, W, in); a[rows, K]^T-weighted sums
+    // dW[G, K] = d[rows, G]^T a[rows, K] are gemm(N, T, K, G, rows, a, d)
+    const dim3 bgrid((unsigned)chunks, (unsigned)((H + 255) / 256));
+    // layer 1: dh = dh1 + dout_s (x) w_out
+    NPD_CHECK_CUDA(cudaMemsetAsync(t->dh, 0, (size_t)BH * sizeof(float), st));
     for (int s = N - 1; s >= 0; --s) {
-        // layer 1: dh = dh1 + dout_s (x) w_out
-        cell_bwd_kernel<false><<<blocks_for(BH), 256, 0, st>>>(sv(1, s), h_of(1, s - 1), t->dh1, nullptr, t->dout + (size_t)s * B,
-                                                               P + t->o_wout, nullptr, t->dgi, t->dgh, acc1i, nullptr, acc1h, B, H);
-        if (is_loss[s])  // d w_out += h1_s^T dout_s
-            NPD_CHECK_CUBLAS(cublasSgemv(t->blas, CUBLAS_OP_N, H, (int)B, &one, h_of(1, s), H, t->dout + (size_t)s * B, 1, &one,
-                                         Gd + t->o_wout, 1));
-        // dW_hh1 += dgh^T h1_{s-1} ; dW_ih1 += dgi^T h0_s
-        if (s > 0)
-            NPD_CHECK_CUBLAS(gemm32(t->blas, t->gemm_mode, CUBLAS_OP_N, CUBLAS_OP_T, H, G, (int)B, &one, h_of(1, s - 1), H, t->dgh, G, &one,
-                                         Gd + t->o_whh1, H));
-        NPD_CHECK_CUBLAS(gemm32(t->blas, t->gemm_mode, CUBLAS_OP_N, CUBLAS_OP_T, H, G, (int)B, &one, h_of(0, s), H, t->dgi, G, &one,
-                                     Gd + t->o_wih1, H));
-        // dh1 (for step s-1) = dh * z (already written) + dgh W_hh1 ; dx1 = dgi W_ih1
-        if (s > 0)
-            NPD_CHECK_CUBLAS(gemm32(t->blas, t->gemm_mode, CUBLAS_OP_N, CUBLAS_OP_N, H, (int)B, G, &one, P + t->o_whh1, H, t->dgh, G, &one, t->dh1, H));
-        NPD_CHECK_CUBLAS(gemm32(t->blas, t->gemm_mode, CUBLAS_OP_N, CUBLAS_OP_N, H, (int)B, G, &one, P + t->o_wih1, H, t->dgi, G, &zero, t->dx1, H));
-        // layer 0: dh = dh0 + dx1
-        cell_bwd_kernel<true><<<blocks_for(BH), 256, 0, st>>>(sv(0, s), h_of(0, s - 1), t->dh0, t->dx1, nullptr, nullptr,
-                                                              t->fb + (size_t)s * B, t->dgi, t->dgh, acc0p, acc0n, acc0h, B, H);
-        if (s > 0) {
-            NPD_CHECK_CUBLAS(gemm32(t->blas, t->gemm_mode, CUBLAS_OP_N, CUBLAS_OP_T, H, G, (int)B, &one, h_of(0, s - 1), H, t->dgh, G, &one,
-                                         Gd + t->o_whh0, H));
-            NPD_CHECK_CUBLAS(gemm32(t->blas, t->gemm_mode, CUBLAS_OP_N, CUBLAS_OP_N, H, (int)B, G, &one, P + t->o_whh0, H, t->dgh, G, &one, t->dh0, H));
-        }
+        cell_bwd_kernel<false><<<bgrid, 256, 0, st>>>(sv(1, s), qs, h_of(1, s - 1), t->dh, nullptr, t->dout + (size_t)s * B, P + t->o_wout,
+                                                      nullptr, t->dgi + (size_t)s * BG, t->dgh + (size_t)s * BG, part1, B, H);
+        if (s > 0)  // dh1 (for step s-1) = dh * z (already written) + dgh W_hh1
+            NPD_CHECK_CUBLAS(gemm32(t->blas, mode, CUBLAS_OP_N, CUBLAS_OP_N, H, (int)B, G, &one, P + t->o_whh1, H, t->dgh + (size_t)s * BG, G,
+                                    &one, t->dh, H));
     }
-    // bias gradients and the two one-hot columns of W_ih0 from the per-row accumulators
-    const unsigned cg = (unsigned)((G + 31) / 32);
-    colsum_kernel<<<cg, 256, 0, st>>>(acc0p, nullptr, Gd + t->o_wih0 + N + 1, I, B, G, 0);  // feedback +1 -> column N+1
-    colsum_kernel<<<cg, 256, 0, st>>>(acc0n, nullptr, Gd + t->o_wih0 + N, I, B, G, 0);      // feedback -1 -> column N
-    colsum_kernel<<<cg, 256, 0, st>>>(acc0p, acc0n, Gd + t->o_bih0, 1, B, G, 0);
-    colsum_kernel<<<cg, 256, 0, st>>>(acc0h, nullptr, Gd + t->o_bhh0, 1, B, G, 0);
-    colsum_kernel<<<cg, 256, 0, st>>>(acc1i, nullptr, Gd + t->o_bih1, 1, B, G, 0);
-    colsum_kernel<<<cg, 256, 0, st>>>(acc1h, nullptr, Gd + t->o_bhh1, 1, B, G, 0);
-    // d W_ih0[:, :N] = (sum_s dgi0_s)^T y  -- y is the same in every step
-    add_kernel<<<blocks_for(BG), 256, 0, st>>>(acc0p, acc0n, BG);
-    NPD_CHECK_CUBLAS(gemm32(t->blas, t->gemm_mode, CUBLAS_OP_N, CUBLAS_OP_T, N, G, (int)B, &one, y, N, acc0p, G, &zero, Gd + t->o_wih0, I));
-    // the GEMM above wrote rows of width N with leading dimension I: columns N, N+1 were untouched (set by the colsums)
+    // all steps at once: dx1 = dgi1 W_ih1 ; dW_ih1 = dgi1^T h0 ; dW_hh1 = dgh1[1:]^T h1[:-1] ; d w_out = h1^T dout
+    NPD_CHECK_CUBLAS(gemm32(t->blas, mode, CUBLAS_OP_N, CUBLAS_OP_N, H, NB, G, &one, P + t->o_wih1, H, t->dgi, G, &zero, t->dx1, H));
+    NPD_CHECK_CUBLAS(gemm32(t->blas, mode, CUBLAS_OP_N, CUBLAS_OP_T, H, G, NB, &one, h_all(0), H, t->dgi, G, &zero, Gd + t->o_wih1, H));
+    NPD_CHECK_CUBLAS(gemm32(t->blas, mode, CUBLAS_OP_N, CUBLAS_OP_T, H, G, NB - (int)B, &one, h_all(1), H, t->dgh + (size_t)BG, G, &zero,
+                            Gd + t->o_whh1, H));
+    NPD_CHECK_CUBLAS(cublasSgemv(t->blas, CUBLAS_OP_N, H, NB, &one, h_all(1), H, t->dout, 1, &zero, Gd + t->o_wout, 1));  // dout = 0 off the loss set
+    // layer 0: dh = dh0 + dx1_s ; dgi / dgh are reused for this layer's gate gradients
+    NPD_CHECK_CUDA(cudaMemsetAsync(t->dh, 0, (size_t)BH * sizeof(float), st));
+    for (int s = N - 1; s >= 0; --s) {
+        cell_bwd_kernel<true><<<bgrid, 256, 0, st>>>(sv(0, s), qs, h_of(0, s - 1), t->dh, t->dx1 + (size_t)s * BH, nullptr, nullptr,
+                                                     t->fb + (size_t)s * B, t->dgi + (size_t)s * BG, t->dgh + (size_t)s * BG, part0, B, H);
+        if (s > 0)
+            NPD_CHECK_CUBLAS(gemm32(t->blas, mode, CUBLAS_OP_N, CUBLAS_OP_N, H, (int)B, G, &one, P + t->o_whh0, H, t->dgh + (size_t)s * BG, G,
+                                    &one, t->dh, H));
+    }
+    NPD_CHECK_CUBLAS(gemm32(t->blas, mode, CUBLAS_OP_N, CUBLAS_OP_T, H, G, NB - (int)B, &one, h_all(0), H, t->dgh + (size_t)BG, G, &zero,
+                            Gd + t->o_whh0, H));
+    // d W_ih0[:, :N] = (sum_s dgi0_s)^T y  -- y is the same in every step; the sum over steps lands in gy
+    colsum_kernel<<<blocks_for(BG, 32), 256, 0, st>>>(t->dgi, nullptr, BG, t->gy, 1, N, BG);
+    NPD_CHECK_CUBLAS(gemm32(t->blas, mode, CUBLAS_OP_N, CUBLAS_OP_T, N, G, (int)B, &one, y, N, t->gy, G, &zero, Gd + t->o_wih0, I));
+    // (rows of width N with leading dimension I: columns N, N+1 are set below)
+    // bias gradients and the two one-hot columns of W_ih0 from the column-sum partials [chunks][7][H]
+    const int64_t pld = 7 * (int64_t)H;
+    const unsigned c3 = blocks_for(G, 32), c2 = blocks_for(2 * H, 32), c1 = blocks_for(H, 32);
+    colsum_kernel<<<c3, 256, 0, st>>>(part0, nullptr, pld, Gd + t->o_wih0 + N + 1, I, chunks, G);           // feedback +1 -> column N+1
+    colsum_kernel<<<c3, 256, 0, st>>>(part0 + 3 * H, nullptr, pld, Gd + t->o_wih0 + N, I, chunks, G);       // feedback -1 -> column N
+    colsum_kernel<<<c3, 256, 0, st>>>(part0, part0 + 3 * H, pld, Gd + t->o_bih0, 1, chunks, G);
+    colsum_kernel<<<c2, 256, 0, st>>>(part0, part0 + 3 * H, pld, Gd + t->o_bhh0, 1, chunks, 2 * H);        // r, z parts = dgi's
+    colsum_kernel<<<c1, 256, 0, st>>>(part0 + 6 * H, nullptr, pld, Gd + t->o_bhh0 + 2 * H, 1, chunks, H);
+    colsum_kernel<<<c3, 256, 0, st>>>(part1, nullptr, pld, Gd + t->o_bih1, 1, chunks, G);
+    colsum_kernel<<<c2, 256, 0, st>>>(part1, nullptr, pld, Gd + t->o_bhh1, 1, chunks, 2 * H);
+    colsum_kernel<<<c1, 256, 0, st>>>(part1 + 6 * H, nullptr, pld, Gd + t->o_bhh1 + 2 * H, 1, chunks, H);
     sum_kernel<<<64, 256, 0, st>>>(t->dout, (int64_t)N * B, Gd + t->o_bout, 0);
     NPD_CHECK_CUDA(cudaGetLastError());
     // ---- clip + AdamW ----
