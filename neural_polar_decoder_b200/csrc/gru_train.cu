@@ -19,8 +19,8 @@
 //   backward  layer 1 for t = N-1..0 (fused gate-gradient kernel -> dgi1[t], dgh1[t]; dh1 += dgh1[t] W_hh1), then for
 //             ALL steps at once d x1 = dgi1 W_ih1, dW_ih1 = dgi1^T h0, dW_hh1 = dgh1[1:]^T h1[:-1]; layer 0 the same
 //             way.  The detached feedback carries no gradient, so this order is valid for both forcing modes.  Weight
-//             gradients are therefore 4 GEMMs with K = N B instead of 4 N accumulating GEMMs with K = B (those were 55 %
-//             of the first version's time: 6 output tiles on 148 SMs).  Bias and one-hot-column gradients: every thread
+//             gradients are therefore 3 batched GEMMs (one slice per step, summed by a column-sum kernel) instead of 4 N
+//             dependent accumulating GEMMs with K = B (55 % of the first version's time: 24 output tiles on 148 SMs).  Bias and one-hot-column gradients: every thread
 //             of the gate-gradient kernel owns one unit of 8 consecutive rows and keeps their column sums in registers;
 //             the [B/8, 7, H] partials are reduced once at the end (deterministic).
 //   update    one fused kernel: global grad-norm clip coefficient + AdamW.
@@ -56,6 +56,17 @@ static cublasStatus_t gemm32(cublasHandle_t h, int mode, cublasOperation_t ta, c
                         CUBLAS_GEMM_DEFAULT);
 }
 
+// the same GEMM for `batch` (A, B, C) triples at fixed strides
+static cublasStatus_t gemm32_batched(cublasHandle_t h, int mode, cublasOperation_t ta, cublasOperation_t tb, int m, int n, int k,
+                                     const float *alpha, const float *A, int lda, long long sa, const float *B, int ldb,
+                                     long long sb, const float *beta, float *C, int ldc, long long sc, int batch)
+{
+    const cublasComputeType_t ct = mode == 1 ? CUBLAS_COMPUTE_32F_FAST_TF32 : mode == 2 ? CUBLAS_COMPUTE_32F_FAST_16BF
+                                 : mode == 3 ? CUBLAS_COMPUTE_32F_FAST_16F : CUBLAS_COMPUTE_32F_PEDANTIC;
+    return cublasGemmStridedBatchedEx(h, ta, tb, m, n, k, alpha, A, CUDA_R_32F, lda, sa, B, CUDA_R_32F, ldb, sb, beta, C,
+                                      CUDA_R_32F, ldc, sc, batch, ct, CUBLAS_GEMM_DEFAULT);
+}
+
 struct npd_gru_trainer {
     int N, H, I;        // code length (= steps), hidden size, layer-0 input width N + 2
     int64_t max_batch;
@@ -76,6 +87,7 @@ struct npd_gru_trainer {
     float *dgi, *dgh;   // [N steps][B,3H]  gate gradients of the layer being processed; dgi doubles as W_ih1 . h0 of all
                         //                  steps in the forward pass
     float *dx1;         // [N steps][B,H]   gradient entering layer 0 from layer 1
+    float *wpart;       // [N steps][3H,H]  per-step slices of a weight gradient (split-K by hand, see weight_grad)
     float *part;        // [2 layers][ceil(B/8)][7][H] column sums of the gate gradients, see cell_bwd_kernel
     float *dh, *zeros;  // [B,H]
     float *fb;          // [N][B] feedback entering step t (+-1)
@@ -332,6 +344,7 @@ NPD_API int npd_gru_trainer_create(int N, int H, int64_t max_batch, const float 
     TR_ALLOC(t->saved, 2 * Ns * 5 * BH);
     TR_ALLOC(t->gy, BG); TR_ALLOC(t->gh, BG);
     TR_ALLOC(t->dgi, Ns * BG); TR_ALLOC(t->dgh, Ns * BG); TR_ALLOC(t->dx1, Ns * BH);
+    TR_ALLOC(t->wpart, Ns * G * Hs);
     TR_ALLOC(t->part, 2 * chunks * 7 * Hs);
     TR_ALLOC(t->dh, BH); TR_ALLOC(t->zeros, BH);
     TR_ALLOC(t->fb, Ns * B); TR_ALLOC(t->out, Ns * B); TR_ALLOC(t->dout, Ns * B);
@@ -358,7 +371,7 @@ NPD_API int npd_gru_trainer_destroy(npd_gru_trainer_t *t)
 {
     if (!t) return NPD_OK;
     if (t->blas) cublasDestroy(t->blas);
-    float *ptrs[] = {t->p, t->saved, t->gy, t->gh, t->dgi, t->dgh, t->dx1, t->part, t->dh, t->zeros, t->fb, t->out, t->dout,
+    float *ptrs[] = {t->p, t->saved, t->gy, t->gh, t->dgi, t->dgh, t->dx1, t->wpart, t->part, t->dh, t->zeros, t->fb, t->out, t->dout,
                      t->scal};
     for (float *p : ptrs) if (p) cudaFree(p);
     if (t->is_loss) cudaFree(t->is_loss);
@@ -473,11 +486,19 @@ NPD_API int npd_gru_train_step(npd_gru_trainer_t *t, const npd_code_t *loss_code
             NPD_CHECK_CUBLAS(gemm32(t->blas, mode, CUBLAS_OP_N, CUBLAS_OP_N, H, (int)B, G, &one, P + t->o_whh1, H, t->dgh + (size_t)s * BG, G,
                                     &one, t->dh, H));
     }
+    // dW[G, H] = d[steps * B, G]^T a[steps * B, H].  As ONE GEMM the 3H x H output is 24 tiles for 148 SMs and the library does
+    // not split K = steps * B on its own (2.9 ms each); one GEMM per step's rows into its own slice + a column sum over
+    // the slices fills the machine (deterministic: fixed slice order).
+    auto weight_grad = [&](const float *a, const float *d, int steps, float *dW) -> cublasStatus_t {
+        cublasStatus_t e = gemm32_batched(t->blas, mode, CUBLAS_OP_N, CUBLAS_OP_T, H, G, (int)B, &one, a, H, (long long)BH, d, G,
+                                          (long long)BG, &zero, t->wpart, H, (long long)G * H, steps);
+        colsum_kernel<<<blocks_for((int64_t)G * H, 32), 256, 0, st>>>(t->wpart, nullptr, (int64_t)G * H, dW, 1, steps, (int64_t)G * H);
+        return e;
+    };
     // all steps at once: dx1 = dgi1 W_ih1 ; dW_ih1 = dgi1^T h0 ; dW_hh1 = dgh1[1:]^T h1[:-1] ; d w_out = h1^T dout
     NPD_CHECK_CUBLAS(gemm32(t->blas, mode, CUBLAS_OP_N, CUBLAS_OP_N, H, NB, G, &one, P + t->o_wih1, H, t->dgi, G, &zero, t->dx1, H));
-    NPD_CHECK_CUBLAS(gemm32(t->blas, mode, CUBLAS_OP_N, CUBLAS_OP_T, H, G, NB, &one, h_all(0), H, t->dgi, G, &zero, Gd + t->o_wih1, H));
-    NPD_CHECK_CUBLAS(gemm32(t->blas, mode, CUBLAS_OP_N, CUBLAS_OP_T, H, G, NB - (int)B, &one, h_all(1), H, t->dgh + (size_t)BG, G, &zero,
-                            Gd + t->o_whh1, H));
+    NPD_CHECK_CUBLAS(weight_grad(h_all(0), t->dgi, N, Gd + t->o_wih1));
+    NPD_CHECK_CUBLAS(weight_grad(h_all(1), t->dgh + (size_t)BG, N - 1, Gd + t->o_whh1));
     NPD_CHECK_CUBLAS(cublasSgemv(t->blas, CUBLAS_OP_N, H, NB, &one, h_all(1), H, t->dout, 1, &zero, Gd + t->o_wout, 1));  // dout = 0 off the loss set
     // layer 0: dh = dh0 + dx1_s ; dgi / dgh are reused for this layer's gate gradients
     NPD_CHECK_CUDA(cudaMemsetAsync(t->dh, 0, (size_t)BH * sizeof(float), st));
@@ -488,8 +509,7 @@ NPD_API int npd_gru_train_step(npd_gru_trainer_t *t, const npd_code_t *loss_code
             NPD_CHECK_CUBLAS(gemm32(t->blas, mode, CUBLAS_OP_N, CUBLAS_OP_N, H, (int)B, G, &one, P + t->o_whh0, H, t->dgh + (size_t)s * BG, G,
                                     &one, t->dh, H));
     }
-    NPD_CHECK_CUBLAS(gemm32(t->blas, mode, CUBLAS_OP_N, CUBLAS_OP_T, H, G, NB - (int)B, &one, h_all(0), H, t->dgh + (size_t)BG, G, &zero,
-                            Gd + t->o_whh0, H));
+    NPD_CHECK_CUBLAS(weight_grad(h_all(0), t->dgh + (size_t)BG, N - 1, Gd + t->o_whh0));
     // d W_ih0[:, :N] = (sum_s dgi0_s)^T y  -- y is the same in every step; the sum over steps lands in gy
     colsum_kernel<<<blocks_for(BG, 32), 256, 0, st>>>(t->dgi, nullptr, BG, t->gy, 1, N, BG);
     NPD_CHECK_CUBLAS(gemm32(t->blas, mode, CUBLAS_OP_N, CUBLAS_OP_T, N, G, (int)B, &one, y, N, t->gy, G, &zero, Gd + t->o_wih0, I));
