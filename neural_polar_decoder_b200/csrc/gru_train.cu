@@ -93,6 +93,7 @@ struct npd_gru_trainer {
     float *fb;          // [N][B] feedback entering step t (+-1)
     float *out, *dout;  // [N][B] logits, d loss / d logit
     float *scal;        // [4]: loss sum, grad norm^2, spare
+    float *wcol;        // [2][3H] the one-hot columns of W_ih0, contiguous
     unsigned char *is_loss;    // [N] device copy of the loss set's indicator
     unsigned char *h_is_loss;  // [N] what is_loss holds (uploaded only when the loss set changes)
     int is_loss_valid;
@@ -105,13 +106,15 @@ constexpr int kRowsPerThread = 8;  // cell_bwd_kernel: rows whose column sums on
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // ---- forward gate kernel: one thread per (row b, unit j) -------------------------------------------------------
-// LAYER0: gi = gy[b, g*H+j] + b_ih[g*H+j] + W_ih0[g*H+j, N + idx(fb[b])]   (one-hot feedback = column select)
+// LAYER0: gi = gy[b, g*H+j] + b_ih[g*H+j] + W_ih0[g*H+j, N + idx(fb[b])]   (one-hot feedback = column select; the two
+//         columns are copied out contiguously once per iteration, wcol [2][3H] -- read in place they are 4 (N + 2) bytes
+//         apart, one sector per lane)
 // else  : gi = gi_buf[b, g*H+j] + b_ih[g*H+j]
 // sv points at quantity 0 of this (layer, step); the five saved quantities are qs floats apart
 template <bool LAYER0>
 __global__ void __launch_bounds__(256) cell_fwd_kernel(const float *__restrict__ gi_src, const float *__restrict__ gh,
                                                        const float *__restrict__ b_ih, const float *__restrict__ b_hh,
-                                                       const float *__restrict__ w_ih0, int I, int N,
+                                                       const float *__restrict__ wcol,
                                                        const float *__restrict__ fb, const float *__restrict__ h_prev,
                                                        float *__restrict__ sv, size_t qs, int64_t B, int H)
 {
@@ -123,10 +126,10 @@ __global__ void __launch_bounds__(256) cell_fwd_kernel(const float *__restrict__
     float giz = gi_src[b * 3 * H + H + j] + b_ih[H + j];
     float gin = gi_src[b * 3 * H + 2 * H + j] + b_ih[2 * H + j];
     if (LAYER0) {
-        const int col = N + (fb[b] > 0.0f ? 1 : 0);  // get_onehot (rnn_all.py:258-260): +1 -> [0,1], -1 / 0 -> [1,0]
-        gir += w_ih0[(size_t)j * I + col];
-        giz += w_ih0[(size_t)(H + j) * I + col];
-        gin += w_ih0[(size_t)(2 * H + j) * I + col];
+        const float *wc = wcol + (fb[b] > 0.0f ? 3 * H : 0);  // get_onehot (rnn_all.py:258-260): +1 -> [0,1], -1 / 0 -> [1,0]
+        gir += wc[j];
+        giz += wc[H + j];
+        gin += wc[2 * H + j];
     }
     const float ghr = gh[b * 3 * H + j] + b_hh[j];
     const float ghz = gh[b * 3 * H + H + j] + b_hh[H + j];
@@ -140,6 +143,13 @@ __global__ void __launch_bounds__(256) cell_fwd_kernel(const float *__restrict__
     sv[2 * qs + idx] = n;
     sv[3 * qs + idx] = ghn;
     sv[4 * qs + idx] = (1.0f - z) * n + z * hp;
+}
+
+// wcol[c][g] = W_ih0[g, N + c]
+__global__ void __launch_bounds__(256) onehot_cols_kernel(const float *__restrict__ w_ih0, float *__restrict__ wcol, int I, int N, int G)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2 * G) wcol[i] = w_ih0[(size_t)(i % G) * I + N + i / G];
 }
 
 // feedback of all steps under teacher forcing: +1 into step 0 (rnn_all.py:444), gt[:, t-1] into step t (447)
@@ -349,6 +359,7 @@ NPD_API int npd_gru_trainer_create(int N, int H, int64_t max_batch, const float 
     TR_ALLOC(t->dh, BH); TR_ALLOC(t->zeros, BH);
     TR_ALLOC(t->fb, Ns * B); TR_ALLOC(t->out, Ns * B); TR_ALLOC(t->dout, Ns * B);
     TR_ALLOC(t->scal, 4);
+    TR_ALLOC(t->wcol, 2 * G);
 #undef TR_ALLOC
     t->h_is_loss = (unsigned char *)malloc(Ns);
     if (!t->h_is_loss || cudaMalloc((void **)&t->is_loss, Ns) != cudaSuccess) {
@@ -372,7 +383,7 @@ NPD_API int npd_gru_trainer_destroy(npd_gru_trainer_t *t)
     if (!t) return NPD_OK;
     if (t->blas) cublasDestroy(t->blas);
     float *ptrs[] = {t->p, t->saved, t->gy, t->gh, t->dgi, t->dgh, t->dx1, t->wpart, t->part, t->dh, t->zeros, t->fb, t->out, t->dout,
-                     t->scal};
+                     t->scal, t->wcol};
     for (float *p : ptrs) if (p) cudaFree(p);
     if (t->is_loss) cudaFree(t->is_loss);
     free(t->h_is_loss);
@@ -439,13 +450,13 @@ NPD_API int npd_gru_train_step(npd_gru_trainer_t *t, const npd_code_t *loss_code
     // gemm(T, N, G, rows, K, W, in)
     auto layer0_step = [&](int s) -> cublasStatus_t {
         cublasStatus_t e = gemm32(t->blas, mode, CUBLAS_OP_T, CUBLAS_OP_N, G, (int)B, H, &one, P + t->o_whh0, H, h_of(0, s - 1), H, &zero, t->gh, G);
-        cell_fwd_kernel<true><<<blocks_for(BH), 256, 0, st>>>(t->gy, t->gh, P + t->o_bih0, P + t->o_bhh0, P + t->o_wih0, I, N,
+        cell_fwd_kernel<true><<<blocks_for(BH), 256, 0, st>>>(t->gy, t->gh, P + t->o_bih0, P + t->o_bhh0, t->wcol,
                                                               t->fb + (size_t)s * B, h_of(0, s - 1), sv(0, s), qs, B, H);
         return e;
     };
     auto layer1_step = [&](int s) -> cublasStatus_t {
         cublasStatus_t e = gemm32(t->blas, mode, CUBLAS_OP_T, CUBLAS_OP_N, G, (int)B, H, &one, P + t->o_whh1, H, h_of(1, s - 1), H, &zero, t->gh, G);
-        cell_fwd_kernel<false><<<blocks_for(BH), 256, 0, st>>>(t->dgi + (size_t)s * BG, t->gh, P + t->o_bih1, P + t->o_bhh1, nullptr, I, N,
+        cell_fwd_kernel<false><<<blocks_for(BH), 256, 0, st>>>(t->dgi + (size_t)s * BG, t->gh, P + t->o_bih1, P + t->o_bhh1, nullptr,
                                                                nullptr, h_of(1, s - 1), sv(1, s), qs, B, H);
         return e;
     };
@@ -456,6 +467,7 @@ NPD_API int npd_gru_train_step(npd_gru_trainer_t *t, const npd_code_t *loss_code
     };
     // gy[B,3H] = y[B,N] . W_ih0[:, :N]^T
     NPD_CHECK_CUBLAS(gemm32(t->blas, mode, CUBLAS_OP_T, CUBLAS_OP_N, G, (int)B, N, &one, P + t->o_wih0, I, y, N, &zero, t->gy, G));
+    onehot_cols_kernel<<<blocks_for(2 * G), 256, 0, st>>>(P + t->o_wih0, t->wcol, I, N, G);
     teacher_fb_kernel<<<blocks_for((int64_t)N * B), 256, 0, st>>>(gt, t->fb, B, N);  // student forcing overwrites steps >= 1
     if (teacher_forced) {
         for (int s = 0; s < N; ++s) NPD_CHECK_CUBLAS(layer0_step(s));

@@ -98,6 +98,37 @@ def test_train_step_flagship_shape_vs_oracle(teacher):
     assert np.median(d) <= 1e-7 and np.mean(d > 1e-5) < 0.02, (float(np.median(d)), float(np.mean(d > 1e-5)))
 
 
+@pytest.mark.parametrize("teacher", [True, False])
+def test_train_step_ragged_shapes_vs_oracle(teacher):
+    """Batch not a multiple of the gate-gradient kernel's 8-row groups, smaller than the trainer's max_batch (the all-steps
+    operands are laid out for the CALL's batch), H not a multiple of the warp / block widths; two calls on one trainer."""
+    from neural_polar_decoder_b200 import synth
+    from neural_polar_decoder_b200.rnn_all import RNN_Model, RNN_decoder, get_code
+    from neural_polar_decoder_b200.train import GRUTrainer, _blob
+    N, K, H = 16, 7, 24
+    code = get_code("Polar", "polar", N, K)
+    sd = synth.gru_state_dict(9, N, H, 2, head_gain=2.0)
+    net = RNN_Model('GRU', N + 2, H, 1, 2, N, 0, 0)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    dec = RNN_decoder('y_input', N, code.info_inds, onehot=True)
+    tr = GRUTrainer(net, N, 40)
+    blob = _blob(net)
+    rs = np.random.RandomState(4)
+    for B in (13, 37, 1):
+        msg = (1.0 - 2.0 * rs.randint(0, 2, size=(B, K))).astype(np.float32)
+        gt = np.ones((B, N), np.float32)
+        gt[:, code.info_inds] = msg
+        y = (code.encode(torch.from_numpy(msg).cuda()).cpu().numpy() + rs.randn(B, N)).astype(np.float32)
+        _, grad, loss, norm, logits, _ = oracle.gru_train_step(blob, y, gt, N, H, code.info_inds, teacher, 1e-3, 0.25)
+        l2, n2, lg = tr.step(dec._loss_code(code.info_inds), torch.from_numpy(y).cuda(), torch.from_numpy(gt).cuda(), teacher,
+                             1e-3, 0.25, want_logits=True, apply_update=False)
+        assert l2 == pytest.approx(loss, rel=5e-5) and n2 == pytest.approx(norm, rel=5e-4), B
+        if teacher:
+            np.testing.assert_allclose(lg.cpu().numpy(), logits, atol=2e-5)
+        ours = tr.get("grads") * min(1.0, 0.25 / (n2 + 1e-6))  # apply_update=False leaves the gradient unclipped
+        assert _relerr(ours, grad) <= 5e-4, (B, _relerr(ours, grad))
+
+
 def test_training_loop_learns_and_writes_reference_checkpoint(tmp_path, monkeypatch):
     """`python -m neural_polar_decoder_b200.rnn_all <run_crisp.sh-style flags>` without --test: a short K = 4 stage trains
     on the GPU (loss falls), leaves {'net','step','args'} where the reference would, and the TESTING block then loads it."""
