@@ -387,6 +387,8 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("NPD_BENCH_WORKLOAD", "default"))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU codewords per step (0 = workload default)")
+    ap.add_argument("--chunk", type=int, default=0, help="mc* workloads: exact chunk size (0 = the workload's, rounded to whole "
+                    "decoder rounds by sweep.sc_round_chunk)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="default workload without the other workloads")
     ap.add_argument("--no-parity", action="store_true")
@@ -704,9 +706,13 @@ def bench_mc(args, w, rank, world, local_rank):
     import torch.distributed as dist
     from neural_polar_decoder_b200 import _lib, utils, sweep
     lib = _lib.load()
-    N, K, F, snr, chunk = w["N"], w["K"], w["batch"], w["snr"], w["chunk"]
+    N, K, F, snr = w["N"], w["K"], w["batch"], w["snr"]
     code = make_code(w)
     h = code._handle()
+    # chunks of whole decoder rounds (the persistent SC kernel: 148 SMs x resident warps x 8 codewords per round), and a
+    # step of whole chunks
+    chunk = args.chunk if getattr(args, "chunk", 0) > 0 else sweep.sc_round_chunk(code, w["chunk"])
+    F = max(1, F // chunk) * chunk
     dev = torch.device("cuda", local_rank)
     sigma = float(np.float32(utils.snr_db2sigma(snr)))
     scale = utils.llr_scale(snr)
@@ -774,7 +780,8 @@ def bench_mc(args, w, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"chunk": chunk, "frames_per_gpu": F * args.steps,
+        "config": {"chunk": chunk, "chunk_rounds": chunk / float(max(1, lib.npd_sc_round_codewords(h.h))),
+                   "frames_per_gpu": F * args.steps, "frames_per_step": F,
                    "l2_policy": "two chunks in flight; a chunk's y (%d MB) makes one HBM round trip" % (chunk * N * 4 >> 20),
                    "step": "npd_mc_sc_sweep over batch_per_gpu frames (Philox counters = global frame index); one NCCL "
                            "all-reduce of the 3 counters at the end of the timed region when n_gpus > 1"},

@@ -92,6 +92,13 @@ int npd_gen_encode_awgn(const npd_code_t *code, float *msg, float *x, float *y, 
 int npd_sc_decode(const npd_code_t *code, const float *y, float llr_scale, const float *use_gt,
                   float *leaf_llr, float *decoded, int64_t B, void *stream);
 
+/* npd_sc_round_codewords: the decisions-only decoder for N >= 256 is a persistent kernel -- every resident warp decodes
+ * groups of 8 codewords in rounds -- so a call (or a sweep chunk, npd_mc_sc_sweep) whose B is a multiple of this number
+ * leaves no partly filled last round (B = 131072 at N = 1024 is 9.2 rounds and costs 10).  0 for codes decoded by the
+ * dynamically scheduled kernels (N < 256, PAC).  The loops of polar.py:1258-1291 choose their own batch; sweep.py uses
+ * this to size the chunks of the fused sweep. */
+int64_t npd_sc_round_codewords(const npd_code_t *code);
+
 /* npd_pac_sc_decode: PAC.pac_sc_decode(y, snr, use_gt_codeword) (pac_code.py:534-573): min-sum SC
  * without priors + convolutional-state tracking.  Outputs leaf_llr[B,N] (optional), v_hat[B,K]
  * (= v_hat[:, B-set], 0 where a tie left v undecided), u_hat[B,N] (optional). */

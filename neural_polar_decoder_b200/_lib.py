@@ -25,6 +25,7 @@ SIGNATURES = {
     "npd_awgn": (_int, [_vp, _vp, _i64, _int, _f32, _u64, _u32, _u64, _vp]),
     "npd_gen_encode_awgn": (_int, [_vp, _vp, _vp, _vp, _i64, _f32, _u64, _u32, _u64, _vp]),
     "npd_sc_decode": (_int, [_vp, _vp, _f32, _vp, _vp, _vp, _i64, _vp]),
+    "npd_sc_round_codewords": (_i64, [_vp]),
     "npd_scl_decode": (_int, [_vp, _vp, _f32, _int, _vp, _vp, _i64, _vp]),
     "npd_scl_decode_host": (_int, [_vp, _vp, _f32, _int, _vp, _vp, _i64]),
     "npd_pac_sc_decode": (_int, [_vp, _vp, _f32, _vp, _vp, _vp, _vp, _i64, _vp]),

@@ -1298,10 +1298,10 @@ int scratch_pool(cudaMemPool_t *out)
 int npd_scratch_pool(cudaMemPool_t *out) { return scratch_pool(out); }  // shared with gru_decode.cu (residual state)
 namespace {
 
-int launch_quad_n(const npd_code *code, const int n, ScParams p, cudaStream_t st)
+// resident configuration of sc_quad_kernel<n>: scratch levels, shared memory per warp, warps per block, blocks per SM
+struct QuadResidency { int gl; size_t per_warp; int wpb, blocks_per_sm; };
+int quad_residency(const npd_code *code, const int n, const DeviceProps &dp, QuadResidency *out)
 {
-    DeviceProps dp;
-    if (npd_get_device_props(&dp)) return NPD_ECUDA;
     // N >= 2048: levels n-2 and n-3 (3/4 of the stored tree) go to a global scratch: 22 KB instead of 70 KB of shared
     // memory per warp at N = 4096, 10 warps per SM instead of 3 (1.17e7 -> 1.62e7 cw/s; one scratch level: 1.57e7).
     // At N = 1024 the same change measures slower at every occupancy (best: one scratch level, 16 warps, 0.835 ms per
@@ -1309,7 +1309,6 @@ int launch_quad_n(const npd_code *code, const int n, ScParams p, cudaStream_t st
     // (NPD_SC_GTOP10 = 1 | 2 turns it on for experiments).
     const int gl = n >= 11 ? max(0, min(2, env_int("NPD_SC_GTOP", 2)))  // scratch levels: 0, 1 or 2
                            : n == 10 ? max(0, min(2, env_int("NPD_SC_GTOP10", 0))) : 0;
-    const bool gtop = gl > 0;
     const size_t per_warp = quad_warp_smem_bytes(n, gl);
     const size_t budget = (size_t)dp.smem_optin;
     if (per_warp + 1024 > budget) {
@@ -1337,6 +1336,19 @@ int launch_quad_n(const npd_code *code, const int n, ScParams p, cudaStream_t st
             if (b >= 1 && 5 * b * w >= 6 * best) { best = b * w; wpb = w; blocks_per_sm = b; }
         }
     }
+    out->gl = gl; out->per_warp = per_warp; out->wpb = wpb; out->blocks_per_sm = blocks_per_sm;
+    return NPD_OK;
+}
+
+int launch_quad_n(const npd_code *code, const int n, ScParams p, cudaStream_t st)
+{
+    DeviceProps dp;
+    if (npd_get_device_props(&dp)) return NPD_ECUDA;
+    QuadResidency qr;
+    if (int rc = quad_residency(code, n, dp, &qr)) return rc;
+    const int gl = qr.gl, wpb = qr.wpb, blocks_per_sm = qr.blocks_per_sm;
+    const bool gtop = gl > 0;
+    const size_t per_warp = qr.per_warp;
     const int64_t ngroups = (p.B + 7) / 8;
     int64_t grid = (int64_t)dp.sm_count * blocks_per_sm;
     const int64_t need = (ngroups + wpb - 1) / wpb;
@@ -1613,6 +1625,19 @@ int npd_sc_decode_count(const npd_code *code, const float *y, float llr_scale, c
                                                           (unsigned long long *)counts, (unsigned long long)B);
     NPD_CHECK_CUDA(cudaGetLastError());
     return NPD_OK;
+}
+
+// codewords one full round of the persistent decisions-only kernel decodes on this device (0: the code runs on the lane
+// kernel, whose blocks are scheduled dynamically)
+NPD_API int64_t npd_sc_round_codewords(const npd_code_t *code)
+{
+    if (!code || code->pac_g != 0 || code->n < 8) return 0;
+    DeviceProps dp;
+    if (npd_get_device_props(&dp)) return 0;
+    QuadResidency qr;
+    // N = 4096 decodes as 1024-leaf sub-blocks (launch_quad_split)
+    if (quad_residency(code, code->n >= 12 ? 10 : code->n, dp, &qr)) return 0;
+    return (int64_t)dp.sm_count * qr.blocks_per_sm * qr.wpb * 8;
 }
 
 NPD_API int npd_sc_decode(const npd_code_t *code, const float *y, float llr_scale,

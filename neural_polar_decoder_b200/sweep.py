@@ -226,8 +226,18 @@ def finalize(counts, K):
     return (c[:, 0] / (frames * K)).tolist(), (c[:, 1] / frames).tolist(), c[:, 2].astype(np.int64).tolist()
 
 
+def sc_round_chunk(polar, chunk):
+    """`chunk` rounded to a whole number of rounds of the persistent SC kernel (npd_sc_round_codewords): a chunk of 9.2
+    rounds costs 10.  Unchanged for codes the dynamically scheduled kernels decode."""
+    rnd = int(_lib.load().npd_sc_round_codewords(polar._handle().h))
+    if rnd <= 0 or chunk < rnd:
+        return int(chunk)
+    return (int(chunk) + rnd // 2) // rnd * rnd
+
+
 def mc_sc_sweep(polar, snr_range, total_frames, chunk=1 << 17, seed=0, rank=None, world=None, group=None):
-    """SC BER/BLER of `total_frames` frames per SNR point, fused on the device (npd_mc_sc_sweep)."""
+    """SC BER/BLER of `total_frames` frames per SNR point, fused on the device (npd_mc_sc_sweep).  `chunk` is rounded to
+    whole rounds of the decoder (sc_round_chunk); the counts do not depend on it (Philox counters = global frame index)."""
     import torch.distributed as dist
     _lib.require_cuda()
     collective = rank is None  # explicit (rank, world) = a caller-simulated shard: no all-reduce, the caller sums
@@ -240,7 +250,7 @@ def mc_sc_sweep(polar, snr_range, total_frames, chunk=1 << 17, seed=0, rank=None
     dev = torch.device("cuda", torch.cuda.current_device())
     snr_range = list(snr_range)
     counts = torch.zeros(len(snr_range), 3, dtype=torch.int64, device=dev)
-    chunk = int(max(1, min(chunk, max(hi - lo, 1))))
+    chunk = int(max(1, min(sc_round_chunk(polar, chunk), max(hi - lo, 1))))
     ws_bytes = lib.npd_mc_sc_workspace_bytes(h.h, chunk)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     for si, snr in enumerate(snr_range):
