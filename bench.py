@@ -61,7 +61,7 @@ WORKLOADS = {
                   desc="fused SC Monte-Carlo sweep Polar(256,128), 2 dB: generate + encode + AWGN + SC + count on the device"),
     "mc1024": dict(kind="mc", N=1024, K=512, snr=2.0, batch=5 << 20, chunk=1 << 17,
                    desc="fused SC Monte-Carlo sweep Polar(1024,512), 2 dB: generate + encode + AWGN + SC + count on the device"),
-    "mc4096": dict(kind="mc", N=4096, K=2048, snr=2.0, batch=1 << 20, chunk=1 << 15,
+    "mc4096": dict(kind="mc", N=4096, K=2048, snr=2.0, batch=1 << 20, chunk=1 << 16,
                    desc="fused SC Monte-Carlo sweep Polar(4096,2048), 2 dB: generate + encode + AWGN + SC + count on the device"),
     "train64": dict(kind="train", N=64, K=22, snr=0.0, batch=4096, tf32=0,
                     desc="CRISP GRU(2x512) training iteration Polar(64,22), run_crisp.sh batch 4096, teacher-forced: forward + "

@@ -112,6 +112,28 @@ def test_mc_sc_sweep_split_invariance_and_curve():
         assert abs(ber[i] - ref_ber[i]) <= hw + 5e-6, ("ber", snr, ber[i], ref_ber[i], hw)  # ref_ber has 5 digits
 
 
+def test_sc_round_chunk_and_chunk_invariance():
+    """npd_sc_round_codewords: a whole number of resident groups of 8 per SM for the persistent kernel (N >= 256), 0 for the
+    lane-kernel codes; sweep.sc_round_chunk rounds to it; the sweep's counters do not depend on the chunk size."""
+    from neural_polar_decoder_b200 import PolarCode, _lib, construct
+    from neural_polar_decoder_b200.sweep import mc_sc_sweep, sc_round_chunk
+    lib = _lib.load()
+    assert lib.npd_sc_round_codewords(_polar64()._handle().h) == 0
+    assert sc_round_chunk(_polar64(), 40000) == 40000
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    for n, K in ((8, 128), (10, 512), (12, 2048)):
+        code = PolarCode(n, K, None, F=construct.pw_frozen_set(1 << n, K))
+        rnd = lib.npd_sc_round_codewords(code._handle().h)
+        assert rnd > 0 and rnd % (8 * sms) == 0, (n, rnd)
+        assert sc_round_chunk(code, 3 * rnd + 5) == 3 * rnd and sc_round_chunk(code, rnd // 2) == rnd // 2
+    code = PolarCode(10, 512, None, F=construct.pw_frozen_set(1024, 512))
+    rnd = lib.npd_sc_round_codewords(code._handle().h)
+    frames = 2 * rnd + 1234
+    a = mc_sc_sweep(code, [2.0], frames, chunk=rnd, seed=3, rank=0, world=1)[3]
+    b = mc_sc_sweep(code, [2.0], frames, chunk=5000, seed=3, rank=0, world=1)[3]
+    assert torch.equal(a, b) and int(a[0, 2]) == frames
+
+
 def test_mc_decoder_sweep_gru_statistics():
     """GRU sweep through the generic driver: frame counts and split invariance over simulated ranks."""
     from neural_polar_decoder_b200 import synth
