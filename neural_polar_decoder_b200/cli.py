@@ -63,6 +63,8 @@ _ARGS = [
     ("progressive_path", str, None), ("load_path", str, None), ("run_dumer", "bool", True), ("run_ML", "bool", False),
     ("hard_decision", "flag", False), ("gpu", int, -2), ("anomaly", "flag", False), ("only_args", "flag", False),
     ("use_ynn", "flag", False), ("reverse_order", "flag", False), ("print_cust", "flag", False), ("fresh", "flag", False),
+    # not a reference flag: arithmetic of the training step's GEMMs (npd_gru_trainer_create; fp32 = the reference's)
+    ("train_gemm", str, "fp32", ["fp32", "tf32", "bf16", "fp16"]),
 ]
 
 # default PAC generator polynomial per code length (rnn_all.py:217-235)

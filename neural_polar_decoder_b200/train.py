@@ -134,7 +134,7 @@ def run_train(args, out=print):
     if os.path.dirname(final_path):
         os.makedirs(os.path.dirname(final_path), exist_ok=True)
     bs = args.batch_size
-    trainer = GRUTrainer(net, args.N, bs)
+    trainer = GRUTrainer(net, args.N, bs, tf32=("fp32", "tf32", "bf16", "fp16").index(getattr(args, "train_gemm", "fp32")))
     loss_code = decoder._loss_code(code.info_inds)
     info = torch.as_tensor(np.asarray(code.info_inds), device=dev)
     out("Training ({}, {}). Need to save for: {} \n Save path: {}".format(args.K, args.N, args.model_save_per, results_path))

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--final_steps", type=int, default=1500)
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--test_size", type=int, default=100000)
+    ap.add_argument("--train_gemm", default="fp32", choices=["fp32", "tf32", "bf16", "fp16"])
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "r02_gpu_curriculum.json"))
     a = ap.parse_args()
     work = tempfile.mkdtemp(prefix="npd_gpu_train_")
@@ -36,8 +37,8 @@ def main():
         argv = ("--code Polar --rate_profile rev_polar --target_K %d --N 64 --K %d --decoding_type y_input --rnn_feature_size 512 "
                 "--num_steps %d --batch_size %d --rnn_depth 2 --model_save_per 1000000 --tfr_min 1 --tfr_max 1 --dec_train_snr 0 "
                 "--lr 0.001 --scheduler step --lr_decay 2000 --lr_decay_gamma 0.95 --onehot --id gpu%d --print_freq 100 "
-                "--save_path %s --test_snr_start -2 --test_snr_end 2 --snr_points 5 --test_size %d --test_batch_size 10000"
-                % (a.K, K, a.final_steps if last else a.steps, a.batch, K, save, a.test_size)).split()
+                "--save_path %s --test_snr_start -2 --test_snr_end 2 --snr_points 5 --test_size %d --test_batch_size 10000 "
+                "--train_gemm %s" % (a.K, K, a.final_steps if last else a.steps, a.batch, K, save, a.test_size, a.train_gemm)).split()
         if prev:
             argv += ["--load_path", prev]
         args = cli.get_args(argv)
@@ -50,7 +51,7 @@ def main():
                                                                     losses[-1][1]), flush=True)
         prev = save
     res = cli.run_test(args, out=lambda *x: None)
-    out = {"what": "run_crisp.sh-style curriculum trained on the GPU (fp32, npd_gru_train_step), then the TESTING block",
+    out = {"what": "run_crisp.sh-style curriculum trained on the GPU (%s GEMMs, npd_gru_train_step), then the TESTING block" % a.train_gemm,
            "batch": a.batch, "stages": stages, "train_seconds": sum(s["seconds"] for s in stages), "total_seconds": time.time() - t0,
            "test_size": a.test_size, "snr_range": res["snr_range"], "bers_RNN": res["bers_RNN"], "blers_RNN": res["blers_RNN"],
            "bers_SC": res["bers_SC"], "blers_SC": res["blers_SC"],
