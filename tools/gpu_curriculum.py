@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--train_gemm", default="fp32", choices=["fp32", "tf32", "bf16", "fp16"])
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "r02_gpu_curriculum.json"))
     a = ap.parse_args()
+    a.out = os.path.abspath(a.out)
     work = tempfile.mkdtemp(prefix="npd_gpu_train_")
     os.chdir(work)
     torch.manual_seed(0)
