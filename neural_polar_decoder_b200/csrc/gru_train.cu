@@ -25,7 +25,10 @@
 //             the [B/8, 7, H] partials are reduced once at the end (deterministic).
 //   update    one fused kernel: global grad-norm clip coefficient + AdamW.
 // The GEMMs are plain library GEMMs (cublasGemmEx on fp32 data; inner products in fp32, or on TF32 / bf16 / fp16 tensor
-// cores with fp32 accumulation); everything else is this file.
+// cores with fp32 accumulation) -- except the forward pass's recurrent GEMMs in TF32 mode, which run together with their
+// gate kernel as ONE hand-written tcgen05 kernel per layer-step (gru_train_tc.cuh: TMA-fed kind::tf32 MMAs into TMEM, gate
+// math in the epilogue, TMA stores of the saved quantities) when H is a multiple of 128 and the batch of 128.
+// Everything else is this file.
 #include <cublas_v2.h>
 #include <math.h>
 #include <stdlib.h>
@@ -34,6 +37,7 @@
 #include <vector>
 
 #include "npd_common.cuh"
+#include "gru_train_tc.cuh"
 
 #define NPD_CHECK_CUBLAS(expr)                                                        \
     do {                                                                              \
@@ -97,6 +101,10 @@ struct npd_gru_trainer {
     unsigned char *is_loss;    // [N] device copy of the loss set's indicator
     unsigned char *h_is_loss;  // [N] what is_loss holds (uploaded only when the loss set changes)
     int is_loss_valid;
+    // fused TF32 layer-step kernel (gru_train_tc.cuh): GEMM mode 1, H a multiple of 128, tensor-map encoder available
+    int tc_ok;
+    int64_t tc_batch;            // batch the state tensor maps were built for
+    CUtensorMap tm_s, tm_w[2], tm_gi[2];  // saved state [2 x 5 x N x B, H]; per layer W_hh [3H, H] and the input projection
 };
 
 namespace {
@@ -374,6 +382,13 @@ NPD_API int npd_gru_trainer_create(int N, int H, int64_t max_batch, const float 
     t->gemm_mode = tf32 < 0 ? 0 : tf32 > 3 ? 3 : tf32;
     NPD_CHECK_CUBLAS(cublasSetMathMode(t->blas, t->gemm_mode ? CUBLAS_DEFAULT_MATH : CUBLAS_PEDANTIC_MATH));
     NPD_CHECK_CUBLAS(cublasSetPointerMode(t->blas, CUBLAS_POINTER_MODE_HOST));
+    if (t->gemm_mode == 1 && H % gru_tc::TU == 0) {
+        t->tc_ok = gru_tc::encode_map(&t->tm_w[0], t->p + t->o_whh0, G, Hs) && gru_tc::encode_map(&t->tm_w[1], t->p + t->o_whh1, G, Hs);
+        if (t->tc_ok) {
+            NPD_CHECK_CUDA(cudaFuncSetAttribute(gru_tc::gru_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gru_tc::SMEM_BYTES));
+            NPD_CHECK_CUDA(cudaFuncSetAttribute(gru_tc::gru_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gru_tc::SMEM_BYTES));
+        }
+    }
     *out = t;
     return NPD_OK;
 }
@@ -448,13 +463,39 @@ NPD_API int npd_gru_train_step(npd_gru_trainer_t *t, const npd_code_t *loss_code
     // ---- forward ----
     // row-major [rows, cols] arrays are cuBLAS column-major [cols, rows]: out[rows, G] = in[rows, K] . W[G, K]^T is
     // gemm(T, N, G, rows, K, W, in)
+    if (t->tc_ok && t->tc_batch != B) {  // the saved state and the projections are laid out for the call's batch
+        t->tc_ok = gru_tc::encode_map(&t->tm_s, t->saved, 10 * (uint64_t)N * (uint64_t)B, (uint64_t)H) &&
+                   gru_tc::encode_map(&t->tm_gi[0], t->gy, (uint64_t)B, (uint64_t)G) &&
+                   gru_tc::encode_map(&t->tm_gi[1], t->dgi, (uint64_t)N * (uint64_t)B, (uint64_t)G);
+        t->tc_batch = B;
+    }
+    const bool tc = t->tc_ok != 0 && B % gru_tc::TM == 0 && 10 * (int64_t)N * B <= 0x7fffffffLL;
+    const dim3 tc_grid((unsigned)(B / gru_tc::TM), (unsigned)(H / gru_tc::TU));
+    auto tc_step = [&](int layer, int s) {
+        gru_tc::FwdParams fp{};
+        fp.b_ih = P + (layer == 0 ? t->o_bih0 : t->o_bih1);
+        fp.b_hh = P + (layer == 0 ? t->o_bhh0 : t->o_bhh1);
+        fp.wcol = layer == 0 ? t->wcol : nullptr;
+        fp.fb = layer == 0 ? t->fb + (size_t)s * B : nullptr;
+        fp.B = B; fp.H = H;
+        fp.gi_row0 = layer == 0 ? 0 : (int)((int64_t)s * B);
+        fp.hprev_row0 = s > 0 ? (int)((((int64_t)layer * 5 + 4) * N + (s - 1)) * B) : 0;
+        for (int q = 0; q < 5; ++q) fp.out_row0[q] = (int)((((int64_t)layer * 5 + q) * N + s) * B);
+        fp.zero_h = s == 0;
+        if (layer == 0)
+            gru_tc::gru_fwd_tc_kernel<true><<<tc_grid, gru_tc::THREADS, gru_tc::SMEM_BYTES, st>>>(fp, t->tm_s, t->tm_w[0], t->tm_gi[0]);
+        else
+            gru_tc::gru_fwd_tc_kernel<false><<<tc_grid, gru_tc::THREADS, gru_tc::SMEM_BYTES, st>>>(fp, t->tm_s, t->tm_w[1], t->tm_gi[1]);
+    };
     auto layer0_step = [&](int s) -> cublasStatus_t {
+        if (tc) { tc_step(0, s); return CUBLAS_STATUS_SUCCESS; }
         cublasStatus_t e = gemm32(t->blas, mode, CUBLAS_OP_T, CUBLAS_OP_N, G, (int)B, H, &one, P + t->o_whh0, H, h_of(0, s - 1), H, &zero, t->gh, G);
         cell_fwd_kernel<true><<<blocks_for(BH), 256, 0, st>>>(t->gy, t->gh, P + t->o_bih0, P + t->o_bhh0, t->wcol,
                                                               t->fb + (size_t)s * B, h_of(0, s - 1), sv(0, s), qs, B, H);
         return e;
     };
     auto layer1_step = [&](int s) -> cublasStatus_t {
+        if (tc) { tc_step(1, s); return CUBLAS_STATUS_SUCCESS; }
         cublasStatus_t e = gemm32(t->blas, mode, CUBLAS_OP_T, CUBLAS_OP_N, G, (int)B, H, &one, P + t->o_whh1, H, h_of(1, s - 1), H, &zero, t->gh, G);
         cell_fwd_kernel<false><<<blocks_for(BH), 256, 0, st>>>(t->dgi + (size_t)s * BG, t->gh, P + t->o_bih1, P + t->o_bhh1, nullptr,
                                                                nullptr, h_of(1, s - 1), sv(1, s), qs, B, H);

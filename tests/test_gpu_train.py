@@ -178,3 +178,37 @@ def test_train_step_tensor_core_gemm_modes(mode, rel):
         res[m] = (loss, norm, tr.get("grads"))
     assert res[mode][0] == pytest.approx(res[0][0], rel=2e-3)
     assert _relerr(res[mode][2], res[0][2]) <= rel, _relerr(res[mode][2], res[0][2])
+
+
+@pytest.mark.parametrize("teacher", [True, False])
+def test_train_fused_tf32_layer_step_matches_library_path(teacher):
+    """GEMM mode 1, H % 128 == 0, batch % 128 == 0: the forward layer-steps run on the fused tcgen05 kernel
+    (csrc/gru_train_tc.cuh: TMA-fed kind::tf32 MMAs, gates in the epilogue, TMA stores of the saved quantities).  The same rows
+    inside a batch of 257 take the library-GEMM + gate-kernel path; logits of a row do not depend on the batch, so the two
+    must agree to TF32 round-off, and both must sit within TF32 precision of the fp32 parity mode."""
+    from neural_polar_decoder_b200 import synth
+    from neural_polar_decoder_b200.rnn_all import RNN_Model, RNN_decoder, get_code
+    from neural_polar_decoder_b200.train import GRUTrainer
+    N, K, H, B = 32, 16, 256, 256
+    code = get_code("Polar", "polar", N, K)
+    sd = synth.gru_state_dict(6, N, H, 2, head_gain=2.0)
+    rs = np.random.RandomState(8)
+    msg = (1.0 - 2.0 * rs.randint(0, 2, size=(B + 1, K))).astype(np.float32)
+    gt = np.ones((B + 1, N), np.float32)
+    gt[:, code.info_inds] = msg
+    y = torch.from_numpy((code.encode(torch.from_numpy(msg).cuda()).cpu().numpy() + rs.randn(B + 1, N)).astype(np.float32)).cuda()
+    gt = torch.from_numpy(gt).cuda()
+    out = {}
+    for name, mode, rows in (("fused", 1, B), ("library", 1, B + 1), ("fp32", 0, B)):
+        net = RNN_Model('GRU', N + 2, H, 1, 2, N, 0, 0)
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        dec = RNN_decoder('y_input', N, code.info_inds, onehot=True)
+        tr = GRUTrainer(net, N, B + 1, tf32=mode)
+        loss, norm, logits = tr.step(dec._loss_code(code.info_inds), y[:rows].contiguous(), gt[:rows].contiguous(), teacher, 1e-3,
+                                     0.25, apply_update=False, want_logits=True)
+        out[name] = (loss, logits[:B].cpu().numpy(), tr.get("grads"))
+    if teacher:  # student forcing feeds decisions back: a TF32-sized logit difference near zero may flip a later input
+        assert np.abs(out["fused"][1] - out["library"][1]).max() <= 5e-3
+        assert np.abs(out["fused"][1] - out["fp32"][1]).max() <= 5e-3
+    assert out["fused"][0] == pytest.approx(out["fp32"][0], rel=2e-3)
+    assert _relerr(out["fused"][2], out["fp32"][2]) <= 2e-2
