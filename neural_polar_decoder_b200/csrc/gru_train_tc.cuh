@@ -175,14 +175,14 @@ __global__ void __launch_bounds__(THREADS, 1) gru_fwd_tc_kernel(const FwdParams 
             load_inputs(0);
             load_inputs(1);
             for (int cb = 0; cb < N_CB; ++cb) {
+                if (cb + 2 < N_CB) {  // refill the input buffer as soon as block cb's inputs sit in registers
+                    mbar_wait(bar_in_empty + 8 * (cb & 1), (cb >> 1) & 1);
+                    load_inputs(cb + 2);
+                }
                 mbar_wait(bar_out_full, cb & 1);
 #pragma unroll
                 for (int q = 0; q < 5; ++q) tma_store_2d(&tm_s, u0 + cb * KB, p.out_row0[q] + row0, s0 + (8 + q) * BOX_BYTES);
                 bulk_commit();
-                if (cb + 2 < N_CB) {
-                    mbar_wait(bar_in_empty + 8 * (cb & 1), (cb >> 1) & 1);
-                    load_inputs(cb + 2);
-                }
                 bulk_wait_read0();         // the stores have read the staging boxes
                 mbar_arrive(bar_out_empty);
             }
