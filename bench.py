@@ -709,10 +709,8 @@ def bench_mc(args, w, rank, world, local_rank):
     N, K, F, snr = w["N"], w["K"], w["batch"], w["snr"]
     code = make_code(w)
     h = code._handle()
-    # chunks of whole decoder rounds (the persistent SC kernel: 148 SMs x resident warps x 8 codewords per round), and a
-    # step of whole chunks
+    # chunks of whole decoder rounds (the persistent SC kernel: 148 SMs x resident warps x 8 codewords per round)
     chunk = args.chunk if getattr(args, "chunk", 0) > 0 else sweep.sc_round_chunk(code, w["chunk"])
-    F = max(1, F // chunk) * chunk
     dev = torch.device("cuda", local_rank)
     sigma = float(np.float32(utils.snr_db2sigma(snr)))
     scale = utils.llr_scale(snr)
@@ -781,7 +779,7 @@ def bench_mc(args, w, rank, world, local_rank):
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"chunk": chunk, "chunk_rounds": chunk / float(max(1, lib.npd_sc_round_codewords(h.h))),
-                   "frames_per_gpu": F * args.steps, "frames_per_step": F,
+                   "frames_per_gpu": F * args.steps,
                    "l2_policy": "two chunks in flight; a chunk's y (%d MB) makes one HBM round trip" % (chunk * N * 4 >> 20),
                    "step": "npd_mc_sc_sweep over batch_per_gpu frames (Philox counters = global frame index); one NCCL "
                            "all-reduce of the 3 counters at the end of the timed region when n_gpus > 1"},
