@@ -214,13 +214,17 @@ int npd_mc_gru_sweep(const npd_gru_t *gru, const npd_code_t *code, const npd_cod
  * One iteration of the reference's training loop for rnn_type GRU / 'y_input' / onehot / 2 layers / Linear(H,1) head
  * (rnn_all.py:1399-1437): decoder.decode(net, True, y, gt, tfr) teacher-forced (425-449) or student-forced (463-489),
  * MSELoss on the loss positions (1413), backward, clip_grad_norm_(clip) (1432), torch.optim.AdamW step (1346, 1435;
- * betas 0.9 / 0.999, eps 1e-8, weight_decay 0.01).  fp32 throughout.  The trainer owns parameters, gradients, Adam
+ * betas 0.9 / 0.999, eps 1e-8, weight_decay 0.01).  fp32 data throughout.  The trainer owns parameters, gradients, Adam
  * moments and the saved activations for up to max_batch codewords.
  *   h_params : host fp32 blob in state_dict order: rnn.weight_ih_l0 [3H,N+2], rnn.weight_hh_l0 [3H,H], rnn.bias_ih_l0,
  *              rnn.bias_hh_l0 [3H], rnn.weight_ih_l1 [3H,H], rnn.weight_hh_l1 [3H,H], rnn.bias_ih_l1, rnn.bias_hh_l1,
  *              linear.weight [H], linear.bias [1]  (npd_gru_trainer_param_count(N, H) floats)
  *   tf32     : GEMM arithmetic on the fp32 data: 0 = fp32 (parity mode), 1 = TF32, 2 = bf16, 3 = fp16 tensor cores (fp32
- *              accumulation; master weights, saved activations, gate math and the optimizer stay fp32) */
+ *              accumulation; master weights, saved activations, gate math and the optimizer stay fp32).  In mode 1, with
+ *              H a multiple of 128 and a batch that is a multiple of 128, the forward pass's recurrent GEMM and gate math of
+ *              a layer-step run as one tcgen05 kernel (csrc/gru_train_tc.cuh; sigma / tanh through ex2.approx + rcp.approx,
+ *              relative error 1e-7); every other shape or mode uses library GEMMs + the exact gate kernels
+ *   apply_update = 0 leaves the gradient UNCLIPPED (the clip coefficient is applied inside the update kernel) */
 typedef struct npd_gru_trainer npd_gru_trainer_t;
 size_t npd_gru_trainer_param_count(int N, int H);
 int npd_gru_trainer_create(int N, int H, int64_t max_batch, const float *h_params, int tf32,
