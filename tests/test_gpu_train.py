@@ -212,3 +212,24 @@ def test_train_fused_tf32_layer_step_matches_library_path(teacher):
         assert np.abs(out["fused"][1] - out["fp32"][1]).max() <= 5e-3
     assert out["fused"][0] == pytest.approx(out["fp32"][0], rel=2e-3)
     assert _relerr(out["fused"][2], out["fp32"][2]) <= 2e-2
+
+
+def test_training_loop_on_a_pac_code(tmp_path, monkeypatch):
+    """BASELINE config 3's code family: the same training loop on PAC(16,8) (RM profile, convolutional pre-coder): the loss set
+    is the PAC rate profile, the genie tensor carries the message on it; loss falls and the TESTING block runs the PAC
+    branch (pac_sc_decode next to the GRU)."""
+    from neural_polar_decoder_b200 import cli
+    from neural_polar_decoder_b200.train import run_train
+    monkeypatch.chdir(tmp_path)
+    torch.manual_seed(0)
+    import random
+    random.seed(0)
+    argv = ("--code PAC --rate_profile RM --N 16 --K 8 --decoding_type y_input --rnn_feature_size 128 --num_steps 200 "
+            "--batch_size 512 --rnn_depth 2 --tfr_min 1 --tfr_max 1 --dec_train_snr 1 --lr 0.003 --onehot --id tpac --print_freq 50 "
+            "--test_size 4000 --test_batch_size 2000 --test_snr_start 0 --test_snr_end 4 --snr_points 3 --fresh "
+            "--train_gemm tf32").split()
+    args = cli.get_args(argv)
+    losses = run_train(args, out=lambda *a: None)
+    assert losses[-1][1] < 0.7 * losses[0][1], losses
+    res = cli.run_test(args, out=lambda *a: None)
+    assert res["step"] == 200 and res["bers_RNN"][-1] < 0.3
