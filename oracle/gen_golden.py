@@ -485,6 +485,8 @@ if __name__ == "__main__":
         gru_trained_cases()
     if "gru_trained_gpu" in todo:
         gru_trained_cases("crisp_gru_N64_K22_H512_gputrained", "gru_trained_gpu")
+    if "gru_trained_gpu_tenth" in todo:  # tools/gpu_curriculum.py --train_gemm tf32 --steps 500 --final_steps 10000
+        gru_trained_cases("crisp_gru_N64_K22_H512_gputrained_tenth", "gru_trained_gpu_tenth")
     if "conv_trained" in todo:
         conv_trained_cases()
     if "gru_cond" in todo:
