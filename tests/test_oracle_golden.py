@@ -94,6 +94,30 @@ def test_gru_oracle_against_reference_fixtures(golden):
         assert np.array_equal(dec[safe], g[nm + "_decoded"][safe])
 
 
+@pytest.mark.parametrize("ckpt,fixture", [("crisp_gru_N64_K22_H512", "gru_trained"),
+                                          ("crisp_gru_N64_K22_H512_gputrained", "gru_trained_gpu"),
+                                          ("crisp_gru_N64_K22_H512_gputrained_tenth", "gru_trained_gpu_tenth")])
+def test_gru_oracle_on_trained_checkpoints(golden, ckpt, fixture):
+    """The oracle is the checker of bench.py's in-bench parity test on the TRAINED Polar(64,22), H = 512 checkpoints: pin it on
+    those weights too -- forced-feedback logits and free-running decisions against what the live reference produced
+    (oracle/gen_golden.py gru_trained_cases), at fp32 round-off."""
+    import os
+    import torch
+    from conftest import GOLDEN
+    path = os.path.join(GOLDEN, ckpt + ".pt")
+    if not os.path.exists(path):
+        pytest.skip("no %s checkpoint" % ckpt)
+    g = golden(fixture)
+    N, K, H = [int(v) for v in g["cfg"]]
+    sd = torch.load(path, map_location="cpu", weights_only=False)["net"]
+    rows = slice(0, 288, 3)  # 96 of the 288 frames, all three SNR points
+    dec, lg = oracle.gru_decode(sd, g["y"][rows], N, g["info"], forced=g["decoded"][rows])
+    np.testing.assert_allclose(lg, g["logits"][rows], rtol=0, atol=3e-5)
+    free, _ = oracle.gru_decode(sd, g["y"][rows], N, g["info"])
+    safe = np.cumsum(np.abs(g["logits"][rows]) <= 1e-4, axis=1) == 0  # no logit within round-off of zero so far
+    assert np.array_equal(free[safe], g["decoded"][rows][safe])
+
+
 def test_conv_oracle_against_reference_fixtures(golden):
     from neural_polar_decoder_b200 import synth
     g = golden("conv")
