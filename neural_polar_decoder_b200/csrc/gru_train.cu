@@ -384,9 +384,11 @@ NPD_API int npd_gru_trainer_create(int N, int H, int64_t max_batch, const float 
     NPD_CHECK_CUBLAS(cublasSetPointerMode(t->blas, CUBLAS_POINTER_MODE_HOST));
     if (t->gemm_mode == 1 && H % gru_tc::TU == 0) {
         t->tc_ok = gru_tc::encode_map(&t->tm_w[0], t->p + t->o_whh0, G, Hs) && gru_tc::encode_map(&t->tm_w[1], t->p + t->o_whh1, G, Hs);
-        if (t->tc_ok) {
-            NPD_CHECK_CUDA(cudaFuncSetAttribute(gru_tc::gru_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gru_tc::SMEM_BYTES));
-            NPD_CHECK_CUDA(cudaFuncSetAttribute(gru_tc::gru_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gru_tc::SMEM_BYTES));
+        if (t->tc_ok &&
+            (cudaFuncSetAttribute(gru_tc::gru_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gru_tc::SMEM_BYTES) != cudaSuccess ||
+             cudaFuncSetAttribute(gru_tc::gru_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gru_tc::SMEM_BYTES) != cudaSuccess)) {
+            (void)cudaGetLastError();
+            t->tc_ok = 0;  // the library-GEMM path of the same mode
         }
     }
     *out = t;
