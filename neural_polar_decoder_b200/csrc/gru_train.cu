@@ -95,7 +95,7 @@ struct npd_gru_trainer {
     float *part;        // [2 layers][ceil(B/8)][7][H] column sums of the gate gradients, see cell_bwd_kernel
     float *dh, *zeros;  // [B,H]
     float *fb;          // [N][B] feedback entering step t (+-1)
-    float *out, *dout;  // [N][B] logits, d loss / d logit
+    float *out, *dout, *lsq;  // [N][B] logits, d loss / d logit, squared error (0 off the loss set)
     float *scal;        // [4]: loss sum, grad norm^2, spare
     float *wcol;        // [2][3H] the one-hot columns of W_ih0, contiguous
     unsigned char *is_loss;    // [N] device copy of the loss set's indicator
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const float *__restrict__
                                                        int N, int t0, int nsteps, const unsigned char *__restrict__ is_loss_t,
                                                        int write_fb, float inv_count, float *__restrict__ out,
                                                        float *__restrict__ dout, float *__restrict__ fb,
-                                                       float *__restrict__ logits_out, float *loss_sum, int64_t B, int H)
+                                                       float *__restrict__ logits_out, float *__restrict__ lsq, int64_t B, int H)
 {
     const int lane = threadIdx.x & 31;
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -192,13 +192,14 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const float *__restrict__
         const float o = s + b_out[0];
         out[(int64_t)t * B + b] = o;
         if (logits_out) logits_out[b * N + t] = o;
-        float d = 0.0f;
+        float d = 0.0f, sq = 0.0f;
         if (is_loss) {
             const float e = o - gt[b * N + t];
             d = 2.0f * e * inv_count;           // d mean((o - target)^2) / d o
-            atomicAdd(loss_sum, e * e);
+            sq = e * e;
         }
         dout[(int64_t)t * B + b] = d;
+        lsq[(int64_t)t * B + b] = sq;           // summed once per iteration (90 k atomics on one word cost 0.1 ms here)
         if (write_fb && t + 1 < N)
             // student forcing feeds sign(decoded[:, t]) where decoded is the logit on loss (= info) positions and stays
             // +1 elsewhere (rnn_all.py:463-489); sign(0) = 0 one-hots like -1
@@ -365,7 +366,7 @@ NPD_API int npd_gru_trainer_create(int N, int H, int64_t max_batch, const float 
     TR_ALLOC(t->wpart, Ns * G * Hs);
     TR_ALLOC(t->part, 2 * chunks * 7 * Hs);
     TR_ALLOC(t->dh, BH); TR_ALLOC(t->zeros, BH);
-    TR_ALLOC(t->fb, Ns * B); TR_ALLOC(t->out, Ns * B); TR_ALLOC(t->dout, Ns * B);
+    TR_ALLOC(t->fb, Ns * B); TR_ALLOC(t->out, Ns * B); TR_ALLOC(t->dout, Ns * B); TR_ALLOC(t->lsq, Ns * B);
     TR_ALLOC(t->scal, 4);
     TR_ALLOC(t->wcol, 2 * G);
 #undef TR_ALLOC
@@ -399,7 +400,7 @@ NPD_API int npd_gru_trainer_destroy(npd_gru_trainer_t *t)
 {
     if (!t) return NPD_OK;
     if (t->blas) cublasDestroy(t->blas);
-    float *ptrs[] = {t->p, t->saved, t->gy, t->gh, t->dgi, t->dgh, t->dx1, t->wpart, t->part, t->dh, t->zeros, t->fb, t->out, t->dout,
+    float *ptrs[] = {t->p, t->saved, t->gy, t->gh, t->dgi, t->dgh, t->dx1, t->wpart, t->part, t->dh, t->zeros, t->fb, t->out, t->dout, t->lsq,
                      t->scal, t->wcol};
     for (float *p : ptrs) if (p) cudaFree(p);
     if (t->is_loss) cudaFree(t->is_loss);
@@ -506,7 +507,7 @@ NPD_API int npd_gru_train_step(npd_gru_trainer_t *t, const npd_code_t *loss_code
     auto head = [&](int t0, int nsteps, int write_fb) {
         head_fwd_kernel<<<blocks_for((int64_t)nsteps * B * 32), 256, 0, st>>>(h_of(1, t0), P + t->o_wout, P + t->o_bout, gt, N, t0, nsteps,
                                                                              t->is_loss, write_fb, inv_count, t->out, t->dout, t->fb,
-                                                                             logits_out, t->scal, B, H);
+                                                                             logits_out, t->lsq, B, H);
     };
     // gy[B,3H] = y[B,N] . W_ih0[:, :N]^T
     NPD_CHECK_CUBLAS(gemm32(t->blas, mode, CUBLAS_OP_T, CUBLAS_OP_N, G, (int)B, N, &one, P + t->o_wih0, I, y, N, &zero, t->gy, G));
@@ -527,6 +528,7 @@ NPD_API int npd_gru_train_step(npd_gru_trainer_t *t, const npd_code_t *loss_code
             head(s, 1, 1);
         }
     }
+    sum_kernel<<<64, 256, 0, st>>>(t->lsq, (int64_t)N * B, t->scal, 0);  // loss numerator
     NPD_CHECK_CUDA(cudaGetLastError());
     // ---- backward ----
     // in[rows, G] . W[G, K] -> out[rows, K] is gemm(N, N, K, rows, G, W, in); a[rows, K]^T-weighted sums
